@@ -1,0 +1,525 @@
+// Vanilla CFR as a depth-ordered sweep (replaces rlpoker/cfr/cfr.py:105-122,158-255 and
+// rlpoker/cfr/cfr_util.py:14-58 of the reference).
+//
+// One iteration = forward reach propagation level by level, backward counterfactual values level by
+// level with the regret / own-reach contributions of every decision node scattered into a
+// jagged-diagonal scratch, then one accumulate kernel that adds each information set's contributions
+// in ascending node order (the order the reference's recursion visits them), and regret matching.
+// Every product and sum is written in the reference's operand order and the library is compiled with
+// -fmad=false, so regrets, action counts and strategies are bit-identical to the reference.
+#include <memory>
+
+#include "cfr.cuh"
+
+using rlp::fail;
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kTopBlock = 1024;
+
+struct View {
+    const int32_t *first_child, *colbase, *srank, *krank;
+    const int8_t *player;
+    const double *cprob, *sigma;
+    const int64_t *koff_col, *koff_iset;
+    double *pc, *p1, *p2, *val1, *val2, *contrib_r, *contrib_o;
+    const IterState *iter;
+};
+
+// ---- forward: reach of the children of node i (cfr.py:180,208,217) -----------------------------
+__device__ __forceinline__ void fwd_node(const View &v, int64_t i) {
+    int pl = v.player[i];
+    if (pl < 0) return;
+    int fc = v.first_child[i], n = v.first_child[i + 1] - fc;
+    double c = v.pc[i], a = v.p1[i], b = v.p2[i];
+    const double *sg = pl > 0 ? v.sigma + v.colbase[i] : nullptr;
+    for (int k = 0; k < n; ++k) {
+        int j = fc + k;
+        if (v.player[j] < 0) continue;                 // terminals need no reach
+        double e = pl == 0 ? v.cprob[j] : sg[k];
+        v.pc[j] = pl == 0 ? e * c : c;
+        v.p1[j] = pl == 1 ? e * a : a;
+        v.p2[j] = pl == 2 ? e * b : b;
+    }
+}
+
+// ---- backward: value of node i from its children, and its contributions (cfr.py:177-186,204-242) --
+template <bool ZS>
+__device__ __forceinline__ void bwd_node(const View &v, int64_t i, double w) {
+    int pl = v.player[i];
+    if (pl < 0) return;
+    int fc = v.first_child[i], n = v.first_child[i + 1] - fc;
+    const double *sg = pl > 0 ? v.sigma + v.colbase[i] : nullptr;
+    double a1 = 0.0, a2 = 0.0;
+    for (int k = 0; k < n; ++k) {
+        double e = pl == 0 ? v.cprob[fc + k] : sg[k];
+        a1 = a1 + e * v.val1[fc + k];
+        if (!ZS) a2 = a2 + e * v.val2[fc + k];
+    }
+    v.val1[i] = a1;
+    if (!ZS) v.val2[i] = a2;
+    if (pl == 0) return;
+    double c = v.pc[i], x1 = v.p1[i], x2 = v.p2[i];
+    double opp = pl == 1 ? c * x2 : c * x1;            // pi_c * pi_{-i}
+    double own = pl == 1 ? x1 : x2;
+    double vp = pl == 1 ? a1 : (ZS ? -a1 : a2);
+    int kk = v.krank[i];
+    double *dst = v.contrib_r + v.koff_col[kk] + v.colbase[i];
+    for (int k = 0; k < n; ++k) {
+        double va = pl == 1 ? v.val1[fc + k] : (ZS ? -v.val1[fc + k] : v.val2[fc + k]);
+        dst[k] = w * (va - vp) * opp;                 // weight * (v_a - v) * pi_minus_i
+    }
+    v.contrib_o[v.koff_iset[kk] + v.srank[i]] = w * own;   // (weight * pi_i), times sigma in accumulate
+}
+
+__device__ __forceinline__ double iter_weight(const IterState *it) { return it->linear ? (double)it->t : 1.0; }
+
+__global__ void __launch_bounds__(kBlock) k_fwd_level(View v, int64_t lo, int64_t hi) {
+    int64_t i = lo + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < hi) fwd_node(v, i);
+}
+
+template <bool ZS>
+__global__ void __launch_bounds__(kBlock) k_bwd_level(View v, int64_t lo, int64_t hi) {
+    int64_t i = lo + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < hi) bwd_node<ZS>(v, i, iter_weight(v.iter));
+}
+
+// The shallow top of the tree (a few thousand nodes over several levels) in ONE block.
+struct TopLevels { long long off[18]; int n; };
+
+__global__ void __launch_bounds__(kTopBlock) k_fwd_top(View v, TopLevels tl) {
+    for (int l = 0; l < tl.n; ++l) {
+        for (int64_t i = tl.off[l] + threadIdx.x; i < tl.off[l + 1]; i += kTopBlock) fwd_node(v, i);
+        __syncthreads();
+    }
+}
+
+template <bool ZS>
+__global__ void __launch_bounds__(kTopBlock) k_bwd_top(View v, TopLevels tl) {
+    double w = iter_weight(v.iter);
+    for (int l = tl.n - 1; l >= 0; --l) {
+        for (int64_t i = tl.off[l] + threadIdx.x; i < tl.off[l + 1]; i += kTopBlock) bwd_node<ZS>(v, i, w);
+        __syncthreads();
+    }
+}
+
+// ---- accumulate + regret matching (cfr.py:244-252, cfr_util.py:14-58) -------------------------------
+// One thread per information set (internal, size-sorted order => neighbouring threads stream
+// neighbouring columns of every jagged diagonal).
+__global__ void __launch_bounds__(kBlock)
+k_accumulate_rm(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
+                const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
+                const double *__restrict__ contrib_r, const double *__restrict__ contrib_o, double *R, double *S,
+                double *sigma, uint8_t *flags, IterState *iter, int advance) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s == 0 && advance) iter->t += 1;       // every reader of iter->t ran in an earlier kernel
+    if (s >= I) return;
+    int size = iset_size[s];
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    if (na <= 4) {
+        double r[4], sa[4], sg[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            if (a < na) { r[a] = R[c0 + a]; sa[a] = S[c0 + a]; sg[a] = sigma[c0 + a]; }
+        for (int k = 0; k < size; ++k) {
+            const double *cr = contrib_r + koff_col[k] + c0;
+            double wo = contrib_o[koff_iset[k] + s];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (a < na) { r[a] = r[a] + cr[a]; sa[a] = sa[a] + wo * sg[a]; }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            if (a < na) { R[c0 + a] = r[a]; S[c0 + a] = sa[a]; }
+    } else {
+        for (int a = 0; a < na; ++a) {
+            double r = R[c0 + a], sa = S[c0 + a], sg = sigma[c0 + a];
+            for (int k = 0; k < size; ++k) {
+                r = r + contrib_r[koff_col[k] + c0 + a];
+                sa = sa + contrib_o[koff_iset[k] + s] * sg;
+            }
+            R[c0 + a] = r;
+            S[c0 + a] = sa;
+        }
+    }
+    rlp::regret_matching(R + c0, na, sigma + c0);
+    flags[s] = 7;
+}
+
+// Multi-GPU split: local deltas into delta[0..Q) (regret) and delta[Q..2Q) (strategy sum), canonical order.
+__global__ void __launch_bounds__(kBlock)
+k_local_delta(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
+              const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
+              const int64_t *__restrict__ canon_of_col, const double *__restrict__ contrib_r,
+              const double *__restrict__ contrib_o, const double *__restrict__ sigma, double *delta) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= I) return;
+    int size = iset_size[s];
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    for (int a = 0; a < na; ++a) {
+        double r = 0.0, sa = 0.0, sg = sigma[c0 + a];
+        for (int k = 0; k < size; ++k) {
+            r = r + contrib_r[koff_col[k] + c0 + a];
+            sa = sa + contrib_o[koff_iset[k] + s] * sg;
+        }
+        int64_t q = canon_of_col[c0 + a];
+        delta[q] = r;
+        delta[Q + q] = sa;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_apply_delta(int32_t I, int64_t Q, const int64_t *__restrict__ col_off, const int64_t *__restrict__ canon_of_col,
+              const double *__restrict__ delta, double *R, double *S, double *sigma, uint8_t *flags, IterState *iter) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s == 0) iter->t += 1;
+    if (s >= I) return;
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    for (int a = 0; a < na; ++a) {
+        int64_t q = canon_of_col[c0 + a];
+        R[c0 + a] = R[c0 + a] + delta[q];
+        S[c0 + a] = S[c0 + a] + delta[Q + q];
+    }
+    rlp::regret_matching(R + c0, na, sigma + c0);
+    flags[s] = 7;
+}
+
+// ---- average strategy (cfr.py:32-41 / extensive_game.py:67-77) -----------------------------------
+__global__ void __launch_bounds__(kBlock)
+k_average(int32_t I, const int64_t *__restrict__ col_off, const double *__restrict__ S, double *avg) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= I) return;
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    rlp::Neumaier acc;
+    for (int a = 0; a < na; ++a) acc.add(S[c0 + a]);
+    double tot = acc.total();
+    for (int a = 0; a < na; ++a) avg[c0 + a] = tot > 0.0 ? S[c0 + a] / tot : 1.0 / (double)na;
+}
+
+__global__ void __launch_bounds__(kBlock) k_uniform(int32_t I, const int64_t *__restrict__ col_off, double *sigma) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= I) return;
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    for (int a = 0; a < na; ++a) sigma[c0 + a] = 1.0 / (double)na;
+}
+
+__global__ void k_set_iter(IterState *it, long long t, int linear) {
+    it->t = t;
+    it->linear = linear;
+}
+
+__global__ void __launch_bounds__(kBlock) k_permute(int64_t Q, const int64_t *__restrict__ canon_of_col, const double *src,
+                                                    double *dst, int to_internal) {
+    int64_t q = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (q >= Q) return;
+    if (to_internal) dst[q] = src[canon_of_col[q]]; else dst[canon_of_col[q]] = src[q];
+}
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+View make_view(rlp_cfr *c) {
+    rlp_tree *t = c->tree;
+    View v;
+    v.first_child = t->first_child.p; v.colbase = t->colbase.p; v.srank = t->srank.p; v.krank = t->krank.p;
+    v.player = t->player.p; v.cprob = t->cprob.p; v.sigma = c->sigma.p;
+    v.koff_col = t->koff_col.p; v.koff_iset = t->koff_iset.p;
+    v.pc = c->pc.p; v.p1 = c->p1.p; v.p2 = c->p2.p; v.val1 = c->val1.p; v.val2 = c->val2.p;
+    v.contrib_r = c->contrib_r.p; v.contrib_o = c->contrib_o.p; v.iter = c->iter.p;
+    return v;
+}
+
+// forward + backward sweep of one iteration on stream s; returns #kernels via *count
+template <bool ZS>
+int enqueue_sweep(rlp_cfr *c, cudaStream_t s, int *count, const IterState *iter = nullptr) {
+    rlp_tree *t = c->tree;
+    View v = make_view(c);
+    if (iter) v.iter = iter;
+    int L = t->L, top = std::min<int>(t->top_levels, L - 1);   // parents live on levels 0 .. L-2
+    TopLevels tl;
+    tl.n = std::min(top, 17);
+    top = tl.n;
+    for (int l = 0; l <= tl.n; ++l) tl.off[l] = t->level_off[l];
+    int n = 0;
+    if (top > 0) { k_fwd_top<<<1, kTopBlock, 0, s>>>(v, tl); RLP_LAUNCH_CHECK(); ++n; }
+    for (int l = top; l + 1 < L; ++l) {
+        int64_t lo = t->level_off[l], hi = t->level_off[l + 1];
+        k_fwd_level<<<grid_for(hi - lo), kBlock, 0, s>>>(v, lo, hi); RLP_LAUNCH_CHECK(); ++n;
+    }
+    for (int l = L - 2; l >= top; --l) {
+        int64_t lo = t->level_off[l], hi = t->level_off[l + 1];
+        k_bwd_level<ZS><<<grid_for(hi - lo), kBlock, 0, s>>>(v, lo, hi); RLP_LAUNCH_CHECK(); ++n;
+    }
+    if (top > 0) { k_bwd_top<ZS><<<1, kTopBlock, 0, s>>>(v, tl); RLP_LAUNCH_CHECK(); ++n; }
+    *count = n;
+    return RLP_OK;
+}
+
+int enqueue_iteration(rlp_cfr *c, cudaStream_t s, int *count) {
+    rlp_tree *t = c->tree;
+    int n = 0;
+    int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n) : enqueue_sweep<false>(c, s, &n);
+    if (rc) return rc;
+    if (t->I > 0) {
+        k_accumulate_rm<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_col.p,
+                                                        t->koff_iset.p, c->contrib_r.p, c->contrib_o.p, c->R.p, c->S.p,
+                                                        c->sigma.p, c->flags.p, c->iter.p, 1);
+        RLP_LAUNCH_CHECK(); ++n;
+    }
+    *count = n;
+    return RLP_OK;
+}
+
+constexpr int kGraphUnroll = 8;
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+namespace rlp {
+int launch_average(rlp_cfr *c, cudaStream_t s) {
+    rlp_tree *t = c->tree;
+    if (t->I == 0) return RLP_OK;
+    k_average<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->S.p, c->avg.p);
+    RLP_LAUNCH_CHECK();
+    return RLP_OK;
+}
+int permute(rlp_tree *t, const double *src, double *dst, int to_internal, cudaStream_t s) {
+    if (t->Q == 0) return RLP_OK;
+    k_permute<<<grid_for(t->Q), kBlock, 0, s>>>(t->Q, t->d_canon_of_col.p, src, dst, to_internal);
+    RLP_LAUNCH_CHECK();
+    return RLP_OK;
+}
+}  // namespace rlp
+
+extern "C" void rlp_cfr_free(rlp_cfr *c) { delete c; }
+
+extern "C" int rlp_cfr_reset(rlp_cfr *c, void *stream_) {
+    if (!c) return fail(RLP_ERR_INVALID, "null solver");
+    cudaStream_t s = (cudaStream_t)stream_;
+    rlp_tree *t = c->tree;
+    RLP_CUDA(cudaMemsetAsync(c->R.p, 0, c->R.bytes(), s));
+    RLP_CUDA(cudaMemsetAsync(c->S.p, 0, c->S.bytes(), s));
+    RLP_CUDA(cudaMemsetAsync(c->cum_imm.p, 0, c->cum_imm.bytes(), s));
+    RLP_CUDA(cudaMemsetAsync(c->flags.p, 0, c->flags.bytes(), s));
+    RLP_CUDA(cudaMemsetAsync(c->iter.p, 0, 2 * sizeof(IterState), s));
+    if (t->I > 0) { k_uniform<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->sigma.p); RLP_LAUNCH_CHECK(); }
+    c->nodes_touched = 0;
+    c->external_state = false;
+    return RLP_OK;
+}
+
+extern "C" int rlp_cfr_create(rlp_tree *t, void *stream_, rlp_cfr **out) {
+    if (!t || !out) return fail(RLP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    cudaStream_t s = (cudaStream_t)stream_;
+    std::unique_ptr<rlp_cfr> c(new (std::nothrow) rlp_cfr);
+    if (!c) return fail(RLP_ERR_NOMEM, "out of host memory");
+    c->tree = t;
+    size_t Q = (size_t)t->Q, N = (size_t)t->N;
+    RLP_CUDA(c->R.alloc(Q)); RLP_CUDA(c->S.alloc(Q)); RLP_CUDA(c->sigma.alloc(Q)); RLP_CUDA(c->avg.alloc(Q));
+    RLP_CUDA(c->cum_imm.alloc(Q)); RLP_CUDA(c->tmpQ.alloc(Q)); RLP_CUDA(c->delta.alloc(2 * Q));
+    RLP_CUDA(c->flags.alloc((size_t)t->I));
+    RLP_CUDA(c->pc.alloc(N)); RLP_CUDA(c->p1.alloc(N)); RLP_CUDA(c->p2.alloc(N));
+    RLP_CUDA(c->val1.alloc(N)); RLP_CUDA(c->vbr.alloc(N));
+    if (!t->zero_sum) RLP_CUDA(c->val2.alloc(N));
+    RLP_CUDA(c->contrib_r.alloc((size_t)t->NC)); RLP_CUDA(c->contrib_o.alloc((size_t)t->ND));
+    RLP_CUDA(c->astar.alloc((size_t)t->I));
+    RLP_CUDA(c->iter.alloc(2));    // [1] stays {t=0, linear=0}: weight 1.0 for metric sweeps
+    RLP_CUDA(c->scalars.alloc(16));
+    // terminal values never change: val = payoff everywhere, interior nodes are rewritten every sweep
+    RLP_CUDA(cudaMemcpyAsync(c->val1.p, t->pay1.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s));
+    if (!t->zero_sum) RLP_CUDA(cudaMemcpyAsync(c->val2.p, t->pay2.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s));
+    const double one = 1.0;
+    RLP_CUDA(cudaMemcpyAsync(c->pc.p, &one, sizeof(double), cudaMemcpyHostToDevice, s));
+    RLP_CUDA(cudaMemcpyAsync(c->p1.p, &one, sizeof(double), cudaMemcpyHostToDevice, s));
+    RLP_CUDA(cudaMemcpyAsync(c->p2.p, &one, sizeof(double), cudaMemcpyHostToDevice, s));
+    RLP_CUDA(cudaStreamSynchronize(s));
+    int rc = rlp_cfr_reset(c.get(), stream_);
+    if (rc) return rc;
+    *out = c.release();
+    return RLP_OK;
+}
+
+static int ensure_graph(rlp_cfr *c) {
+    if (c->graph_exec) return RLP_OK;
+    cudaStream_t cap;
+    RLP_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaStreamDestroy(cap); return fail(RLP_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
+    uint64_t before = rlp::g_launches.load();
+    int total = 0, rc = RLP_OK;
+    for (int u = 0; u < kGraphUnroll && rc == RLP_OK; ++u) {
+        int n = 0;
+        rc = enqueue_iteration(c, cap, &n);
+        total += n;
+    }
+    e = cudaStreamEndCapture(cap, &c->graph);
+    rlp::g_launches.store(before);      // capture records, it does not launch
+    cudaStreamDestroy(cap);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(RLP_ERR_CUDA, "end capture: %s", cudaGetErrorString(e));
+    RLP_CUDA(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+    c->graph_kernels = total;
+    return RLP_OK;
+}
+
+extern "C" int rlp_cfr_vanilla_iters(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, void *stream_) {
+    if (!c || n_iters < 0) return fail(RLP_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    k_set_iter<<<1, 1, 0, s>>>(c->iter.p, (long long)t0, linear_weight);
+    RLP_LAUNCH_CHECK();
+    int64_t left = n_iters;
+    if (left >= kGraphUnroll) {
+        int rc = ensure_graph(c);
+        if (rc) return rc;
+        for (; left >= kGraphUnroll; left -= kGraphUnroll) {
+            RLP_CUDA(cudaGraphLaunch(c->graph_exec, s));
+            rlp::g_launches.fetch_add(c->graph_kernels, std::memory_order_relaxed);
+        }
+    }
+    for (; left > 0; --left) {
+        int n = 0;
+        int rc = enqueue_iteration(c, s, &n);
+        if (rc) return rc;
+    }
+    c->nodes_touched += 2ull * (uint64_t)c->tree->N * (uint64_t)n_iters;
+    return RLP_OK;
+}
+
+extern "C" uint64_t rlp_nodes_touched(rlp_cfr *c) { return c ? c->nodes_touched : 0; }
+
+extern "C" int rlp_cfr_local_sweep(rlp_cfr *c, int64_t t_iter, int linear_weight, void *stream_) {
+    if (!c) return fail(RLP_ERR_INVALID, "null solver");
+    cudaStream_t s = (cudaStream_t)stream_;
+    rlp_tree *t = c->tree;
+    k_set_iter<<<1, 1, 0, s>>>(c->iter.p, (long long)t_iter, linear_weight);
+    RLP_LAUNCH_CHECK();
+    int n = 0;
+    int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n) : enqueue_sweep<false>(c, s, &n);
+    if (rc) return rc;
+    if (t->I > 0) {
+        k_local_delta<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->Q, t->iset_size.p, t->col_off.p, t->koff_col.p,
+                                                      t->koff_iset.p, t->d_canon_of_col.p, c->contrib_r.p,
+                                                      c->contrib_o.p, c->sigma.p, c->delta.p);
+        RLP_LAUNCH_CHECK();
+    }
+    return RLP_OK;
+}
+
+extern "C" void *rlp_cfr_delta_ptr(rlp_cfr *c) { return c ? (void *)c->delta.p : nullptr; }
+
+extern "C" int rlp_cfr_apply_delta(rlp_cfr *c, void *stream_) {
+    if (!c) return fail(RLP_ERR_INVALID, "null solver");
+    cudaStream_t s = (cudaStream_t)stream_;
+    rlp_tree *t = c->tree;
+    if (t->I > 0) {
+        k_apply_delta<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->Q, t->col_off.p, t->d_canon_of_col.p, c->delta.p,
+                                                      c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p);
+        RLP_LAUNCH_CHECK();
+    }
+    c->nodes_touched += 2ull * (uint64_t)t->N;
+    return RLP_OK;
+}
+
+// ---- I/O in canonical order -----------------------------------------------------------------------
+namespace rlp { int permute(rlp_tree *t, const double *src, double *dst, int to_internal, cudaStream_t s); }
+
+static double *which_buffer(rlp_cfr *c, int which) {
+    switch (which) {
+        case RLP_REGRET: return c->R.p;
+        case RLP_STRAT_SUM: return c->S.p;
+        case RLP_SIGMA: return c->sigma.p;
+        case RLP_AVERAGE: return c->avg.p;
+        case RLP_CUM_IMM_REGRET: return c->cum_imm.p;
+        default: return nullptr;
+    }
+}
+
+extern "C" int rlp_cfr_read(rlp_cfr *c, int which, double *dst, void *stream_) {
+    if (!c || !dst) return fail(RLP_ERR_INVALID, "null argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    double *src = which_buffer(c, which);
+    if (!src) return fail(RLP_ERR_INVALID, "unknown array %d", which);
+    if (which == RLP_AVERAGE) { int rc = rlp::launch_average(c, s); if (rc) return rc; }
+    int rc = rlp::permute(c->tree, src, c->tmpQ.p, 0, s);
+    if (rc) return rc;
+    RLP_CUDA(cudaMemcpyAsync(dst, c->tmpQ.p, sizeof(double) * (size_t)c->tree->Q, cudaMemcpyDeviceToHost, s));
+    RLP_CUDA(cudaStreamSynchronize(s));
+    return RLP_OK;
+}
+
+extern "C" int rlp_cfr_write(rlp_cfr *c, int which, const double *src, void *stream_) {
+    if (!c || !src) return fail(RLP_ERR_INVALID, "null argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    double *dst = which_buffer(c, which);
+    if (!dst || which == RLP_AVERAGE) return fail(RLP_ERR_INVALID, "array %d is not writable", which);
+    RLP_CUDA(cudaMemcpyAsync(c->tmpQ.p, src, sizeof(double) * (size_t)c->tree->Q, cudaMemcpyHostToDevice, s));
+    int rc = rlp::permute(c->tree, c->tmpQ.p, dst, 1, s);
+    if (rc) return rc;
+    RLP_CUDA(cudaStreamSynchronize(s));
+    return RLP_OK;
+}
+
+extern "C" int rlp_cfr_read_flags(rlp_cfr *c, uint8_t *dst, void *stream_) {
+    if (!c || !dst) return fail(RLP_ERR_INVALID, "null argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    rlp_tree *t = c->tree;
+    std::vector<uint8_t> tmp((size_t)t->I);
+    RLP_CUDA(cudaMemcpyAsync(tmp.data(), c->flags.p, (size_t)t->I, cudaMemcpyDeviceToHost, s));
+    RLP_CUDA(cudaStreamSynchronize(s));
+    for (int32_t k = 0; k < t->I; ++k) dst[t->iset_of_srank[k]] = tmp[k];
+    return RLP_OK;
+}
+
+// ---- immediate regret (cfr_metrics.py:13-78), one strategy per call ------------------------------------
+namespace {
+__global__ void __launch_bounds__(kBlock)
+k_imm_regret(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
+             const int64_t *__restrict__ koff_col, const double *__restrict__ contrib_r, double *cum, double *per_iset,
+             double inv_steps) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= I) return;
+    int size = iset_size[s];
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    double mx = 0.0;
+    for (int a = 0; a < na; ++a) {
+        double r = 0.0;
+        for (int k = 0; k < size; ++k) r = r + contrib_r[koff_col[k] + c0 + a];
+        double cu = cum[c0 + a] + r;
+        cum[c0 + a] = cu;
+        mx = (a == 0 || cu > mx) ? cu : mx;
+    }
+    per_iset[s] = inv_steps * mx;
+}
+}  // namespace
+
+extern "C" int rlp_cfr_immediate_regret_step(rlp_cfr *c, int64_t step, const int32_t *order, double *out, void *stream_) {
+    if (!c || !out || step < 0) return fail(RLP_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    rlp_tree *t = c->tree;
+    int n = 0;
+    int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n, c->iter.p + 1) : enqueue_sweep<false>(c, s, &n, c->iter.p + 1);
+    if (rc) return rc;
+    double inv = 1.0 / (double)(1 + step);
+    // per-information-set values land in the (otherwise idle) own-reach scratch: ND >= I doubles
+    double *per_iset = c->contrib_o.p;
+    if (t->I > 0) {
+        k_imm_regret<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_col.p, c->contrib_r.p,
+                                                     c->cum_imm.p, per_iset, inv);
+        RLP_LAUNCH_CHECK();
+    }
+    std::vector<double> h((size_t)t->I);
+    RLP_CUDA(cudaMemcpyAsync(h.data(), per_iset, sizeof(double) * (size_t)t->I, cudaMemcpyDeviceToHost, s));
+    RLP_CUDA(cudaStreamSynchronize(s));
+    // builtin sum() over the reference's dict order (cfr_metrics.py:74) -- I scalars, host side
+    rlp::Neumaier acc;
+    for (int32_t k = 0; k < t->I; ++k) acc.add(h[t->srank_of_iset[order ? order[k] : k]]);
+    *out = acc.total();
+    return RLP_OK;
+}

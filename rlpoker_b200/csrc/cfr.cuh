@@ -1,0 +1,39 @@
+// Solver state shared by the CFR, best-response and sampled-traversal translation units.
+#pragma once
+#include "tree.cuh"
+
+struct IterState {
+    long long t;        // iteration about to run
+    int linear;         // weight = t if linear else 1.0 (cfr.py:106)
+    int pad;
+    unsigned long long touched;   // device-side nodes_touched (sampled variants)
+};
+
+struct rlp_cfr {
+    rlp_tree *tree = nullptr;
+    // [Q] internal pair order
+    rlp::DevBuf<double> R, S, sigma, avg, cum_imm, tmpQ, delta;
+    rlp::DevBuf<uint8_t> flags;              // [I] internal order; bit0 in_R, bit1 in_S/alpha, bit2 in_sigma
+    // per-node scratch
+    rlp::DevBuf<double> pc, p1, p2, val1, val2, vbr;
+    rlp::DevBuf<double> contrib_r, contrib_o;
+    rlp::DevBuf<int32_t> astar;              // [I] best-response action per information set
+    rlp::DevBuf<IterState> iter;
+    rlp::DevBuf<double> scalars;             // small device scratch for reductions
+    uint64_t nodes_touched = 0;
+    bool external_state = false;             // S holds alpha of AverageStrategy
+    // CUDA graph of one vanilla iteration
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_kernels = 0;
+    ~rlp_cfr() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (graph) cudaGraphDestroy(graph);
+    }
+};
+
+namespace rlp {
+// implemented in cfr.cu, used by br.cu / sampled.cu
+int launch_average(rlp_cfr *c, cudaStream_t s);                        // c->avg <- average strategy
+int launch_best_response(rlp_cfr *c, const double *sigma_int, int player, double *value_dev, cudaStream_t s);
+}  // namespace rlp

@@ -1,0 +1,187 @@
+// rlp_tree_upload: validate a flattened game, derive the device layout, copy it to HBM.
+#include <algorithm>
+#include <memory>
+#include <new>
+#include <numeric>
+
+#include "tree.cuh"
+
+namespace rlp {
+thread_local char g_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace rlp
+
+using rlp::fail;
+
+int64_t rlp_tree::bytes() const {
+    return (int64_t)(first_child.bytes() + colbase.bytes() + srank.bytes() + krank.bytes() + player.bytes() +
+                     cprob.bytes() + pay1.bytes() + pay2.bytes() + koff_col.bytes() + koff_iset.bytes() +
+                     iset_size.bytes() + iset_level.bytes() + iset_player.bytes() + col_off.bytes() +
+                     iset_node_off.bytes() + iset_nodes.bytes() + d_canon_of_col.bytes());
+}
+
+extern "C" const char *rlp_last_error(void) { return rlp::g_error; }
+extern "C" int rlp_version(void) { return 1; }
+extern "C" uint64_t rlp_kernel_launches(void) { return rlp::g_launches.load(); }
+
+extern "C" int rlp_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(RLP_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+extern "C" void rlp_tree_free(rlp_tree *t) { delete t; }
+extern "C" int64_t rlp_tree_bytes(const rlp_tree *t) { return t ? t->bytes() : 0; }
+
+extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree **out) {
+    if (!d || !out) return fail(RLP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t N = d->num_nodes;
+    const int32_t I = d->num_infosets;
+    const int32_t L = d->num_levels;
+    if (N < 1 || N >= (int64_t)INT32_MAX || I < 0 || L < 1) return fail(RLP_ERR_INVALID, "bad sizes");
+    if (!d->first_child || !d->player || !d->infoset || !d->cprob || !d->u1 || !d->u2 || !d->act_off || !d->level_off)
+        return fail(RLP_ERR_INVALID, "null array in rlp_tree_desc");
+    if (d->level_off[0] != 0 || d->level_off[1] != 1 || d->level_off[L] != N)
+        return fail(RLP_ERR_INVALID, "level_off must start at the root and end at num_nodes");
+    if (d->first_child[0] != 1 && N > 1) return fail(RLP_ERR_INVALID, "first_child[0] must be 1 (breadth-first order)");
+
+    std::unique_ptr<rlp_tree> t(new (std::nothrow) rlp_tree);
+    if (!t) return fail(RLP_ERR_NOMEM, "out of host memory");
+    t->N = N; t->I = I; t->L = L;
+    t->level_off.assign(d->level_off, d->level_off + L + 1);
+    t->act_off.assign(d->act_off, d->act_off + I + 1);
+    t->Q = I ? d->act_off[I] : 0;
+
+    // ---- validation + information-set sizes ------------------------------------------------
+    std::vector<int32_t> size(I, 0), level(I, -1);
+    std::vector<int8_t> owner(I, 0);
+    bool zs = true;
+    int32_t max_act = 0;
+    for (int32_t lv = 0; lv < L; ++lv) {
+        if (d->level_off[lv + 1] < d->level_off[lv]) return fail(RLP_ERR_INVALID, "level_off not monotone");
+        for (int64_t i = d->level_off[lv]; i < d->level_off[lv + 1]; ++i) {
+            int pl = d->player[i];
+            int64_t nc = (int64_t)d->first_child[i + 1] - d->first_child[i];
+            if (nc < 0 || d->first_child[i] < 1 || d->first_child[i + 1] > N)
+                return fail(RLP_ERR_INVALID, "first_child out of range at node %lld", (long long)i);
+            if (pl == -1) {
+                if (nc != 0) return fail(RLP_ERR_INVALID, "terminal node %lld has children", (long long)i);
+                if (d->u2[i] != -d->u1[i]) zs = false;
+                continue;
+            }
+            if (pl < 0 || pl > 2) return fail(RLP_ERR_INVALID, "player %d at node %lld", pl, (long long)i);
+            if (nc == 0) return fail(RLP_ERR_INVALID, "non-terminal node %lld has no children", (long long)i);
+            if (d->first_child[i] < d->level_off[lv + 1] || d->first_child[i + 1] > d->level_off[std::min(lv + 2, L)])
+                return fail(RLP_ERR_INVALID, "children of node %lld are not on the next level", (long long)i);
+            if (pl == 0) continue;
+            int32_t is = d->infoset[i];
+            if (is < 0 || is >= I) return fail(RLP_ERR_INVALID, "information set %d at node %lld", is, (long long)i);
+            if (nc != d->act_off[is + 1] - d->act_off[is])
+                return fail(RLP_ERR_INVALID, "node %lld disagrees with its information set on #actions", (long long)i);
+            if (nc > rlp::kMaxActions) return fail(RLP_ERR_UNSUPPORTED, "more than %d actions", rlp::kMaxActions);
+            if (size[is] == 0) { level[is] = lv; owner[is] = (int8_t)pl; }
+            else if (level[is] != lv || owner[is] != pl)
+                return fail(RLP_ERR_INVALID, "information set %d spans depths or players", is);
+            size[is]++;
+            max_act = std::max<int32_t>(max_act, (int32_t)nc);
+        }
+    }
+    for (int32_t is = 0; is < I; ++is)
+        if (size[is] == 0) return fail(RLP_ERR_INVALID, "information set %d has no nodes", is);
+    t->zero_sum = zs;
+    t->max_act = max_act;
+
+    // ---- internal order: descending size, stable ---------------------------------------------
+    t->iset_of_srank.resize(I);
+    std::iota(t->iset_of_srank.begin(), t->iset_of_srank.end(), 0);
+    std::stable_sort(t->iset_of_srank.begin(), t->iset_of_srank.end(),
+                     [&](int32_t a, int32_t b) { return size[a] > size[b]; });
+    t->srank_of_iset.resize(I);
+    t->col_off_h.assign(I + 1, 0);
+    std::vector<int32_t> size_s(I), level_s(I);
+    std::vector<int8_t> owner_s(I);
+    for (int32_t s = 0; s < I; ++s) {
+        int32_t is = t->iset_of_srank[s];
+        t->srank_of_iset[is] = s;
+        size_s[s] = size[is]; level_s[s] = level[is]; owner_s[s] = owner[is];
+        t->col_off_h[s + 1] = t->col_off_h[s] + (d->act_off[is + 1] - d->act_off[is]);
+    }
+    t->canon_of_col.resize(t->Q);
+    for (int32_t s = 0; s < I; ++s) {
+        int32_t is = t->iset_of_srank[s];
+        for (int64_t a = 0; a < t->col_off_h[s + 1] - t->col_off_h[s]; ++a)
+            t->canon_of_col[t->col_off_h[s] + a] = d->act_off[is] + a;
+    }
+    t->Kmax = I ? size_s[0] : 0;
+    // koff[k]: start of the k-th jagged diagonal
+    std::vector<int64_t> koff_col(t->Kmax + 1, 0), koff_iset(t->Kmax + 1, 0);
+    {
+        int32_t alive = I;   // information sets with size > k
+        for (int32_t k = 0; k < t->Kmax; ++k) {
+            while (alive > 0 && size_s[alive - 1] <= k) --alive;
+            koff_col[k + 1] = koff_col[k] + t->col_off_h[alive];
+            koff_iset[k + 1] = koff_iset[k] + alive;
+        }
+    }
+    t->NC = koff_col[t->Kmax];
+    t->ND = koff_iset[t->Kmax];
+
+    // ---- per-node tables -----------------------------------------------------------------------
+    std::vector<int32_t> colbase(N, -1), srank(N, -1), krank(N, -1), seen(I, 0);
+    std::vector<int64_t> node_off(I + 1, 0);
+    for (int32_t s = 0; s < I; ++s) node_off[s + 1] = node_off[s] + size_s[s];
+    std::vector<int32_t> nodes(t->ND);
+    for (int64_t i = 0; i < N; ++i) {
+        if (d->player[i] <= 0) continue;
+        int32_t s = t->srank_of_iset[d->infoset[i]];
+        srank[i] = s;
+        colbase[i] = (int32_t)t->col_off_h[s];
+        krank[i] = seen[s];
+        nodes[node_off[s] + seen[s]] = (int32_t)i;
+        seen[s]++;
+    }
+    // leading levels one block can sweep
+    int32_t top = 0;
+    while (top < L && d->level_off[top + 1] - d->level_off[top] <= 4096) ++top;
+    t->top_levels = top;
+
+    // ---- upload ----------------------------------------------------------------------------------
+    std::vector<int32_t> fc(d->first_child, d->first_child + N + 1);
+    std::vector<int8_t> pl(d->player, d->player + N);
+    std::vector<double> cp(d->cprob, d->cprob + N), p1(d->u1, d->u1 + N);
+    RLP_CUDA(t->first_child.upload(fc, stream));
+    RLP_CUDA(t->player.upload(pl, stream));
+    RLP_CUDA(t->colbase.upload(colbase, stream));
+    RLP_CUDA(t->srank.upload(srank, stream));
+    RLP_CUDA(t->krank.upload(krank, stream));
+    RLP_CUDA(t->cprob.upload(cp, stream));
+    RLP_CUDA(t->pay1.upload(p1, stream));
+    if (!zs) {
+        std::vector<double> p2(d->u2, d->u2 + N);
+        RLP_CUDA(t->pay2.upload(p2, stream));
+        RLP_CUDA(cudaStreamSynchronize(stream));
+    }
+    RLP_CUDA(t->koff_col.upload(koff_col, stream));
+    RLP_CUDA(t->koff_iset.upload(koff_iset, stream));
+    RLP_CUDA(t->iset_size.upload(size_s, stream));
+    RLP_CUDA(t->iset_level.upload(level_s, stream));
+    RLP_CUDA(t->iset_player.upload(owner_s, stream));
+    RLP_CUDA(t->col_off.upload(t->col_off_h, stream));
+    RLP_CUDA(t->iset_node_off.upload(node_off, stream));
+    RLP_CUDA(t->iset_nodes.upload(nodes, stream));
+    RLP_CUDA(t->d_canon_of_col.upload(t->canon_of_col, stream));
+    RLP_CUDA(cudaStreamSynchronize(stream));     // host vectors die at scope exit
+    *out = t.release();
+    return RLP_OK;
+}

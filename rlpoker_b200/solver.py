@@ -1,0 +1,175 @@
+"""Device-side solver objects: thin, typed wrappers over the C ABI (include/rlpoker_b200.h).
+
+``DeviceTree`` = a flattened game resident in HBM; ``DeviceCFR`` = regrets / action counts /
+strategy + scratch for that tree.  The reference keeps all of this in Python dicts
+(rlpoker/cfr/cfr.py:78-99); here the dicts exist only at the API edge.
+"""
+import ctypes as C
+
+import numpy as np
+
+from rlpoker_b200 import _lib
+from rlpoker_b200._lib import (RLP_AVERAGE, RLP_CHANCE_SAMPLED, RLP_CUM_IMM_REGRET, RLP_EXTERNAL_SAMPLED, RLP_REGRET,
+                               RLP_SIGMA, RLP_STRAT_SUM, check, ptr)
+
+
+def _stream_ptr(stream):
+    """cudaStream_t of a torch stream / int / None (None = torch's current stream when torch has
+    initialised CUDA, else the legacy default stream)."""
+    if stream is None:
+        try:
+            import torch
+            if torch.cuda.is_initialized():
+                return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        except Exception:
+            pass
+        return C.c_void_p(0)
+    if hasattr(stream, 'cuda_stream'):
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+class DeviceTree:
+    def __init__(self, flat_tree, stream=None):
+        _lib.require_device()
+        ft = self.flat = flat_tree
+        self._keep = [np.ascontiguousarray(ft.first_child, np.int32), np.ascontiguousarray(ft.player, np.int8),
+                      np.ascontiguousarray(ft.infoset, np.int32), np.ascontiguousarray(ft.cprob, np.float64),
+                      np.ascontiguousarray(ft.u1, np.float64), np.ascontiguousarray(ft.u2, np.float64),
+                      np.ascontiguousarray(ft.act_off, np.int64), np.ascontiguousarray(ft.level_off, np.int64)]
+        k = self._keep
+        desc = _lib.TreeDesc(
+            num_nodes=ft.num_nodes, num_infosets=ft.num_infosets, num_levels=ft.num_levels,
+            first_child=ptr(k[0], _lib._i32p), player=ptr(k[1], _lib._i8p), infoset=ptr(k[2], _lib._i32p),
+            cprob=ptr(k[3], _lib._dp), u1=ptr(k[4], _lib._dp), u2=ptr(k[5], _lib._dp),
+            act_off=ptr(k[6], _lib._i64p), level_off=ptr(k[7], _lib._i64p))
+        self.handle = C.c_void_p()
+        check(_lib.load().rlp_tree_upload(C.byref(desc), _stream_ptr(stream), C.byref(self.handle)))
+        self._keep = None
+        self.num_pairs = ft.num_pairs
+
+    @property
+    def device_bytes(self):
+        return _lib.load().rlp_tree_bytes(self.handle)
+
+    def best_response(self, sigma, player, want_argmax=False, stream=None):
+        """(value[, argmax[I]]) of ``player``'s best response to the complete strategy array sigma[Q]."""
+        sigma = np.ascontiguousarray(sigma, np.float64)
+        assert sigma.shape == (self.num_pairs,)
+        value = C.c_double()
+        arg = np.empty(self.flat.num_infosets, np.int32) if want_argmax else None
+        check(_lib.load().rlp_best_response(self.handle, ptr(sigma, _lib._dp), int(player), C.byref(value),
+                                            ptr(arg, _lib._i32p) if want_argmax else None, _stream_ptr(stream)))
+        return (value.value, arg) if want_argmax else value.value
+
+    def exploitability(self, sigma, stream=None):
+        return self.best_response(sigma, 1, stream=stream) + self.best_response(sigma, 2, stream=stream)
+
+    def expected_value(self, sigma, stream=None):
+        sigma = np.ascontiguousarray(sigma, np.float64)
+        out = np.empty(2)
+        check(_lib.load().rlp_expected_value(self.handle, ptr(sigma, _lib._dp), ptr(out, _lib._dp), _stream_ptr(stream)))
+        return float(out[0]), float(out[1])
+
+    def close(self):
+        # scratch solvers created by rlp_best_response keep a pointer to the tree; trees are long-lived
+        self.handle = None
+
+
+def device_tree(game_or_flat, stream=None):
+    """Flatten (once) and upload (once per game object)."""
+    from rlpoker_b200.flatten import FlatTree, flatten
+    if isinstance(game_or_flat, DeviceTree):
+        return game_or_flat
+    if isinstance(game_or_flat, FlatTree):
+        ft, holder = game_or_flat, game_or_flat
+    else:
+        ft, holder = flatten(game_or_flat), game_or_flat
+    dt = getattr(holder, '_device_tree', None)
+    if dt is None:
+        dt = DeviceTree(ft, stream=stream)
+        try:
+            holder._device_tree = dt
+        except AttributeError:
+            pass
+    return dt
+
+
+class DeviceCFR:
+    def __init__(self, tree, stream=None):
+        self.tree = tree
+        self.handle = C.c_void_p()
+        check(_lib.load().rlp_cfr_create(tree.handle, _stream_ptr(stream), C.byref(self.handle)))
+        self.t = 0
+
+    def __del__(self):
+        h, self.handle = getattr(self, 'handle', None), None
+        if h:
+            try:
+                _lib.load().rlp_cfr_free(h)
+            except Exception:
+                pass
+
+    def reset(self, stream=None):
+        check(_lib.load().rlp_cfr_reset(self.handle, _stream_ptr(stream)))
+        self.t = 0
+
+    def vanilla(self, n_iters, linear_weight=False, stream=None):
+        check(_lib.load().rlp_cfr_vanilla_iters(self.handle, self.t, int(n_iters), int(bool(linear_weight)),
+                                                _stream_ptr(stream)))
+        self.t += int(n_iters)
+
+    def sampled(self, variant, n_iters, lanes=1, seed=0, linear_weight=False, stream=None):
+        check(_lib.load().rlp_cfr_sampled_iters(self.handle, int(variant), int(lanes), int(seed), self.t, int(n_iters),
+                                                int(bool(linear_weight)), _stream_ptr(stream)))
+        self.t += int(n_iters)
+
+    def read(self, which, stream=None):
+        out = np.empty(self.tree.num_pairs, np.float64)
+        check(_lib.load().rlp_cfr_read(self.handle, which, ptr(out, _lib._dp), _stream_ptr(stream)))
+        return out
+
+    def write(self, which, values, stream=None):
+        values = np.ascontiguousarray(values, np.float64)
+        assert values.shape == (self.tree.num_pairs,)
+        check(_lib.load().rlp_cfr_write(self.handle, which, ptr(values, _lib._dp), _stream_ptr(stream)))
+
+    def flags(self, stream=None):
+        out = np.empty(self.tree.flat.num_infosets, np.uint8)
+        check(_lib.load().rlp_cfr_read_flags(self.handle, ptr(out, _lib._u8p), _stream_ptr(stream)))
+        return out
+
+    regrets = property(lambda self: self.read(RLP_REGRET))
+    strategy_sum = property(lambda self: self.read(RLP_STRAT_SUM))
+    sigma = property(lambda self: self.read(RLP_SIGMA))
+    average = property(lambda self: self.read(RLP_AVERAGE))
+
+    @property
+    def nodes_touched(self):
+        return int(_lib.load().rlp_nodes_touched(self.handle))
+
+    def exploitability(self, which=RLP_AVERAGE, stream=None):
+        """(total, BR1, BR2) of the average (default) or current strategy, computed on the device."""
+        out = np.empty(3)
+        check(_lib.load().rlp_cfr_exploitability(self.handle, which, ptr(out, _lib._dp), _stream_ptr(stream)))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def immediate_regret_step(self, step, order=None, stream=None):
+        out = C.c_double()
+        if order is not None:
+            order = np.ascontiguousarray(order, np.int32)
+        check(_lib.load().rlp_cfr_immediate_regret_step(self.handle, int(step),
+                                                        ptr(order, _lib._i32p) if order is not None else None,
+                                                        C.byref(out), _stream_ptr(stream)))
+        return out.value
+
+    # multi-GPU split
+    def local_sweep(self, linear_weight=False, stream=None):
+        check(_lib.load().rlp_cfr_local_sweep(self.handle, self.t, int(bool(linear_weight)), _stream_ptr(stream)))
+
+    def delta_ptr(self):
+        return _lib.load().rlp_cfr_delta_ptr(self.handle)
+
+    def apply_delta(self, stream=None):
+        check(_lib.load().rlp_cfr_apply_delta(self.handle, _stream_ptr(stream)))
+        self.t += 1
