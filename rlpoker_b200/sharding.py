@@ -1,0 +1,158 @@
+"""Deal sharding of a flattened game across ranks.
+
+Below the root chance deals the tree is a forest of subtrees that share only the strategy (read) and the
+per-information-set accumulators (write).  Rank r keeps a contiguous, size-balanced range of the depth-``cut``
+subtrees plus their ancestors; information-set numbering stays GLOBAL so the per-pair deltas of all ranks
+line up and one sum-allreduce per iteration (2*Q doubles) completes the update.  Reach probabilities of the
+kept nodes are unchanged because chance probabilities are kept as they are.
+"""
+import numpy as np
+
+from rlpoker_b200.flatten import FlatTree
+
+
+class _Sharded(FlatTree):
+    """Rank-local tree; ``global_nodes[i]`` is the id of local node i in the full tree."""
+    __slots__ = ('global_nodes',)
+
+
+def choose_cut(ft, world):
+    """Shallowest depth d such that every node above d is a chance node and depth d has >= 8*world nodes
+    (falls back to the deepest all-chance prefix)."""
+    best = None
+    for d in range(1, ft.num_levels):
+        above = ft.player[:ft.level_off[d]]
+        if np.any(above != 0):
+            break
+        best = d
+        if ft.level_off[d + 1] - ft.level_off[d] >= 8 * world:
+            break
+    if best is None:
+        raise ValueError("this game does not shard: the root is not a chance node (run replicas instead)")
+    return best
+
+
+def subtree_sizes(ft):
+    size = np.ones(ft.num_nodes, np.int64)
+    for d in range(ft.num_levels - 1, 0, -1):
+        lo, hi = int(ft.level_off[d]), int(ft.level_off[d + 1])
+        np.add.at(size, ft.parent[lo:hi], size[lo:hi])
+    return size
+
+
+def shard_ranges(ft, world, cut=None):
+    """[(lo, hi)) node-id ranges of depth-``cut`` subtree roots per rank, balanced by subtree size."""
+    cut = choose_cut(ft, world) if cut is None else cut
+    lo, hi = int(ft.level_off[cut]), int(ft.level_off[cut + 1])
+    sizes = subtree_sizes(ft)[lo:hi]
+    csum = np.concatenate([[0], np.cumsum(sizes)])
+    bounds = [lo + int(np.searchsorted(csum, csum[-1] * r / world, side='left')) for r in range(world)] + [hi]
+    bounds[0] = lo
+    return cut, [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def shard_flat_tree(ft, rank, world, cut=None):
+    """The rank-local FlatTree (global information-set ids; possibly empty information sets)."""
+    if world == 1:
+        return ft
+    cut, ranges = shard_ranges(ft, world, cut)
+    lo, hi = ranges[rank]
+    n = ft.num_nodes
+    keep = np.zeros(n, bool)
+    keep[lo:hi] = True
+    for d in range(cut + 1, ft.num_levels):                   # descendants
+        a, b = int(ft.level_off[d]), int(ft.level_off[d + 1])
+        keep[a:b] = keep[ft.parent[a:b]]
+    for d in range(cut, 0, -1):                               # ancestors
+        a, b = int(ft.level_off[d]), int(ft.level_off[d + 1])
+        keep[ft.parent[a:b][keep[a:b]]] = True
+    new_id = np.cumsum(keep) - 1
+    idx = np.flatnonzero(keep)
+    out = _Sharded()
+    out.num_nodes = len(idx)
+    out.parent = np.where(ft.parent[idx] >= 0, new_id[np.maximum(ft.parent[idx], 0)], -1).astype(np.int32)
+    for name in ('player', 'infoset', 'cprob', 'u1', 'u2', 'label', 'hidden'):
+        setattr(out, name, getattr(ft, name)[idx].copy())
+    out.labels = ft.labels
+    out._keys, out._key_fn = None, (lambda: ft.info_set_keys)
+    _finalize_sharded(out, ft)
+    out.global_nodes = idx
+    return out
+
+
+def _finalize_sharded(out, full):
+    """Like FlatTree.finalize but with the GLOBAL information-set tables (empty sets allowed)."""
+    n = out.num_nodes
+    counts = np.bincount(out.parent[1:], minlength=n).astype(np.int64)
+    out.first_child = np.zeros(n + 1, np.int32)
+    out.first_child[0] = 1
+    out.first_child[1:] = 1 + np.cumsum(counts)
+    out.slot = (np.arange(n, dtype=np.int64) - out.first_child[np.maximum(out.parent, 0)]).astype(np.int32)
+    out.slot[0] = 0
+    out.depth = np.zeros(n, np.int32)
+    level_off = [0, 1]
+    while level_off[-1] < n:
+        hi = level_off[-1]
+        nxt = int(out.first_child[hi])
+        out.depth[hi:nxt] = len(level_off) - 1
+        level_off.append(nxt)
+    out.level_off = np.asarray(level_off, np.int64)
+    out.num_infosets = full.num_infosets
+    out.nact, out.act_off = full.nact, full.act_off
+    out.iset_player, out.iset_depth = full.iset_player, full.iset_depth
+    dec = np.flatnonzero(out.player > 0)
+    isets = out.infoset[dec]
+    order = np.argsort(isets, kind='stable')
+    out.iset_nodes = dec[order].astype(np.int32)
+    out.iset_node_off = np.zeros(full.num_infosets + 1, np.int64)
+    np.cumsum(np.bincount(isets, minlength=full.num_infosets), out=out.iset_node_off[1:])
+    out.zero_sum = full.zero_sum
+
+
+
+
+# ---------------------------------------------------------------------------------------------------
+# the per-iteration exchange
+
+
+def allreduce_delta(delta, group=None):
+    """Sum the [2*Q] (regret || strategy-sum) delta buffer over all ranks, in place (NCCL on CUDA
+    tensors, gloo on CPU tensors)."""
+    import torch.distributed as dist
+    dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
+    return delta
+
+
+class _DeviceArray:
+    """CUDA-array-interface view of library-owned device memory (so torch can all-reduce it in place)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {'shape': (count,), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+
+
+class ShardedCFR:
+    """Vanilla CFR with the deal subtrees sharded over the ranks of a torch.distributed group.
+
+    Every rank holds the full [Q] regret / strategy-sum / strategy arrays (replicated, kept identical by
+    construction) and sweeps only its own subtrees; one all-reduce of the deltas per iteration.  Summation
+    order across ranks differs from the single-GPU order, so parity with the reference is by tolerance
+    (1e-9 on strategies) rather than bit-exact."""
+
+    def __init__(self, flat_tree, rank, world, group=None, stream=None):
+        import torch
+        from rlpoker_b200.solver import DeviceCFR, DeviceTree
+        self.rank, self.world, self.group = rank, world, group
+        self.full = flat_tree
+        self.local = shard_flat_tree(flat_tree, rank, world)
+        self.tree = DeviceTree(self.local, stream=stream)
+        self.solver = DeviceCFR(self.tree, stream=stream)
+        self.delta = torch.as_tensor(_DeviceArray(self.solver.delta_ptr(), 2 * flat_tree.num_pairs), device='cuda')
+        self.nodes_touched = 0
+
+    def iterate(self, n_iters, linear_weight=False):
+        for _ in range(int(n_iters)):
+            self.solver.local_sweep(linear_weight=linear_weight)
+            if self.world > 1:
+                allreduce_delta(self.delta, self.group)
+            self.solver.apply_delta()
+        self.nodes_touched += 2 * self.full.num_nodes * int(n_iters)
