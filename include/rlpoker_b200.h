@@ -113,6 +113,10 @@ int rlp_cfr_vanilla_iters(rlp_cfr *cfr, int64_t t0, int64_t n_iters, int linear_
 int rlp_cfr_sampled_iters(rlp_cfr *cfr, int variant, int64_t lanes, uint64_t seed, int64_t t0,
                           int64_t n_iters, int linear_weight, void *stream);
 
+/* AverageStrategy update with the solver's current strategy (cfr_util.py:109-198): full-tree walk, pruned
+ * below information sets that have no strategy entry; alpha lives in the RLP_STRAT_SUM array. */
+int rlp_cfr_update_average(rlp_cfr *cfr, double weight, void *stream);
+
 /* Copy a [Q] array (canonical order) to / from host memory.  RLP_AVERAGE (read only) is
  * cfr.py:32-41 for vanilla / chance-sampled state and AverageStrategy.compute_strategy
  * (cfr_util.py:95-106) for external-sampled state; absent information sets come out uniform. */
@@ -121,6 +125,7 @@ int rlp_cfr_write(rlp_cfr *cfr, int which, const double *src, void *stream);
 /* [I] flags: bit0 information set has a regret entry, bit1 an action-count / alpha entry,
  * bit2 a strategy entry in the reference's dicts (matters for the sampled variants only). */
 int rlp_cfr_read_flags(rlp_cfr *cfr, uint8_t *dst, void *stream);
+int rlp_cfr_write_flags(rlp_cfr *cfr, const uint8_t *src, void *stream);
 /* CFRState.nodes_touched (rlpoker/cfr/cfr_util.py:5-11). */
 uint64_t rlp_nodes_touched(rlp_cfr *cfr);
 

@@ -49,9 +49,11 @@ SYMBOLS = {
     'rlp_cfr_reset': (C.c_int, [_vp, _vp]),
     'rlp_cfr_vanilla_iters': (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, _vp]),
     'rlp_cfr_sampled_iters': (C.c_int, [_vp, C.c_int, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int, _vp]),
+    'rlp_cfr_update_average': (C.c_int, [_vp, C.c_double, _vp]),
     'rlp_cfr_read': (C.c_int, [_vp, C.c_int, _dp, _vp]),
     'rlp_cfr_write': (C.c_int, [_vp, C.c_int, _dp, _vp]),
     'rlp_cfr_read_flags': (C.c_int, [_vp, _u8p, _vp]),
+    'rlp_cfr_write_flags': (C.c_int, [_vp, _u8p, _vp]),
     'rlp_nodes_touched': (C.c_uint64, [_vp]),
     'rlp_cfr_exploitability': (C.c_int, [_vp, C.c_int, _dp, _vp]),
     'rlp_cfr_immediate_regret_step': (C.c_int, [_vp, C.c_int64, _i32p, _dp, _vp]),

@@ -146,7 +146,7 @@ k_accumulate_rm(int32_t I, const int32_t *__restrict__ iset_size, const int64_t 
         }
     }
     rlp::regret_matching(R + c0, na, sigma + c0);
-    flags[s] = 7;
+    flags[s] = 1; flags[I + s] = 1; flags[2 * I + s] = 1;
 }
 
 // Multi-GPU split: local deltas into delta[0..Q) (regret) and delta[Q..2Q) (strategy sum), canonical order.
@@ -186,7 +186,7 @@ k_apply_delta(int32_t I, int64_t Q, const int64_t *__restrict__ col_off, const i
         S[c0 + a] = S[c0 + a] + delta[Q + q];
     }
     rlp::regret_matching(R + c0, na, sigma + c0);
-    flags[s] = 7;
+    flags[s] = 1; flags[I + s] = 1; flags[2 * I + s] = 1;
 }
 
 // ---- average strategy (cfr.py:32-41 / extensive_game.py:67-77) -----------------------------------
@@ -309,6 +309,7 @@ extern "C" int rlp_cfr_reset(rlp_cfr *c, void *stream_) {
     RLP_CUDA(cudaMemsetAsync(c->iter.p, 0, 2 * sizeof(IterState), s));
     if (t->I > 0) { k_uniform<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->sigma.p); RLP_LAUNCH_CHECK(); }
     c->nodes_touched = 0;
+    c->touched_dirty = false;
     c->external_state = false;
     return RLP_OK;
 }
@@ -323,7 +324,7 @@ extern "C" int rlp_cfr_create(rlp_tree *t, void *stream_, rlp_cfr **out) {
     size_t Q = (size_t)t->Q, N = (size_t)t->N;
     RLP_CUDA(c->R.alloc(Q)); RLP_CUDA(c->S.alloc(Q)); RLP_CUDA(c->sigma.alloc(Q)); RLP_CUDA(c->avg.alloc(Q));
     RLP_CUDA(c->cum_imm.alloc(Q)); RLP_CUDA(c->tmpQ.alloc(Q)); RLP_CUDA(c->delta.alloc(2 * Q));
-    RLP_CUDA(c->flags.alloc((size_t)t->I));
+    RLP_CUDA(c->flags.alloc(3 * (size_t)t->I));
     RLP_CUDA(c->pc.alloc(N)); RLP_CUDA(c->p1.alloc(N)); RLP_CUDA(c->p2.alloc(N));
     RLP_CUDA(c->val1.alloc(N)); RLP_CUDA(c->vbr.alloc(N));
     if (!t->zero_sum) RLP_CUDA(c->val2.alloc(N));
@@ -391,7 +392,15 @@ extern "C" int rlp_cfr_vanilla_iters(rlp_cfr *c, int64_t t0, int64_t n_iters, in
     return RLP_OK;
 }
 
-extern "C" uint64_t rlp_nodes_touched(rlp_cfr *c) { return c ? c->nodes_touched : 0; }
+extern "C" uint64_t rlp_nodes_touched(rlp_cfr *c) {
+    if (!c) return 0;
+    unsigned long long dev = 0;
+    if (c->touched_dirty) {      // sampled lanes count on the device
+        cudaDeviceSynchronize();
+        cudaMemcpy(&dev, &c->iter.p->touched, sizeof(dev), cudaMemcpyDeviceToHost);
+    }
+    return c->nodes_touched + dev;
+}
 
 extern "C" int rlp_cfr_local_sweep(rlp_cfr *c, int64_t t_iter, int linear_weight, void *stream_) {
     if (!c) return fail(RLP_ERR_INVALID, "null solver");
@@ -469,10 +478,12 @@ extern "C" int rlp_cfr_read_flags(rlp_cfr *c, uint8_t *dst, void *stream_) {
     if (!c || !dst) return fail(RLP_ERR_INVALID, "null argument");
     cudaStream_t s = (cudaStream_t)stream_;
     rlp_tree *t = c->tree;
-    std::vector<uint8_t> tmp((size_t)t->I);
-    RLP_CUDA(cudaMemcpyAsync(tmp.data(), c->flags.p, (size_t)t->I, cudaMemcpyDeviceToHost, s));
+    size_t I = (size_t)t->I;
+    std::vector<uint8_t> tmp(3 * I);
+    RLP_CUDA(cudaMemcpyAsync(tmp.data(), c->flags.p, 3 * I, cudaMemcpyDeviceToHost, s));
     RLP_CUDA(cudaStreamSynchronize(s));
-    for (int32_t k = 0; k < t->I; ++k) dst[t->iset_of_srank[k]] = tmp[k];
+    for (size_t k = 0; k < I; ++k)
+        dst[t->iset_of_srank[k]] = (uint8_t)((tmp[k] ? 1 : 0) | (tmp[I + k] ? 2 : 0) | (tmp[2 * I + k] ? 4 : 0));
     return RLP_OK;
 }
 
@@ -521,5 +532,20 @@ extern "C" int rlp_cfr_immediate_regret_step(rlp_cfr *c, int64_t step, const int
     rlp::Neumaier acc;
     for (int32_t k = 0; k < t->I; ++k) acc.add(h[t->srank_of_iset[order ? order[k] : k]]);
     *out = acc.total();
+    return RLP_OK;
+}
+
+extern "C" int rlp_cfr_write_flags(rlp_cfr *c, const uint8_t *src, void *stream_) {
+    if (!c || !src) return fail(RLP_ERR_INVALID, "null argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    rlp_tree *t = c->tree;
+    size_t I = (size_t)t->I;
+    std::vector<uint8_t> tmp(3 * I);
+    for (size_t k = 0; k < I; ++k) {
+        uint8_t f = src[t->iset_of_srank[k]];
+        tmp[k] = f & 1; tmp[I + k] = (f >> 1) & 1; tmp[2 * I + k] = (f >> 2) & 1;
+    }
+    RLP_CUDA(cudaMemcpyAsync(c->flags.p, tmp.data(), 3 * I, cudaMemcpyHostToDevice, s));
+    RLP_CUDA(cudaStreamSynchronize(s));
     return RLP_OK;
 }

@@ -13,14 +13,15 @@ struct rlp_cfr {
     rlp_tree *tree = nullptr;
     // [Q] internal pair order
     rlp::DevBuf<double> R, S, sigma, avg, cum_imm, tmpQ, delta;
-    rlp::DevBuf<uint8_t> flags;              // [I] internal order; bit0 in_R, bit1 in_S/alpha, bit2 in_sigma
+    rlp::DevBuf<uint8_t> flags;              // [3][I] internal order: in_R | in_S (or alpha) | in_sigma dict membership
     // per-node scratch
     rlp::DevBuf<double> pc, p1, p2, val1, val2, vbr;
     rlp::DevBuf<double> contrib_r, contrib_o;
     rlp::DevBuf<int32_t> astar;              // [I] best-response action per information set
     rlp::DevBuf<IterState> iter;
     rlp::DevBuf<double> scalars;             // small device scratch for reductions
-    uint64_t nodes_touched = 0;
+    uint64_t nodes_touched = 0;              // host-side count (vanilla); sampled lanes count in iter->touched
+    bool touched_dirty = false;
     bool external_state = false;             // S holds alpha of AverageStrategy
     // CUDA graph of one vanilla iteration
     cudaGraph_t graph = nullptr;

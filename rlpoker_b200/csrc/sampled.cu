@@ -1,4 +1,293 @@
+// Sampled CFR as independent traversal lanes (replaces the recursions of rlpoker/cfr/cfr.py:158-255 with
+// use_chance_sampling=True and rlpoker/cfr/external_cfr.py:82-173) plus the full-tree average-strategy
+// walk of rlpoker/cfr/cfr_util.py:109-198 as a forward level sweep.
+//
+// One thread = one traversal (lane, traversing player): an explicit-stack depth-first walk over the
+// breadth-first arrays against the strategy frozen for the iteration; chance (and, for external
+// sampling, opponent) actions are drawn with the reference's sampler (rlpoker/util.py:17-27 ->
+// numpy RandomState.choice: normalise, cumsum, renormalise, searchsorted-right) from a counter-based
+// Philox-4x32-10 stream keyed (seed; iteration, lane, player, draw index), so a CPU run fed the same
+// stream reproduces every lane exactly.  lanes == 1 is the reference algorithm bit for bit (plain adds in
+// visit order); lanes > 1 is mini-batch MCCFR with fp64 atomics (order of adds not deterministic).
 #include "cfr.cuh"
-extern "C" int rlp_cfr_sampled_iters(rlp_cfr *, int, int64_t, uint64_t, int64_t, int64_t, int, void *) {
-    return rlp::fail(RLP_ERR_UNSUPPORTED, "sampled CFR not built yet");
+
+using rlp::fail;
+
+namespace {
+constexpr int kBlock = 128;
+constexpr int kMaxDepth = 32;
+constexpr int kMaxAct = 8;        // widest information set the lane kernels handle
+constexpr int kMaxChance = 128;   // widest chance node (numpy's pairwise sum is restated up to here)
+inline unsigned grid_for(int64_t n, int b = kBlock) { return (unsigned)((n + b - 1) / b); }
+
+struct LaneView {
+    const int32_t *first_child, *colbase, *srank;
+    const int8_t *player;
+    const double *cprob, *pay1, *pay2, *sigma;
+    double *R, *S;
+    uint8_t *in_R, *in_S, *in_next;       // [I] each
+    IterState *iter;
+    uint64_t seed;
+    int zero_sum;
+    int atomic;                            // lanes > 1
+};
+
+// np.sum over a short contiguous double array: sequential below 8 elements, 8 running sums above
+// (numpy/core/src/umath/loops_utils.h pairwise sum, n <= 128).
+__device__ inline double numpy_sum(const double *p, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += p[i];
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = p[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += p[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += p[i];
+    return res;
+}
+
+// RandomState.choice(len(p), p=p/np.sum(p)) given the uniform u.
+__device__ inline int draw(const double *p, int n, double u) {
+    double tot = numpy_sum(p, n);
+    double last = 0.0;
+    for (int a = 0; a < n; ++a) last += p[a] / tot;
+    double run = 0.0;
+    int idx = 0;
+    for (int a = 0; a < n; ++a) {
+        run += p[a] / tot;
+        if (run / last <= u) idx = a + 1; else break;
+    }
+    return idx < n ? idx : n - 1;
+}
+
+struct Frame {
+    int node;
+    int k;            // next child to visit
+    double value;     // running expectation
+    double pc, p1, p2;
+    double va[kMaxAct];
+};
+
+__device__ inline void add(double *p, double x, int atomic) {
+    if (atomic) atomicAdd(p, x); else *p = *p + x;
+}
+
+// variant 0: chance-sampled CFR (cfr.py:158-255); variant 1: external sampling (external_cfr.py:82-173)
+template <int VARIANT>
+__global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes) {
+    int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (tid >= 2 * lanes) return;
+    const uint32_t lane = (uint32_t)(tid >> 1);
+    const int me = (int)(tid & 1) + 1;                  // traversing player
+    const uint64_t iteration = (uint64_t)v.iter->t;
+    const double w = v.iter->linear ? (double)v.iter->t : 1.0;
+    uint32_t ndraw = 0;
+    unsigned long long touched = 0;
+    Frame st[kMaxDepth];
+    int sp = 0;
+    st[0].node = 0; st[0].k = 0; st[0].value = 0.0; st[0].pc = 1.0; st[0].p1 = 1.0; st[0].p2 = 1.0;
+    touched++;
+    double ret = 0.0;      // value returned by the frame that just finished
+    bool have_ret = false;
+    while (sp >= 0) {
+        Frame &f = st[sp];
+        const int node = f.node;
+        const int pl = v.player[node];
+        if (pl < 0) {                                   // terminal: utility of the traverser
+            ret = me == 1 ? v.pay1[node] : (v.zero_sum ? -v.pay1[node] : v.pay2[node]);
+            have_ret = true;
+            --sp;
+            continue;
+        }
+        const int fc = v.first_child[node];
+        const int n = v.first_child[node + 1] - fc;
+        const bool sampled_here = pl == 0 || (VARIANT == 1 && pl != me);
+        if (sampled_here) {
+            if (have_ret) { --sp; continue; }           // the sampled child returned: pass its value up unchanged
+            const double *p = pl == 0 ? v.cprob + fc : v.sigma + v.colbase[node];
+            int a = draw(p, n, rlp::philox_uniform(v.seed, iteration, lane, (uint32_t)(me - 1), ndraw++));
+            Frame &c = st[sp + 1];
+            c.node = fc + a; c.k = 0; c.value = 0.0; c.pc = f.pc; c.p1 = f.p1; c.p2 = f.p2;
+            ++sp; touched++;
+            continue;
+        }
+        // decision node whose actions are all explored (chance-sampled: every player node; external: own nodes)
+        const double *sg = v.sigma + v.colbase[node];
+        if (have_ret) {                                  // child f.k-1 just returned
+            have_ret = false;
+            int a = f.k - 1;
+            f.va[a] = ret;
+            f.value += sg[a] * ret;
+        }
+        if (f.k < n) {
+            int a = f.k++;
+            Frame &c = st[sp + 1];
+            c.node = fc + a; c.k = 0; c.value = 0.0;
+            c.pc = f.pc;
+            c.p1 = (VARIANT == 0 && pl == 1) ? sg[a] * f.p1 : f.p1;
+            c.p2 = (VARIANT == 0 && pl == 2) ? sg[a] * f.p2 : f.p2;
+            ++sp; touched++;
+            continue;
+        }
+        // all children done: update (cfr.py:229-252 / external_cfr.py:143-157)
+        const int s = v.srank[node];
+        if (VARIANT == 0) {
+            v.in_R[s] = 1;
+            if (pl == me) {
+                double pi_minus = me == 2 ? f.pc * f.p1 : f.pc * f.p2;
+                double pi_own = me == 1 ? f.p1 : f.p2;
+                double *R = v.R + v.colbase[node], *S = v.S + v.colbase[node];
+                for (int a = 0; a < n; ++a) {
+                    add(R + a, w * (f.va[a] - f.value) * pi_minus, v.atomic);
+                    add(S + a, w * pi_own * sg[a], v.atomic);
+                }
+                v.in_S[s] = 1;
+                v.in_next[s] = 1;
+            }
+        } else {
+            double *R = v.R + v.colbase[node];
+            for (int a = 0; a < n; ++a) add(R + a, f.va[a] - f.value, v.atomic);
+            v.in_R[s] = 1;
+            v.in_next[s] = 1;
+        }
+        ret = f.value;
+        have_ret = true;
+        --sp;
+    }
+    atomicAdd(&v.iter->touched, touched);
+}
+
+__global__ void k_set_iter2(IterState *it, long long t, int linear) {
+    it->t = t;
+    it->linear = linear;
+}
+
+// sigma <- regret matching of R for every information set; advance the iteration counter.
+__global__ void __launch_bounds__(kBlock)
+k_rm_all(int32_t I, const int64_t *__restrict__ col_off, const double *__restrict__ R, double *sigma, IterState *iter) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s == 0) iter->t += 1;
+    if (s >= I) return;
+    int64_t c0 = col_off[s];
+    rlp::regret_matching(R + c0, (int)(col_off[s + 1] - c0), sigma + c0);
+}
+
+// ---- AverageStrategy walk (cfr_util.py:109-198) as a forward level sweep ------------------------------
+struct WalkView {
+    const int32_t *first_child, *colbase, *srank, *krank;
+    const int8_t *player;
+    const double *sigma;
+    const uint8_t *present;     // strategy membership (in_next)
+    const int64_t *koff_iset;
+    double *alive, *p1, *p2, *contrib_o;
+    uint8_t *in_alpha;
+    double weight;
+};
+
+__global__ void __launch_bounds__(kBlock) k_walk_level(WalkView v, int64_t lo, int64_t hi) {
+    int64_t i = lo + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= hi) return;
+    int pl = v.player[i];
+    if (pl < 0) return;
+    int fc = v.first_child[i], n = v.first_child[i + 1] - fc;
+    bool alive = v.alive[i] != 0.0;
+    double a = v.p1[i], b = v.p2[i];
+    const double *sg = nullptr;
+    if (pl > 0) {
+        int s = v.srank[i];
+        bool ok = alive && v.present[s];
+        // pruned / unreached nodes add +0.0, which leaves alpha unchanged bit for bit
+        v.contrib_o[v.koff_iset[v.krank[i]] + s] = ok ? (pl == 1 ? a : b) * v.weight : 0.0;
+        if (ok) v.in_alpha[s] = 1;
+        alive = ok;
+        sg = v.sigma + v.colbase[i];
+    }
+    for (int k = 0; k < n; ++k) {
+        int j = fc + k;
+        if (v.player[j] < 0) continue;
+        v.alive[j] = alive ? 1.0 : 0.0;
+        v.p1[j] = pl == 1 ? a * sg[k] : a;
+        v.p2[j] = pl == 2 ? b * sg[k] : b;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_walk_accumulate(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
+                  const int64_t *__restrict__ koff_iset, const double *__restrict__ contrib_o,
+                  const double *__restrict__ sigma, double *alpha) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= I) return;
+    int size = iset_size[s];
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    for (int a = 0; a < na; ++a) {
+        double acc = alpha[c0 + a], sg = sigma[c0 + a];
+        for (int k = 0; k < size; ++k) acc = acc + sg * contrib_o[koff_iset[k] + s];
+        alpha[c0 + a] = acc;
+    }
+}
+}  // namespace
+
+namespace rlp {
+int launch_average_walk(rlp_cfr *c, double weight, cudaStream_t s) {
+    rlp_tree *t = c->tree;
+    WalkView v;
+    v.first_child = t->first_child.p; v.colbase = t->colbase.p; v.srank = t->srank.p; v.krank = t->krank.p;
+    v.player = t->player.p; v.sigma = c->sigma.p; v.present = c->flags.p + 2 * (size_t)t->I;
+    v.koff_iset = t->koff_iset.p; v.alive = c->pc.p; v.p1 = c->p1.p; v.p2 = c->p2.p; v.contrib_o = c->contrib_o.p;
+    v.in_alpha = c->flags.p + (size_t)t->I; v.weight = weight;
+    // root: alive, both reaches 1.0 -- pc[0]/p1[0]/p2[0] hold 1.0 permanently (rlp_cfr_create)
+    for (int l = 0; l + 1 < t->L; ++l) {
+        int64_t lo = t->level_off[l], hi = t->level_off[l + 1];
+        k_walk_level<<<grid_for(hi - lo), kBlock, 0, s>>>(v, lo, hi); RLP_LAUNCH_CHECK();
+    }
+    if (t->I > 0) {
+        k_walk_accumulate<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_iset.p,
+                                                          c->contrib_o.p, c->sigma.p, c->S.p);
+        RLP_LAUNCH_CHECK();
+    }
+    return RLP_OK;
+}
+}  // namespace rlp
+
+extern "C" int rlp_cfr_update_average(rlp_cfr *c, double weight, void *stream_) {
+    if (!c) return fail(RLP_ERR_INVALID, "null solver");
+    c->external_state = true;
+    return rlp::launch_average_walk(c, weight, (cudaStream_t)stream_);
+}
+
+extern "C" int rlp_cfr_sampled_iters(rlp_cfr *c, int variant, int64_t lanes, uint64_t seed, int64_t t0, int64_t n_iters,
+                                     int linear_weight, void *stream_) {
+    if (!c || lanes < 1 || n_iters < 0) return fail(RLP_ERR_INVALID, "bad argument");
+    if (variant != RLP_CHANCE_SAMPLED && variant != RLP_EXTERNAL_SAMPLED) return fail(RLP_ERR_INVALID, "variant %d", variant);
+    rlp_tree *t = c->tree;
+    if (t->L > kMaxDepth) return fail(RLP_ERR_UNSUPPORTED, "tree deeper than %d levels", kMaxDepth);
+    if (t->max_act > kMaxAct) return fail(RLP_ERR_UNSUPPORTED, "more than %d actions in an information set", kMaxAct);
+    if (t->max_chance > kMaxChance) return fail(RLP_ERR_UNSUPPORTED, "chance node wider than %d", kMaxChance);
+    if (lanes > (int64_t)1 << 31) return fail(RLP_ERR_INVALID, "too many lanes");
+    cudaStream_t s = (cudaStream_t)stream_;
+    LaneView v;
+    v.first_child = t->first_child.p; v.colbase = t->colbase.p; v.srank = t->srank.p; v.player = t->player.p;
+    v.cprob = t->cprob.p; v.pay1 = t->pay1.p; v.pay2 = t->pay2.p; v.sigma = c->sigma.p; v.R = c->R.p; v.S = c->S.p;
+    v.in_R = c->flags.p; v.in_S = c->flags.p + (size_t)t->I; v.in_next = c->flags.p + 2 * (size_t)t->I;
+    v.iter = c->iter.p; v.seed = seed; v.zero_sum = t->zero_sum ? 1 : 0; v.atomic = lanes > 1;
+    k_set_iter2<<<1, 1, 0, s>>>(c->iter.p, (long long)t0, linear_weight);     // keeps the running touched count
+    RLP_LAUNCH_CHECK();
+    if (variant == RLP_EXTERNAL_SAMPLED) c->external_state = true;
+    for (int64_t it = 0; it < n_iters; ++it) {
+        if (variant == RLP_CHANCE_SAMPLED) k_lanes<0><<<grid_for(2 * lanes), kBlock, 0, s>>>(v, lanes);
+        else k_lanes<1><<<grid_for(2 * lanes), kBlock, 0, s>>>(v, lanes);
+        RLP_LAUNCH_CHECK();
+        if (t->I > 0) { k_rm_all<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->R.p, c->sigma.p, c->iter.p); RLP_LAUNCH_CHECK(); }
+        if (variant == RLP_EXTERNAL_SAMPLED) {
+            int rc = rlp::launch_average_walk(c, 1.0, s);
+            if (rc) return rc;
+        }
+    }
+    c->touched_dirty = true;
+    return RLP_OK;
 }

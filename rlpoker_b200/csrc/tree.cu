@@ -67,7 +67,7 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
     std::vector<int32_t> size(I, 0), level(I, -1);
     std::vector<int8_t> owner(I, 0);
     bool zs = true;
-    int32_t max_act = 0;
+    int32_t max_act = 0, max_chance = 0;
     for (int32_t lv = 0; lv < L; ++lv) {
         if (d->level_off[lv + 1] < d->level_off[lv]) return fail(RLP_ERR_INVALID, "level_off not monotone");
         for (int64_t i = d->level_off[lv]; i < d->level_off[lv + 1]; ++i) {
@@ -84,7 +84,7 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
             if (nc == 0) return fail(RLP_ERR_INVALID, "non-terminal node %lld has no children", (long long)i);
             if (d->first_child[i] < d->level_off[lv + 1] || d->first_child[i + 1] > d->level_off[std::min(lv + 2, L)])
                 return fail(RLP_ERR_INVALID, "children of node %lld are not on the next level", (long long)i);
-            if (pl == 0) continue;
+            if (pl == 0) { max_chance = std::max<int32_t>(max_chance, (int32_t)nc); continue; }
             int32_t is = d->infoset[i];
             if (is < 0 || is >= I) return fail(RLP_ERR_INVALID, "information set %d at node %lld", is, (long long)i);
             if (nc != d->act_off[is + 1] - d->act_off[is])
@@ -100,6 +100,7 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
     // information sets without nodes are legal: a deal-sharded rank sees only part of each set
     t->zero_sum = zs;
     t->max_act = max_act;
+    t->max_chance = max_chance;
 
     // ---- internal order: descending size, stable ---------------------------------------------
     t->iset_of_srank.resize(I);

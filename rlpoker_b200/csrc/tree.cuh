@@ -24,6 +24,7 @@ struct rlp_tree {
     int64_t NC = 0;        // sum over decision nodes of #actions (regret-contribution slots)
     int32_t Kmax = 0;      // largest information set
     int32_t max_act = 0;
+    int32_t max_chance = 0;   // widest chance node
     bool zero_sum = false;
     int32_t top_levels = 0;   // leading levels small enough to be swept by one block
     std::vector<int64_t> level_off;

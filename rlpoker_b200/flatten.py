@@ -213,3 +213,31 @@ def array_to_strategy_dict(ft, values, present=None, order=None, wrap=None):
         entry = {a: float(values[lo + j]) for j, a in enumerate(ft.actions_of(i))}
         out[keys[i]] = wrap(entry) if wrap else entry
     return out
+
+
+def postorder_infoset_order(ft):
+    """Information sets ordered by first appearance in depth-first POST-order of the decision nodes: the dict
+    order in which cfr_metrics.compute_immediate_regret (cfr_metrics.py:40-52,74) sums its per-set terms.
+    Vectorised: pre-order rank from subtree sizes, post rank = pre - depth + size - 1."""
+    n = ft.num_nodes
+    fc = ft.first_child.astype(np.int64)
+    size = np.ones(n, np.int64)
+    levels = ft.level_off
+    for d in range(ft.num_levels - 2, -1, -1):
+        lo, hi, nxt = int(levels[d]), int(levels[d + 1]), int(levels[d + 2])
+        csum = np.concatenate([[0], np.cumsum(size[hi:nxt])])
+        size[lo:hi] += csum[fc[lo + 1:hi + 1] - hi] - csum[fc[lo:hi] - hi]
+    pre = np.zeros(n, np.int64)
+    for d in range(ft.num_levels - 1):
+        lo, hi, nxt = int(levels[d]), int(levels[d + 1]), int(levels[d + 2])
+        if nxt == hi:
+            break
+        csum = np.concatenate([[0], np.cumsum(size[hi:nxt])])
+        par = ft.parent[hi:nxt].astype(np.int64)
+        pre[hi:nxt] = pre[par] + 1 + csum[:-1] - csum[fc[par] - hi]
+    post = pre - ft.depth + size - 1
+    dec = np.flatnonzero(ft.player > 0)
+    by_post = dec[np.argsort(post[dec], kind='stable')]
+    isets = ft.infoset[by_post]
+    _, first = np.unique(isets, return_index=True)
+    return isets[np.sort(first)].astype(np.int32)

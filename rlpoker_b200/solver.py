@@ -139,6 +139,16 @@ class DeviceCFR:
         check(_lib.load().rlp_cfr_read_flags(self.handle, ptr(out, _lib._u8p), _stream_ptr(stream)))
         return out
 
+    def write_flags(self, mask, bit=None, stream=None):
+        """Set the dict-membership flags: ``mask`` is a [I] bitmask, or a boolean array for one ``bit`` (1, 2, 4)
+        merged into the current flags."""
+        mask = np.asarray(mask)
+        if bit is not None:
+            cur = self.flags()
+            mask = (cur & ~np.uint8(bit)) | np.where(mask.astype(bool), np.uint8(bit), np.uint8(0))
+        mask = np.ascontiguousarray(mask, np.uint8)
+        check(_lib.load().rlp_cfr_write_flags(self.handle, ptr(mask, _lib._u8p), _stream_ptr(stream)))
+
     regrets = property(lambda self: self.read(RLP_REGRET))
     strategy_sum = property(lambda self: self.read(RLP_STRAT_SUM))
     sigma = property(lambda self: self.read(RLP_SIGMA))

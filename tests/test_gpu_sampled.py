@@ -1,0 +1,101 @@
+"""GPU parity of the sampled variants: device lanes vs the CPU oracle consuming the SAME Philox stream."""
+import numpy as np
+import pytest
+
+from conftest import make_game, oracle_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def _solver(name):
+    from rlpoker_b200.solver import DeviceCFR, device_tree
+    return DeviceCFR(device_tree(make_game(name)))
+
+
+def _flags(o):
+    return (o.in_R > 0) * 1 + (o.in_S > 0) * 2 + (o.in_sigma > 0) * 4
+
+
+@pytest.mark.parametrize('name,T', [('leduc3', 60), ('ocp4', 200), ('leduc2', 100)])
+def test_chance_sampled_single_lane_bit_exact(name, T):
+    from oracle import oracle as orc
+    from rlpoker_b200._lib import RLP_CHANCE_SAMPLED
+    s = _solver(name)
+    o = orc.Oracle(oracle_tree(name))
+    seed = 1234567
+    for chunk in (1, 7, T - 8):
+        s.sampled(RLP_CHANCE_SAMPLED, chunk, lanes=1, seed=seed)
+        o.cfr_recursive(chunk, sampling=True, rng=orc.rng_philox(seed))
+        assert np.array_equal(s.regrets, o.R)
+        assert np.array_equal(s.strategy_sum, o.S)
+        assert np.array_equal(s.sigma, o.sigma)
+        assert np.array_equal(s.flags(), _flags(o))
+        assert s.nodes_touched == o.nodes_touched
+    assert abs(s.exploitability()[0] - o.exploitability(o.average_strategy()[0])) < 1e-12
+
+
+def test_chance_sampled_linear_weight():
+    from oracle import oracle as orc
+    from rlpoker_b200._lib import RLP_CHANCE_SAMPLED
+    s = _solver('leduc2')
+    o = orc.Oracle(oracle_tree('leduc2'))
+    s.sampled(RLP_CHANCE_SAMPLED, 20, lanes=1, seed=5, linear_weight=True)
+    o.cfr_recursive(20, sampling=True, linear_weight=True, rng=orc.rng_philox(5))
+    assert np.array_equal(s.regrets, o.R) and np.array_equal(s.strategy_sum, o.S)
+
+
+@pytest.mark.parametrize('name,T', [('rps', 50), ('leduc3', 80), ('ocp4', 150)])
+def test_external_single_lane_bit_exact(name, T):
+    from oracle import oracle as orc
+    from rlpoker_b200._lib import RLP_EXTERNAL_SAMPLED
+    s = _solver(name)
+    o = orc.Oracle(oracle_tree(name))
+    seed = 42
+    for chunk in (1, 5, T - 6):
+        s.sampled(RLP_EXTERNAL_SAMPLED, chunk, lanes=1, seed=seed)
+        o.external(chunk, orc.rng_philox(seed))
+        assert np.array_equal(s.regrets, o.R)
+        assert np.array_equal(s.strategy_sum, o.S)          # alpha
+        assert np.array_equal(s.sigma, o.sigma)
+        assert np.array_equal(s.flags(), _flags(o))
+        assert s.nodes_touched == o.nodes_touched
+    assert np.array_equal(s.average, o.alpha_strategy())
+    assert abs(s.exploitability()[0] - o.exploitability(o.alpha_strategy())) < 1e-12
+
+
+@pytest.mark.parametrize('variant', ['chance', 'external'])
+def test_batched_lanes_match_oracle_to_rounding(variant):
+    """lanes > 1: same traversals as the oracle's lane loop, summed with atomics (order differs)."""
+    from oracle import oracle as orc
+    from rlpoker_b200._lib import RLP_CHANCE_SAMPLED, RLP_EXTERNAL_SAMPLED
+    s = _solver('leduc3')
+    o = orc.Oracle(oracle_tree('leduc3'))
+    lanes, T, seed = 96, 6, 99
+    if variant == 'chance':
+        s.sampled(RLP_CHANCE_SAMPLED, T, lanes=lanes, seed=seed)
+        o.cfr_recursive(T, sampling=True, lanes=lanes, rng=orc.rng_philox(seed))
+    else:
+        s.sampled(RLP_EXTERNAL_SAMPLED, T, lanes=lanes, seed=seed)
+        o.external(T, orc.rng_philox(seed), lanes=lanes)
+    assert s.nodes_touched == o.nodes_touched
+    np.testing.assert_allclose(s.regrets, o.R, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(s.strategy_sum, o.S, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(s.flags(), _flags(o))
+
+
+def test_sampled_convergence_statistics(golden):
+    """Exploitability after 2000 chance-sampled iterations: the reference (numpy RNG, seed 0) got 1.1967;
+    different random streams scatter around that.  16 Philox seeds must bracket it."""
+    from rlpoker_b200._lib import RLP_CHANCE_SAMPLED
+    want = golden['chance_sampled_leduc3']
+    if want['T'] != 2000:
+        pytest.skip('quick golden set')
+    vals = []
+    s = _solver('leduc3')
+    for seed in range(16):
+        s.reset()
+        s.sampled(RLP_CHANCE_SAMPLED, 2000, lanes=1, seed=seed)
+        vals.append(s.exploitability()[0])
+    vals = np.array(vals)
+    se = vals.std(ddof=1)
+    assert abs(want['exploitability'] - vals.mean()) < 3 * se + 0.05, (vals.mean(), se, want['exploitability'])
