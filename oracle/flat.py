@@ -101,7 +101,8 @@ def finish(t):
     return t
 
 
-def from_arrays(num_nodes, parent, first_child, player, infoset, label, hidden, cprob, u1, u2, labels=None):
+def from_arrays(num_nodes, parent, first_child, player, infoset, label, hidden, cprob, u1, u2, labels=None,
+                nact=None):
     """Wrap arrays produced elsewhere (e.g. the product's Leduc generator, once it has been
     checked against flatten_game on small decks) so the C oracle can run on large trees."""
     t = OracleTree()
@@ -131,17 +132,22 @@ def from_arrays(num_nodes, parent, first_child, player, infoset, label, hidden, 
     t.level_off = np.array(level_off, np.int64)
     dec = np.flatnonzero(t.infoset >= 0)
     ids = t.infoset[dec]
-    ni = int(ids.max()) + 1 if len(dec) else 0
+    ni = (int(ids.max()) + 1 if len(dec) else 0) if nact is None else len(nact)
     t.num_infosets = ni
     o = np.argsort(ids, kind='stable')
     t.iset_nodes = dec[o].astype(np.int32)
     t.iset_node_off = np.zeros(ni + 1, np.int64)
     t.iset_node_off[1:] = np.cumsum(np.bincount(ids, minlength=ni))
-    rep = t.iset_nodes[t.iset_node_off[:-1]]
-    t.nact = (t.first_child[rep + 1] - t.first_child[rep]).astype(np.int32)
+    if nact is None:
+        rep = t.iset_nodes[t.iset_node_off[:-1]]
+        t.nact = (t.first_child[rep + 1] - t.first_child[rep]).astype(np.int32)
+        t.iset_player = t.player[rep].astype(np.int8)
+    else:                       # a shard: information sets keep the full game's numbering, some are empty
+        t.nact = np.ascontiguousarray(nact, np.int32)
+        t.iset_player = np.zeros(ni, np.int8)
+        t.iset_player[ids] = t.player[dec]
     t.act_off = np.zeros(ni + 1, np.int64)
     t.act_off[1:] = np.cumsum(t.nact)
-    t.iset_player = t.player[rep].astype(np.int8)
     return t
 
 
