@@ -13,6 +13,8 @@
 
 using rlp::fail;
 
+namespace rlp { int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter); }
+
 namespace {
 
 constexpr int kBlock = 256;
@@ -239,6 +241,10 @@ View make_view(rlp_cfr *c) {
 template <bool ZS>
 int enqueue_sweep(rlp_cfr *c, cudaStream_t s, int *count, const IterState *iter = nullptr) {
     rlp_tree *t = c->tree;
+    if (t->tiles.enabled) {                 // shared-memory tiled sweep: one launch instead of one per level
+        *count = 1;
+        return rlp::launch_tile_sweep(c, s, iter);
+    }
     View v = make_view(c);
     if (iter) v.iter = iter;
     int L = t->L, top = std::min<int>(t->top_levels, L - 1);   // parents live on levels 0 .. L-2

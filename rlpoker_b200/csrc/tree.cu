@@ -1,5 +1,6 @@
 // rlp_tree_upload: validate a flattened game, derive the device layout, copy it to HBM.
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <new>
 #include <numeric>
@@ -21,11 +22,17 @@ int fail(int code, const char *fmt, ...) {
 
 using rlp::fail;
 
+namespace rlp {
+int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> &colbase,
+                const std::vector<int32_t> &srank, const std::vector<int32_t> &krank,
+                const std::vector<int64_t> &koff_col, const std::vector<int64_t> &koff_iset, cudaStream_t stream);
+}
+
 int64_t rlp_tree::bytes() const {
     return (int64_t)(first_child.bytes() + colbase.bytes() + srank.bytes() + krank.bytes() + player.bytes() +
                      cprob.bytes() + pay1.bytes() + pay2.bytes() + koff_col.bytes() + koff_iset.bytes() +
                      iset_size.bytes() + iset_level.bytes() + iset_player.bytes() + col_off.bytes() +
-                     iset_node_off.bytes() + iset_nodes.bytes() + d_canon_of_col.bytes());
+                     iset_node_off.bytes() + iset_nodes.bytes() + d_canon_of_col.bytes()) + tiles.bytes();
 }
 
 extern "C" const char *rlp_last_error(void) { return rlp::g_error; }
@@ -182,6 +189,13 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
     RLP_CUDA(t->iset_nodes.upload(nodes, stream));
     RLP_CUDA(t->d_canon_of_col.upload(t->canon_of_col, stream));
     RLP_CUDA(cudaStreamSynchronize(stream));     // host vectors die at scope exit
+    {
+        const char *no_tiles = getenv("RLP_NO_TILES");
+        if (!(no_tiles && no_tiles[0] == '1')) {
+            int rc = rlp::build_tiles(d, t.get(), colbase, srank, krank, koff_col, koff_iset, stream);
+            if (rc) return rc;
+        }
+    }
     *out = t.release();
     return RLP_OK;
 }

@@ -14,6 +14,7 @@
 // with unit stride while adding in ascending node order (= the reference's visit order).
 #pragma once
 #include "common.cuh"
+#include "tiles.cuh"
 
 struct rlp_tree {
     int64_t N = 0;
@@ -44,6 +45,7 @@ struct rlp_tree {
     rlp::DevBuf<int64_t> iset_node_off;           // [I+1] internal order
     rlp::DevBuf<int32_t> iset_nodes;              // [ND]
     rlp::DevBuf<int64_t> d_canon_of_col;          // [Q]
+    TileSet tiles;                                // subtree tiles for the shared-memory sweep (may be disabled)
 
     int64_t bytes() const;
 };

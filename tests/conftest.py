@@ -65,3 +65,31 @@ def games():
 @pytest.fixture(scope='session')
 def otrees():
     return oracle_tree
+
+
+def random_game(seed, depth=6, zero_sum=False, p_stop=0.18, max_act=5):
+    """A random extensive game: the acting player, #actions and hidden_from depend only on the depth, so nodes
+    of one information set agree on their actions; random chance probabilities, float payoffs."""
+    from rlpoker_b200.extensive_game import ExtensiveGame, ExtensiveGameNode
+    rng = np.random.RandomState(seed)
+    who = [int(rng.randint(0, 3)) for _ in range(depth)]
+    who[0] = 0 if seed % 2 == 0 else 1
+    nact = [int(rng.randint(2, max_act + 1)) for _ in range(depth)]
+    hidden = [[p for p in (1, 2) if rng.rand() < 0.4] for _ in range(depth)]
+
+    def build(d, path):
+        if d == depth or (d > 1 and rng.rand() < p_stop):
+            u1 = float(np.round(rng.standard_normal() * 3, 3))
+            u2 = -u1 if zero_sum else float(np.round(rng.standard_normal() * 3, 3))
+            return ExtensiveGameNode(-1, action_list=path, utility={1: u1, 2: u2})
+        node = ExtensiveGameNode(who[d], action_list=path, hidden_from=list(hidden[d]))
+        acts = ['a%d_%d' % (d, k) for k in range(nact[d])]
+        if who[d] == 0:
+            p = rng.rand(len(acts)) + 0.1
+            p /= p.sum()
+            node.chance_probs = dict(zip(acts, p.tolist()))
+        for a in acts:
+            node.children[a] = build(d + 1, path + (a,))
+        return node
+
+    return ExtensiveGame(build(0, ()))
