@@ -10,14 +10,15 @@ using rlp::fail;
 
 namespace {
 
-constexpr size_t kSmemSmall = 99 * 1024;     // two CTAs per SM
-constexpr size_t kSmemLarge = 200 * 1024;    // one CTA per SM
+constexpr size_t kSmemSmall = 110 * 1024;    // two CTAs per SM
+constexpr size_t kSmemLarge = 220 * 1024;    // one CTA per SM
 
-size_t tile_smem(int64_t n_nodes, int64_t n_nt, bool zs) {
+size_t tile_smem(int64_t n_nodes, int64_t n_nt, int64_t n_cp, bool zs) {
     size_t b = 0;
     b += sizeof(double) * (size_t)n_nodes * (zs ? 1 : 2);   // val1 (val2)
-    b += sizeof(double) * 2 * (size_t)n_nt;                 // p1, p2
-    b += sizeof(TileRec) * (size_t)n_nt;
+    b += sizeof(double) * 3 * (size_t)n_nt;                 // p1, p2, static chance reach
+    b += sizeof(double) * (size_t)n_cp;                     // chance probabilities
+    b += (sizeof(TileRec) + sizeof(TileAux)) * (size_t)n_nt;
     b += sizeof(unsigned short) * (size_t)n_nodes;
     return b + 64;
 }
@@ -31,10 +32,16 @@ struct TileView {
     const double *pc, *pay1, *pay2, *cprob, *sigma;
     double *contrib_r, *contrib_o, *root_val;
     const IterState *iter;
-    int max_nodes, max_nt;
+    int max_nodes, max_nt, max_cp;
 };
 
-template <bool ZS>
+constexpr int kRegAct = 4;      // information sets up to this wide keep their strategy row in registers
+
+// One CTA sweeps one tile.  Ownership is static: non-terminal rank i belongs to thread i % blockDim, slot
+// i / blockDim (< R), so the strategy rows of a thread's nodes are fetched ONCE into registers while the
+// topology is being staged, and both passes then run out of shared memory and registers only -- no global
+// load sits on the level-to-level dependency chain.
+template <bool ZS, int R, bool WIDE>
 __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDesc td;
@@ -42,18 +49,41 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     double *val2 = val1 + (ZS ? 0 : v.max_nodes);
     double *sp1 = val2 + v.max_nodes;
     double *sp2 = sp1 + v.max_nt;
-    TileRec *rec = reinterpret_cast<TileRec *>(sp2 + v.max_nt);
+    double *spc = sp2 + v.max_nt;
+    double *scp = spc + v.max_nt;
+    TileAux *saux = reinterpret_cast<TileAux *>(scp + v.max_cp);
+    TileRec *rec = reinterpret_cast<TileRec *>(saux + v.max_nt);
     unsigned short *ntof = reinterpret_cast<unsigned short *>(rec + v.max_nt);
 
     const int tid = threadIdx.x, bd = blockDim.x;
-    if (tid < (int)(sizeof(TileDesc) / sizeof(int))) reinterpret_cast<int *>(&td)[tid] = reinterpret_cast<const int *>(v.desc + blockIdx.x)[tid];
+    if (tid < (int)(sizeof(TileDesc) / sizeof(int)))
+        reinterpret_cast<int *>(&td)[tid] = reinterpret_cast<const int *>(v.desc + blockIdx.x)[tid];
     __syncthreads();
     const double w = v.iter->linear ? (double)v.iter->t : 1.0;
+    const int n_nt = td.n_nt;
 
-    // ---- stage the tile: topology to shared memory, terminal payoffs into the value array ----------
+    // ---- stage the tile; the owner threads fetch their strategy rows as soon as they know where -------
+    double sg[R][kRegAct];
     {
+        const TileAux *gaux = v.aux + td.nt_off;
         const TileRec *grec = v.rec + td.nt_off;
-        for (int i = tid; i < td.n_nt; i += bd) rec[i] = grec[i];
+        const double *gpc = v.pc + td.nt_off;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            int i = m * bd + tid;
+            if (i < n_nt) {
+                TileAux ax = gaux[i];
+                TileRec r = grec[i];
+                saux[i] = ax;
+                rec[i] = r;
+                spc[i] = gpc[i];
+                if (!WIDE && r.player > 0) {
+                    const double *row = v.sigma + ax.colbase;
+#pragma unroll
+                    for (int k = 0; k < kRegAct; ++k) sg[m][k] = k < r.nchild ? row[k] : 0.0;
+                }
+            }
+        }
         const unsigned short *gnt = v.ntof + td.node_off;
         for (int i = tid; i < td.n_nodes; i += bd) ntof[i] = gnt[i];
         const unsigned short *glid = v.term_lid + td.term_off;
@@ -62,16 +92,19 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
             val1[glid[i]] = gp1[i];
             if (!ZS) val2[glid[i]] = v.pay2[td.term_off + i];
         }
+        const double *gcp = v.cprob + td.cp_off;
+        for (int i = tid; i < td.n_cp; i += bd) scp[i] = gcp[i];
         if (tid == 0) { sp1[0] = td.root_p1; sp2[0] = td.root_p2; }
     }
     __syncthreads();
 
-    const TileAux *aux = v.aux + td.nt_off;
-    const double *cp = v.cprob + td.cp_off;
-
     // ---- forward: strategy reach of every non-terminal node (cfr.py:208,217) ----------------------
     for (int l = 0; l + 1 < td.n_levels; ++l) {
-        for (int i = td.lvl_nt[l] + tid; i < td.lvl_nt[l + 1]; i += bd) {
+        const int lo = td.lvl_nt[l], hi = td.lvl_nt[l + 1];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int i = m * bd + tid;
+            if (i < lo || i >= hi) continue;
             TileRec r = rec[i];
             double a = sp1[i], b = sp2[i];
             if (r.player == 0) {
@@ -79,12 +112,22 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
                     unsigned short c = ntof[r.first_child + k];
                     if (c != 0xFFFF) { sp1[c] = a; sp2[c] = b; }
                 }
-            } else {
-                const double *sg = v.sigma + aux[i].colbase;
+            } else if constexpr (WIDE) {
+                const double *row = v.sigma + saux[i].colbase;
                 for (int k = 0; k < r.nchild; ++k) {
                     unsigned short c = ntof[r.first_child + k];
                     if (c == 0xFFFF) continue;
-                    double e = sg[k];
+                    double e = row[k];
+                    sp1[c] = r.player == 1 ? e * a : a;
+                    sp2[c] = r.player == 2 ? e * b : b;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRegAct; ++k) {
+                    if (k >= r.nchild) break;
+                    unsigned short c = ntof[r.first_child + k];
+                    if (c == 0xFFFF) continue;
+                    double e = sg[m][k];
                     sp1[c] = r.player == 1 ? e * a : a;
                     sp2[c] = r.player == 2 ? e * b : b;
                 }
@@ -94,14 +137,17 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     }
 
     // ---- backward: values, and the contributions of every decision node (cfr.py:177-186,204-242) ---
-    const double *pcs = v.pc + td.nt_off;
     for (int l = td.n_levels - 1; l >= 0; --l) {
-        for (int i = td.lvl_nt[l] + tid; i < td.lvl_nt[l + 1]; i += bd) {
+        const int lo = td.lvl_nt[l], hi = td.lvl_nt[l + 1];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int i = m * bd + tid;
+            if (i < lo || i >= hi) continue;
             TileRec r = rec[i];
-            const int fc = r.first_child, n = r.nchild;
+            const int fc = r.first_child, n = r.nchild, pl = r.player;
             double a1 = 0.0, a2 = 0.0;
-            if (r.player == 0) {
-                const double *e = cp + r.cp_off;
+            if (pl == 0) {
+                const double *e = scp + r.cp_off;
                 for (int k = 0; k < n; ++k) {
                     a1 = a1 + e[k] * val1[fc + k];
                     if (!ZS) a2 = a2 + e[k] * val2[fc + k];
@@ -110,24 +156,46 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
                 if (!ZS) val2[r.lid] = a2;
                 continue;
             }
-            TileAux ax = aux[i];
-            const double *sg = v.sigma + ax.colbase;
-            for (int k = 0; k < n; ++k) {
-                double e = sg[k];
-                a1 = a1 + e * val1[fc + k];
-                if (!ZS) a2 = a2 + e * val2[fc + k];
+            TileAux ax = saux[i];
+            double va[WIDE ? 1 : kRegAct];
+            if constexpr (WIDE) {
+                const double *row = v.sigma + ax.colbase;
+                for (int k = 0; k < n; ++k) {
+                    a1 = a1 + row[k] * val1[fc + k];
+                    if (!ZS) a2 = a2 + row[k] * val2[fc + k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRegAct; ++k) {
+                    if (k < n) {
+                        double x = val1[fc + k];
+                        a1 = a1 + sg[m][k] * x;
+                        if (!ZS) {
+                            double y = val2[fc + k];
+                            a2 = a2 + sg[m][k] * y;
+                            va[k] = pl == 1 ? x : y;
+                        } else {
+                            va[k] = pl == 1 ? x : -x;
+                        }
+                    }
+                }
             }
             val1[r.lid] = a1;
             if (!ZS) val2[r.lid] = a2;
-            const int pl = r.player;
-            double c = pcs[i], x1 = sp1[i], x2 = sp2[i];
+            double c = spc[i], x1 = sp1[i], x2 = sp2[i];
             double opp = pl == 1 ? c * x2 : c * x1;
             double own = pl == 1 ? x1 : x2;
             double vp = pl == 1 ? a1 : (ZS ? -a1 : a2);
             double *dst = v.contrib_r + ax.slot_r;
-            for (int k = 0; k < n; ++k) {
-                double va = pl == 1 ? val1[fc + k] : (ZS ? -val1[fc + k] : val2[fc + k]);
-                dst[k] = w * (va - vp) * opp;
+            if constexpr (WIDE) {
+                for (int k = 0; k < n; ++k) {
+                    double x = pl == 1 ? val1[fc + k] : (ZS ? -val1[fc + k] : val2[fc + k]);
+                    dst[k] = w * (x - vp) * opp;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRegAct; ++k)
+                    if (k < n) dst[k] = w * (va[k] - vp) * opp;
             }
             v.contrib_o[ax.slot_o] = w * own;
         }
@@ -180,7 +248,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     for (size_t budget : {kSmemSmall, kSmemLarge}) {
         auto fits = [&](int64_t v) {
             return pl[v] >= 0 && cn[v] <= 65535 && cce[v] <= 65535 && height[v] + 1 <= kMaxTileLevels &&
-                   tile_smem(cn[v], cnt[v], zs) <= budget;
+                   tile_smem(cn[v], cnt[v], cce[v], zs) <= budget;
         };
         roots.clear();
         ok = true;
@@ -216,7 +284,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     std::vector<int32_t> local;          // local id -> global id
     std::vector<int32_t> ldepth;
     int64_t o_node = 0, o_nt = 0, o_term = 0, o_cp = 0;
-    int max_nodes = 0, max_nt = 0;
+    int max_nodes = 0, max_nt = 0, max_cp = 0;
     for (size_t k = 0; k < T; ++k) {
         const int32_t r = roots[k];
         TileDesc &td = desc[k];
@@ -269,6 +337,8 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
         for (int l = level + 1; l <= kMaxTileLevels; ++l) td.lvl_nt[l] = nt;
         max_nodes = std::max(max_nodes, td.n_nodes);
         max_nt = std::max(max_nt, td.n_nt);
+        max_cp = std::max(max_cp, cpo);
+        td.n_cp = cpo;
         o_node += td.n_nodes; o_nt += td.n_nt; o_term += td.n_term; o_cp += cpo;
     }
     if (koff_col.back() >= (int64_t)INT32_MAX) return RLP_OK;     // slots are 32-bit
@@ -276,10 +346,16 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     ts.num_tiles = (int)T;
     ts.max_nodes = max_nodes;
     ts.max_nt = max_nt;
-    ts.smem_bytes = tile_smem(max_nodes, max_nt, zs);
-    if (ts.smem_bytes > 220 * 1024) return RLP_OK;               // (max_nodes, max_nt) came from different tiles
-    ts.block = budget_used == kSmemSmall ? 512 : 1024;
-    if (max_nt < 256) ts.block = 128; else if (max_nt < 1024) ts.block = 256;
+    ts.max_cp = max_cp;
+    ts.smem_bytes = tile_smem(max_nodes, max_nt, max_cp, zs);
+    if (ts.smem_bytes > 226 * 1024) return RLP_OK;               // (max_nodes, max_nt) came from different tiles
+    (void)budget_used;
+    // smallest block that keeps every thread at <= 2 owned nodes, else 1024 threads with up to 4
+    ts.block = 1024;
+    for (int b : {128, 256, 512}) if ((max_nt + b - 1) / b <= 2) { ts.block = b; break; }
+    ts.slots = (max_nt + ts.block - 1) / ts.block;
+    if (ts.slots > 4) return RLP_OK;
+    ts.wide = t->max_act > kRegAct;
     RLP_CUDA(ts.desc.upload(desc, stream));
     RLP_CUDA(ts.ntof.upload(ntof, stream));
     RLP_CUDA(ts.term_lid.upload(term_lid, stream));
@@ -296,6 +372,28 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
 }
 
 // One tiled sweep (replaces the per-level forward/backward launches of enqueue_sweep).
+template <bool ZS, int R, bool WIDE>
+static int launch_variant(const TileSet &ts, const TileView &v, cudaStream_t s) {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        RLP_CUDA(cudaFuncSetAttribute(k_tile_sweep<ZS, R, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        attr_set = true;
+    }
+    k_tile_sweep<ZS, R, WIDE><<<ts.num_tiles, ts.block, ts.smem_bytes, s>>>(v);
+    RLP_LAUNCH_CHECK();
+    return RLP_OK;
+}
+
+template <bool ZS, bool WIDE>
+static int launch_slots(const TileSet &ts, const TileView &v, cudaStream_t s) {
+    switch (ts.slots) {
+        case 1: return launch_variant<ZS, 1, WIDE>(ts, v, s);
+        case 2: return launch_variant<ZS, 2, WIDE>(ts, v, s);
+        case 3: return launch_variant<ZS, 3, WIDE>(ts, v, s);
+        default: return launch_variant<ZS, 4, WIDE>(ts, v, s);
+    }
+}
+
 int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter) {
     rlp_tree *t = c->tree;
     TileSet &ts = t->tiles;
@@ -303,17 +401,9 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter) {
     v.desc = ts.desc.p; v.ntof = ts.ntof.p; v.term_lid = ts.term_lid.p; v.rec = ts.rec.p; v.aux = ts.aux.p;
     v.pc = ts.pc.p; v.pay1 = ts.pay1.p; v.pay2 = ts.pay2.p; v.cprob = ts.cprob.p; v.sigma = c->sigma.p;
     v.contrib_r = c->contrib_r.p; v.contrib_o = c->contrib_o.p; v.root_val = ts.root_val.p;
-    v.iter = iter ? iter : c->iter.p; v.max_nodes = ts.max_nodes; v.max_nt = ts.max_nt;
-    static thread_local bool attr_set[2] = {false, false};
-    if (t->zero_sum) {
-        if (!attr_set[1]) { RLP_CUDA(cudaFuncSetAttribute(k_tile_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_set[1] = true; }
-        k_tile_sweep<true><<<ts.num_tiles, ts.block, ts.smem_bytes, s>>>(v);
-    } else {
-        if (!attr_set[0]) { RLP_CUDA(cudaFuncSetAttribute(k_tile_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_set[0] = true; }
-        k_tile_sweep<false><<<ts.num_tiles, ts.block, ts.smem_bytes, s>>>(v);
-    }
-    RLP_LAUNCH_CHECK();
-    return RLP_OK;
+    v.iter = iter ? iter : c->iter.p; v.max_nodes = ts.max_nodes; v.max_nt = ts.max_nt; v.max_cp = ts.max_cp;
+    if (t->zero_sum) return ts.wide ? launch_slots<true, true>(ts, v, s) : launch_slots<true, false>(ts, v, s);
+    return ts.wide ? launch_slots<false, true>(ts, v, s) : launch_slots<false, false>(ts, v, s);
 }
 
 }  // namespace rlp

@@ -23,7 +23,7 @@ struct TileDesc {
     long long cp_off;       // into cprob
     int n_nodes, n_nt, n_term, n_levels;
     int root_global;        // breadth-first id of the tile root
-    int pad;
+    int n_cp;               // chance edges inside the tile
     double root_p1, root_p2;            // strategy reach of the root (1.0 below an all-chance trunk)
     int lvl_nt[kMaxTileLevels + 1];     // non-terminal rank ranges per local level
 };
@@ -41,7 +41,9 @@ struct TileAux {            // 16 bytes
 struct TileSet {
     bool enabled = false;
     int num_tiles = 0;
-    int max_nodes = 0, max_nt = 0;
+    int max_nodes = 0, max_nt = 0, max_cp = 0;
+    int slots = 1;          // owned non-terminal nodes per thread (template parameter R)
+    bool wide = false;      // some information set is wider than the register-cached strategy row
     size_t smem_bytes = 0;
     int block = 512;
     rlp::DevBuf<TileDesc> desc;

@@ -75,7 +75,7 @@ def random_game(seed, depth=6, zero_sum=False, p_stop=0.18, max_act=5):
     who = [int(rng.randint(0, 3)) for _ in range(depth)]
     who[0] = 0 if seed % 2 == 0 else 1
     nact = [int(rng.randint(2, max_act + 1)) for _ in range(depth)]
-    hidden = [[p for p in (1, 2) if rng.rand() < 0.4] for _ in range(depth)]
+    hidden = [[p for p in (1, 2) if rng.rand() < 0.4 and p != who[d]] for d in range(depth)]   # perfect recall
 
     def build(d, path):
         if d == depth or (d > 1 and rng.rand() < p_stop):
