@@ -67,18 +67,22 @@ def otrees():
     return oracle_tree
 
 
-def random_game(seed, depth=6, zero_sum=False, p_stop=0.18, max_act=5):
-    """A random extensive game: the acting player, #actions and hidden_from depend only on the depth, so nodes
-    of one information set agree on their actions; random chance probabilities, float payoffs."""
+def random_game(seed, depth=6, zero_sum=False, max_act=5):
+    """A random extensive game with perfect recall: the acting player, #actions and hidden_from depend only on
+    the depth, so nodes of one information set agree on their actions; where an action is visible to both
+    players its first child may be a leaf (so leaves sit at several depths while every set of nodes a player
+    cannot tell apart is all-terminal or all-internal, which the reference's br() assumes); random chance
+    probabilities, float payoffs."""
     from rlpoker_b200.extensive_game import ExtensiveGame, ExtensiveGameNode
     rng = np.random.RandomState(seed)
     who = [int(rng.randint(0, 3)) for _ in range(depth)]
     who[0] = 0 if seed % 2 == 0 else 1
     nact = [int(rng.randint(2, max_act + 1)) for _ in range(depth)]
     hidden = [[p for p in (1, 2) if rng.rand() < 0.4 and p != who[d]] for d in range(depth)]   # perfect recall
+    early_leaf = [d >= 1 and not hidden[d] and rng.rand() < 0.7 for d in range(depth)]
 
-    def build(d, path):
-        if d == depth or (d > 1 and rng.rand() < p_stop):
+    def build(d, path, leaf):
+        if d == depth or leaf:
             u1 = float(np.round(rng.standard_normal() * 3, 3))
             u2 = -u1 if zero_sum else float(np.round(rng.standard_normal() * 3, 3))
             return ExtensiveGameNode(-1, action_list=path, utility={1: u1, 2: u2})
@@ -88,8 +92,8 @@ def random_game(seed, depth=6, zero_sum=False, p_stop=0.18, max_act=5):
             p = rng.rand(len(acts)) + 0.1
             p /= p.sum()
             node.chance_probs = dict(zip(acts, p.tolist()))
-        for a in acts:
-            node.children[a] = build(d + 1, path + (a,))
+        for k, a in enumerate(acts):
+            node.children[a] = build(d + 1, path + (a,), early_leaf[d] and k == 0)
         return node
 
-    return ExtensiveGame(build(0, ()))
+    return ExtensiveGame(build(0, (), False))
