@@ -13,7 +13,7 @@
 
 using rlp::fail;
 
-namespace rlp { int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter); }
+namespace rlp { int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches); }
 
 namespace {
 
@@ -151,6 +151,64 @@ k_accumulate_rm(int32_t I, const int32_t *__restrict__ iset_size, const int64_t 
     flags[s] = 1; flags[I + s] = 1; flags[2 * I + s] = 1;
 }
 
+// Same, four lanes per information set (one per action; information sets of <= 4 actions): 4x the loads in
+// flight, and the regret-matching normaliser is formed from the four lanes' regrets by shuffles.
+__global__ void __launch_bounds__(kBlock)
+k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
+                 const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
+                 const double *__restrict__ contrib_r, const double *__restrict__ contrib_o, double *R, double *S,
+                 double *sigma, uint8_t *flags, IterState *iter, int advance) {
+    const int gid = blockIdx.x * kBlock + threadIdx.x;
+    const int s = gid >> 2, a = gid & 3;
+    if (gid == 0 && advance) iter->t += 1;
+    const bool valid = s < I;
+    const int size = valid ? iset_size[s] : 0;
+    const int64_t c0 = valid ? col_off[s] : 0;
+    const int na = valid ? (int)(col_off[s + 1] - c0) : 0;
+    const bool active = a < na;
+    double r = 0.0, sa = 0.0, sg = 0.0;
+    if (active) { r = R[c0 + a]; sa = S[c0 + a]; sg = sigma[c0 + a]; }
+    if (active) {
+        const double *cr = contrib_r + c0 + a;
+        const double *co = contrib_o + s;
+#pragma unroll 4
+        for (int k = 0; k < size; ++k) {
+            r = r + cr[koff_col[k]];
+            sa = sa + co[koff_iset[k]] * sg;
+        }
+        R[c0 + a] = r;
+        S[c0 + a] = sa;
+    }
+    // regret matching over the (up to) four lanes of this information set
+    const unsigned lane = threadIdx.x & 31u, base = lane & ~3u;
+    double rr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rr[j] = __shfl_sync(0xffffffffu, r, base + j);
+    if (!active) return;
+    double mx = rr[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) if (j < na) mx = rr[j] > mx ? rr[j] : mx;
+    double out;
+    if (mx <= 0.0) {
+        out = 1.0 / (double)na;
+    } else {
+        rlp::Neumaier acc;
+        double mine = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < na) {
+                double p = rr[j] > 0.0 ? rr[j] : 0.0;
+                p = p > rlp::kEpsilon ? p : rlp::kEpsilon;
+                acc.add(p);
+                if (j == a) mine = p;
+            }
+        }
+        out = mine / acc.total();
+    }
+    sigma[c0 + a] = out;
+    if (a == 0) { flags[s] = 1; flags[I + s] = 1; flags[2 * I + s] = 1; }
+}
+
 // Multi-GPU split: local deltas into delta[0..Q) (regret) and delta[Q..2Q) (strategy sum), canonical order.
 __global__ void __launch_bounds__(kBlock)
 k_local_delta(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
@@ -242,8 +300,7 @@ template <bool ZS>
 int enqueue_sweep(rlp_cfr *c, cudaStream_t s, int *count, const IterState *iter = nullptr) {
     rlp_tree *t = c->tree;
     if (t->tiles.enabled) {                 // shared-memory tiled sweep: one launch instead of one per level
-        *count = 1;
-        return rlp::launch_tile_sweep(c, s, iter);
+        return rlp::launch_tile_sweep(c, s, iter, count);
     }
     View v = make_view(c);
     if (iter) v.iter = iter;
@@ -273,9 +330,15 @@ int enqueue_iteration(rlp_cfr *c, cudaStream_t s, int *count) {
     int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n) : enqueue_sweep<false>(c, s, &n);
     if (rc) return rc;
     if (t->I > 0) {
-        k_accumulate_rm<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_col.p,
-                                                        t->koff_iset.p, c->contrib_r.p, c->contrib_o.p, c->R.p, c->S.p,
-                                                        c->sigma.p, c->flags.p, c->iter.p, 1);
+        if (t->max_act <= 4)
+            k_accumulate_rm4<<<grid_for(4 * (int64_t)t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p,
+                                                                       t->koff_col.p, t->koff_iset.p, c->contrib_r.p,
+                                                                       c->contrib_o.p, c->R.p, c->S.p, c->sigma.p,
+                                                                       c->flags.p, c->iter.p, 1);
+        else
+            k_accumulate_rm<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_col.p,
+                                                            t->koff_iset.p, c->contrib_r.p, c->contrib_o.p, c->R.p,
+                                                            c->S.p, c->sigma.p, c->flags.p, c->iter.p, 1);
         RLP_LAUNCH_CHECK(); ++n;
     }
     *count = n;

@@ -1,8 +1,9 @@
-// Tiled sweep: host-side tiling of a flattened game + the kernel that sweeps one tile per CTA in shared
-// memory (forward reach, backward counterfactual values, regret / own-reach contributions).
+// Tiled sweep: host-side two-tier tiling of a flattened game (see tiles.cuh) and the kernels that sweep it.
 // Same arithmetic, operand for operand, as the level sweep in cfr.cu (and therefore as the reference's
 // cfr_recursive, rlpoker/cfr/cfr.py:158-255); only where the intermediates live changes.
 #include <algorithm>
+#include <map>
+#include <string>
 
 #include "cfr.cuh"
 
@@ -10,8 +11,10 @@ using rlp::fail;
 
 namespace {
 
-constexpr size_t kSmemSmall = 110 * 1024;    // two CTAs per SM
+constexpr size_t kSmemSmall = 48 * 1024;     // several CTAs per SM
+constexpr size_t kSmemMid = 110 * 1024;      // two CTAs per SM
 constexpr size_t kSmemLarge = 220 * 1024;    // one CTA per SM
+constexpr int kRegAct = 4;      // information sets up to this wide keep their strategy row in registers
 
 size_t tile_smem(int64_t n_nodes, int64_t n_nt, int64_t n_cp, bool zs) {
     size_t b = 0;
@@ -23,25 +26,26 @@ size_t tile_smem(int64_t n_nodes, int64_t n_nt, int64_t n_cp, bool zs) {
     return b + 64;
 }
 
-// ------------------------------------------------------------------------------------ kernel
+// ------------------------------------------------------------------------------------ upper tiles
 struct TileView {
     const TileDesc *desc;
-    const unsigned short *ntof, *term_lid;
+    const unsigned short *ntof, *term_lid, *portal_lid;
     const TileRec *rec;
     const TileAux *aux;
     const double *pc, *pay1, *pay2, *cprob, *sigma;
     double *contrib_r, *contrib_o, *root_val;
+    double *portal_p1, *portal_p2;
+    const double *portal_v1, *portal_v2;
     const IterState *iter;
     int max_nodes, max_nt, max_cp;
 };
 
-constexpr int kRegAct = 4;      // information sets up to this wide keep their strategy row in registers
-
-// One CTA sweeps one tile.  Ownership is static: non-terminal rank i belongs to thread i % blockDim, slot
+// One CTA sweeps one upper tile.  Ownership is static: non-terminal rank i belongs to thread i % blockDim, slot
 // i / blockDim (< R), so the strategy rows of a thread's nodes are fetched ONCE into registers while the
-// topology is being staged, and both passes then run out of shared memory and registers only -- no global
-// load sits on the level-to-level dependency chain.
-template <bool ZS, int R, bool WIDE>
+// topology is being staged, and the passes then run out of shared memory and registers only.
+// PHASE 0: forward only, reach written to the portal leaves.  PHASE 1: forward + backward, portal leaves read
+// the values the micro kernel left; contributions of the tile's decision nodes are scattered.
+template <bool ZS, int R, bool WIDE, int PHASE>
 __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDesc td;
@@ -56,9 +60,10 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     unsigned short *ntof = reinterpret_cast<unsigned short *>(rec + v.max_nt);
 
     const int tid = threadIdx.x, bd = blockDim.x;
-    if (tid < (int)(sizeof(TileDesc) / sizeof(int)))
-        reinterpret_cast<int *>(&td)[tid] = reinterpret_cast<const int *>(v.desc + blockIdx.x)[tid];
+    for (int i = tid; i < (int)(sizeof(TileDesc) / sizeof(int)); i += bd)
+        reinterpret_cast<int *>(&td)[i] = reinterpret_cast<const int *>(v.desc + blockIdx.x)[i];
     __syncthreads();
+    if (PHASE == 0 && td.n_portal == 0) return;
     const double w = v.iter->linear ? (double)v.iter->t : 1.0;
     const int n_nt = td.n_nt;
 
@@ -86,55 +91,64 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
         }
         const unsigned short *gnt = v.ntof + td.node_off;
         for (int i = tid; i < td.n_nodes; i += bd) ntof[i] = gnt[i];
-        const unsigned short *glid = v.term_lid + td.term_off;
-        const double *gp1 = v.pay1 + td.term_off;
-        for (int i = tid; i < td.n_term; i += bd) {
-            val1[glid[i]] = gp1[i];
-            if (!ZS) val2[glid[i]] = v.pay2[td.term_off + i];
+        if (PHASE == 1) {
+            const unsigned short *glid = v.term_lid + td.term_off;
+            const double *gp1 = v.pay1 + td.term_off;
+            for (int i = tid; i < td.n_term; i += bd) {
+                val1[glid[i]] = gp1[i];
+                if (!ZS) val2[glid[i]] = v.pay2[td.term_off + i];
+            }
+            const unsigned short *plid = v.portal_lid + td.portal_off;
+            for (int i = tid; i < td.n_portal; i += bd) {
+                val1[plid[i]] = v.portal_v1[td.portal_off + i];
+                if (!ZS) val2[plid[i]] = v.portal_v2[td.portal_off + i];
+            }
+            const double *gcp = v.cprob + td.cp_off;
+            for (int i = tid; i < td.n_cp; i += bd) scp[i] = gcp[i];
         }
-        const double *gcp = v.cprob + td.cp_off;
-        for (int i = tid; i < td.n_cp; i += bd) scp[i] = gcp[i];
         if (tid == 0) { sp1[0] = td.root_p1; sp2[0] = td.root_p2; }
     }
     __syncthreads();
 
     // ---- forward: strategy reach of every non-terminal node (cfr.py:208,217) ----------------------
-    for (int l = 0; l + 1 < td.n_levels; ++l) {
+    for (int l = 0; l < td.n_levels; ++l) {
         const int lo = td.lvl_nt[l], hi = td.lvl_nt[l + 1];
 #pragma unroll
         for (int m = 0; m < R; ++m) {
             const int i = m * bd + tid;
             if (i < lo || i >= hi) continue;
             TileRec r = rec[i];
-            double a = sp1[i], b = sp2[i];
+            const double a = sp1[i], b = sp2[i];
+            const double *row = (WIDE && r.player > 0) ? v.sigma + saux[i].colbase : nullptr;
+            auto put = [&](int k, double e) {
+                unsigned short c = ntof[r.first_child + k];
+                if (c == 0xFFFF) return;
+                double x = r.player == 1 ? e * a : a;
+                double y = r.player == 2 ? e * b : b;
+                if (c & 0x8000) {
+                    if (PHASE == 0) {
+                        long long g = td.portal_off + (c & 0x7FFF);
+                        v.portal_p1[g] = x;
+                        v.portal_p2[g] = y;
+                    }
+                } else {
+                    sp1[c] = x;
+                    sp2[c] = y;
+                }
+            };
             if (r.player == 0) {
-                for (int k = 0; k < r.nchild; ++k) {
-                    unsigned short c = ntof[r.first_child + k];
-                    if (c != 0xFFFF) { sp1[c] = a; sp2[c] = b; }
-                }
+                for (int k = 0; k < r.nchild; ++k) put(k, 1.0);
             } else if constexpr (WIDE) {
-                const double *row = v.sigma + saux[i].colbase;
-                for (int k = 0; k < r.nchild; ++k) {
-                    unsigned short c = ntof[r.first_child + k];
-                    if (c == 0xFFFF) continue;
-                    double e = row[k];
-                    sp1[c] = r.player == 1 ? e * a : a;
-                    sp2[c] = r.player == 2 ? e * b : b;
-                }
+                for (int k = 0; k < r.nchild; ++k) put(k, row[k]);
             } else {
 #pragma unroll
-                for (int k = 0; k < kRegAct; ++k) {
-                    if (k >= r.nchild) break;
-                    unsigned short c = ntof[r.first_child + k];
-                    if (c == 0xFFFF) continue;
-                    double e = sg[m][k];
-                    sp1[c] = r.player == 1 ? e * a : a;
-                    sp2[c] = r.player == 2 ? e * b : b;
-                }
+                for (int k = 0; k < kRegAct; ++k)
+                    if (k < r.nchild) put(k, sg[m][k]);
             }
         }
         __syncthreads();
     }
+    if (PHASE == 0) return;
 
     // ---- backward: values, and the contributions of every decision node (cfr.py:177-186,204-242) ---
     for (int l = td.n_levels - 1; l >= 0; --l) {
@@ -204,6 +218,114 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     if (tid == 0) v.root_val[blockIdx.x] = val1[0];
 }
 
+// ------------------------------------------------------------------------------------ micro subtrees
+struct MicroView {
+    const MicroTmpl *tmpl;
+    const unsigned short *cls;
+    const int *colbase, *slot_r, *slot_o;      // [micro_nt][P]
+    const double *pay1, *pay2;                 // [micro_term][P]
+    const double *pc, *sigma;
+    const double *portal_p1, *portal_p2;
+    double *portal_v1, *portal_v2;
+    double *contrib_r, *contrib_o;
+    const IterState *iter;
+    int P, num_classes;
+};
+
+constexpr int kMicroBlock = 128;
+
+// One thread = one micro subtree: forward reach then backward values over <= 8 decision nodes in the template's
+// breadth-first order; scratch is a thread-interleaved slice of shared memory (bank-conflict free).
+template <bool ZS>
+__global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
+    __shared__ double sq1[kMicroNt * kMicroBlock], sq2[kMicroNt * kMicroBlock], sv1[kMicroNt * kMicroBlock];
+    __shared__ double sv2[ZS ? 1 : kMicroNt * kMicroBlock];
+    __shared__ MicroTmpl stm[kMicroSmemClasses];
+    const int tid = threadIdx.x;
+    const bool in_smem = v.num_classes <= kMicroSmemClasses;
+    if (in_smem) {
+        const int words = v.num_classes * (int)(sizeof(MicroTmpl) / sizeof(int));
+        for (int i = tid; i < words; i += kMicroBlock)
+            reinterpret_cast<int *>(stm)[i] = reinterpret_cast<const int *>(v.tmpl)[i];
+        __syncthreads();
+    }
+    const long long p = (long long)blockIdx.x * kMicroBlock + tid;
+    if (p >= v.P) return;
+    const long long P = v.P;
+    const MicroTmpl *tm = in_smem ? &stm[v.cls[p]] : v.tmpl + v.cls[p];
+    const double w = v.iter->linear ? (double)v.iter->t : 1.0;
+    const double pcv = v.pc[p];
+    const int n_nt = tm->n_nt;
+#define Q1(r) sq1[(r) * kMicroBlock + tid]
+#define Q2(r) sq2[(r) * kMicroBlock + tid]
+#define V1(r) sv1[(r) * kMicroBlock + tid]
+#define V2(r) sv2[(r) * kMicroBlock + tid]
+    Q1(0) = v.portal_p1[p];
+    Q2(0) = v.portal_p2[p];
+    // forward (cfr.py:208,217)
+    for (int r = 0; r + 1 < n_nt; ++r) {
+        const int j = tm->nt_node[r];
+        const int pl = tm->player[j], fc = tm->first_child[j], n = tm->nchild[j];
+        const double *row = v.sigma + v.colbase[r * P + p];
+        const double a = Q1(r), b = Q2(r);
+        for (int k = 0; k < n; ++k) {
+            const int rk = tm->rank[fc + k];
+            if (rk & 0x80) continue;
+            const double e = row[k];
+            Q1(rk) = pl == 1 ? e * a : a;
+            Q2(rk) = pl == 2 ? e * b : b;
+        }
+    }
+    // backward (cfr.py:204-242)
+    for (int r = n_nt - 1; r >= 0; --r) {
+        const int j = tm->nt_node[r];
+        const int pl = tm->player[j], fc = tm->first_child[j], n = tm->nchild[j];
+        const double *row = v.sigma + v.colbase[r * P + p];
+        double a1 = 0.0, a2 = 0.0;
+        double va[kMicroAct];
+#pragma unroll
+        for (int k = 0; k < kMicroAct; ++k) {
+            if (k < n) {
+                const int rk = tm->rank[fc + k];
+                double x, y = 0.0;
+                if (rk & 0x80) {
+                    x = v.pay1[(rk & 0x7F) * P + p];
+                    if (!ZS) y = v.pay2[(rk & 0x7F) * P + p];
+                } else {
+                    x = V1(rk);
+                    if (!ZS) y = V2(rk);
+                }
+                const double e = row[k];
+                a1 = a1 + e * x;
+                if (!ZS) a2 = a2 + e * y;
+                va[k] = pl == 1 ? x : (ZS ? -x : y);
+            }
+        }
+        V1(r) = a1;
+        if (!ZS) V2(r) = a2;
+        const double x1 = Q1(r), x2 = Q2(r);
+        const double opp = pl == 1 ? pcv * x2 : pcv * x1;
+        const double own = pl == 1 ? x1 : x2;
+        const double vp = pl == 1 ? a1 : (ZS ? -a1 : a2);
+        double *dst = v.contrib_r + v.slot_r[r * P + p];
+#pragma unroll
+        for (int k = 0; k < kMicroAct; ++k)
+            if (k < n) dst[k] = w * (va[k] - vp) * opp;
+        v.contrib_o[v.slot_o[r * P + p]] = w * own;
+    }
+    v.portal_v1[p] = V1(0);
+    if (!ZS) v.portal_v2[p] = V2(0);
+#undef Q1
+#undef Q2
+#undef V1
+#undef V2
+}
+
+__global__ void k_fill(double *p, long long n, double x) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = x;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------ host
@@ -220,47 +342,75 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     TileSet &ts = t->tiles;
     ts.enabled = false;
     if (N < 2) return RLP_OK;
+    if (koff_col.back() >= (int64_t)INT32_MAX) return RLP_OK;     // slots are 32-bit
     const bool zs = t->zero_sum;
 
     std::vector<int32_t> parent(N, -1);
     for (int64_t i = 0; i < N; ++i)
         for (int32_t c = fc[i]; c < fc[i + 1]; ++c) parent[c] = (int32_t)i;
-    std::vector<int32_t> cn(N, 1), cnt(N, 0), cce(N, 0);
-    std::vector<uint8_t> height(N, 0);
+
+    // ---- micro subtrees: maximal, <= 32 nodes, <= 8 non-terminals, no chance node, <= 8 children --------
+    std::vector<int32_t> cn(N, 1), cnt(N, 0);
+    std::vector<uint8_t> bad(N, 0);
     bool wide = false;
     for (int64_t i = N - 1; i >= 0; --i) {
-        if (pl[i] >= 0) cnt[i] += 1;
         int nc = fc[i + 1] - fc[i];
         if (nc > 255) wide = true;
-        if (pl[i] == 0) cce[i] += nc;
+        if (pl[i] >= 0) cnt[i] += 1;
+        if (pl[i] == 0 || nc > kMicroAct) bad[i] = 1;
         if (i > 0) {
             int32_t p = parent[i];
-            cn[p] += cn[i]; cnt[p] += cnt[i]; cce[p] += cce[i];
-            height[p] = std::max<int>(height[p], std::min(254, height[i] + 1));
+            cn[p] = std::min(1 << 20, cn[p] + cn[i]);
+            cnt[p] = std::min(1 << 20, cnt[p] + cnt[i]);
+            bad[p] |= bad[i];
         }
     }
     if (wide) return RLP_OK;
+    auto micro_ok = [&](int64_t v) { return pl[v] > 0 && !bad[v] && cn[v] <= kMicroNodes && cnt[v] <= kMicroNt; };
+    std::vector<uint8_t> kind(N, 0);       // 0 upper, 1 micro root, 2 inside a micro subtree
+    for (int64_t v = 0; v < N; ++v) {
+        uint8_t pk = v == 0 ? 0 : kind[parent[v]];
+        if (pk != 0) kind[v] = 2;
+        else if (micro_ok(v)) kind[v] = 1;
+    }
 
-    std::vector<uint8_t> status(N);        // 0 trunk, 1 tile root, 2 inside a tile
+    // ---- upper tree statistics (micro roots count as leaves) -------------------------------------------
+    std::vector<int32_t> un(N, 0), unt(N, 0), uce(N, 0);
+    std::vector<uint8_t> height(N, 0);
+    for (int64_t i = N - 1; i >= 0; --i) {
+        if (kind[i] == 2) continue;
+        un[i] += 1;
+        if (kind[i] == 0 && pl[i] >= 0) unt[i] += 1;
+        if (kind[i] == 0 && pl[i] == 0) uce[i] += fc[i + 1] - fc[i];
+        if (i > 0) {
+            int32_t p = parent[i];
+            un[p] = std::min(1 << 24, un[p] + un[i]);
+            unt[p] += unt[i]; uce[p] += uce[i];
+            height[p] = std::max<int>(height[p], std::min(254, height[i] + 1));
+        }
+    }
+
+    // ---- upper tile roots: maximal upper subtrees that fit; everything above must be chance ---------------
+    std::vector<uint8_t> status(N, 0);     // upper nodes: 0 trunk, 1 tile root, 2 inside an upper tile
     std::vector<int32_t> roots;
     bool ok = false;
-    size_t budget_used = 0;
-    for (size_t budget : {kSmemSmall, kSmemLarge}) {
+    for (size_t budget : {kSmemSmall, kSmemMid, kSmemLarge}) {
         auto fits = [&](int64_t v) {
-            return pl[v] >= 0 && cn[v] <= 65535 && cce[v] <= 65535 && height[v] + 1 <= kMaxTileLevels &&
-                   tile_smem(cn[v], cnt[v], cce[v], zs) <= budget;
+            return kind[v] == 0 && pl[v] >= 0 && un[v] <= 32767 && uce[v] <= 65535 && height[v] + 1 <= kMaxTileLevels &&
+                   tile_smem(un[v], unt[v], uce[v], zs) <= budget;
         };
         roots.clear();
         ok = true;
         for (int64_t v = 0; v < N && ok; ++v) {
+            if (kind[v] == 2) continue;
             uint8_t ps = v == 0 ? 0 : status[parent[v]];
             if (ps != 0) { status[v] = 2; continue; }
+            if (kind[v] == 1) { status[v] = 0; continue; }      // a portal hanging off the trunk
             if (fits(v)) { status[v] = 1; roots.push_back((int32_t)v); continue; }
             status[v] = 0;
             if (pl[v] > 0) ok = false;            // a decision node above the cut: not handled by the tiled path
         }
-        if (ok && !roots.empty()) { budget_used = budget; break; }
-        ok = false;
+        if (ok) break;
     }
     if (!ok) return RLP_OK;
 
@@ -270,95 +420,168 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     for (int64_t i = 0; i < N; ++i)
         for (int32_t c = fc[i]; c < fc[i + 1]; ++c) pcs[c] = pl[i] == 0 ? d->cprob[c] * pcs[i] : pcs[i];
 
+    // ---- build the upper tiles; portals are numbered tile-major ----------------------------------------------
     const size_t T = roots.size();
     std::vector<TileDesc> desc(T);
-    int64_t tot_nodes = 0, tot_nt = 0, tot_term = 0, tot_cp = 0;
-    for (size_t k = 0; k < T; ++k) {
-        int32_t r = roots[k];
-        tot_nodes += cn[r]; tot_nt += cnt[r]; tot_term += cn[r] - cnt[r]; tot_cp += cce[r];
-    }
-    std::vector<unsigned short> ntof(tot_nodes), term_lid(tot_term);
-    std::vector<TileRec> rec(tot_nt);
-    std::vector<TileAux> aux(tot_nt);
-    std::vector<double> pc(tot_nt), pay1(tot_term), pay2(zs ? 0 : tot_term), cprob(tot_cp);
-    std::vector<int32_t> local;          // local id -> global id
-    std::vector<int32_t> ldepth;
-    int64_t o_node = 0, o_nt = 0, o_term = 0, o_cp = 0;
+    std::vector<unsigned short> ntof, term_lid, portal_lid;
+    std::vector<TileRec> rec;
+    std::vector<TileAux> aux;
+    std::vector<double> pc, pay1, pay2, cprob;
+    std::vector<int32_t> portal_node;      // portal index -> global node id of the micro root
+    std::vector<int32_t> local, ldepth;
     int max_nodes = 0, max_nt = 0, max_cp = 0;
     for (size_t k = 0; k < T; ++k) {
         const int32_t r = roots[k];
         TileDesc &td = desc[k];
         memset(&td, 0, sizeof(td));
-        td.node_off = o_node; td.nt_off = o_nt; td.term_off = o_term; td.cp_off = o_cp;
-        td.n_nodes = cn[r]; td.n_nt = cnt[r]; td.n_term = cn[r] - cnt[r];
+        td.node_off = (long long)ntof.size(); td.nt_off = (long long)rec.size();
+        td.term_off = (long long)term_lid.size(); td.cp_off = (long long)cprob.size();
+        td.portal_off = (long long)portal_node.size();
         td.root_global = r; td.root_p1 = 1.0; td.root_p2 = 1.0;
         local.clear(); ldepth.clear();
         local.push_back(r); ldepth.push_back(0);
         for (size_t q = 0; q < local.size(); ++q) {
             int32_t g = local[q];
+            if (kind[g] == 1) continue;                        // portal leaf: do not descend
             for (int32_t c = fc[g]; c < fc[g + 1]; ++c) { local.push_back(c); ldepth.push_back(ldepth[q] + 1); }
         }
-        // children of local node q start at local id first_child_local: running count in BFS order
-        int nt = 0, term = 0, cpo = 0, next_child = 1, level = -1;
+        int nt = 0, cpo = 0, next_child = 1, level = -1, nportal = 0, nterm = 0;
         for (size_t q = 0; q < local.size(); ++q) {
             int32_t g = local[q];
+            if (kind[g] == 1) {
+                ntof.push_back((unsigned short)(0x8000 | nportal));
+                portal_lid.push_back((unsigned short)q);
+                portal_node.push_back(g);
+                ++nportal;
+                continue;
+            }
             if (pl[g] < 0) {
-                ntof[o_node + q] = 0xFFFF;
-                term_lid[o_term + term] = (unsigned short)q;
-                pay1[o_term + term] = d->u1[g];
-                if (!zs) pay2[o_term + term] = d->u2[g];
-                ++term;
+                ntof.push_back(0xFFFF);
+                term_lid.push_back((unsigned short)q);
+                pay1.push_back(d->u1[g]);
+                if (!zs) pay2.push_back(d->u2[g]);
+                ++nterm;
                 continue;
             }
             while (level < ldepth[q]) td.lvl_nt[++level] = nt;
-            ntof[o_node + q] = (unsigned short)nt;
+            ntof.push_back((unsigned short)nt);
             int nc = fc[g + 1] - fc[g];
-            TileRec &rc = rec[o_nt + nt];
+            TileRec rc;
             rc.first_child = (unsigned short)next_child;
             rc.lid = (unsigned short)q;
             rc.nchild = (unsigned char)nc;
             rc.player = (unsigned char)pl[g];
             rc.cp_off = 0;
-            TileAux &ax = aux[o_nt + nt];
-            ax.colbase = ax.slot_r = ax.slot_o = ax.pad = 0;
+            TileAux ax{0, 0, 0, 0};
             if (pl[g] == 0) {
                 rc.cp_off = (unsigned short)cpo;
-                for (int32_t c = fc[g]; c < fc[g + 1]; ++c) cprob[o_cp + cpo++] = d->cprob[c];
+                for (int32_t c = fc[g]; c < fc[g + 1]; ++c) { cprob.push_back(d->cprob[c]); ++cpo; }
             } else {
                 ax.colbase = colbase[g];
                 ax.slot_r = (int)(koff_col[krank[g]] + colbase[g]);
                 ax.slot_o = (int)(koff_iset[krank[g]] + srank[g]);
             }
-            pc[o_nt + nt] = pcs[g];
+            rec.push_back(rc);
+            aux.push_back(ax);
+            pc.push_back(pcs[g]);
             next_child += nc;
             ++nt;
         }
+        if (nportal > 0x7FFF || nt > 0x7FFF) return RLP_OK;
+        td.n_nodes = (int)local.size(); td.n_nt = nt; td.n_term = nterm; td.n_cp = cpo; td.n_portal = nportal;
         td.n_levels = level + 1;
         for (int l = level + 1; l <= kMaxTileLevels; ++l) td.lvl_nt[l] = nt;
         max_nodes = std::max(max_nodes, td.n_nodes);
         max_nt = std::max(max_nt, td.n_nt);
         max_cp = std::max(max_cp, cpo);
-        td.n_cp = cpo;
-        o_node += td.n_nodes; o_nt += td.n_nt; o_term += td.n_term; o_cp += cpo;
     }
-    if (koff_col.back() >= (int64_t)INT32_MAX) return RLP_OK;     // slots are 32-bit
+    // portals that hang directly off the (all-chance) trunk: reach (1, 1) for ever, value unused
+    for (int64_t v = 0; v < N; ++v)
+        if (kind[v] == 1 && status[v] == 0) portal_node.push_back((int32_t)v);
 
+    // ---- micro instances: one per portal, shapes deduplicated into templates ----------------------------------
+    const int64_t P = (int64_t)portal_node.size();
+    std::map<std::string, int> class_of;
+    std::vector<MicroTmpl> tmpl;
+    std::vector<unsigned short> m_class(P);
+    int mnt = 0, mterm = 0;
+    std::vector<int32_t> loc;
+    for (int64_t p = 0; p < P; ++p) {
+        loc.clear();
+        loc.push_back(portal_node[p]);
+        for (size_t q = 0; q < loc.size(); ++q)
+            for (int32_t c = fc[loc[q]]; c < fc[loc[q] + 1]; ++c) loc.push_back(c);
+        std::string sig;
+        sig.reserve(loc.size() * 2);
+        for (int32_t g : loc) { sig.push_back((char)(pl[g] + 2)); sig.push_back((char)(fc[g + 1] - fc[g])); }
+        auto it = class_of.find(sig);
+        int cls;
+        if (it == class_of.end()) {
+            cls = (int)tmpl.size();
+            if (cls >= 65535) return RLP_OK;
+            class_of.emplace(sig, cls);
+            MicroTmpl tm;
+            memset(&tm, 0, sizeof(tm));
+            int nt = 0, term = 0, next_child = 1;
+            for (size_t q = 0; q < loc.size(); ++q) {
+                int32_t g = loc[q];
+                int nc = fc[g + 1] - fc[g];
+                tm.player[q] = (unsigned char)(pl[g] < 0 ? 0xFF : pl[g]);
+                tm.nchild[q] = (unsigned char)nc;
+                tm.first_child[q] = (unsigned char)next_child;
+                next_child += nc;
+                if (pl[g] < 0) tm.rank[q] = (unsigned char)(0x80 | term++);
+                else { tm.nt_node[nt] = (unsigned char)q; tm.rank[q] = (unsigned char)nt++; }
+            }
+            tm.n = (unsigned char)loc.size(); tm.n_nt = (unsigned char)nt; tm.n_term = (unsigned char)term;
+            tmpl.push_back(tm);
+            mnt = std::max(mnt, nt);
+            mterm = std::max(mterm, term);
+        } else {
+            cls = it->second;
+        }
+        m_class[p] = (unsigned short)cls;
+    }
+    std::vector<int> m_colbase((size_t)mnt * P, 0), m_slot_r((size_t)mnt * P, 0), m_slot_o((size_t)mnt * P, 0);
+    std::vector<double> m_pay1((size_t)mterm * P, 0.0), m_pay2(zs ? 0 : (size_t)mterm * P, 0.0), m_pc(P);
+    for (int64_t p = 0; p < P; ++p) {
+        loc.clear();
+        loc.push_back(portal_node[p]);
+        for (size_t q = 0; q < loc.size(); ++q)
+            for (int32_t c = fc[loc[q]]; c < fc[loc[q] + 1]; ++c) loc.push_back(c);
+        int nt = 0, term = 0;
+        for (int32_t g : loc) {
+            if (pl[g] < 0) {
+                m_pay1[(size_t)term * P + p] = d->u1[g];
+                if (!zs) m_pay2[(size_t)term * P + p] = d->u2[g];
+                ++term;
+            } else {
+                m_colbase[(size_t)nt * P + p] = colbase[g];
+                m_slot_r[(size_t)nt * P + p] = (int)(koff_col[krank[g]] + colbase[g]);
+                m_slot_o[(size_t)nt * P + p] = (int)(koff_iset[krank[g]] + srank[g]);
+                ++nt;
+            }
+        }
+        m_pc[p] = pcs[portal_node[p]];
+    }
+
+    // ---- launch geometry of the upper tiles -------------------------------------------------------------------
     ts.num_tiles = (int)T;
-    ts.max_nodes = max_nodes;
-    ts.max_nt = max_nt;
-    ts.max_cp = max_cp;
-    ts.smem_bytes = tile_smem(max_nodes, max_nt, max_cp, zs);
+    ts.max_nodes = max_nodes; ts.max_nt = max_nt; ts.max_cp = max_cp;
+    ts.smem_bytes = T ? tile_smem(max_nodes, max_nt, max_cp, zs) : 0;
     if (ts.smem_bytes > 226 * 1024) return RLP_OK;               // (max_nodes, max_nt) came from different tiles
-    (void)budget_used;
-    // smallest block that keeps every thread at <= 2 owned nodes, else 1024 threads with up to 4
     ts.block = 1024;
-    for (int b : {128, 256, 512}) if ((max_nt + b - 1) / b <= 2) { ts.block = b; break; }
-    ts.slots = (max_nt + ts.block - 1) / ts.block;
+    for (int b : {64, 128, 256, 512})
+        if ((max_nt + b - 1) / b <= 2) { ts.block = b; break; }
+    ts.slots = std::max(1, (max_nt + ts.block - 1) / ts.block);
     if (ts.slots > 4) return RLP_OK;
     ts.wide = t->max_act > kRegAct;
+    ts.num_micro = (int)P; ts.num_classes = (int)tmpl.size(); ts.micro_nt = mnt; ts.micro_term = mterm;
+
     RLP_CUDA(ts.desc.upload(desc, stream));
     RLP_CUDA(ts.ntof.upload(ntof, stream));
     RLP_CUDA(ts.term_lid.upload(term_lid, stream));
+    RLP_CUDA(ts.portal_lid.upload(portal_lid, stream));
     RLP_CUDA(ts.rec.upload(rec, stream));
     RLP_CUDA(ts.aux.upload(aux, stream));
     RLP_CUDA(ts.pc.upload(pc, stream));
@@ -366,44 +589,90 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     RLP_CUDA(ts.pay2.upload(pay2, stream));
     RLP_CUDA(ts.cprob.upload(cprob, stream));
     RLP_CUDA(ts.root_val.alloc(T));
+    RLP_CUDA(ts.tmpl.upload(tmpl, stream));
+    RLP_CUDA(ts.m_class.upload(m_class, stream));
+    RLP_CUDA(ts.m_colbase.upload(m_colbase, stream));
+    RLP_CUDA(ts.m_slot_r.upload(m_slot_r, stream));
+    RLP_CUDA(ts.m_slot_o.upload(m_slot_o, stream));
+    RLP_CUDA(ts.m_pay1.upload(m_pay1, stream));
+    RLP_CUDA(ts.m_pay2.upload(m_pay2, stream));
+    RLP_CUDA(ts.m_pc.upload(m_pc, stream));
+    RLP_CUDA(ts.portal_p1.alloc((size_t)P)); RLP_CUDA(ts.portal_p2.alloc((size_t)P));
+    RLP_CUDA(ts.portal_v1.alloc((size_t)P)); RLP_CUDA(ts.portal_v2.alloc(zs ? 0 : (size_t)P));
+    if (P > 0) {
+        unsigned g = (unsigned)((P + 255) / 256);
+        k_fill<<<g, 256, 0, stream>>>(ts.portal_p1.p, P, 1.0); RLP_LAUNCH_CHECK();
+        k_fill<<<g, 256, 0, stream>>>(ts.portal_p2.p, P, 1.0); RLP_LAUNCH_CHECK();
+    }
     RLP_CUDA(cudaStreamSynchronize(stream));
     ts.enabled = true;
     return RLP_OK;
 }
 
-// One tiled sweep (replaces the per-level forward/backward launches of enqueue_sweep).
-template <bool ZS, int R, bool WIDE>
+template <bool ZS, int R, bool WIDE, int PHASE>
 static int launch_variant(const TileSet &ts, const TileView &v, cudaStream_t s) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        RLP_CUDA(cudaFuncSetAttribute(k_tile_sweep<ZS, R, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        RLP_CUDA(cudaFuncSetAttribute(k_tile_sweep<ZS, R, WIDE, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
-    k_tile_sweep<ZS, R, WIDE><<<ts.num_tiles, ts.block, ts.smem_bytes, s>>>(v);
+    k_tile_sweep<ZS, R, WIDE, PHASE><<<ts.num_tiles, ts.block, ts.smem_bytes, s>>>(v);
     RLP_LAUNCH_CHECK();
     return RLP_OK;
 }
 
-template <bool ZS, bool WIDE>
+template <bool ZS, bool WIDE, int PHASE>
 static int launch_slots(const TileSet &ts, const TileView &v, cudaStream_t s) {
     switch (ts.slots) {
-        case 1: return launch_variant<ZS, 1, WIDE>(ts, v, s);
-        case 2: return launch_variant<ZS, 2, WIDE>(ts, v, s);
-        case 3: return launch_variant<ZS, 3, WIDE>(ts, v, s);
-        default: return launch_variant<ZS, 4, WIDE>(ts, v, s);
+        case 1: return launch_variant<ZS, 1, WIDE, PHASE>(ts, v, s);
+        case 2: return launch_variant<ZS, 2, WIDE, PHASE>(ts, v, s);
+        case 3: return launch_variant<ZS, 3, WIDE, PHASE>(ts, v, s);
+        default: return launch_variant<ZS, 4, WIDE, PHASE>(ts, v, s);
     }
 }
 
-int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter) {
+template <int PHASE>
+static int launch_upper(rlp_tree *t, const TileSet &ts, const TileView &v, cudaStream_t s) {
+    if (t->zero_sum) return ts.wide ? launch_slots<true, true, PHASE>(ts, v, s) : launch_slots<true, false, PHASE>(ts, v, s);
+    return ts.wide ? launch_slots<false, true, PHASE>(ts, v, s) : launch_slots<false, false, PHASE>(ts, v, s);
+}
+
+// One tiled sweep: [upper tiles, reach to portals] -> [micro subtrees] -> [upper tiles, values from portals].
+int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches) {
     rlp_tree *t = c->tree;
     TileSet &ts = t->tiles;
     TileView v;
-    v.desc = ts.desc.p; v.ntof = ts.ntof.p; v.term_lid = ts.term_lid.p; v.rec = ts.rec.p; v.aux = ts.aux.p;
+    v.desc = ts.desc.p; v.ntof = ts.ntof.p; v.term_lid = ts.term_lid.p; v.portal_lid = ts.portal_lid.p;
+    v.rec = ts.rec.p; v.aux = ts.aux.p;
     v.pc = ts.pc.p; v.pay1 = ts.pay1.p; v.pay2 = ts.pay2.p; v.cprob = ts.cprob.p; v.sigma = c->sigma.p;
     v.contrib_r = c->contrib_r.p; v.contrib_o = c->contrib_o.p; v.root_val = ts.root_val.p;
+    v.portal_p1 = ts.portal_p1.p; v.portal_p2 = ts.portal_p2.p; v.portal_v1 = ts.portal_v1.p; v.portal_v2 = ts.portal_v2.p;
     v.iter = iter ? iter : c->iter.p; v.max_nodes = ts.max_nodes; v.max_nt = ts.max_nt; v.max_cp = ts.max_cp;
-    if (t->zero_sum) return ts.wide ? launch_slots<true, true>(ts, v, s) : launch_slots<true, false>(ts, v, s);
-    return ts.wide ? launch_slots<false, true>(ts, v, s) : launch_slots<false, false>(ts, v, s);
+    int n = 0;
+    if (ts.num_tiles > 0 && ts.num_micro > 0) {
+        int rc = launch_upper<0>(t, ts, v, s);
+        if (rc) return rc;
+        ++n;
+    }
+    if (ts.num_micro > 0) {
+        MicroView m;
+        m.tmpl = ts.tmpl.p; m.cls = ts.m_class.p; m.colbase = ts.m_colbase.p; m.slot_r = ts.m_slot_r.p;
+        m.slot_o = ts.m_slot_o.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;
+        m.portal_p1 = ts.portal_p1.p; m.portal_p2 = ts.portal_p2.p; m.portal_v1 = ts.portal_v1.p;
+        m.portal_v2 = ts.portal_v2.p; m.contrib_r = c->contrib_r.p; m.contrib_o = c->contrib_o.p;
+        m.iter = v.iter; m.P = ts.num_micro; m.num_classes = ts.num_classes;
+        unsigned g = (unsigned)((ts.num_micro + kMicroBlock - 1) / kMicroBlock);
+        if (t->zero_sum) k_micro<true><<<g, kMicroBlock, 0, s>>>(m); else k_micro<false><<<g, kMicroBlock, 0, s>>>(m);
+        RLP_LAUNCH_CHECK();
+        ++n;
+    }
+    if (ts.num_tiles > 0) {
+        int rc = launch_upper<1>(t, ts, v, s);
+        if (rc) return rc;
+        ++n;
+    }
+    if (launches) *launches = n;
+    return RLP_OK;
 }
 
 }  // namespace rlp

@@ -1,31 +1,40 @@
-// Subtree tiles: the part of the tree below a cut is split into subtrees ("tiles") small enough for one
-// CTA to sweep entirely in shared memory -- forward reach and backward values never touch HBM; only the
-// per-decision-node contributions (regret terms, own reach) leave the SM.
+// Two-tier tiling of the tree below an all-chance trunk.
 //
-// A tile is stored in tile-local breadth-first order (children of a node stay contiguous).  Per tile, in HBM:
-//   ntof[n_nodes]   u16  non-terminal rank of every local node (0xFFFF = terminal)
-//   rec[n_nt]       8 B  per non-terminal: first child (local id), own local id, #children, player,
-//                        offset of its chance probabilities
-//   aux[n_nt]       16 B per non-terminal: internal pair base of its information set, its slots in the two
-//                        jagged-diagonal contribution arrays
-//   pc[n_nt]        f64  chance reach of the node (static: it does not depend on the strategy)
-//   term_lid/pay    per terminal: local id and player-1 payoff (player-2 payoff only for non-zero-sum games)
-//   cprob           chance probabilities of the tile's chance edges
+//  * MICRO subtrees: maximal subtrees with <= 32 nodes, <= 8 decision nodes, no chance node (in Leduc: every
+//    23-node betting round after the board card).  One THREAD sweeps one micro subtree, forward and backward,
+//    with no barrier at all; its scratch (reach and values of <= 8 nodes) sits in a thread-interleaved slice of
+//    shared memory.  Subtrees of equal shape share one template; per-instance data (information-set columns,
+//    contribution slots, payoffs) is stored slot-major so a warp reads consecutive words.
+//  * UPPER tiles: what remains above the micro subtrees is cut into maximal subtrees that fit one CTA's shared
+//    memory (in Leduc: the round-1 betting nodes and board-deal chance nodes of one (hole1, hole2) deal); the
+//    micro roots appear in them as "portal" leaves.  Phase 0 sweeps reach down to the portals, the micro kernel
+//    runs, phase 1 redoes the (tiny) forward pass and sweeps values up from the portals.
+//
+// Reach and node values never touch HBM except at the portals (24 B per micro subtree); only the per-decision-node
+// contributions (regret terms, own reach) leave the SM, into the jagged-diagonal scratch the accumulate kernel
+// streams.
 #pragma once
 #include "common.cuh"
 
 constexpr int kMaxTileLevels = 32;
+constexpr int kMicroNodes = 32;     // nodes per micro subtree
+constexpr int kMicroNt = 8;         // decision nodes per micro subtree
+constexpr int kMicroAct = 8;        // widest node inside a micro subtree
+constexpr int kMicroSmemClasses = 12;
 
 struct TileDesc {
     long long node_off;     // into ntof
     long long nt_off;       // into rec / aux / pc
     long long term_off;     // into term_lid / pay
     long long cp_off;       // into cprob
+    long long portal_off;   // first portal (= micro instance) index of this tile
     int n_nodes, n_nt, n_term, n_levels;
     int root_global;        // breadth-first id of the tile root
     int n_cp;               // chance edges inside the tile
+    int n_portal, pad;
     double root_p1, root_p2;            // strategy reach of the root (1.0 below an all-chance trunk)
     int lvl_nt[kMaxTileLevels + 1];     // non-terminal rank ranges per local level
+    int pad2;
 };
 
 struct TileRec {            // 8 bytes
@@ -38,21 +47,43 @@ struct TileAux {            // 16 bytes
     int colbase, slot_r, slot_o, pad;
 };
 
+// Shape of a micro subtree in local breadth-first order.
+struct MicroTmpl {
+    unsigned char n, n_nt, n_term, pad;
+    unsigned char player[kMicroNodes];
+    unsigned char first_child[kMicroNodes];
+    unsigned char nchild[kMicroNodes];
+    unsigned char rank[kMicroNodes];        // non-terminal rank, or 0x80 | terminal rank
+    unsigned char nt_node[kMicroNt];        // local id of the r-th non-terminal
+};
+
 struct TileSet {
     bool enabled = false;
+    // upper tiles
     int num_tiles = 0;
     int max_nodes = 0, max_nt = 0, max_cp = 0;
     int slots = 1;          // owned non-terminal nodes per thread (template parameter R)
     bool wide = false;      // some information set is wider than the register-cached strategy row
     size_t smem_bytes = 0;
-    int block = 512;
+    int block = 128;
     rlp::DevBuf<TileDesc> desc;
-    rlp::DevBuf<unsigned short> ntof, term_lid;
+    rlp::DevBuf<unsigned short> ntof, term_lid, portal_lid;
     rlp::DevBuf<TileRec> rec;
     rlp::DevBuf<TileAux> aux;
     rlp::DevBuf<double> pc, pay1, pay2, cprob, root_val;
+    // micro subtrees (instance p == portal p)
+    int num_micro = 0, num_classes = 0, micro_nt = 0, micro_term = 0;
+    rlp::DevBuf<MicroTmpl> tmpl;
+    rlp::DevBuf<unsigned short> m_class;            // [P]
+    rlp::DevBuf<int> m_colbase, m_slot_r, m_slot_o; // [micro_nt][P]
+    rlp::DevBuf<double> m_pay1, m_pay2;             // [micro_term][P]
+    rlp::DevBuf<double> m_pc;                       // [P]
+    rlp::DevBuf<double> portal_p1, portal_p2, portal_v1, portal_v2;   // [P]
     int64_t bytes() const {
-        return (int64_t)(desc.bytes() + ntof.bytes() + term_lid.bytes() + rec.bytes() + aux.bytes() + pc.bytes() +
-                         pay1.bytes() + pay2.bytes() + cprob.bytes() + root_val.bytes());
+        return (int64_t)(desc.bytes() + ntof.bytes() + term_lid.bytes() + portal_lid.bytes() + rec.bytes() +
+                         aux.bytes() + pc.bytes() + pay1.bytes() + pay2.bytes() + cprob.bytes() + root_val.bytes() +
+                         tmpl.bytes() + m_class.bytes() + m_colbase.bytes() + m_slot_r.bytes() + m_slot_o.bytes() +
+                         m_pay1.bytes() + m_pay2.bytes() + m_pc.bytes() + portal_p1.bytes() + portal_p2.bytes() +
+                         portal_v1.bytes() + portal_v2.bytes());
     }
 };
