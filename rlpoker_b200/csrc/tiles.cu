@@ -219,6 +219,14 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
 }
 
 // ------------------------------------------------------------------------------------ micro subtrees
+
+constexpr int kMicroBlock = 64;
+
+// One thread = one micro subtree.  Everything the sweep needs from HBM/L2 -- information-set columns,
+// contribution slots, the strategy probability of every edge, the payoff of every leaf -- is fetched up front in
+// two batches of independent loads into a thread-interleaved (bank-conflict-free) slice of shared memory; the
+// forward and backward passes over the <= 8 decision nodes then touch shared memory only, so no global load
+// sits on the node-to-node dependency chain.
 struct MicroView {
     const MicroTmpl *tmpl;
     const unsigned short *cls;
@@ -229,19 +237,23 @@ struct MicroView {
     double *portal_v1, *portal_v2;
     double *contrib_r, *contrib_o;
     const IterState *iter;
-    int P, num_classes;
+    int P, num_classes, mn, mnt;
 };
 
-constexpr int kMicroBlock = 128;
-
-// One thread = one micro subtree: forward reach then backward values over <= 8 decision nodes in the template's
-// breadth-first order; scratch is a thread-interleaved slice of shared memory (bank-conflict free).
 template <bool ZS>
 __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
-    __shared__ double sq1[kMicroNt * kMicroBlock], sq2[kMicroNt * kMicroBlock], sv1[kMicroNt * kMicroBlock];
-    __shared__ double sv2[ZS ? 1 : kMicroNt * kMicroBlock];
+    extern __shared__ __align__(16) unsigned char micro_smem[];
     __shared__ MicroTmpl stm[kMicroSmemClasses];
     const int tid = threadIdx.x;
+    const int mn = v.mn, mnt = v.mnt;
+    double *ssig = reinterpret_cast<double *>(micro_smem);            // [mn][bd]  strategy prob of the edge INTO node j
+    double *sv1 = ssig + mn * kMicroBlock;                            // [mn][bd]  value of node j (player 1)
+    double *sv2 = sv1 + mn * kMicroBlock;                             // [mn][bd]  (non-zero-sum only)
+    double *sq1 = sv2 + (ZS ? 0 : mn * kMicroBlock);                  // [mnt][bd] reach by non-terminal rank
+    double *sq2 = sq1 + mnt * kMicroBlock;
+    int *scb = reinterpret_cast<int *>(sq2 + mnt * kMicroBlock);      // [mnt][bd] information-set column base
+    int *ssr = scb + mnt * kMicroBlock;                               // [mnt][bd] slot in contrib_r
+    int *sso = ssr + mnt * kMicroBlock;                               // [mnt][bd] slot in contrib_o
     const bool in_smem = v.num_classes <= kMicroSmemClasses;
     if (in_smem) {
         const int words = v.num_classes * (int)(sizeof(MicroTmpl) / sizeof(int));
@@ -254,71 +266,67 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
     const long long P = v.P;
     const MicroTmpl *tm = in_smem ? &stm[v.cls[p]] : v.tmpl + v.cls[p];
     const double w = v.iter->linear ? (double)v.iter->t : 1.0;
+    const int n = tm->n, n_nt = tm->n_nt;
+#define AT(arr, i) arr[(i) * kMicroBlock + tid]
+    // batch 1: per-decision-node integers (coalesced: slot-major layout)
+#pragma unroll 4
+    for (int r = 0; r < n_nt; ++r) {
+        AT(scb, r) = v.colbase[r * P + p];
+        AT(ssr, r) = v.slot_r[r * P + p];
+        AT(sso, r) = v.slot_o[r * P + p];
+    }
     const double pcv = v.pc[p];
-    const int n_nt = tm->n_nt;
-#define Q1(r) sq1[(r) * kMicroBlock + tid]
-#define Q2(r) sq2[(r) * kMicroBlock + tid]
-#define V1(r) sv1[(r) * kMicroBlock + tid]
-#define V2(r) sv2[(r) * kMicroBlock + tid]
-    Q1(0) = v.portal_p1[p];
-    Q2(0) = v.portal_p2[p];
+    AT(sq1, 0) = v.portal_p1[p];
+    AT(sq2, 0) = v.portal_p2[p];
+    // batch 2: strategy probability of every edge, payoff of every leaf (independent loads)
+#pragma unroll 4
+    for (int j = 1; j < n; ++j) {
+        AT(ssig, j) = v.sigma[AT(scb, tm->par_rank[j]) + tm->par_slot[j]];
+        const int rk = tm->rank[j];
+        if (rk & 0x80) {
+            AT(sv1, j) = v.pay1[(rk & 0x7F) * P + p];
+            if (!ZS) AT(sv2, j) = v.pay2[(rk & 0x7F) * P + p];
+        }
+    }
     // forward (cfr.py:208,217)
     for (int r = 0; r + 1 < n_nt; ++r) {
         const int j = tm->nt_node[r];
-        const int pl = tm->player[j], fc = tm->first_child[j], n = tm->nchild[j];
-        const double *row = v.sigma + v.colbase[r * P + p];
-        const double a = Q1(r), b = Q2(r);
-        for (int k = 0; k < n; ++k) {
+        const int pl = tm->player[j], fc = tm->first_child[j], nc = tm->nchild[j];
+        const double a = AT(sq1, r), b = AT(sq2, r);
+        for (int k = 0; k < nc; ++k) {
             const int rk = tm->rank[fc + k];
             if (rk & 0x80) continue;
-            const double e = row[k];
-            Q1(rk) = pl == 1 ? e * a : a;
-            Q2(rk) = pl == 2 ? e * b : b;
+            const double e = AT(ssig, fc + k);
+            AT(sq1, rk) = pl == 1 ? e * a : a;
+            AT(sq2, rk) = pl == 2 ? e * b : b;
         }
     }
     // backward (cfr.py:204-242)
     for (int r = n_nt - 1; r >= 0; --r) {
         const int j = tm->nt_node[r];
-        const int pl = tm->player[j], fc = tm->first_child[j], n = tm->nchild[j];
-        const double *row = v.sigma + v.colbase[r * P + p];
+        const int pl = tm->player[j], fc = tm->first_child[j], nc = tm->nchild[j];
         double a1 = 0.0, a2 = 0.0;
-        double va[kMicroAct];
-#pragma unroll
-        for (int k = 0; k < kMicroAct; ++k) {
-            if (k < n) {
-                const int rk = tm->rank[fc + k];
-                double x, y = 0.0;
-                if (rk & 0x80) {
-                    x = v.pay1[(rk & 0x7F) * P + p];
-                    if (!ZS) y = v.pay2[(rk & 0x7F) * P + p];
-                } else {
-                    x = V1(rk);
-                    if (!ZS) y = V2(rk);
-                }
-                const double e = row[k];
-                a1 = a1 + e * x;
-                if (!ZS) a2 = a2 + e * y;
-                va[k] = pl == 1 ? x : (ZS ? -x : y);
-            }
+        for (int k = 0; k < nc; ++k) {
+            const double e = AT(ssig, fc + k);
+            a1 = a1 + e * AT(sv1, fc + k);
+            if (!ZS) a2 = a2 + e * AT(sv2, fc + k);
         }
-        V1(r) = a1;
-        if (!ZS) V2(r) = a2;
-        const double x1 = Q1(r), x2 = Q2(r);
+        AT(sv1, j) = a1;
+        if (!ZS) AT(sv2, j) = a2;
+        const double x1 = AT(sq1, r), x2 = AT(sq2, r);
         const double opp = pl == 1 ? pcv * x2 : pcv * x1;
         const double own = pl == 1 ? x1 : x2;
         const double vp = pl == 1 ? a1 : (ZS ? -a1 : a2);
-        double *dst = v.contrib_r + v.slot_r[r * P + p];
-#pragma unroll
-        for (int k = 0; k < kMicroAct; ++k)
-            if (k < n) dst[k] = w * (va[k] - vp) * opp;
-        v.contrib_o[v.slot_o[r * P + p]] = w * own;
+        double *dst = v.contrib_r + AT(ssr, r);
+        for (int k = 0; k < nc; ++k) {
+            const double x = pl == 1 ? AT(sv1, fc + k) : (ZS ? -AT(sv1, fc + k) : AT(sv2, fc + k));
+            dst[k] = w * (x - vp) * opp;
+        }
+        v.contrib_o[AT(sso, r)] = w * own;
     }
-    v.portal_v1[p] = V1(0);
-    if (!ZS) v.portal_v2[p] = V2(0);
-#undef Q1
-#undef Q2
-#undef V1
-#undef V2
+    v.portal_v1[p] = AT(sv1, 0);
+    if (!ZS) v.portal_v2[p] = AT(sv2, 0);
+#undef AT
 }
 
 __global__ void k_fill(double *p, long long n, double x) {
@@ -504,7 +512,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     std::map<std::string, int> class_of;
     std::vector<MicroTmpl> tmpl;
     std::vector<unsigned short> m_class(P);
-    int mnt = 0, mterm = 0;
+    int mnt = 0, mterm = 0, mnodes = 0;
     std::vector<int32_t> loc;
     for (int64_t p = 0; p < P; ++p) {
         loc.clear();
@@ -529,14 +537,18 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
                 tm.player[q] = (unsigned char)(pl[g] < 0 ? 0xFF : pl[g]);
                 tm.nchild[q] = (unsigned char)nc;
                 tm.first_child[q] = (unsigned char)next_child;
-                next_child += nc;
                 if (pl[g] < 0) tm.rank[q] = (unsigned char)(0x80 | term++);
-                else { tm.nt_node[nt] = (unsigned char)q; tm.rank[q] = (unsigned char)nt++; }
+                else {
+                    for (int k = 0; k < nc; ++k) { tm.par_rank[next_child + k] = (unsigned char)nt; tm.par_slot[next_child + k] = (unsigned char)k; }
+                    tm.nt_node[nt] = (unsigned char)q; tm.rank[q] = (unsigned char)nt++;
+                }
+                next_child += nc;
             }
             tm.n = (unsigned char)loc.size(); tm.n_nt = (unsigned char)nt; tm.n_term = (unsigned char)term;
             tmpl.push_back(tm);
             mnt = std::max(mnt, nt);
             mterm = std::max(mterm, term);
+            mnodes = std::max(mnodes, (int)loc.size());
         } else {
             cls = it->second;
         }
@@ -576,7 +588,8 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     ts.slots = std::max(1, (max_nt + ts.block - 1) / ts.block);
     if (ts.slots > 4) return RLP_OK;
     ts.wide = t->max_act > kRegAct;
-    ts.num_micro = (int)P; ts.num_classes = (int)tmpl.size(); ts.micro_nt = mnt; ts.micro_term = mterm;
+    ts.num_micro = (int)P; ts.num_classes = (int)tmpl.size(); ts.micro_nt = mnt; ts.micro_term = mterm; ts.micro_nodes = mnodes;
+    ts.micro_smem = (size_t)kMicroBlock * ((size_t)mnodes * 8 * (zs ? 2 : 3) + (size_t)mnt * (16 + 12));
 
     RLP_CUDA(ts.desc.upload(desc, stream));
     RLP_CUDA(ts.ntof.upload(ntof, stream));
@@ -660,9 +673,16 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
         m.slot_o = ts.m_slot_o.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;
         m.portal_p1 = ts.portal_p1.p; m.portal_p2 = ts.portal_p2.p; m.portal_v1 = ts.portal_v1.p;
         m.portal_v2 = ts.portal_v2.p; m.contrib_r = c->contrib_r.p; m.contrib_o = c->contrib_o.p;
-        m.iter = v.iter; m.P = ts.num_micro; m.num_classes = ts.num_classes;
+        m.iter = v.iter; m.P = ts.num_micro; m.num_classes = ts.num_classes; m.mn = ts.micro_nodes; m.mnt = ts.micro_nt;
         unsigned g = (unsigned)((ts.num_micro + kMicroBlock - 1) / kMicroBlock);
-        if (t->zero_sum) k_micro<true><<<g, kMicroBlock, 0, s>>>(m); else k_micro<false><<<g, kMicroBlock, 0, s>>>(m);
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            RLP_CUDA(cudaFuncSetAttribute(k_micro<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            RLP_CUDA(cudaFuncSetAttribute(k_micro<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        if (t->zero_sum) k_micro<true><<<g, kMicroBlock, ts.micro_smem, s>>>(m);
+        else k_micro<false><<<g, kMicroBlock, ts.micro_smem, s>>>(m);
         RLP_LAUNCH_CHECK();
         ++n;
     }

@@ -55,6 +55,8 @@ struct MicroTmpl {
     unsigned char nchild[kMicroNodes];
     unsigned char rank[kMicroNodes];        // non-terminal rank, or 0x80 | terminal rank
     unsigned char nt_node[kMicroNt];        // local id of the r-th non-terminal
+    unsigned char par_rank[kMicroNodes];    // non-terminal rank of the parent
+    unsigned char par_slot[kMicroNodes];    // which child of the parent
 };
 
 struct TileSet {
@@ -72,7 +74,8 @@ struct TileSet {
     rlp::DevBuf<TileAux> aux;
     rlp::DevBuf<double> pc, pay1, pay2, cprob, root_val;
     // micro subtrees (instance p == portal p)
-    int num_micro = 0, num_classes = 0, micro_nt = 0, micro_term = 0;
+    int num_micro = 0, num_classes = 0, micro_nt = 0, micro_term = 0, micro_nodes = 0;
+    size_t micro_smem = 0;
     rlp::DevBuf<MicroTmpl> tmpl;
     rlp::DevBuf<unsigned short> m_class;            // [P]
     rlp::DevBuf<int> m_colbase, m_slot_r, m_slot_o; // [micro_nt][P]
