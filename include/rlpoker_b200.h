@@ -72,6 +72,9 @@ int rlp_tree_upload(const rlp_tree_desc *desc, void *stream, rlp_tree **out);
 void rlp_tree_free(rlp_tree *tree);
 /* Device bytes held by the tree. */
 int64_t rlp_tree_bytes(const rlp_tree *tree);
+/* Layout facts: which = 0 tiled sweep in use, 1 #upper tiles, 2 #micro subtrees, 3 #micro shapes, 4 #shapes with a
+ * compiled straight-line kernel, 5 zero-sum, 6 largest information set, 7 upper-tile block size, 8 its shared memory. */
+int64_t rlp_tree_stat(const rlp_tree *tree, int which);
 
 /*
  * Native Leduc generator: writes the same arrays flatten() produces from

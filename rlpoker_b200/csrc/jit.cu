@@ -1,0 +1,169 @@
+// Shape-specialised micro-subtree kernels.
+//
+// The interpreter in tiles.cu (k_micro) walks a template with dynamic indices, which forces the per-thread scratch
+// into shared memory and costs ~2 800 instructions per subtree.  All micro subtrees of one class have the SAME
+// shape, so at upload time this file writes the sweep of that shape out as straight-line CUDA C++ -- every index a
+// literal, every intermediate a named double -- and compiles it for sm_100a with NVRTC (--fmad=false, like the rest
+// of the library).  The result keeps the whole subtree in registers, issues all of its loads up front, and runs
+// ~6x fewer instructions.  The arithmetic, operand for operand, is that of k_micro / cfr.cu / the reference's
+// cfr_recursive (rlpoker/cfr/cfr.py:158-255).  If NVRTC is unavailable (or RLP_NO_JIT=1) the interpreter is used.
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <sstream>
+#include <string>
+
+#include "cfr.cuh"
+
+using rlp::fail;
+
+namespace {
+
+struct Nvrtc {
+    void *handle = nullptr;
+    bool tried = false;
+    decltype(&nvrtcCreateProgram) create = nullptr;
+    decltype(&nvrtcCompileProgram) compile = nullptr;
+    decltype(&nvrtcGetCUBINSize) cubin_size = nullptr;
+    decltype(&nvrtcGetCUBIN) cubin = nullptr;
+    decltype(&nvrtcGetProgramLogSize) log_size = nullptr;
+    decltype(&nvrtcGetProgramLog) log = nullptr;
+    decltype(&nvrtcDestroyProgram) destroy = nullptr;
+    bool load() {
+        if (tried) return handle != nullptr;
+        tried = true;
+        for (const char *name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (handle) break;
+        }
+        if (!handle) return false;
+#define RLP_SYM(field, sym) field = (decltype(field))dlsym(handle, #sym); if (!field) { handle = nullptr; return false; }
+        RLP_SYM(create, nvrtcCreateProgram)
+        RLP_SYM(compile, nvrtcCompileProgram)
+        RLP_SYM(cubin_size, nvrtcGetCUBINSize)
+        RLP_SYM(cubin, nvrtcGetCUBIN)
+        RLP_SYM(log_size, nvrtcGetProgramLogSize)
+        RLP_SYM(log, nvrtcGetProgramLog)
+        RLP_SYM(destroy, nvrtcDestroyProgram)
+#undef RLP_SYM
+        return true;
+    }
+};
+Nvrtc g_nvrtc;
+
+// Straight-line sweep of one shape.  Names: cb/sr/so{r} = column base / slots of decision node r; s{j} = strategy
+// probability of the edge into local node j; x{j} (y{j}) = player-1 (player-2) value of node j; q1_{r}, q2_{r} reach.
+std::string generate(const MicroTmpl &tm, bool zs) {
+    std::ostringstream o;
+    o.precision(17);
+    o << "struct IterState { long long t; int linear; int pad; unsigned long long touched; };\n"
+         "extern \"C\" __global__ void __launch_bounds__(128) micro_k(\n"
+         "    const int* __restrict__ colbase, const int* __restrict__ slot_r, const int* __restrict__ slot_o,\n"
+         "    const double* __restrict__ pay1, const double* __restrict__ pay2, const double* __restrict__ pc,\n"
+         "    const double* __restrict__ sigma, const double* __restrict__ portal_p1, const double* __restrict__ portal_p2,\n"
+         "    double* __restrict__ portal_v1, double* __restrict__ portal_v2, double* __restrict__ contrib_r,\n"
+         "    double* __restrict__ contrib_o, const IterState* __restrict__ iter, long long P,\n"
+         "    const int* __restrict__ inst, int count) {\n"
+         "  const int i = blockIdx.x * blockDim.x + threadIdx.x;\n"
+         "  if (i >= count) return;\n"
+         "  const long long p = inst ? (long long)inst[i] : (long long)i;\n"
+         "  const double w = iter->linear ? (double)iter->t : 1.0;\n";
+    const int n = tm.n, n_nt = tm.n_nt;
+    for (int r = 0; r < n_nt; ++r)
+        o << "  const int cb" << r << " = colbase[" << r << " * P + p], sr" << r << " = slot_r[" << r << " * P + p], so"
+          << r << " = slot_o[" << r << " * P + p];\n";
+    o << "  const double pcv = pc[p];\n  const double q1_0 = portal_p1[p], q2_0 = portal_p2[p];\n";
+    for (int j = 1; j < n; ++j)
+        o << "  const double s" << j << " = sigma[cb" << (int)tm.par_rank[j] << " + " << (int)tm.par_slot[j] << "];\n";
+    for (int j = 0; j < n; ++j)
+        if (tm.rank[j] & 0x80) {
+            int tr = tm.rank[j] & 0x7F;
+            o << "  const double x" << j << " = pay1[" << tr << " * P + p];\n";
+            if (!zs) o << "  const double y" << j << " = pay2[" << tr << " * P + p];\n";
+        }
+    // forward
+    for (int r = 0; r < n_nt; ++r) {
+        int j = tm.nt_node[r], pl = tm.player[j];
+        for (int k = 0; k < tm.nchild[j]; ++k) {
+            int c = tm.first_child[j] + k;
+            if (tm.rank[c] & 0x80) continue;
+            int rc = tm.rank[c];
+            o << "  const double q1_" << rc << " = " << (pl == 1 ? "s" + std::to_string(c) + " * " : "") << "q1_" << r << ";\n";
+            o << "  const double q2_" << rc << " = " << (pl == 2 ? "s" + std::to_string(c) + " * " : "") << "q2_" << r << ";\n";
+        }
+    }
+    // backward
+    for (int r = n_nt - 1; r >= 0; --r) {
+        int j = tm.nt_node[r], pl = tm.player[j], fc = tm.first_child[j], nc = tm.nchild[j];
+        o << "  double a" << j << " = 0.0;\n";
+        for (int k = 0; k < nc; ++k) o << "  a" << j << " = a" << j << " + s" << (fc + k) << " * x" << (fc + k) << ";\n";
+        o << "  const double x" << j << " = a" << j << ";\n";
+        if (!zs) {
+            o << "  double b" << j << " = 0.0;\n";
+            for (int k = 0; k < nc; ++k) o << "  b" << j << " = b" << j << " + s" << (fc + k) << " * y" << (fc + k) << ";\n";
+            o << "  const double y" << j << " = b" << j << ";\n";
+        }
+        o << "  {\n    const double opp = " << (pl == 1 ? "pcv * q2_" : "pcv * q1_") << r << ";\n"
+          << "    const double own = " << (pl == 1 ? "q1_" : "q2_") << r << ";\n"
+          << "    const double vp = " << (pl == 1 ? "x" + std::to_string(j) : (zs ? "-x" + std::to_string(j) : "y" + std::to_string(j))) << ";\n";
+        for (int k = 0; k < nc; ++k) {
+            std::string va = pl == 1 ? "x" + std::to_string(fc + k) : (zs ? "-x" + std::to_string(fc + k) : "y" + std::to_string(fc + k));
+            o << "    contrib_r[sr" << r << " + " << k << "] = w * (" << va << " - vp) * opp;\n";
+        }
+        o << "    contrib_o[so" << r << "] = w * own;\n  }\n";
+    }
+    o << "  portal_v1[p] = x0;\n";
+    if (!zs) o << "  portal_v2[p] = y0;\n";
+    o << "}\n";
+    return o.str();
+}
+
+}  // namespace
+
+namespace rlp {
+
+// Compile the straight-line kernel of `tm`; returns RLP_OK with *kernel == nullptr when JIT is unavailable.
+int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *kernel, std::string *log_out) {
+    *kernel = nullptr;
+    *lib_out = nullptr;
+    const char *no_jit = getenv("RLP_NO_JIT");
+    if (no_jit && no_jit[0] == '1') return RLP_OK;
+    if (!g_nvrtc.load()) return RLP_OK;
+    std::string src = generate(tm, zs);
+    nvrtcProgram prog;
+    if (g_nvrtc.create(&prog, src.c_str(), "micro_k.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return RLP_OK;
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17"};
+    nvrtcResult res = g_nvrtc.compile(prog, 4, opts);
+    if (res != NVRTC_SUCCESS) {
+        size_t n = 0;
+        g_nvrtc.log_size(prog, &n);
+        std::string log(n, '\0');
+        if (n) g_nvrtc.log(prog, &log[0]);
+        if (log_out) *log_out = log;
+        g_nvrtc.destroy(&prog);
+        return RLP_OK;                          // fall back to the interpreter
+    }
+    size_t sz = 0;
+    g_nvrtc.cubin_size(prog, &sz);
+    std::vector<char> cubin(sz);
+    g_nvrtc.cubin(prog, cubin.data());
+    g_nvrtc.destroy(&prog);
+    cudaLibrary_t lib;
+    if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return RLP_OK;
+    }
+    cudaKernel_t k;
+    if (cudaLibraryGetKernel(&k, lib, "micro_k") != cudaSuccess) {
+        cudaGetLastError();
+        cudaLibraryUnload(lib);
+        return RLP_OK;
+    }
+    *lib_out = lib;
+    *kernel = k;
+    return RLP_OK;
+}
+
+std::string jit_micro_source(const MicroTmpl &tm, bool zs) { return generate(tm, zs); }
+
+}  // namespace rlp

@@ -339,6 +339,8 @@ __global__ void k_fill(double *p, long long n, double x) {
 // ------------------------------------------------------------------------------------ host
 namespace rlp {
 
+int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *kernel, std::string *log_out);
+
 // Called by rlp_tree_upload once the per-node information-set tables exist.  Leaves t->tiles disabled
 // (level-sweep fallback) when the tree cannot be tiled under an all-chance trunk.
 int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> &colbase,
@@ -618,6 +620,30 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
         k_fill<<<g, 256, 0, stream>>>(ts.portal_p2.p, P, 1.0); RLP_LAUNCH_CHECK();
     }
     RLP_CUDA(cudaStreamSynchronize(stream));
+    // ---- shape-specialised kernels (jit.cu): all classes or none ------------------------------------------------
+    ts.jit.clear();
+    if (P > 0 && tmpl.size() <= 8) {
+        std::vector<std::vector<int>> members(tmpl.size());
+        if (tmpl.size() > 1)
+            for (int64_t p = 0; p < P; ++p) members[m_class[p]].push_back((int)p);
+        bool all = true;
+        for (size_t c = 0; c < tmpl.size() && all; ++c) {
+            std::unique_ptr<JitClass> jc(new JitClass);
+            std::string log;
+            int rc = jit_micro_kernel(tmpl[c], zs, &jc->lib, &jc->kernel, &log);
+            if (rc) return rc;
+            if (!jc->kernel) { all = false; break; }
+            if (tmpl.size() > 1) {
+                jc->count = (int)members[c].size();
+                RLP_CUDA(jc->inst.upload(members[c], stream));
+            } else {
+                jc->count = (int)P;
+            }
+            ts.jit.push_back(std::move(jc));
+        }
+        if (!all) ts.jit.clear();
+        RLP_CUDA(cudaStreamSynchronize(stream));
+    }
     ts.enabled = true;
     return RLP_OK;
 }
@@ -667,7 +693,21 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
         if (rc) return rc;
         ++n;
     }
-    if (ts.num_micro > 0) {
+    if (ts.num_micro > 0 && !ts.jit.empty()) {
+        const IterState *it = v.iter;
+        long long P = ts.num_micro;
+        for (auto &jc : ts.jit) {
+            if (jc->count == 0) continue;
+            const int *inst = jc->inst.n ? jc->inst.p : nullptr;
+            int count = jc->count;
+            void *args[] = {&ts.m_colbase.p, &ts.m_slot_r.p, &ts.m_slot_o.p, &ts.m_pay1.p, &ts.m_pay2.p, &ts.m_pc.p,
+                            &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
+                            &c->contrib_r.p, &c->contrib_o.p, &it, &P, &inst, &count};
+            RLP_CUDA(cudaLaunchKernel((const void *)jc->kernel, dim3((unsigned)((count + 127) / 128)), dim3(128), args, 0, s));
+            rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
+            ++n;
+        }
+    } else if (ts.num_micro > 0) {
         MicroView m;
         m.tmpl = ts.tmpl.p; m.cls = ts.m_class.p; m.colbase = ts.m_colbase.p; m.slot_r = ts.m_slot_r.p;
         m.slot_o = ts.m_slot_o.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;

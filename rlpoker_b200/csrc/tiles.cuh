@@ -14,6 +14,9 @@
 // contributions (regret terms, own reach) leave the SM, into the jagged-diagonal scratch the accumulate kernel
 // streams.
 #pragma once
+#include <memory>
+#include <string>
+
 #include "common.cuh"
 
 constexpr int kMaxTileLevels = 32;
@@ -59,6 +62,15 @@ struct MicroTmpl {
     unsigned char par_slot[kMicroNodes];    // which child of the parent
 };
 
+// A shape class whose sweep was compiled to straight-line code (jit.cu).
+struct JitClass {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    int count = 0;
+    rlp::DevBuf<int> inst;      // instance (= portal) indices of this class; empty when the class covers 0..P-1
+    ~JitClass() { if (lib) cudaLibraryUnload(lib); }
+};
+
 struct TileSet {
     bool enabled = false;
     // upper tiles
@@ -82,6 +94,7 @@ struct TileSet {
     rlp::DevBuf<double> m_pay1, m_pay2;             // [micro_term][P]
     rlp::DevBuf<double> m_pc;                       // [P]
     rlp::DevBuf<double> portal_p1, portal_p2, portal_v1, portal_v2;   // [P]
+    std::vector<std::unique_ptr<JitClass>> jit;     // one per class when every class compiled, else empty
     int64_t bytes() const {
         return (int64_t)(desc.bytes() + ntof.bytes() + term_lid.bytes() + portal_lid.bytes() + rec.bytes() +
                          aux.bytes() + pc.bytes() + pay1.bytes() + pay2.bytes() + cprob.bytes() + root_val.bytes() +

@@ -49,6 +49,22 @@ extern "C" int rlp_device_count(void) {
 extern "C" void rlp_tree_free(rlp_tree *t) { delete t; }
 extern "C" int64_t rlp_tree_bytes(const rlp_tree *t) { return t ? t->bytes() : 0; }
 
+extern "C" int64_t rlp_tree_stat(const rlp_tree *t, int which) {
+    if (!t) return -1;
+    switch (which) {
+        case 0: return t->tiles.enabled ? 1 : 0;          // tiled sweep in use (else per-level kernels)
+        case 1: return t->tiles.num_tiles;                // upper tiles
+        case 2: return t->tiles.num_micro;                // micro subtrees
+        case 3: return t->tiles.num_classes;              // distinct micro shapes
+        case 4: return (int64_t)t->tiles.jit.size();      // shapes with a compiled straight-line kernel
+        case 5: return t->zero_sum ? 1 : 0;
+        case 6: return t->Kmax;
+        case 7: return t->tiles.block;
+        case 8: return (int64_t)t->tiles.smem_bytes;
+        default: return -1;
+    }
+}
+
 extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree **out) {
     if (!d || !out) return fail(RLP_ERR_INVALID, "null argument");
     *out = nullptr;

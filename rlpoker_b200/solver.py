@@ -52,6 +52,12 @@ class DeviceTree:
     def device_bytes(self):
         return _lib.load().rlp_tree_bytes(self.handle)
 
+    @property
+    def layout(self):
+        names = ['tiled', 'upper_tiles', 'micro_subtrees', 'micro_shapes', 'jit_shapes', 'zero_sum',
+                 'largest_infoset', 'tile_block', 'tile_smem']
+        return {n: int(_lib.load().rlp_tree_stat(self.handle, i)) for i, n in enumerate(names)}
+
     def best_response(self, sigma, player, want_argmax=False, stream=None):
         """(value[, argmax[I]]) of ``player``'s best response to the complete strategy array sigma[Q]."""
         sigma = np.ascontiguousarray(sigma, np.float64)

@@ -8,7 +8,7 @@ from rlpoker_b200.flatten import flatten
 from rlpoker_b200.solver import DeviceCFR, device_tree
 for n in (3, 5):
     t0 = time.time(); g = Leduc.create_game(n); ft = flatten(g); print('build+flatten leduc%d %.2fs N=%d' % (n, time.time() - t0, ft.num_nodes))
-    s = DeviceCFR(device_tree(g))
+    s = DeviceCFR(device_tree(g)); print(s.tree.layout)
     s.vanilla(64); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 2048
