@@ -129,6 +129,10 @@ int rlp_cfr_write(rlp_cfr *cfr, int which, const double *src, void *stream);
  * bit2 a strategy entry in the reference's dicts (matters for the sampled variants only). */
 int rlp_cfr_read_flags(rlp_cfr *cfr, uint8_t *dst, void *stream);
 int rlp_cfr_write_flags(rlp_cfr *cfr, const uint8_t *src, void *stream);
+/* Measurement aid: runs `reps` (+2 warm-up) vanilla iterations with CUDA events between the stages of the sweep and
+ * returns the summed device milliseconds of {upper tiles phase 0, micro subtrees, upper tiles phase 1,
+ * accumulate + regret matching} (level-sweep fallback: {0, 0, all level kernels, accumulate}). */
+int rlp_cfr_profile_stages(rlp_cfr *cfr, int reps, float *out_ms4, void *stream);
 /* CFRState.nodes_touched (rlpoker/cfr/cfr_util.py:5-11). */
 uint64_t rlp_nodes_touched(rlp_cfr *cfr);
 

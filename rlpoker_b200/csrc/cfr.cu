@@ -13,7 +13,7 @@
 
 using rlp::fail;
 
-namespace rlp { int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches); }
+namespace rlp { int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches, cudaEvent_t *marks); }
 
 namespace {
 
@@ -158,21 +158,38 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
                  const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
                  const double *__restrict__ contrib_r, const double *__restrict__ contrib_o, double *R, double *S,
                  double *sigma, uint8_t *flags, IterState *iter, int advance) {
+    constexpr int kTab = 256;                      // diagonals whose offsets are staged in shared memory
+    __shared__ int64_t s_kc[kTab], s_ki[kTab];
+    rlp::pdl_launch_dependents();
     const int gid = blockIdx.x * kBlock + threadIdx.x;
     const int s = gid >> 2, a = gid & 3;
-    if (gid == 0 && advance) iter->t += 1;
     const bool valid = s < I;
     const int size = valid ? iset_size[s] : 0;
     const int64_t c0 = valid ? col_off[s] : 0;
     const int na = valid ? (int)(col_off[s + 1] - c0) : 0;
     const bool active = a < na;
+    {
+        const int kmax = iset_size[0];             // sizes are sorted descending
+        for (int k = threadIdx.x; k < kmax && k < kTab; k += kBlock) { s_kc[k] = koff_col[k]; s_ki[k] = koff_iset[k]; }
+    }
     double r = 0.0, sa = 0.0, sg = 0.0;
-    if (active) { r = R[c0 + a]; sa = S[c0 + a]; sg = sigma[c0 + a]; }
+    __syncthreads();
+    // Only static tables above: under programmatic launch this block may start while ANY earlier kernel of the
+    // chain is still running, so regrets / sums / strategy / contributions are read after the wait.
+    rlp::pdl_wait();
+    if (gid == 0 && advance) iter->t += 1;
     if (active) {
+        r = R[c0 + a]; sa = S[c0 + a];
+        sg = sigma[c0 + a];
         const double *cr = contrib_r + c0 + a;
         const double *co = contrib_o + s;
-#pragma unroll 4
-        for (int k = 0; k < size; ++k) {
+        const int fast = size < kTab ? size : kTab;
+#pragma unroll 5
+        for (int k = 0; k < fast; ++k) {
+            r = r + cr[s_kc[k]];
+            sa = sa + co[s_ki[k]] * sg;
+        }
+        for (int k = fast; k < size; ++k) {
             r = r + cr[koff_col[k]];
             sa = sa + co[koff_iset[k]] * sg;
         }
@@ -297,10 +314,10 @@ View make_view(rlp_cfr *c) {
 
 // forward + backward sweep of one iteration on stream s; returns #kernels via *count
 template <bool ZS>
-int enqueue_sweep(rlp_cfr *c, cudaStream_t s, int *count, const IterState *iter = nullptr) {
+int enqueue_sweep(rlp_cfr *c, cudaStream_t s, int *count, const IterState *iter = nullptr, cudaEvent_t *marks = nullptr) {
     rlp_tree *t = c->tree;
     if (t->tiles.enabled) {                 // shared-memory tiled sweep: one launch instead of one per level
-        return rlp::launch_tile_sweep(c, s, iter, count);
+        return rlp::launch_tile_sweep(c, s, iter, count, marks);
     }
     View v = make_view(c);
     if (iter) v.iter = iter;
@@ -324,23 +341,25 @@ int enqueue_sweep(rlp_cfr *c, cudaStream_t s, int *count, const IterState *iter 
     return RLP_OK;
 }
 
-int enqueue_iteration(rlp_cfr *c, cudaStream_t s, int *count) {
+int enqueue_iteration(rlp_cfr *c, cudaStream_t s, int *count, cudaEvent_t *marks = nullptr) {
     rlp_tree *t = c->tree;
     int n = 0;
-    int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n) : enqueue_sweep<false>(c, s, &n);
+    if (marks && !t->tiles.enabled) RLP_CUDA(cudaEventRecord(marks[0], s));
+    int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n, nullptr, marks) : enqueue_sweep<false>(c, s, &n, nullptr, marks);
     if (rc) return rc;
+    if (marks && !t->tiles.enabled) { for (int k = 1; k <= 3; ++k) RLP_CUDA(cudaEventRecord(marks[k], s)); }
     if (t->I > 0) {
         if (t->max_act <= 4)
-            k_accumulate_rm4<<<grid_for(4 * (int64_t)t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p,
-                                                                       t->koff_col.p, t->koff_iset.p, c->contrib_r.p,
-                                                                       c->contrib_o.p, c->R.p, c->S.p, c->sigma.p,
-                                                                       c->flags.p, c->iter.p, 1);
+            RLP_CUDA(rlp::launch_pdl(k_accumulate_rm4, dim3(grid_for(4 * (int64_t)t->I)), dim3(kBlock), 0, s, t->I,
+                                     t->iset_size.p, t->col_off.p, t->koff_col.p, t->koff_iset.p, c->contrib_r.p,
+                                     c->contrib_o.p, c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, 1));
         else
             k_accumulate_rm<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_col.p,
                                                             t->koff_iset.p, c->contrib_r.p, c->contrib_o.p, c->R.p,
                                                             c->S.p, c->sigma.p, c->flags.p, c->iter.p, 1);
         RLP_LAUNCH_CHECK(); ++n;
     }
+    if (marks) RLP_CUDA(cudaEventRecord(marks[4], s));
     *count = n;
     return RLP_OK;
 }
@@ -415,8 +434,20 @@ extern "C" int rlp_cfr_create(rlp_tree *t, void *stream_, rlp_cfr **out) {
     return RLP_OK;
 }
 
+static int build_graph(rlp_cfr *c);
 static int ensure_graph(rlp_cfr *c) {
     if (c->graph_exec) return RLP_OK;
+    int rc = build_graph(c);
+    if (rc != RLP_OK && rlp::pdl_enabled()) {       // retry without programmatic dependent launch
+        cudaGetLastError();
+        rlp::pdl_disable();
+        if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+        rc = build_graph(c);
+    }
+    return rc;
+}
+
+static int build_graph(rlp_cfr *c) {
     cudaStream_t cap;
     RLP_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
@@ -617,4 +648,30 @@ extern "C" int rlp_cfr_write_flags(rlp_cfr *c, const uint8_t *src, void *stream_
     RLP_CUDA(cudaMemcpyAsync(c->flags.p, tmp.data(), 3 * I, cudaMemcpyHostToDevice, s));
     RLP_CUDA(cudaStreamSynchronize(s));
     return RLP_OK;
+}
+
+// Per-stage device time of `reps` iterations (ms, summed): tiled sweep -> {upper tiles phase 0, micro subtrees,
+// upper tiles phase 1, accumulate + regret matching}; level sweep -> {0, 0, forward + backward levels, accumulate}.
+extern "C" int rlp_cfr_profile_stages(rlp_cfr *c, int reps, float *out_ms4, void *stream_) {
+    if (!c || !out_ms4 || reps < 1) return fail(RLP_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    cudaEvent_t ev[5];
+    for (auto &e : ev) RLP_CUDA(cudaEventCreate(&e));
+    for (int k = 0; k < 4; ++k) out_ms4[k] = 0.f;
+    int rc = RLP_OK;
+    for (int r = 0; r < reps + 2 && rc == RLP_OK; ++r) {
+        int n = 0;
+        rc = enqueue_iteration(c, s, &n, ev);
+        if (rc) break;
+        RLP_CUDA(cudaEventSynchronize(ev[4]));
+        if (r < 2) continue;                      // warm-up
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            RLP_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            out_ms4[k] += ms;
+        }
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    c->nodes_touched += 2ull * (uint64_t)c->tree->N * (uint64_t)(reps + 2);
+    return rc;
 }

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "../../include/rlpoker_b200.h"
@@ -61,6 +62,26 @@ struct DevBuf {
     }
     size_t bytes() const { return sizeof(T) * n; }
 };
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may start while its predecessor
+// in the stream is still running; everything it does before pdl_wait() must touch only data the predecessor
+// never writes (static topology).  pdl_wait() returns once the predecessor has completed and flushed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+void pdl_disable();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 constexpr int kMaxActions = 64;        // widest information set the kernels accept
 constexpr double kEpsilon = 1e-7;      // cfr_util.py:14 default floor

@@ -65,22 +65,26 @@ std::string generate(const MicroTmpl &tm, bool zs) {
          "    double* __restrict__ contrib_o, const IterState* __restrict__ iter, long long P,\n"
          "    const int* __restrict__ inst, int count) {\n"
          "  const int i = blockIdx.x * blockDim.x + threadIdx.x;\n"
-         "  if (i >= count) return;\n"
-         "  const long long p = inst ? (long long)inst[i] : (long long)i;\n"
-         "  const double w = iter->linear ? (double)iter->t : 1.0;\n";
+         "  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
+         "  if (i >= count) { asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); return; }\n"
+         "  const long long p = inst ? (long long)inst[i] : (long long)i;\n";
     const int n = tm.n, n_nt = tm.n_nt;
     for (int r = 0; r < n_nt; ++r)
         o << "  const int cb" << r << " = colbase[" << r << " * P + p], sr" << r << " = slot_r[" << r << " * P + p], so"
           << r << " = slot_o[" << r << " * P + p];\n";
-    o << "  const double pcv = pc[p];\n  const double q1_0 = portal_p1[p], q2_0 = portal_p2[p];\n";
-    for (int j = 1; j < n; ++j)
-        o << "  const double s" << j << " = sigma[cb" << (int)tm.par_rank[j] << " + " << (int)tm.par_slot[j] << "];\n";
+    o << "  const double pcv = pc[p];\n";
     for (int j = 0; j < n; ++j)
         if (tm.rank[j] & 0x80) {
             int tr = tm.rank[j] & 0x7F;
             o << "  const double x" << j << " = pay1[" << tr << " * P + p];\n";
             if (!zs) o << "  const double y" << j << " = pay2[" << tr << " * P + p];\n";
         }
+    // everything above is static topology; below depends on the previous kernels (strategy, portal reach, counter)
+    o << "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");\n"
+         "  const double w = iter->linear ? (double)iter->t : 1.0;\n"
+         "  const double q1_0 = portal_p1[p], q2_0 = portal_p2[p];\n";
+    for (int j = 1; j < n; ++j)
+        o << "  const double s" << j << " = sigma[cb" << (int)tm.par_rank[j] << " + " << (int)tm.par_slot[j] << "];\n";
     // forward
     for (int r = 0; r < n_nt; ++r) {
         int j = tm.nt_node[r], pl = tm.player[j];

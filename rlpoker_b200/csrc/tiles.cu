@@ -63,13 +63,14 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     for (int i = tid; i < (int)(sizeof(TileDesc) / sizeof(int)); i += bd)
         reinterpret_cast<int *>(&td)[i] = reinterpret_cast<const int *>(v.desc + blockIdx.x)[i];
     __syncthreads();
-    if (PHASE == 0 && td.n_portal == 0) return;
-    const double w = v.iter->linear ? (double)v.iter->t : 1.0;
+    rlp::pdl_launch_dependents();
     const int n_nt = td.n_nt;
+    const bool idle = PHASE == 0 && td.n_portal == 0;
 
-    // ---- stage the tile; the owner threads fetch their strategy rows as soon as they know where -------
+    // ---- stage the static part of the tile (topology, payoffs) while the previous kernel may still run ------
     double sg[R][kRegAct];
-    {
+    TileAux my_aux[R];
+    if (!idle) {
         const TileAux *gaux = v.aux + td.nt_off;
         const TileRec *grec = v.rec + td.nt_off;
         const double *gpc = v.pc + td.nt_off;
@@ -77,16 +78,10 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
         for (int m = 0; m < R; ++m) {
             int i = m * bd + tid;
             if (i < n_nt) {
-                TileAux ax = gaux[i];
-                TileRec r = grec[i];
-                saux[i] = ax;
-                rec[i] = r;
+                my_aux[m] = gaux[i];
+                saux[i] = my_aux[m];
+                rec[i] = grec[i];
                 spc[i] = gpc[i];
-                if (!WIDE && r.player > 0) {
-                    const double *row = v.sigma + ax.colbase;
-#pragma unroll
-                    for (int k = 0; k < kRegAct; ++k) sg[m][k] = k < r.nchild ? row[k] : 0.0;
-                }
             }
         }
         const unsigned short *gnt = v.ntof + td.node_off;
@@ -98,15 +93,33 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
                 val1[glid[i]] = gp1[i];
                 if (!ZS) val2[glid[i]] = v.pay2[td.term_off + i];
             }
-            const unsigned short *plid = v.portal_lid + td.portal_off;
-            for (int i = tid; i < td.n_portal; i += bd) {
-                val1[plid[i]] = v.portal_v1[td.portal_off + i];
-                if (!ZS) val2[plid[i]] = v.portal_v2[td.portal_off + i];
-            }
             const double *gcp = v.cprob + td.cp_off;
             for (int i = tid; i < td.n_cp; i += bd) scp[i] = gcp[i];
         }
         if (tid == 0) { sp1[0] = td.root_p1; sp2[0] = td.root_p2; }
+    }
+    // ---- everything below reads what the previous kernels wrote (strategy, portal values, iteration counter) ---
+    rlp::pdl_wait();
+    if (idle) return;
+    const double w = v.iter->linear ? (double)v.iter->t : 1.0;
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+        int i = m * bd + tid;
+        if (!WIDE && i < n_nt) {
+            TileRec r = rec[i];
+            if (r.player > 0) {
+                const double *row = v.sigma + my_aux[m].colbase;
+#pragma unroll
+                for (int k = 0; k < kRegAct; ++k) sg[m][k] = k < r.nchild ? row[k] : 0.0;
+            }
+        }
+    }
+    if (PHASE == 1) {
+        const unsigned short *plid = v.portal_lid + td.portal_off;
+        for (int i = tid; i < td.n_portal; i += bd) {
+            val1[plid[i]] = v.portal_v1[td.portal_off + i];
+            if (!ZS) val2[plid[i]] = v.portal_v2[td.portal_off + i];
+        }
     }
     __syncthreads();
 
@@ -261,11 +274,11 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
             reinterpret_cast<int *>(stm)[i] = reinterpret_cast<const int *>(v.tmpl)[i];
         __syncthreads();
     }
+    rlp::pdl_launch_dependents();
     const long long p = (long long)blockIdx.x * kMicroBlock + tid;
-    if (p >= v.P) return;
+    if (p >= v.P) { rlp::pdl_wait(); return; }
     const long long P = v.P;
     const MicroTmpl *tm = in_smem ? &stm[v.cls[p]] : v.tmpl + v.cls[p];
-    const double w = v.iter->linear ? (double)v.iter->t : 1.0;
     const int n = tm->n, n_nt = tm->n_nt;
 #define AT(arr, i) arr[(i) * kMicroBlock + tid]
     // batch 1: per-decision-node integers (coalesced: slot-major layout)
@@ -276,18 +289,21 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
         AT(sso, r) = v.slot_o[r * P + p];
     }
     const double pcv = v.pc[p];
-    AT(sq1, 0) = v.portal_p1[p];
-    AT(sq2, 0) = v.portal_p2[p];
-    // batch 2: strategy probability of every edge, payoff of every leaf (independent loads)
 #pragma unroll 4
     for (int j = 1; j < n; ++j) {
-        AT(ssig, j) = v.sigma[AT(scb, tm->par_rank[j]) + tm->par_slot[j]];
         const int rk = tm->rank[j];
         if (rk & 0x80) {
             AT(sv1, j) = v.pay1[(rk & 0x7F) * P + p];
             if (!ZS) AT(sv2, j) = v.pay2[(rk & 0x7F) * P + p];
         }
     }
+    rlp::pdl_wait();                 // below: strategy, portal reach, iteration counter
+    const double w = v.iter->linear ? (double)v.iter->t : 1.0;
+    AT(sq1, 0) = v.portal_p1[p];
+    AT(sq2, 0) = v.portal_p2[p];
+    // batch 2: strategy probability of every edge, payoff of every leaf (independent loads)
+#pragma unroll 4
+    for (int j = 1; j < n; ++j) AT(ssig, j) = v.sigma[AT(scb, tm->par_rank[j]) + tm->par_slot[j]];
     // forward (cfr.py:208,217)
     for (int r = 0; r + 1 < n_nt; ++r) {
         const int j = tm->nt_node[r];
@@ -655,8 +671,8 @@ static int launch_variant(const TileSet &ts, const TileView &v, cudaStream_t s) 
         RLP_CUDA(cudaFuncSetAttribute(k_tile_sweep<ZS, R, WIDE, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
-    k_tile_sweep<ZS, R, WIDE, PHASE><<<ts.num_tiles, ts.block, ts.smem_bytes, s>>>(v);
-    RLP_LAUNCH_CHECK();
+    RLP_CUDA(rlp::launch_pdl(k_tile_sweep<ZS, R, WIDE, PHASE>, dim3(ts.num_tiles), dim3(ts.block), ts.smem_bytes, s, v));
+    rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
     return RLP_OK;
 }
 
@@ -677,7 +693,7 @@ static int launch_upper(rlp_tree *t, const TileSet &ts, const TileView &v, cudaS
 }
 
 // One tiled sweep: [upper tiles, reach to portals] -> [micro subtrees] -> [upper tiles, values from portals].
-int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches) {
+int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches, cudaEvent_t *marks) {
     rlp_tree *t = c->tree;
     TileSet &ts = t->tiles;
     TileView v;
@@ -688,11 +704,13 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
     v.portal_p1 = ts.portal_p1.p; v.portal_p2 = ts.portal_p2.p; v.portal_v1 = ts.portal_v1.p; v.portal_v2 = ts.portal_v2.p;
     v.iter = iter ? iter : c->iter.p; v.max_nodes = ts.max_nodes; v.max_nt = ts.max_nt; v.max_cp = ts.max_cp;
     int n = 0;
+    if (marks) RLP_CUDA(cudaEventRecord(marks[0], s));
     if (ts.num_tiles > 0 && ts.num_micro > 0) {
         int rc = launch_upper<0>(t, ts, v, s);
         if (rc) return rc;
         ++n;
     }
+    if (marks) RLP_CUDA(cudaEventRecord(marks[1], s));
     if (ts.num_micro > 0 && !ts.jit.empty()) {
         const IterState *it = v.iter;
         long long P = ts.num_micro;
@@ -703,7 +721,14 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
             void *args[] = {&ts.m_colbase.p, &ts.m_slot_r.p, &ts.m_slot_o.p, &ts.m_pay1.p, &ts.m_pay2.p, &ts.m_pc.p,
                             &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
                             &c->contrib_r.p, &c->contrib_o.p, &it, &P, &inst, &count};
-            RLP_CUDA(cudaLaunchKernel((const void *)jc->kernel, dim3((unsigned)((count + 127) / 128)), dim3(128), args, 0, s));
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)((count + 127) / 128)); cfg.blockDim = dim3(128); cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = rlp::pdl_enabled() ? 1 : 0;
+            RLP_CUDA(cudaLaunchKernelExC(&cfg, (const void *)jc->kernel, args));
             rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
             ++n;
         }
@@ -721,16 +746,18 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
             RLP_CUDA(cudaFuncSetAttribute(k_micro<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set = true;
         }
-        if (t->zero_sum) k_micro<true><<<g, kMicroBlock, ts.micro_smem, s>>>(m);
-        else k_micro<false><<<g, kMicroBlock, ts.micro_smem, s>>>(m);
-        RLP_LAUNCH_CHECK();
+        if (t->zero_sum) RLP_CUDA(rlp::launch_pdl(k_micro<true>, dim3(g), dim3(kMicroBlock), ts.micro_smem, s, m));
+        else RLP_CUDA(rlp::launch_pdl(k_micro<false>, dim3(g), dim3(kMicroBlock), ts.micro_smem, s, m));
+        rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
         ++n;
     }
+    if (marks) RLP_CUDA(cudaEventRecord(marks[2], s));
     if (ts.num_tiles > 0) {
         int rc = launch_upper<1>(t, ts, v, s);
         if (rc) return rc;
         ++n;
     }
+    if (marks) RLP_CUDA(cudaEventRecord(marks[3], s));
     if (launches) *launches = n;
     return RLP_OK;
 }

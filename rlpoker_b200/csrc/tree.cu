@@ -11,6 +11,18 @@ namespace rlp {
 thread_local char g_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+    int v = g_pdl.load();
+    if (v < 0) {
+        const char *e = getenv("RLP_NO_PDL");
+        v = (e && e[0] == '1') ? 0 : 1;
+        g_pdl.store(v);
+    }
+    return v == 1;
+}
+void pdl_disable() { g_pdl.store(0); }
+
 int fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -145,6 +145,14 @@ class DeviceCFR:
         check(_lib.load().rlp_cfr_read_flags(self.handle, ptr(out, _lib._u8p), _stream_ptr(stream)))
         return out
 
+    def profile_stages(self, reps=20, stream=None):
+        """Mean device microseconds per iteration of the sweep stages (see rlp_cfr_profile_stages)."""
+        out = (C.c_float * 4)()
+        check(_lib.load().rlp_cfr_profile_stages(self.handle, int(reps), out, _stream_ptr(stream)))
+        self.t += reps + 2
+        names = ['upper_phase0', 'micro', 'upper_phase1', 'accumulate_rm']
+        return {n: 1e3 * out[i] / reps for i, n in enumerate(names)}
+
     def write_flags(self, mask, bit=None, stream=None):
         """Set the dict-membership flags: ``mask`` is a [I] bitmask, or a boolean array for one ``bit`` (1, 2, 4)
         merged into the current flags."""
