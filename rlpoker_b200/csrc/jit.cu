@@ -127,13 +127,12 @@ std::string generate(const MicroTmpl &tm, bool zs) {
 namespace rlp {
 
 // Compile the straight-line kernel of `tm`; returns RLP_OK with *kernel == nullptr when JIT is unavailable.
-int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *kernel, std::string *log_out) {
-    *kernel = nullptr;
+// Compile `src` for sm_100a and load it; *lib_out stays null when JIT is unavailable or the compile fails.
+static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std::string *log_out) {
     *lib_out = nullptr;
     const char *no_jit = getenv("RLP_NO_JIT");
     if (no_jit && no_jit[0] == '1') return RLP_OK;
     if (!g_nvrtc.load()) return RLP_OK;
-    std::string src = generate(tm, zs);
     nvrtcProgram prog;
     if (g_nvrtc.create(&prog, src.c_str(), "micro_k.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return RLP_OK;
     const char *opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17"};
@@ -157,14 +156,146 @@ int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaK
         cudaGetLastError();
         return RLP_OK;
     }
-    cudaKernel_t k;
-    if (cudaLibraryGetKernel(&k, lib, "micro_k") != cudaSuccess) {
-        cudaGetLastError();
-        cudaLibraryUnload(lib);
-        return RLP_OK;
-    }
     *lib_out = lib;
-    *kernel = k;
+    return RLP_OK;
+}
+
+// Compile the straight-line kernel of `tm`; returns RLP_OK with *kernel == nullptr when JIT is unavailable.
+int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *kernel, std::string *log_out) {
+    *kernel = nullptr;
+    int rc = compile_and_load(generate(tm, zs), lib_out, log_out);
+    if (rc || !*lib_out) return rc;
+    if (cudaLibraryGetKernel(kernel, *lib_out, "micro_k") != cudaSuccess) {
+        cudaGetLastError();
+        cudaLibraryUnload(*lib_out);
+        *lib_out = nullptr;
+        *kernel = nullptr;
+    }
+    return RLP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Upper tiles of one shape (round-1 betting nodes + board-deal chance nodes of a deal, micro roots as portal
+// leaves): one thread per tile, straight-line.  Phase 0 pushes strategy reach down to the portals; phase 1 redoes
+// that (a handful of multiplies), pulls the portal values up through the chance and decision nodes and scatters the
+// contributions of the tile's decision nodes.
+static std::string generate_upper(const UpperShape &sh, bool zs) {
+    std::ostringstream o;
+    const int n = (int)sh.kind.size();
+    std::vector<int> dec_idx(n, -1), term_idx(n, -1), portal_idx(n, -1), edge_idx(n, -1), parent(n, -1), slot(n, 0);
+    int nd = 0, nt = 0, np = 0, ne = 0;
+    for (int j = 0; j < n; ++j) {
+        if (sh.kind[j] == 1 || sh.kind[j] == 2) dec_idx[j] = nd++;
+        else if (sh.kind[j] == -1) term_idx[j] = nt++;
+        else if (sh.kind[j] == 3) portal_idx[j] = np++;
+        for (int k = 0; k < sh.nchild[j]; ++k) {
+            int c = sh.first_child[j] + k;
+            parent[c] = j; slot[c] = k;
+            if (sh.kind[j] == 0) edge_idx[c] = ne++;
+        }
+    }
+    auto S = [](const char *p, int j) { return std::string(p) + std::to_string(j); };
+    o << "struct IterState { long long t; int linear; int pad; unsigned long long touched; };\n";
+    for (int phase = 0; phase < 2; ++phase) {
+        o << "extern \"C\" __global__ void __launch_bounds__(64) upper_k" << phase << "(\n"
+             "    const int* __restrict__ colbase, const int* __restrict__ slot_r, const int* __restrict__ slot_o,\n"
+             "    const double* __restrict__ pcs, const double* __restrict__ cprob, const double* __restrict__ pay1,\n"
+             "    const double* __restrict__ pay2, const long long* __restrict__ poff, const double* __restrict__ sigma,\n"
+             "    double* __restrict__ portal_p1, double* __restrict__ portal_p2, const double* __restrict__ portal_v1,\n"
+             "    const double* __restrict__ portal_v2, double* __restrict__ contrib_r, double* __restrict__ contrib_o,\n"
+             "    double* __restrict__ root_val, const IterState* __restrict__ iter, long long T) {\n"
+             "  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n"
+             "  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
+             "  if (i >= T) { asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); return; }\n"
+             "  const long long po = poff[i];\n";
+        for (int j = 0; j < n; ++j)
+            if (dec_idx[j] >= 0) {
+                int d = dec_idx[j];
+                o << "  const int cb" << j << " = colbase[" << d << " * T + i];\n";
+                if (phase == 1)
+                    o << "  const int sr" << j << " = slot_r[" << d << " * T + i], so" << j << " = slot_o[" << d << " * T + i];\n"
+                      << "  const double pc" << j << " = pcs[" << d << " * T + i];\n";
+            }
+        if (phase == 1) {
+            for (int j = 0; j < n; ++j) {
+                if (edge_idx[j] >= 0) o << "  const double e" << j << " = cprob[" << edge_idx[j] << " * T + i];\n";
+                if (term_idx[j] >= 0) {
+                    o << "  const double x" << j << " = pay1[" << term_idx[j] << " * T + i];\n";
+                    if (!zs) o << "  const double y" << j << " = pay2[" << term_idx[j] << " * T + i];\n";
+                }
+            }
+        }
+        o << "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");\n";
+        if (phase == 1) o << "  const double w = iter->linear ? (double)iter->t : 1.0;\n";
+        for (int j = 1; j < n; ++j)
+            if (parent[j] >= 0 && dec_idx[parent[j]] >= 0)
+                o << "  const double s" << j << " = sigma[cb" << parent[j] << " + " << slot[j] << "];\n";
+        if (phase == 1)
+            for (int j = 0; j < n; ++j)
+                if (portal_idx[j] >= 0) {
+                    o << "  const double x" << j << " = portal_v1[po + " << portal_idx[j] << "];\n";
+                    if (!zs) o << "  const double y" << j << " = portal_v2[po + " << portal_idx[j] << "];\n";
+                }
+        // forward
+        o << "  const double q1_0 = 1.0, q2_0 = 1.0;\n";
+        for (int j = 0; j < n; ++j) {
+            int kd = sh.kind[j];
+            if (kd == -1 || kd == 3) continue;
+            for (int k = 0; k < sh.nchild[j]; ++k) {
+                int c = sh.first_child[j] + k;
+                if (sh.kind[c] == -1) continue;
+                std::string a = (kd == 1 ? S("s", c) + " * " : std::string()) + S("q1_", j);
+                std::string b = (kd == 2 ? S("s", c) + " * " : std::string()) + S("q2_", j);
+                if (sh.kind[c] == 3) {
+                    if (phase == 0)
+                        o << "  portal_p1[po + " << portal_idx[c] << "] = " << a << ";\n  portal_p2[po + " << portal_idx[c]
+                          << "] = " << b << ";\n";
+                } else {
+                    o << "  const double q1_" << c << " = " << a << ";\n  const double q2_" << c << " = " << b << ";\n";
+                }
+            }
+        }
+        if (phase == 0) { o << "}\n"; continue; }
+        // backward
+        for (int j = n - 1; j >= 0; --j) {
+            int kd = sh.kind[j];
+            if (kd == -1 || kd == 3) continue;
+            int fc = sh.first_child[j], nc = sh.nchild[j];
+            o << "  double a" << j << " = 0.0;\n";
+            for (int k = 0; k < nc; ++k)
+                o << "  a" << j << " = a" << j << " + " << (kd == 0 ? S("e", fc + k) : S("s", fc + k)) << " * x" << (fc + k) << ";\n";
+            o << "  const double x" << j << " = a" << j << ";\n";
+            if (!zs) {
+                o << "  double b" << j << " = 0.0;\n";
+                for (int k = 0; k < nc; ++k)
+                    o << "  b" << j << " = b" << j << " + " << (kd == 0 ? S("e", fc + k) : S("s", fc + k)) << " * y" << (fc + k) << ";\n";
+                o << "  const double y" << j << " = b" << j << ";\n";
+            }
+            if (kd == 0) continue;
+            o << "  {\n    const double opp = pc" << j << (kd == 1 ? " * q2_" : " * q1_") << j << ";\n"
+              << "    const double own = " << (kd == 1 ? "q1_" : "q2_") << j << ";\n"
+              << "    const double vp = " << (kd == 1 ? S("x", j) : (zs ? "-" + S("x", j) : S("y", j))) << ";\n";
+            for (int k = 0; k < nc; ++k) {
+                std::string va = kd == 1 ? S("x", fc + k) : (zs ? "-" + S("x", fc + k) : S("y", fc + k));
+                o << "    contrib_r[sr" << j << " + " << k << "] = w * (" << va << " - vp) * opp;\n";
+            }
+            o << "    contrib_o[so" << j << "] = w * own;\n  }\n";
+        }
+        o << "  root_val[i] = x0;\n}\n";
+    }
+    return o.str();
+}
+
+int jit_upper_kernels(const UpperShape &sh, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *k0, cudaKernel_t *k1, std::string *log_out) {
+    *k0 = *k1 = nullptr;
+    int rc = compile_and_load(generate_upper(sh, zs), lib_out, log_out);
+    if (rc || !*lib_out) return rc;
+    if (cudaLibraryGetKernel(k0, *lib_out, "upper_k0") != cudaSuccess || cudaLibraryGetKernel(k1, *lib_out, "upper_k1") != cudaSuccess) {
+        cudaGetLastError();
+        cudaLibraryUnload(*lib_out);
+        *lib_out = nullptr;
+        *k0 = *k1 = nullptr;
+    }
     return RLP_OK;
 }
 

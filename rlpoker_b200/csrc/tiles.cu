@@ -356,6 +356,7 @@ __global__ void k_fill(double *p, long long n, double x) {
 namespace rlp {
 
 int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *kernel, std::string *log_out);
+int jit_upper_kernels(const UpperShape &sh, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *k0, cudaKernel_t *k1, std::string *log_out);
 
 // Called by rlp_tree_upload once the per-node information-set tables exist.  Leaves t->tiles disabled
 // (level-sweep fallback) when the tree cannot be tiled under an all-chance trunk.
@@ -660,7 +661,95 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
         if (!all) ts.jit.clear();
         RLP_CUDA(cudaStreamSynchronize(stream));
     }
+    // ---- upper tiles of ONE shape: straight-line kernels, one thread per tile ---------------------------------------
+    ts.upper_jit.reset();
+    if (T > 0 && max_nodes <= 640 && !ts.jit.empty()) {
+        UpperShape sh;
+        std::vector<std::vector<int32_t>> locals(T);
+        bool same = true;
+        for (size_t k = 0; k < T && same; ++k) {
+            std::vector<int32_t> &lc = locals[k];
+            lc.push_back(roots[k]);
+            for (size_t q = 0; q < lc.size(); ++q) {
+                int32_t g = lc[q];
+                if (kind[g] == 1) continue;
+                for (int32_t c = fc[g]; c < fc[g + 1]; ++c) lc.push_back(c);
+            }
+            UpperShape cur;
+            int next_child = 1;
+            for (int32_t g : lc) {
+                signed char kd = kind[g] == 1 ? 3 : (signed char)pl[g];
+                int nc = kind[g] == 1 ? 0 : fc[g + 1] - fc[g];
+                cur.kind.push_back(kd); cur.nchild.push_back(nc); cur.first_child.push_back(next_child);
+                next_child += nc;
+            }
+            if (k == 0) sh = cur;
+            else same = cur.kind == sh.kind && cur.nchild == sh.nchild;
+        }
+        if (same) {
+            std::unique_ptr<UpperJit> uj(new UpperJit);
+            std::string log;
+            int rc = jit_upper_kernels(sh, zs, &uj->lib, &uj->k0, &uj->k1, &log);
+            if (rc) return rc;
+            if (uj->k0 && uj->k1) {
+                const int n = (int)sh.kind.size();
+                int nd = 0, ne = 0, ntm = 0;
+                for (int j = 0; j < n; ++j) {
+                    if (sh.kind[j] == 1 || sh.kind[j] == 2) ++nd;
+                    if (sh.kind[j] == -1) ++ntm;
+                    if (sh.kind[j] == 0) ne += sh.nchild[j];
+                }
+                std::vector<int> ucb((size_t)nd * T), usr((size_t)nd * T), uso((size_t)nd * T);
+                std::vector<double> upc((size_t)nd * T), ucp((size_t)ne * T), up1((size_t)ntm * T), up2(zs ? 0 : (size_t)ntm * T);
+                std::vector<long long> upo(T);
+                for (size_t k = 0; k < T; ++k) {
+                    int di = 0, e = 0, tt = 0;
+                    for (int j = 0; j < n; ++j) {
+                        int32_t g = locals[k][j];
+                        if (sh.kind[j] == 1 || sh.kind[j] == 2) {
+                            ucb[(size_t)di * T + k] = colbase[g];
+                            usr[(size_t)di * T + k] = (int)(koff_col[krank[g]] + colbase[g]);
+                            uso[(size_t)di * T + k] = (int)(koff_iset[krank[g]] + srank[g]);
+                            upc[(size_t)di * T + k] = pcs[g];
+                            ++di;
+                        } else if (sh.kind[j] == -1) {
+                            up1[(size_t)tt * T + k] = d->u1[g];
+                            if (!zs) up2[(size_t)tt * T + k] = d->u2[g];
+                            ++tt;
+                        } else if (sh.kind[j] == 0) {
+                            for (int32_t c = fc[g]; c < fc[g + 1]; ++c) ucp[(size_t)(e++) * T + k] = d->cprob[c];
+                        }
+                    }
+                    upo[k] = desc[k].portal_off;
+                }
+                uj->T = (long long)T;
+                RLP_CUDA(uj->colbase.upload(ucb, stream)); RLP_CUDA(uj->slot_r.upload(usr, stream));
+                RLP_CUDA(uj->slot_o.upload(uso, stream)); RLP_CUDA(uj->pcs.upload(upc, stream));
+                RLP_CUDA(uj->cprob.upload(ucp, stream)); RLP_CUDA(uj->pay1.upload(up1, stream));
+                RLP_CUDA(uj->pay2.upload(up2, stream)); RLP_CUDA(uj->poff.upload(upo, stream));
+                RLP_CUDA(cudaStreamSynchronize(stream));
+                ts.upper_jit = std::move(uj);
+            }
+        }
+    }
     ts.enabled = true;
+    return RLP_OK;
+}
+
+static int launch_upper_jit(rlp_cfr *c, TileSet &ts, int phase, const IterState *it, cudaStream_t s) {
+    UpperJit &u = *ts.upper_jit;
+    long long T = u.T;
+    void *args[] = {&u.colbase.p, &u.slot_r.p, &u.slot_o.p, &u.pcs.p, &u.cprob.p, &u.pay1.p, &u.pay2.p, &u.poff.p,
+                    &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
+                    &c->contrib_r.p, &c->contrib_o.p, &ts.root_val.p, &it, &T};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((T + 63) / 64)); cfg.blockDim = dim3(64); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = rlp::pdl_enabled() ? 1 : 0;
+    RLP_CUDA(cudaLaunchKernelExC(&cfg, (const void *)(phase == 0 ? u.k0 : u.k1), args));
+    rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
     return RLP_OK;
 }
 
@@ -706,7 +795,7 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
     int n = 0;
     if (marks) RLP_CUDA(cudaEventRecord(marks[0], s));
     if (ts.num_tiles > 0 && ts.num_micro > 0) {
-        int rc = launch_upper<0>(t, ts, v, s);
+        int rc = ts.upper_jit ? launch_upper_jit(c, ts, 0, v.iter, s) : launch_upper<0>(t, ts, v, s);
         if (rc) return rc;
         ++n;
     }
@@ -721,8 +810,7 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
             void *args[] = {&ts.m_colbase.p, &ts.m_slot_r.p, &ts.m_slot_o.p, &ts.m_pay1.p, &ts.m_pay2.p, &ts.m_pc.p,
                             &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
                             &c->contrib_r.p, &c->contrib_o.p, &it, &P, &inst, &count};
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
+            cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)((count + 127) / 128)); cfg.blockDim = dim3(128); cfg.stream = s;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -753,7 +841,7 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
     }
     if (marks) RLP_CUDA(cudaEventRecord(marks[2], s));
     if (ts.num_tiles > 0) {
-        int rc = launch_upper<1>(t, ts, v, s);
+        int rc = ts.upper_jit ? launch_upper_jit(c, ts, 1, v.iter, s) : launch_upper<1>(t, ts, v, s);
         if (rc) return rc;
         ++n;
     }

@@ -62,6 +62,23 @@ struct MicroTmpl {
     unsigned char par_slot[kMicroNodes];    // which child of the parent
 };
 
+// Shape of an upper tile in local breadth-first order (host side; input of the straight-line generator).
+struct UpperShape {
+    std::vector<signed char> kind;      // -1 terminal, 0 chance, 1 / 2 decision node of that player, 3 portal leaf
+    std::vector<int> first_child, nchild;
+};
+
+// All upper tiles share one shape and were compiled to straight-line code: one thread per tile.
+struct UpperJit {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t k0 = nullptr, k1 = nullptr;
+    long long T = 0;
+    rlp::DevBuf<int> colbase, slot_r, slot_o;       // [decision][T]
+    rlp::DevBuf<double> pcs, cprob, pay1, pay2;     // [decision][T], [chance edge][T], [terminal][T]
+    rlp::DevBuf<long long> poff;                    // [T]
+    ~UpperJit() { if (lib) cudaLibraryUnload(lib); }
+};
+
 // A shape class whose sweep was compiled to straight-line code (jit.cu).
 struct JitClass {
     cudaLibrary_t lib = nullptr;
@@ -95,6 +112,7 @@ struct TileSet {
     rlp::DevBuf<double> m_pc;                       // [P]
     rlp::DevBuf<double> portal_p1, portal_p2, portal_v1, portal_v2;   // [P]
     std::vector<std::unique_ptr<JitClass>> jit;     // one per class when every class compiled, else empty
+    std::unique_ptr<UpperJit> upper_jit;            // set when all upper tiles share one compiled shape
     int64_t bytes() const {
         return (int64_t)(desc.bytes() + ntof.bytes() + term_lid.bytes() + portal_lid.bytes() + rec.bytes() +
                          aux.bytes() + pc.bytes() + pay1.bytes() + pay2.bytes() + cprob.bytes() + root_val.bytes() +

@@ -70,6 +70,7 @@ extern "C" int64_t rlp_tree_stat(const rlp_tree *t, int which) {
         case 3: return t->tiles.num_classes;              // distinct micro shapes
         case 4: return (int64_t)t->tiles.jit.size();      // shapes with a compiled straight-line kernel
         case 5: return t->zero_sum ? 1 : 0;
+        case 9: return t->tiles.upper_jit ? 1 : 0;        // upper tiles run as straight-line kernels
         case 6: return t->Kmax;
         case 7: return t->tiles.block;
         case 8: return (int64_t)t->tiles.smem_bytes;

@@ -55,7 +55,7 @@ class DeviceTree:
     @property
     def layout(self):
         names = ['tiled', 'upper_tiles', 'micro_subtrees', 'micro_shapes', 'jit_shapes', 'zero_sum',
-                 'largest_infoset', 'tile_block', 'tile_smem']
+                 'largest_infoset', 'tile_block', 'tile_smem', 'upper_jit']
         return {n: int(_lib.load().rlp_tree_stat(self.handle, i)) for i, n in enumerate(names)}
 
     def best_response(self, sigma, player, want_argmax=False, stream=None):
