@@ -59,6 +59,7 @@ std::string generate(const MicroTmpl &tm, bool zs) {
     o << "struct IterState { long long t; int linear; int pad; unsigned long long touched; };\n"
          "extern \"C\" __global__ void __launch_bounds__(128) micro_k(\n"
          "    const int* __restrict__ colbase, const int* __restrict__ slot_r, const int* __restrict__ slot_o,\n"
+         "    const int* __restrict__ pidx,\n"
          "    const double* __restrict__ pay1, const double* __restrict__ pay2, const double* __restrict__ pc,\n"
          "    const double* __restrict__ sigma, const double* __restrict__ portal_p1, const double* __restrict__ portal_p2,\n"
          "    double* __restrict__ portal_v1, double* __restrict__ portal_v2, double* __restrict__ contrib_r,\n"
@@ -72,7 +73,7 @@ std::string generate(const MicroTmpl &tm, bool zs) {
     for (int r = 0; r < n_nt; ++r)
         o << "  const int cb" << r << " = colbase[" << r << " * P + p], sr" << r << " = slot_r[" << r << " * P + p], so"
           << r << " = slot_o[" << r << " * P + p];\n";
-    o << "  const double pcv = pc[p];\n";
+    o << "  const double pcv = pc[p];\n  const int pi = pidx[p];\n";
     for (int j = 0; j < n; ++j)
         if (tm.rank[j] & 0x80) {
             int tr = tm.rank[j] & 0x7F;
@@ -82,7 +83,7 @@ std::string generate(const MicroTmpl &tm, bool zs) {
     // everything above is static topology; below depends on the previous kernels (strategy, portal reach, counter)
     o << "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");\n"
          "  const double w = iter->linear ? (double)iter->t : 1.0;\n"
-         "  const double q1_0 = portal_p1[p], q2_0 = portal_p2[p];\n";
+         "  const double q1_0 = portal_p1[pi], q2_0 = portal_p2[pi];\n";
     for (int j = 1; j < n; ++j)
         o << "  const double s" << j << " = sigma[cb" << (int)tm.par_rank[j] << " + " << (int)tm.par_slot[j] << "];\n";
     // forward
@@ -116,8 +117,8 @@ std::string generate(const MicroTmpl &tm, bool zs) {
         }
         o << "    contrib_o[so" << r << "] = w * own;\n  }\n";
     }
-    o << "  portal_v1[p] = x0;\n";
-    if (!zs) o << "  portal_v2[p] = y0;\n";
+    o << "  portal_v1[pi] = x0;\n";
+    if (!zs) o << "  portal_v2[pi] = y0;\n";
     o << "}\n";
     return o.str();
 }
@@ -207,7 +208,7 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
              "  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n"
              "  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
              "  if (i >= T) { asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); return; }\n"
-             "  const long long po = poff[i];\n";
+             "  (void)poff;\n";
         for (int j = 0; j < n; ++j)
             if (dec_idx[j] >= 0) {
                 int d = dec_idx[j];
@@ -233,8 +234,8 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
         if (phase == 1)
             for (int j = 0; j < n; ++j)
                 if (portal_idx[j] >= 0) {
-                    o << "  const double x" << j << " = portal_v1[po + " << portal_idx[j] << "];\n";
-                    if (!zs) o << "  const double y" << j << " = portal_v2[po + " << portal_idx[j] << "];\n";
+                    o << "  const double x" << j << " = portal_v1[" << portal_idx[j] << " * T + i];\n";
+                    if (!zs) o << "  const double y" << j << " = portal_v2[" << portal_idx[j] << " * T + i];\n";
                 }
         // forward
         o << "  const double q1_0 = 1.0, q2_0 = 1.0;\n";
@@ -248,8 +249,8 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
                 std::string b = (kd == 2 ? S("s", c) + " * " : std::string()) + S("q2_", j);
                 if (sh.kind[c] == 3) {
                     if (phase == 0)
-                        o << "  portal_p1[po + " << portal_idx[c] << "] = " << a << ";\n  portal_p2[po + " << portal_idx[c]
-                          << "] = " << b << ";\n";
+                        o << "  portal_p1[" << portal_idx[c] << " * T + i] = " << a << ";\n  portal_p2[" << portal_idx[c]
+                          << " * T + i] = " << b << ";\n";
                 } else {
                     o << "  const double q1_" << c << " = " << a << ";\n  const double q2_" << c << " = " << b << ";\n";
                 }

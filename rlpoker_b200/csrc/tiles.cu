@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     if (PHASE == 1) {
         const unsigned short *plid = v.portal_lid + td.portal_off;
         for (int i = tid; i < td.n_portal; i += bd) {
-            val1[plid[i]] = v.portal_v1[td.portal_off + i];
-            if (!ZS) val2[plid[i]] = v.portal_v2[td.portal_off + i];
+            val1[plid[i]] = v.portal_v1[(long long)i * gridDim.x + blockIdx.x];
+            if (!ZS) val2[plid[i]] = v.portal_v2[(long long)i * gridDim.x + blockIdx.x];
         }
     }
     __syncthreads();
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
                 double y = r.player == 2 ? e * b : b;
                 if (c & 0x8000) {
                     if (PHASE == 0) {
-                        long long g = td.portal_off + (c & 0x7FFF);
+                        long long g = (long long)(c & 0x7FFF) * gridDim.x + blockIdx.x;     // [portal rank][tile]
                         v.portal_p1[g] = x;
                         v.portal_p2[g] = y;
                     }
@@ -244,6 +244,7 @@ struct MicroView {
     const MicroTmpl *tmpl;
     const unsigned short *cls;
     const int *colbase, *slot_r, *slot_o;      // [micro_nt][P]
+    const int *pidx;                           // [P] where this instance's portal lives ([portal rank][tile] layout)
     const double *pay1, *pay2;                 // [micro_term][P]
     const double *pc, *sigma;
     const double *portal_p1, *portal_p2;
@@ -299,8 +300,9 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
     }
     rlp::pdl_wait();                 // below: strategy, portal reach, iteration counter
     const double w = v.iter->linear ? (double)v.iter->t : 1.0;
-    AT(sq1, 0) = v.portal_p1[p];
-    AT(sq2, 0) = v.portal_p2[p];
+    const int pi = v.pidx[p];
+    AT(sq1, 0) = v.portal_p1[pi];
+    AT(sq2, 0) = v.portal_p2[pi];
     // batch 2: strategy probability of every edge, payoff of every leaf (independent loads)
 #pragma unroll 4
     for (int j = 1; j < n; ++j) AT(ssig, j) = v.sigma[AT(scb, tm->par_rank[j]) + tm->par_slot[j]];
@@ -340,8 +342,8 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
         }
         v.contrib_o[AT(sso, r)] = w * own;
     }
-    v.portal_v1[p] = AT(sv1, 0);
-    if (!ZS) v.portal_v2[p] = AT(sv2, 0);
+    v.portal_v1[pi] = AT(sv1, 0);
+    if (!ZS) v.portal_v2[pi] = AT(sv2, 0);
 #undef AT
 }
 
@@ -528,6 +530,19 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
 
     // ---- micro instances: one per portal, shapes deduplicated into templates ----------------------------------
     const int64_t P = (int64_t)portal_node.size();
+    // portal reach / value arrays are laid out [portal rank inside its tile][tile] so that the tile-side kernels
+    // (one thread or CTA per tile) touch consecutive words; trunk portals follow.
+    int kp = 0;
+    for (size_t k = 0; k < T; ++k) kp = std::max(kp, desc[k].n_portal);
+    const int64_t portal_len = (int64_t)kp * (int64_t)T + (P - (T ? desc[T - 1].portal_off + desc[T - 1].n_portal : 0));
+    if (portal_len >= (int64_t)INT32_MAX) return RLP_OK;
+    std::vector<int> pidx(P);
+    for (size_t k = 0; k < T; ++k)
+        for (int q = 0; q < desc[k].n_portal; ++q) pidx[desc[k].portal_off + q] = (int)((int64_t)q * (int64_t)T + (int64_t)k);
+    {
+        int64_t first_trunk = T ? desc[T - 1].portal_off + desc[T - 1].n_portal : 0;
+        for (int64_t p = first_trunk; p < P; ++p) pidx[p] = (int)((int64_t)kp * (int64_t)T + (p - first_trunk));
+    }
     std::map<std::string, int> class_of;
     std::vector<MicroTmpl> tmpl;
     std::vector<unsigned short> m_class(P);
@@ -629,12 +644,13 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     RLP_CUDA(ts.m_pay1.upload(m_pay1, stream));
     RLP_CUDA(ts.m_pay2.upload(m_pay2, stream));
     RLP_CUDA(ts.m_pc.upload(m_pc, stream));
-    RLP_CUDA(ts.portal_p1.alloc((size_t)P)); RLP_CUDA(ts.portal_p2.alloc((size_t)P));
-    RLP_CUDA(ts.portal_v1.alloc((size_t)P)); RLP_CUDA(ts.portal_v2.alloc(zs ? 0 : (size_t)P));
-    if (P > 0) {
-        unsigned g = (unsigned)((P + 255) / 256);
-        k_fill<<<g, 256, 0, stream>>>(ts.portal_p1.p, P, 1.0); RLP_LAUNCH_CHECK();
-        k_fill<<<g, 256, 0, stream>>>(ts.portal_p2.p, P, 1.0); RLP_LAUNCH_CHECK();
+    RLP_CUDA(ts.m_pidx.upload(pidx, stream));
+    RLP_CUDA(ts.portal_p1.alloc((size_t)portal_len)); RLP_CUDA(ts.portal_p2.alloc((size_t)portal_len));
+    RLP_CUDA(ts.portal_v1.alloc((size_t)portal_len)); RLP_CUDA(ts.portal_v2.alloc(zs ? 0 : (size_t)portal_len));
+    if (portal_len > 0) {
+        unsigned g = (unsigned)((portal_len + 255) / 256);
+        k_fill<<<g, 256, 0, stream>>>(ts.portal_p1.p, portal_len, 1.0); RLP_LAUNCH_CHECK();
+        k_fill<<<g, 256, 0, stream>>>(ts.portal_p2.p, portal_len, 1.0); RLP_LAUNCH_CHECK();
     }
     RLP_CUDA(cudaStreamSynchronize(stream));
     // ---- shape-specialised kernels (jit.cu): all classes or none ------------------------------------------------
@@ -807,7 +823,7 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
             if (jc->count == 0) continue;
             const int *inst = jc->inst.n ? jc->inst.p : nullptr;
             int count = jc->count;
-            void *args[] = {&ts.m_colbase.p, &ts.m_slot_r.p, &ts.m_slot_o.p, &ts.m_pay1.p, &ts.m_pay2.p, &ts.m_pc.p,
+            void *args[] = {&ts.m_colbase.p, &ts.m_slot_r.p, &ts.m_slot_o.p, &ts.m_pidx.p, &ts.m_pay1.p, &ts.m_pay2.p, &ts.m_pc.p,
                             &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
                             &c->contrib_r.p, &c->contrib_o.p, &it, &P, &inst, &count};
             cudaLaunchConfig_t cfg = {};
@@ -823,7 +839,7 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
     } else if (ts.num_micro > 0) {
         MicroView m;
         m.tmpl = ts.tmpl.p; m.cls = ts.m_class.p; m.colbase = ts.m_colbase.p; m.slot_r = ts.m_slot_r.p;
-        m.slot_o = ts.m_slot_o.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;
+        m.slot_o = ts.m_slot_o.p; m.pidx = ts.m_pidx.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;
         m.portal_p1 = ts.portal_p1.p; m.portal_p2 = ts.portal_p2.p; m.portal_v1 = ts.portal_v1.p;
         m.portal_v2 = ts.portal_v2.p; m.contrib_r = c->contrib_r.p; m.contrib_o = c->contrib_o.p;
         m.iter = v.iter; m.P = ts.num_micro; m.num_classes = ts.num_classes; m.mn = ts.micro_nodes; m.mnt = ts.micro_nt;

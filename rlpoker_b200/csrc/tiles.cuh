@@ -108,6 +108,7 @@ struct TileSet {
     rlp::DevBuf<MicroTmpl> tmpl;
     rlp::DevBuf<unsigned short> m_class;            // [P]
     rlp::DevBuf<int> m_colbase, m_slot_r, m_slot_o; // [micro_nt][P]
+    rlp::DevBuf<int> m_pidx;                        // [P] index of the instance's portal in the portal arrays
     rlp::DevBuf<double> m_pay1, m_pay2;             // [micro_term][P]
     rlp::DevBuf<double> m_pc;                       // [P]
     rlp::DevBuf<double> portal_p1, portal_p2, portal_v1, portal_v2;   // [P]
@@ -116,7 +117,7 @@ struct TileSet {
     int64_t bytes() const {
         return (int64_t)(desc.bytes() + ntof.bytes() + term_lid.bytes() + portal_lid.bytes() + rec.bytes() +
                          aux.bytes() + pc.bytes() + pay1.bytes() + pay2.bytes() + cprob.bytes() + root_val.bytes() +
-                         tmpl.bytes() + m_class.bytes() + m_colbase.bytes() + m_slot_r.bytes() + m_slot_o.bytes() +
+                         tmpl.bytes() + m_class.bytes() + m_pidx.bytes() + m_colbase.bytes() + m_slot_r.bytes() + m_slot_o.bytes() +
                          m_pay1.bytes() + m_pay2.bytes() + m_pc.bytes() + portal_p1.bytes() + portal_p2.bytes() +
                          portal_v1.bytes() + portal_v2.bytes());
     }
