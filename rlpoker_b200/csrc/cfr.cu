@@ -13,7 +13,10 @@
 
 using rlp::fail;
 
-namespace rlp { int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches, cudaEvent_t *marks); }
+namespace rlp {
+int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches, cudaEvent_t *marks);
+int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int stage, int *launches);
+}
 
 namespace {
 
@@ -157,13 +160,14 @@ __global__ void __launch_bounds__(kBlock)
 k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
                  const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
                  const double *__restrict__ contrib_r, const double *__restrict__ contrib_o, double *R, double *S,
-                 double *sigma, uint8_t *flags, IterState *iter, int advance) {
+                 double *sigma, uint8_t *flags, IterState *iter, int advance, const int *__restrict__ list, int count) {
     constexpr int kTab = 256;                      // diagonals whose offsets are staged in shared memory
     __shared__ int64_t s_kc[kTab], s_ki[kTab];
     rlp::pdl_launch_dependents();
     const int gid = blockIdx.x * kBlock + threadIdx.x;
-    const int s = gid >> 2, a = gid & 3;
-    const bool valid = s < I;
+    const int g = gid >> 2, a = gid & 3;
+    const bool valid = g < count;
+    const int s = valid ? (list ? list[g] : g) : 0;
     const int size = valid ? iset_size[s] : 0;
     const int64_t c0 = valid ? col_off[s] : 0;
     const int na = valid ? (int)(col_off[s + 1] - c0) : 0;
@@ -352,7 +356,8 @@ int enqueue_iteration(rlp_cfr *c, cudaStream_t s, int *count, cudaEvent_t *marks
         if (t->max_act <= 4)
             RLP_CUDA(rlp::launch_pdl(k_accumulate_rm4, dim3(grid_for(4 * (int64_t)t->I)), dim3(kBlock), 0, s, t->I,
                                      t->iset_size.p, t->col_off.p, t->koff_col.p, t->koff_iset.p, c->contrib_r.p,
-                                     c->contrib_o.p, c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, 1));
+                                     c->contrib_o.p, c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, 1,
+                                     (const int *)nullptr, (int)t->I));
         else
             k_accumulate_rm<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_col.p,
                                                             t->koff_iset.p, c->contrib_r.p, c->contrib_o.p, c->R.p,
@@ -360,6 +365,47 @@ int enqueue_iteration(rlp_cfr *c, cudaStream_t s, int *count, cudaEvent_t *marks
         RLP_LAUNCH_CHECK(); ++n;
     }
     if (marks) RLP_CUDA(cudaEventRecord(marks[4], s));
+    *count = n;
+    return RLP_OK;
+}
+
+// Two-branch pipeline of `iters` iterations (tiled trees): after the micro kernel, the accumulate + regret matching
+// of the information sets that live only in micro subtrees (A, the bulk) runs on a side stream while the main stream
+// finishes the upper tiles, accumulates the few information sets they touch (B) and already pushes the next
+// iteration's reach down to the portals; the branches join before the next micro kernel.
+bool can_pipeline(rlp_cfr *c) {
+    rlp_tree *t = c->tree;
+    const TileSet &ts = t->tiles;
+    return ts.enabled && t->max_act <= 4 && ts.num_tiles > 0 && ts.num_micro > 0 && ts.acc_a_count > 0 &&
+           ts.acc_b_count > 0 && c->side && c->ev_fork && c->ev_join;
+}
+
+int launch_acc(rlp_cfr *c, cudaStream_t s, const int *list, int count, int advance) {
+    rlp_tree *t = c->tree;
+    RLP_CUDA(rlp::launch_pdl(k_accumulate_rm4, dim3(grid_for(4 * (int64_t)count)), dim3(kBlock), 0, s, t->I,
+                             t->iset_size.p, t->col_off.p, t->koff_col.p, t->koff_iset.p, c->contrib_r.p, c->contrib_o.p,
+                             c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, advance, list, count));
+    rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RLP_OK;
+}
+
+int enqueue_pipelined(rlp_cfr *c, cudaStream_t s, int iters, int *count) {
+    rlp_tree *t = c->tree;
+    TileSet &ts = t->tiles;
+    int n = 0, rc;
+    if ((rc = rlp::launch_tile_stage(c, s, nullptr, 0, &n))) return rc;
+    for (int u = 0; u < iters; ++u) {
+        if ((rc = rlp::launch_tile_stage(c, s, nullptr, 1, &n))) return rc;
+        RLP_CUDA(cudaEventRecord(c->ev_fork, s));
+        RLP_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        if ((rc = launch_acc(c, c->side, ts.acc_list_a.p, ts.acc_a_count, 0))) return rc;
+        RLP_CUDA(cudaEventRecord(c->ev_join, c->side));
+        if ((rc = rlp::launch_tile_stage(c, s, nullptr, 2, &n))) return rc;
+        if ((rc = launch_acc(c, s, ts.acc_list_b.p, ts.acc_b_count, 1))) return rc;
+        n += 2;
+        if (u + 1 < iters && (rc = rlp::launch_tile_stage(c, s, nullptr, 0, &n))) return rc;
+        RLP_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    }
     *count = n;
     return RLP_OK;
 }
@@ -418,6 +464,9 @@ extern "C" int rlp_cfr_create(rlp_tree *t, void *stream_, rlp_cfr **out) {
     if (!t->zero_sum) RLP_CUDA(c->val2.alloc(N));
     RLP_CUDA(c->contrib_r.alloc((size_t)t->NC)); RLP_CUDA(c->contrib_o.alloc((size_t)t->ND));
     RLP_CUDA(c->astar.alloc((size_t)t->I));
+    RLP_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    RLP_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    RLP_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     RLP_CUDA(c->iter.alloc(2));    // [1] stays {t=0, linear=0}: weight 1.0 for metric sweeps
     RLP_CUDA(c->scalars.alloc(16));
     // terminal values never change: val = payoff everywhere, interior nodes are rewritten every sweep
@@ -454,10 +503,14 @@ static int build_graph(rlp_cfr *c) {
     if (e != cudaSuccess) { cudaStreamDestroy(cap); return fail(RLP_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
     uint64_t before = rlp::g_launches.load();
     int total = 0, rc = RLP_OK;
-    for (int u = 0; u < kGraphUnroll && rc == RLP_OK; ++u) {
-        int n = 0;
-        rc = enqueue_iteration(c, cap, &n);
-        total += n;
+    if (can_pipeline(c)) {
+        rc = enqueue_pipelined(c, cap, kGraphUnroll, &total);
+    } else {
+        for (int u = 0; u < kGraphUnroll && rc == RLP_OK; ++u) {
+            int n = 0;
+            rc = enqueue_iteration(c, cap, &n);
+            total += n;
+        }
     }
     e = cudaStreamEndCapture(cap, &c->graph);
     rlp::g_launches.store(before);      // capture records, it does not launch

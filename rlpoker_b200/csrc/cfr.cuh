@@ -27,9 +27,16 @@ struct rlp_cfr {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     int graph_kernels = 0;
+    // side stream + events for the two-branch iteration pipeline (accumulate of the micro-only information sets
+    // overlaps the upper-tile kernels)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ~rlp_cfr() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side) cudaStreamDestroy(side);
     }
 };
 

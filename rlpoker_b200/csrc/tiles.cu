@@ -677,6 +677,19 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
         if (!all) ts.jit.clear();
         RLP_CUDA(cudaStreamSynchronize(stream));
     }
+    // ---- information sets by where their nodes live: A = only inside micro subtrees, B = the rest ----------------
+    {
+        std::vector<uint8_t> in_a((size_t)t->I, 1);
+        for (int64_t g = 0; g < N; ++g)
+            if (pl[g] > 0 && kind[g] == 0) in_a[srank[g]] = 0;
+        std::vector<int> la, lb;
+        for (int32_t r = 0; r < t->I; ++r) (in_a[r] ? la : lb).push_back(r);
+        ts.acc_a_count = (int)la.size();
+        ts.acc_b_count = (int)lb.size();
+        RLP_CUDA(ts.acc_list_a.upload(la, stream));
+        RLP_CUDA(ts.acc_list_b.upload(lb, stream));
+        RLP_CUDA(cudaStreamSynchronize(stream));
+    }
     // ---- upper tiles of ONE shape: straight-line kernels, one thread per tile ---------------------------------------
     ts.upper_jit.reset();
     if (T > 0 && max_nodes <= 640 && !ts.jit.empty()) {
@@ -798,7 +811,22 @@ static int launch_upper(rlp_tree *t, const TileSet &ts, const TileView &v, cudaS
 }
 
 // One tiled sweep: [upper tiles, reach to portals] -> [micro subtrees] -> [upper tiles, values from portals].
+int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int stage, int *launches);
+
 int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *launches, cudaEvent_t *marks) {
+    int n = 0;
+    for (int stage = 0; stage < 3; ++stage) {
+        if (marks) RLP_CUDA(cudaEventRecord(marks[stage], s));
+        int rc = launch_tile_stage(c, s, iter, stage, &n);
+        if (rc) return rc;
+    }
+    if (marks) RLP_CUDA(cudaEventRecord(marks[3], s));
+    if (launches) *launches = n;
+    return RLP_OK;
+}
+
+// stage 0: reach down to the portals; 1: micro subtrees; 2: values up from the portals + upper contributions
+int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int stage, int *launches) {
     rlp_tree *t = c->tree;
     TileSet &ts = t->tiles;
     TileView v;
@@ -809,14 +837,12 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
     v.portal_p1 = ts.portal_p1.p; v.portal_p2 = ts.portal_p2.p; v.portal_v1 = ts.portal_v1.p; v.portal_v2 = ts.portal_v2.p;
     v.iter = iter ? iter : c->iter.p; v.max_nodes = ts.max_nodes; v.max_nt = ts.max_nt; v.max_cp = ts.max_cp;
     int n = 0;
-    if (marks) RLP_CUDA(cudaEventRecord(marks[0], s));
-    if (ts.num_tiles > 0 && ts.num_micro > 0) {
+    if (stage == 0 && ts.num_tiles > 0 && ts.num_micro > 0) {
         int rc = ts.upper_jit ? launch_upper_jit(c, ts, 0, v.iter, s) : launch_upper<0>(t, ts, v, s);
         if (rc) return rc;
         ++n;
     }
-    if (marks) RLP_CUDA(cudaEventRecord(marks[1], s));
-    if (ts.num_micro > 0 && !ts.jit.empty()) {
+    if (stage == 1 && ts.num_micro > 0 && !ts.jit.empty()) {
         const IterState *it = v.iter;
         long long P = ts.num_micro;
         for (auto &jc : ts.jit) {
@@ -836,7 +862,7 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
             rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
             ++n;
         }
-    } else if (ts.num_micro > 0) {
+    } else if (stage == 1 && ts.num_micro > 0) {
         MicroView m;
         m.tmpl = ts.tmpl.p; m.cls = ts.m_class.p; m.colbase = ts.m_colbase.p; m.slot_r = ts.m_slot_r.p;
         m.slot_o = ts.m_slot_o.p; m.pidx = ts.m_pidx.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;
@@ -855,14 +881,12 @@ int launch_tile_sweep(rlp_cfr *c, cudaStream_t s, const IterState *iter, int *la
         rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
         ++n;
     }
-    if (marks) RLP_CUDA(cudaEventRecord(marks[2], s));
-    if (ts.num_tiles > 0) {
+    if (stage == 2 && ts.num_tiles > 0) {
         int rc = ts.upper_jit ? launch_upper_jit(c, ts, 1, v.iter, s) : launch_upper<1>(t, ts, v, s);
         if (rc) return rc;
         ++n;
     }
-    if (marks) RLP_CUDA(cudaEventRecord(marks[3], s));
-    if (launches) *launches = n;
+    if (launches) *launches += n;
     return RLP_OK;
 }
 

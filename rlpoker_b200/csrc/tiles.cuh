@@ -113,6 +113,8 @@ struct TileSet {
     rlp::DevBuf<double> m_pc;                       // [P]
     rlp::DevBuf<double> portal_p1, portal_p2, portal_v1, portal_v2;   // [P]
     std::vector<std::unique_ptr<JitClass>> jit;     // one per class when every class compiled, else empty
+    rlp::DevBuf<int> acc_list_a, acc_list_b;        // internal information-set ids: only-micro / touching upper tiles
+    int acc_a_count = 0, acc_b_count = 0;
     std::unique_ptr<UpperJit> upper_jit;            // set when all upper tiles share one compiled shape
     int64_t bytes() const {
         return (int64_t)(desc.bytes() + ntof.bytes() + term_lid.bytes() + portal_lid.bytes() + rec.bytes() +

@@ -15,8 +15,8 @@ static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
     int v = g_pdl.load();
     if (v < 0) {
-        const char *e = getenv("RLP_NO_PDL");
-        v = (e && e[0] == '1') ? 0 : 1;
+        const char *e = getenv("RLP_PDL");        // opt-in: measured no gain inside CUDA graphs (profiles/README.md)
+        v = (e && e[0] == '1') ? 1 : 0;
         g_pdl.store(v);
     }
     return v == 1;
