@@ -133,6 +133,9 @@ int rlp_cfr_write_flags(rlp_cfr *cfr, const uint8_t *src, void *stream);
  * returns the summed device milliseconds of {upper tiles phase 0, micro subtrees, upper tiles phase 1,
  * accumulate + regret matching} (level-sweep fallback: {0, 0, all level kernels, accumulate}). */
 int rlp_cfr_profile_stages(rlp_cfr *cfr, int reps, float *out_ms4, void *stream);
+/* Debug aid: runs `iters` vanilla iterations while block 0 of every sweep kernel logs {kind, start ns, end ns}
+ * (kind 0 upper phase 0, 1 micro, 2 upper phase 1, 3 accumulate A, 4 accumulate B / all) -- the in-graph schedule. */
+int rlp_cfr_timeline(rlp_cfr *cfr, int iters, unsigned long long *out, int cap_records, int *n_out, void *stream);
 /* CFRState.nodes_touched (rlpoker/cfr/cfr_util.py:5-11). */
 uint64_t rlp_nodes_touched(rlp_cfr *cfr);
 

@@ -55,6 +55,7 @@ SYMBOLS = {
     'rlp_cfr_write': (C.c_int, [_vp, C.c_int, _dp, _vp]),
     'rlp_cfr_read_flags': (C.c_int, [_vp, _u8p, _vp]),
     'rlp_cfr_profile_stages': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float), _vp]),
+    'rlp_cfr_timeline': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int), _vp]),
     'rlp_cfr_write_flags': (C.c_int, [_vp, _u8p, _vp]),
     'rlp_nodes_touched': (C.c_uint64, [_vp]),
     'rlp_cfr_exploitability': (C.c_int, [_vp, C.c_int, _dp, _vp]),

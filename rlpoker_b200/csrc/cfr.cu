@@ -181,6 +181,7 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
     // Only static tables above: under programmatic launch this block may start while ANY earlier kernel of the
     // chain is still running, so regrets / sums / strategy / contributions are read after the wait.
     rlp::pdl_wait();
+    const int tl_slot = rlp_tl_begin(iter, advance ? 4 : 3);
     if (gid == 0 && advance) iter->t += 1;
     if (active) {
         r = R[c0 + a]; sa = S[c0 + a];
@@ -201,6 +202,7 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
         S[c0 + a] = sa;
     }
     // regret matching over the (up to) four lanes of this information set
+    rlp_tl_end(iter, tl_slot);
     const unsigned lane = threadIdx.x & 31u, base = lane & ~3u;
     double rr[4];
 #pragma unroll
@@ -726,5 +728,29 @@ extern "C" int rlp_cfr_profile_stages(rlp_cfr *c, int reps, float *out_ms4, void
     }
     for (auto &e : ev) cudaEventDestroy(e);
     c->nodes_touched += 2ull * (uint64_t)c->tree->N * (uint64_t)(reps + 2);
+    return rc;
+}
+
+// Debug: record the start/end of block 0 of every sweep kernel for the next `iters` iterations (in-graph schedule).
+extern "C" int rlp_cfr_timeline(rlp_cfr *c, int iters, unsigned long long *out, int cap_records, int *n_out, void *stream_) {
+    if (!c || !out || !n_out || cap_records < 1) return fail(RLP_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    RLP_CUDA(c->timeline.alloc(3 * (size_t)cap_records));
+    RLP_CUDA(cudaMemsetAsync(c->timeline.p, 0, c->timeline.bytes(), s));
+    IterState h;
+    RLP_CUDA(cudaMemcpyAsync(&h, c->iter.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    RLP_CUDA(cudaStreamSynchronize(s));
+    long long t0 = h.t;
+    h.tl = c->timeline.p; h.tl_count = 0; h.tl_cap = (unsigned)cap_records;
+    RLP_CUDA(cudaMemcpyAsync(c->iter.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    int rc = rlp_cfr_vanilla_iters(c, t0, iters, h.linear, s);
+    RLP_CUDA(cudaStreamSynchronize(s));
+    IterState h2;
+    RLP_CUDA(cudaMemcpy(&h2, c->iter.p, sizeof(h2), cudaMemcpyDeviceToHost));
+    int n = (int)std::min<unsigned>(h2.tl_count, (unsigned)cap_records);
+    RLP_CUDA(cudaMemcpy(out, c->timeline.p, sizeof(unsigned long long) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+    h2.tl = nullptr; h2.tl_count = 0; h2.tl_cap = 0;
+    RLP_CUDA(cudaMemcpy(c->iter.p, &h2, sizeof(h2), cudaMemcpyHostToDevice));
+    *n_out = n;
     return rc;
 }

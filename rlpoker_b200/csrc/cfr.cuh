@@ -7,7 +7,28 @@ struct IterState {
     int linear;         // weight = t if linear else 1.0 (cfr.py:106)
     int pad;
     unsigned long long touched;   // device-side nodes_touched (sampled variants)
+    unsigned long long *tl;       // optional timeline log (debug): records of {kind, start ns, end ns}
+    unsigned int tl_count, tl_cap;
 };
+
+// Debug timeline: block 0 of a kernel appends {kind, globaltimer at start, at end}.  No-op when it->tl is null.
+__device__ __forceinline__ unsigned long long rlp_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int rlp_tl_begin(const IterState *it, int kind) {
+    if (!it->tl || blockIdx.x != 0 || threadIdx.x != 0) return -1;
+    IterState *m = const_cast<IterState *>(it);
+    unsigned int slot = atomicAdd(&m->tl_count, 1u);
+    if (slot >= m->tl_cap) return -1;
+    m->tl[3 * slot] = (unsigned long long)kind;
+    m->tl[3 * slot + 1] = rlp_now();
+    return (int)slot;
+}
+__device__ __forceinline__ void rlp_tl_end(const IterState *it, int slot) {
+    if (slot >= 0) const_cast<IterState *>(it)->tl[3 * slot + 2] = rlp_now();
+}
 
 struct rlp_cfr {
     rlp_tree *tree = nullptr;
@@ -19,6 +40,7 @@ struct rlp_cfr {
     rlp::DevBuf<double> contrib_r, contrib_o;
     rlp::DevBuf<int32_t> astar;              // [I] best-response action per information set
     rlp::DevBuf<IterState> iter;
+    rlp::DevBuf<unsigned long long> timeline;
     rlp::DevBuf<double> scalars;             // small device scratch for reductions
     uint64_t nodes_touched = 0;              // host-side count (vanilla); sampled lanes count in iter->touched
     bool touched_dirty = false;

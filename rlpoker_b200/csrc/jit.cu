@@ -53,13 +53,25 @@ Nvrtc g_nvrtc;
 
 // Straight-line sweep of one shape.  Names: cb/sr/so{r} = column base / slots of decision node r; s{j} = strategy
 // probability of the edge into local node j; x{j} (y{j}) = player-1 (player-2) value of node j; q1_{r}, q2_{r} reach.
+bool want_timeline() {
+    const char *e = getenv("RLP_TIMELINE");
+    return e && e[0] == '1';
+}
+
 std::string generate(const MicroTmpl &tm, bool zs) {
     std::ostringstream o;
+    const bool tl = want_timeline();
     o.precision(17);
-    o << "struct IterState { long long t; int linear; int pad; unsigned long long touched; };\n"
+    o << "struct IterState { long long t; int linear; int pad; unsigned long long touched; unsigned long long* tl; unsigned int tl_count, tl_cap; };\n"
+         "__device__ __forceinline__ unsigned long long rlp_now() { unsigned long long t; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(t)); return t; }\n"
+         "__device__ __forceinline__ int tl_begin(const IterState* it, int kind) {\n"
+         "  if (!it->tl || blockIdx.x != 0 || threadIdx.x != 0) return -1;\n"
+         "  IterState* m = const_cast<IterState*>(it); unsigned int slot = atomicAdd(&m->tl_count, 1u);\n"
+         "  if (slot >= m->tl_cap) return -1; m->tl[3 * slot] = (unsigned long long)kind; m->tl[3 * slot + 1] = rlp_now(); return (int)slot; }\n"
+         "__device__ __forceinline__ void tl_end(const IterState* it, int slot) { if (slot >= 0) const_cast<IterState*>(it)->tl[3 * slot + 2] = rlp_now(); }\n"
          "extern \"C\" __global__ void __launch_bounds__(128) micro_k(\n"
          "    const int* __restrict__ colbase, const int* __restrict__ slot_r, const int* __restrict__ slot_o,\n"
-         "    const int* __restrict__ pidx,\n"
+         "    const int* __restrict__ pidx, const int* __restrict__ ridx,\n"
          "    const double* __restrict__ pay1, const double* __restrict__ pay2, const double* __restrict__ pc,\n"
          "    const double* __restrict__ sigma, const double* __restrict__ portal_p1, const double* __restrict__ portal_p2,\n"
          "    double* __restrict__ portal_v1, double* __restrict__ portal_v2, double* __restrict__ contrib_r,\n"
@@ -73,7 +85,7 @@ std::string generate(const MicroTmpl &tm, bool zs) {
     for (int r = 0; r < n_nt; ++r)
         o << "  const int cb" << r << " = colbase[" << r << " * P + p], sr" << r << " = slot_r[" << r << " * P + p], so"
           << r << " = slot_o[" << r << " * P + p];\n";
-    o << "  const double pcv = pc[p];\n  const int pi = pidx[p];\n";
+    o << "  const double pcv = pc[p];\n  const int pi = pidx[p], ri = ridx[p];\n";
     for (int j = 0; j < n; ++j)
         if (tm.rank[j] & 0x80) {
             int tr = tm.rank[j] & 0x7F;
@@ -82,8 +94,9 @@ std::string generate(const MicroTmpl &tm, bool zs) {
         }
     // everything above is static topology; below depends on the previous kernels (strategy, portal reach, counter)
     o << "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");\n"
-         "  const double w = iter->linear ? (double)iter->t : 1.0;\n"
-         "  const double q1_0 = portal_p1[pi], q2_0 = portal_p2[pi];\n";
+      << (tl ? "  const int tls = tl_begin(iter, 1);\n" : "")
+      << "  const double w = iter->linear ? (double)iter->t : 1.0;\n"
+         "  const double q1_0 = portal_p1[ri], q2_0 = portal_p2[ri];\n";
     for (int j = 1; j < n; ++j)
         o << "  const double s" << j << " = sigma[cb" << (int)tm.par_rank[j] << " + " << (int)tm.par_slot[j] << "];\n";
     // forward
@@ -119,7 +132,7 @@ std::string generate(const MicroTmpl &tm, bool zs) {
     }
     o << "  portal_v1[pi] = x0;\n";
     if (!zs) o << "  portal_v2[pi] = y0;\n";
-    o << "}\n";
+    o << (tl ? "  tl_end(iter, tls);\n}\n" : "}\n");
     return o.str();
 }
 
@@ -182,13 +195,14 @@ int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaK
 // contributions of the tile's decision nodes.
 static std::string generate_upper(const UpperShape &sh, bool zs) {
     std::ostringstream o;
+    const bool tl = want_timeline();
     const int n = (int)sh.kind.size();
     std::vector<int> dec_idx(n, -1), term_idx(n, -1), portal_idx(n, -1), edge_idx(n, -1), parent(n, -1), slot(n, 0);
     int nd = 0, nt = 0, np = 0, ne = 0;
     for (int j = 0; j < n; ++j) {
         if (sh.kind[j] == 1 || sh.kind[j] == 2) dec_idx[j] = nd++;
         else if (sh.kind[j] == -1) term_idx[j] = nt++;
-        else if (sh.kind[j] == 3) portal_idx[j] = np++;
+        else if (sh.kind[j] == 3) { portal_idx[j] = sh.portal_rank[j]; ++np; }
         for (int k = 0; k < sh.nchild[j]; ++k) {
             int c = sh.first_child[j] + k;
             parent[c] = j; slot[c] = k;
@@ -196,7 +210,13 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
         }
     }
     auto S = [](const char *p, int j) { return std::string(p) + std::to_string(j); };
-    o << "struct IterState { long long t; int linear; int pad; unsigned long long touched; };\n";
+    o << "struct IterState { long long t; int linear; int pad; unsigned long long touched; unsigned long long* tl; unsigned int tl_count, tl_cap; };\n"
+         "__device__ __forceinline__ unsigned long long rlp_now() { unsigned long long t; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(t)); return t; }\n"
+         "__device__ __forceinline__ int tl_begin(const IterState* it, int kind) {\n"
+         "  if (!it->tl || blockIdx.x != 0 || threadIdx.x != 0) return -1;\n"
+         "  IterState* m = const_cast<IterState*>(it); unsigned int slot = atomicAdd(&m->tl_count, 1u);\n"
+         "  if (slot >= m->tl_cap) return -1; m->tl[3 * slot] = (unsigned long long)kind; m->tl[3 * slot + 1] = rlp_now(); return (int)slot; }\n"
+         "__device__ __forceinline__ void tl_end(const IterState* it, int slot) { if (slot >= 0) const_cast<IterState*>(it)->tl[3 * slot + 2] = rlp_now(); }\n";
     for (int phase = 0; phase < 2; ++phase) {
         o << "extern \"C\" __global__ void __launch_bounds__(64) upper_k" << phase << "(\n"
              "    const int* __restrict__ colbase, const int* __restrict__ slot_r, const int* __restrict__ slot_o,\n"
@@ -204,7 +224,8 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
              "    const double* __restrict__ pay2, const long long* __restrict__ poff, const double* __restrict__ sigma,\n"
              "    double* __restrict__ portal_p1, double* __restrict__ portal_p2, const double* __restrict__ portal_v1,\n"
              "    const double* __restrict__ portal_v2, double* __restrict__ contrib_r, double* __restrict__ contrib_o,\n"
-             "    double* __restrict__ root_val, const IterState* __restrict__ iter, long long T) {\n"
+             "    double* __restrict__ root_val, const IterState* __restrict__ iter, long long T,\n"
+             "    const double* __restrict__ fan_v1, const double* __restrict__ fan_v2) {\n"
              "  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n"
              "  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
              "  if (i >= T) { asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); return; }\n"
@@ -226,11 +247,18 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
                 }
             }
         }
-        o << "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");\n";
+        o << "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");\n"
+          << (tl ? (phase == 0 ? "  const int tls = tl_begin(iter, 0);\n" : "  const int tls = tl_begin(iter, 2);\n") : "");
         if (phase == 1) o << "  const double w = iter->linear ? (double)iter->t : 1.0;\n";
         for (int j = 1; j < n; ++j)
             if (parent[j] >= 0 && dec_idx[parent[j]] >= 0)
                 o << "  const double s" << j << " = sigma[cb" << parent[j] << " + " << slot[j] << "];\n";
+        if (phase == 1)
+            for (int j = 0; j < n; ++j)
+                if (sh.kind[j] == 4) {
+                    o << "  const double x" << j << " = fan_v1[" << sh.fan_index[j] << " * T + i];\n";
+                    if (!zs) o << "  const double y" << j << " = fan_v2[" << sh.fan_index[j] << " * T + i];\n";
+                }
         if (phase == 1)
             for (int j = 0; j < n; ++j)
                 if (portal_idx[j] >= 0) {
@@ -241,13 +269,17 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
         o << "  const double q1_0 = 1.0, q2_0 = 1.0;\n";
         for (int j = 0; j < n; ++j) {
             int kd = sh.kind[j];
-            if (kd == -1 || kd == 3) continue;
+            if (kd == -1 || kd == 3 || kd == 4) continue;
             for (int k = 0; k < sh.nchild[j]; ++k) {
                 int c = sh.first_child[j] + k;
                 if (sh.kind[c] == -1) continue;
                 std::string a = (kd == 1 ? S("s", c) + " * " : std::string()) + S("q1_", j);
                 std::string b = (kd == 2 ? S("s", c) + " * " : std::string()) + S("q2_", j);
-                if (sh.kind[c] == 3) {
+                if (sh.kind[c] == 4) {          // chance node whose children are all portals: they inherit its reach
+                    if (phase == 0)
+                        o << "  portal_p1[" << sh.fan_k0[c] << " * T + i] = " << a << ";\n  portal_p2[" << sh.fan_k0[c]
+                          << " * T + i] = " << b << ";\n";
+                } else if (sh.kind[c] == 3) {
                     if (phase == 0)
                         o << "  portal_p1[" << portal_idx[c] << " * T + i] = " << a << ";\n  portal_p2[" << portal_idx[c]
                           << " * T + i] = " << b << ";\n";
@@ -256,11 +288,11 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
                 }
             }
         }
-        if (phase == 0) { o << "}\n"; continue; }
+        if (phase == 0) { o << (tl ? "  tl_end(iter, tls);\n}\n" : "}\n"); continue; }
         // backward
         for (int j = n - 1; j >= 0; --j) {
             int kd = sh.kind[j];
-            if (kd == -1 || kd == 3) continue;
+            if (kd == -1 || kd == 3 || kd == 4) continue;
             int fc = sh.first_child[j], nc = sh.nchild[j];
             o << "  double a" << j << " = 0.0;\n";
             for (int k = 0; k < nc; ++k)
@@ -282,7 +314,7 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
             }
             o << "    contrib_o[so" << j << "] = w * own;\n  }\n";
         }
-        o << "  root_val[i] = x0;\n}\n";
+        o << "  root_val[i] = x0;\n" << (tl ? "  tl_end(iter, tls);\n}\n" : "}\n");
     }
     return o.str();
 }

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
     // ---- everything below reads what the previous kernels wrote (strategy, portal values, iteration counter) ---
     rlp::pdl_wait();
     if (idle) return;
+    const int tl_slot = rlp_tl_begin(v.iter, PHASE == 0 ? 0 : 2);
     const double w = v.iter->linear ? (double)v.iter->t : 1.0;
 #pragma unroll
     for (int m = 0; m < R; ++m) {
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
         }
         __syncthreads();
     }
-    if (PHASE == 0) return;
+    if (PHASE == 0) { rlp_tl_end(v.iter, tl_slot); return; }
 
     // ---- backward: values, and the contributions of every decision node (cfr.py:177-186,204-242) ---
     for (int l = td.n_levels - 1; l >= 0; --l) {
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
         __syncthreads();
     }
     if (tid == 0) v.root_val[blockIdx.x] = val1[0];
+    rlp_tl_end(v.iter, tl_slot);
 }
 
 // ------------------------------------------------------------------------------------ micro subtrees
@@ -245,6 +247,7 @@ struct MicroView {
     const unsigned short *cls;
     const int *colbase, *slot_r, *slot_o;      // [micro_nt][P]
     const int *pidx;                           // [P] where this instance's portal lives ([portal rank][tile] layout)
+    const int *ridx;                           // [P] where its root reach is (its chance parent's slot, if any)
     const double *pay1, *pay2;                 // [micro_term][P]
     const double *pc, *sigma;
     const double *portal_p1, *portal_p2;
@@ -299,10 +302,11 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
         }
     }
     rlp::pdl_wait();                 // below: strategy, portal reach, iteration counter
+    const int tl_slot = rlp_tl_begin(v.iter, 1);
     const double w = v.iter->linear ? (double)v.iter->t : 1.0;
-    const int pi = v.pidx[p];
-    AT(sq1, 0) = v.portal_p1[pi];
-    AT(sq2, 0) = v.portal_p2[pi];
+    const int pi = v.pidx[p], ri = v.ridx[p];
+    AT(sq1, 0) = v.portal_p1[ri];
+    AT(sq2, 0) = v.portal_p2[ri];
     // batch 2: strategy probability of every edge, payoff of every leaf (independent loads)
 #pragma unroll 4
     for (int j = 1; j < n; ++j) AT(ssig, j) = v.sigma[AT(scb, tm->par_rank[j]) + tm->par_slot[j]];
@@ -344,7 +348,30 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
     }
     v.portal_v1[pi] = AT(sv1, 0);
     if (!ZS) v.portal_v2[pi] = AT(sv2, 0);
+    rlp_tl_end(v.iter, tl_slot);
 #undef AT
+}
+
+// Chance nodes whose children are all portals (in Leduc: the board deal): value = sum over children, in child
+// order, of chance probability x the value the micro kernel left at the portal.  One thread per (node, tile).
+template <bool ZS>
+__global__ void __launch_bounds__(128)
+k_fanin(const FanDesc *__restrict__ fd, int F, long long T, const double *__restrict__ cp, const double *__restrict__ pv1,
+        const double *__restrict__ pv2, double *__restrict__ out1, double *__restrict__ out2) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)F * T) return;
+    const int f = (int)(gid / T);
+    const long long i = gid - (long long)f * T;
+    const FanDesc d = fd[f];
+    double a1 = 0.0, a2 = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < d.nchild; ++c) {
+        const double e = cp[(long long)(d.e0 + c) * T + i];
+        a1 = a1 + e * pv1[(long long)(d.k0 + c) * T + i];
+        if (!ZS) a2 = a2 + e * pv2[(long long)(d.k0 + c) * T + i];
+    }
+    out1[gid] = a1;
+    if (!ZS) out2[gid] = a2;
 }
 
 __global__ void k_fill(double *p, long long n, double x) {
@@ -457,6 +484,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     std::vector<TileAux> aux;
     std::vector<double> pc, pay1, pay2, cprob;
     std::vector<int32_t> portal_node;      // portal index -> global node id of the micro root
+    std::vector<int32_t> prank(N, -1);     // micro root -> rank of its portal inside its tile
     std::vector<int32_t> local, ldepth;
     int max_nodes = 0, max_nt = 0, max_cp = 0;
     for (size_t k = 0; k < T; ++k) {
@@ -480,6 +508,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
             if (kind[g] == 1) {
                 ntof.push_back((unsigned short)(0x8000 | nportal));
                 portal_lid.push_back((unsigned short)q);
+                prank[g] = nportal;
                 portal_node.push_back(g);
                 ++nportal;
                 continue;
@@ -644,7 +673,9 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     RLP_CUDA(ts.m_pay1.upload(m_pay1, stream));
     RLP_CUDA(ts.m_pay2.upload(m_pay2, stream));
     RLP_CUDA(ts.m_pc.upload(m_pc, stream));
+    std::vector<int> ridx(pidx);
     RLP_CUDA(ts.m_pidx.upload(pidx, stream));
+    RLP_CUDA(ts.m_ridx.upload(ridx, stream));
     RLP_CUDA(ts.portal_p1.alloc((size_t)portal_len)); RLP_CUDA(ts.portal_p2.alloc((size_t)portal_len));
     RLP_CUDA(ts.portal_v1.alloc((size_t)portal_len)); RLP_CUDA(ts.portal_v2.alloc(zs ? 0 : (size_t)portal_len));
     if (portal_len > 0) {
@@ -696,24 +727,37 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
         UpperShape sh;
         std::vector<std::vector<int32_t>> locals(T);
         bool same = true;
+        auto is_fan = [&](int32_t g) {          // chance node of the upper tree whose children are all portals
+            if (kind[g] != 0 || pl[g] != 0 || fc[g + 1] - fc[g] < 2) return false;
+            for (int32_t c = fc[g]; c < fc[g + 1]; ++c) if (kind[c] != 1) return false;
+            return true;
+        };
         for (size_t k = 0; k < T && same; ++k) {
             std::vector<int32_t> &lc = locals[k];
             lc.push_back(roots[k]);
             for (size_t q = 0; q < lc.size(); ++q) {
                 int32_t g = lc[q];
-                if (kind[g] == 1) continue;
+                if (kind[g] == 1 || is_fan(g)) continue;
                 for (int32_t c = fc[g]; c < fc[g + 1]; ++c) lc.push_back(c);
             }
             UpperShape cur;
-            int next_child = 1;
+            int next_child = 1, nfan = 0;
             for (int32_t g : lc) {
-                signed char kd = kind[g] == 1 ? 3 : (signed char)pl[g];
-                int nc = kind[g] == 1 ? 0 : fc[g + 1] - fc[g];
+                bool fan = is_fan(g);
+                signed char kd = kind[g] == 1 ? 3 : (fan ? 4 : (signed char)pl[g]);
+                int nc = (kind[g] == 1 || fan) ? 0 : fc[g + 1] - fc[g];
                 cur.kind.push_back(kd); cur.nchild.push_back(nc); cur.first_child.push_back(next_child);
+                cur.portal_rank.push_back(kind[g] == 1 ? prank[g] : -1);
+                cur.fan_index.push_back(fan ? nfan++ : -1);
+                cur.fan_k0.push_back(fan ? prank[fc[g]] : -1);
                 next_child += nc;
             }
             if (k == 0) sh = cur;
-            else same = cur.kind == sh.kind && cur.nchild == sh.nchild;
+            else same = cur.kind == sh.kind && cur.nchild == sh.nchild && cur.portal_rank == sh.portal_rank &&
+                        cur.fan_k0 == sh.fan_k0;
+            if (same && k > 0)                       // fan nodes must also agree on their fan-out
+                for (size_t j = 0; j < lc.size() && same; ++j)
+                    if (sh.kind[j] == 4) same = fc[lc[j] + 1] - fc[lc[j]] == fc[locals[0][j] + 1] - fc[locals[0][j]];
         }
         if (same) {
             std::unique_ptr<UpperJit> uj(new UpperJit);
@@ -752,6 +796,37 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
                     upo[k] = desc[k].portal_off;
                 }
                 uj->T = (long long)T;
+                // fan-in chance nodes: descriptors, their chance probabilities, and where their portals read reach
+                std::vector<FanDesc> fans;
+                int fan_edges = 0;
+                for (int j = 0; j < n; ++j)
+                    if (sh.kind[j] == 4) {
+                        int32_t g0 = locals[0][j];
+                        FanDesc fdsc{sh.fan_k0[j], fc[g0 + 1] - fc[g0], fan_edges, 0};
+                        fan_edges += fdsc.nchild;
+                        fans.push_back(fdsc);
+                    }
+                std::vector<double> fcp((size_t)fan_edges * T);
+                if (!fans.empty()) {
+                    for (size_t k = 0; k < T; ++k) {
+                        int f = 0;
+                        for (int j = 0; j < n; ++j)
+                            if (sh.kind[j] == 4) {
+                                int32_t g = locals[k][j];
+                                const FanDesc &fdsc = fans[f++];
+                                for (int c = 0; c < fdsc.nchild; ++c) {
+                                    fcp[(size_t)(fdsc.e0 + c) * T + k] = d->cprob[fc[g] + c];
+                                    ridx[desc[k].portal_off + fdsc.k0 + c] = (int)((int64_t)fdsc.k0 * (int64_t)T + (int64_t)k);
+                                }
+                            }
+                    }
+                    RLP_CUDA(ts.m_ridx.upload(ridx, stream));
+                }
+                uj->num_fan = (int)fans.size();
+                RLP_CUDA(uj->fan.upload(fans, stream));
+                RLP_CUDA(uj->fan_cp.upload(fcp, stream));
+                RLP_CUDA(uj->fan_v1.alloc(fans.size() * T));
+                RLP_CUDA(uj->fan_v2.alloc(zs ? 0 : fans.size() * T));
                 RLP_CUDA(uj->colbase.upload(ucb, stream)); RLP_CUDA(uj->slot_r.upload(usr, stream));
                 RLP_CUDA(uj->slot_o.upload(uso, stream)); RLP_CUDA(uj->pcs.upload(upc, stream));
                 RLP_CUDA(uj->cprob.upload(ucp, stream)); RLP_CUDA(uj->pay1.upload(up1, stream));
@@ -770,7 +845,16 @@ static int launch_upper_jit(rlp_cfr *c, TileSet &ts, int phase, const IterState 
     long long T = u.T;
     void *args[] = {&u.colbase.p, &u.slot_r.p, &u.slot_o.p, &u.pcs.p, &u.cprob.p, &u.pay1.p, &u.pay2.p, &u.poff.p,
                     &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
-                    &c->contrib_r.p, &c->contrib_o.p, &ts.root_val.p, &it, &T};
+                    &c->contrib_r.p, &c->contrib_o.p, &ts.root_val.p, &it, &T, &u.fan_v1.p, &u.fan_v2.p};
+    if (phase == 1 && u.num_fan > 0) {
+        long long total = (long long)u.num_fan * T;
+        unsigned g = (unsigned)((total + 127) / 128);
+        if (c->tree->zero_sum)
+            k_fanin<true><<<g, 128, 0, s>>>(u.fan.p, u.num_fan, T, u.fan_cp.p, ts.portal_v1.p, ts.portal_v2.p, u.fan_v1.p, u.fan_v2.p);
+        else
+            k_fanin<false><<<g, 128, 0, s>>>(u.fan.p, u.num_fan, T, u.fan_cp.p, ts.portal_v1.p, ts.portal_v2.p, u.fan_v1.p, u.fan_v2.p);
+        RLP_LAUNCH_CHECK();
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((T + 63) / 64)); cfg.blockDim = dim3(64); cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -849,7 +933,7 @@ int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int sta
             if (jc->count == 0) continue;
             const int *inst = jc->inst.n ? jc->inst.p : nullptr;
             int count = jc->count;
-            void *args[] = {&ts.m_colbase.p, &ts.m_slot_r.p, &ts.m_slot_o.p, &ts.m_pidx.p, &ts.m_pay1.p, &ts.m_pay2.p, &ts.m_pc.p,
+            void *args[] = {&ts.m_colbase.p, &ts.m_slot_r.p, &ts.m_slot_o.p, &ts.m_pidx.p, &ts.m_ridx.p, &ts.m_pay1.p, &ts.m_pay2.p, &ts.m_pc.p,
                             &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
                             &c->contrib_r.p, &c->contrib_o.p, &it, &P, &inst, &count};
             cudaLaunchConfig_t cfg = {};
@@ -865,7 +949,7 @@ int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int sta
     } else if (stage == 1 && ts.num_micro > 0) {
         MicroView m;
         m.tmpl = ts.tmpl.p; m.cls = ts.m_class.p; m.colbase = ts.m_colbase.p; m.slot_r = ts.m_slot_r.p;
-        m.slot_o = ts.m_slot_o.p; m.pidx = ts.m_pidx.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;
+        m.slot_o = ts.m_slot_o.p; m.pidx = ts.m_pidx.p; m.ridx = ts.m_ridx.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;
         m.portal_p1 = ts.portal_p1.p; m.portal_p2 = ts.portal_p2.p; m.portal_v1 = ts.portal_v1.p;
         m.portal_v2 = ts.portal_v2.p; m.contrib_r = c->contrib_r.p; m.contrib_o = c->contrib_o.p;
         m.iter = v.iter; m.P = ts.num_micro; m.num_classes = ts.num_classes; m.mn = ts.micro_nodes; m.mnt = ts.micro_nt;

@@ -64,9 +64,15 @@ struct MicroTmpl {
 
 // Shape of an upper tile in local breadth-first order (host side; input of the straight-line generator).
 struct UpperShape {
-    std::vector<signed char> kind;      // -1 terminal, 0 chance, 1 / 2 decision node of that player, 3 portal leaf
+    // -1 terminal, 0 chance, 1 / 2 decision node of that player, 3 portal leaf,
+    // 4 "fan-in" leaf: a chance node whose children are all portals (summed by k_fanin, not by the tile kernel)
+    std::vector<signed char> kind;
     std::vector<int> first_child, nchild;
+    std::vector<int> portal_rank;       // kind 3: rank of the portal inside its tile
+    std::vector<int> fan_index, fan_k0; // kind 4: index of the fan-in node, portal rank of its first child
 };
+
+struct FanDesc { int k0, nchild, e0, pad; };
 
 // All upper tiles share one shape and were compiled to straight-line code: one thread per tile.
 struct UpperJit {
@@ -76,6 +82,10 @@ struct UpperJit {
     rlp::DevBuf<int> colbase, slot_r, slot_o;       // [decision][T]
     rlp::DevBuf<double> pcs, cprob, pay1, pay2;     // [decision][T], [chance edge][T], [terminal][T]
     rlp::DevBuf<long long> poff;                    // [T]
+    int num_fan = 0;                                // fan-in chance nodes per tile
+    rlp::DevBuf<FanDesc> fan;                       // [num_fan]
+    rlp::DevBuf<double> fan_cp;                     // [fan chance edge][T]
+    rlp::DevBuf<double> fan_v1, fan_v2;             // [num_fan][T]
     ~UpperJit() { if (lib) cudaLibraryUnload(lib); }
 };
 
@@ -109,6 +119,7 @@ struct TileSet {
     rlp::DevBuf<unsigned short> m_class;            // [P]
     rlp::DevBuf<int> m_colbase, m_slot_r, m_slot_o; // [micro_nt][P]
     rlp::DevBuf<int> m_pidx;                        // [P] index of the instance's portal in the portal arrays
+    rlp::DevBuf<int> m_ridx;                        // [P] where to read its root reach (the chance parent's slot when it has one)
     rlp::DevBuf<double> m_pay1, m_pay2;             // [micro_term][P]
     rlp::DevBuf<double> m_pc;                       // [P]
     rlp::DevBuf<double> portal_p1, portal_p2, portal_v1, portal_v2;   // [P]
@@ -119,7 +130,7 @@ struct TileSet {
     int64_t bytes() const {
         return (int64_t)(desc.bytes() + ntof.bytes() + term_lid.bytes() + portal_lid.bytes() + rec.bytes() +
                          aux.bytes() + pc.bytes() + pay1.bytes() + pay2.bytes() + cprob.bytes() + root_val.bytes() +
-                         tmpl.bytes() + m_class.bytes() + m_pidx.bytes() + m_colbase.bytes() + m_slot_r.bytes() + m_slot_o.bytes() +
+                         tmpl.bytes() + m_class.bytes() + m_pidx.bytes() + m_ridx.bytes() + m_colbase.bytes() + m_slot_r.bytes() + m_slot_o.bytes() +
                          m_pay1.bytes() + m_pay2.bytes() + m_pc.bytes() + portal_p1.bytes() + portal_p2.bytes() +
                          portal_v1.bytes() + portal_v2.bytes());
     }

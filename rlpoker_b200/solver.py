@@ -153,6 +153,18 @@ class DeviceCFR:
         names = ['upper_phase0', 'micro', 'upper_phase1', 'accumulate_rm']
         return {n: 1e3 * out[i] / reps for i, n in enumerate(names)}
 
+    def timeline(self, iters=16, stream=None):
+        """[(kind, start_us, end_us)] of block 0 of every sweep kernel over `iters` iterations, relative to the first."""
+        cap = 8 * iters + 16
+        buf = (C.c_uint64 * (3 * cap))()
+        n = C.c_int()
+        check(_lib.load().rlp_cfr_timeline(self.handle, int(iters), buf, cap, C.byref(n), _stream_ptr(stream)))
+        self.t += iters
+        rec = [(int(buf[3 * i]), buf[3 * i + 1], buf[3 * i + 2]) for i in range(n.value)]
+        rec.sort(key=lambda r: r[1])
+        t0 = rec[0][1] if rec else 0
+        return [(k, (a - t0) / 1e3, (b - t0) / 1e3) for k, a, b in rec]
+
     def write_flags(self, mask, bit=None, stream=None):
         """Set the dict-membership flags: ``mask`` is a [I] bitmask, or a boolean array for one ``bit`` (1, 2, 4)
         merged into the current flags."""
