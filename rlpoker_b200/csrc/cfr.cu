@@ -161,8 +161,6 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
                  const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
                  const double *__restrict__ contrib_r, const double *__restrict__ contrib_o, double *R, double *S,
                  double *sigma, uint8_t *flags, IterState *iter, int advance, const int *__restrict__ list, int count) {
-    constexpr int kTab = 256;                      // diagonals whose offsets are staged in shared memory
-    __shared__ int64_t s_kc[kTab], s_ki[kTab];
     rlp::pdl_launch_dependents();
     const int gid = blockIdx.x * kBlock + threadIdx.x;
     const int g = gid >> 2, a = gid & 3;
@@ -172,12 +170,7 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
     const int64_t c0 = valid ? col_off[s] : 0;
     const int na = valid ? (int)(col_off[s + 1] - c0) : 0;
     const bool active = a < na;
-    {
-        const int kmax = iset_size[0];             // sizes are sorted descending
-        for (int k = threadIdx.x; k < kmax && k < kTab; k += kBlock) { s_kc[k] = koff_col[k]; s_ki[k] = koff_iset[k]; }
-    }
     double r = 0.0, sa = 0.0, sg = 0.0;
-    __syncthreads();
     // Only static tables above: under programmatic launch this block may start while ANY earlier kernel of the
     // chain is still running, so regrets / sums / strategy / contributions are read after the wait.
     rlp::pdl_wait();
@@ -188,20 +181,22 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
         sg = sigma[c0 + a];
         const double *cr = contrib_r + c0 + a;
         const double *co = contrib_o + s;
-        const int fast = size < kTab ? size : kTab;
-#pragma unroll 5
-        for (int k = 0; k < fast; ++k) {
-            r = r + cr[s_kc[k]];
-            sa = sa + co[s_ki[k]] * sg;
+        // batches of 8 diagonals: 16 independent loads in flight, then the ordered adds
+        int k = 0;
+        for (; k + 8 <= size; k += 8) {
+            double x[8], y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { x[j] = cr[koff_col[k + j]]; y[j] = co[koff_iset[k + j]]; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { r = r + x[j]; sa = sa + y[j] * sg; }
         }
-        for (int k = fast; k < size; ++k) {
+        for (; k < size; ++k) {
             r = r + cr[koff_col[k]];
             sa = sa + co[koff_iset[k]] * sg;
         }
         R[c0 + a] = r;
         S[c0 + a] = sa;
     }
-    // regret matching over the (up to) four lanes of this information set
     rlp_tl_end(iter, tl_slot);
     const unsigned lane = threadIdx.x & 31u, base = lane & ~3u;
     double rr[4];

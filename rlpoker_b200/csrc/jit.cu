@@ -53,6 +53,13 @@ Nvrtc g_nvrtc;
 
 // Straight-line sweep of one shape.  Names: cb/sr/so{r} = column base / slots of decision node r; s{j} = strategy
 // probability of the edge into local node j; x{j} (y{j}) = player-1 (player-2) value of node j; q1_{r}, q2_{r} reach.
+// Resident CTAs per SM requested for the micro kernel (caps registers: 8 -> 64 regs, one wave for Leduc-13).
+int micro_min_blocks() {
+    const char *e = getenv("RLP_MICRO_MINBLOCKS");
+    int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 16 ? 16 : v);
+}
+
 bool want_timeline() {
     const char *e = getenv("RLP_TIMELINE");
     return e && e[0] == '1';
@@ -69,7 +76,7 @@ std::string generate(const MicroTmpl &tm, bool zs) {
          "  IterState* m = const_cast<IterState*>(it); unsigned int slot = atomicAdd(&m->tl_count, 1u);\n"
          "  if (slot >= m->tl_cap) return -1; m->tl[3 * slot] = (unsigned long long)kind; m->tl[3 * slot + 1] = rlp_now(); return (int)slot; }\n"
          "__device__ __forceinline__ void tl_end(const IterState* it, int slot) { if (slot >= 0) const_cast<IterState*>(it)->tl[3 * slot + 2] = rlp_now(); }\n"
-         "extern \"C\" __global__ void __launch_bounds__(128) micro_k(\n"
+         "extern \"C\" __global__ void __launch_bounds__(128, " << micro_min_blocks() << ") micro_k(\n"
          "    const int* __restrict__ colbase, const int* __restrict__ slot_r, const int* __restrict__ slot_o,\n"
          "    const int* __restrict__ pidx, const int* __restrict__ ridx,\n"
          "    const double* __restrict__ pay1, const double* __restrict__ pay2, const double* __restrict__ pc,\n"

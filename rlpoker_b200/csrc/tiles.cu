@@ -364,8 +364,22 @@ k_fanin(const FanDesc *__restrict__ fd, int F, long long T, const double *__rest
     const long long i = gid - (long long)f * T;
     const FanDesc d = fd[f];
     double a1 = 0.0, a2 = 0.0;
-#pragma unroll 4
-    for (int c = 0; c < d.nchild; ++c) {
+    int c = 0;
+    for (; c + 8 <= d.nchild; c += 8) {          // 16 (24) independent loads in flight, then the ordered adds
+        double e[8], x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            e[j] = cp[(long long)(d.e0 + c + j) * T + i];
+            x[j] = pv1[(long long)(d.k0 + c + j) * T + i];
+            if (!ZS) y[j] = pv2[(long long)(d.k0 + c + j) * T + i];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a1 = a1 + e[j] * x[j];
+            if (!ZS) a2 = a2 + e[j] * y[j];
+        }
+    }
+    for (; c < d.nchild; ++c) {
         const double e = cp[(long long)(d.e0 + c) * T + i];
         a1 = a1 + e * pv1[(long long)(d.k0 + c) * T + i];
         if (!ZS) a2 = a2 + e * pv2[(long long)(d.k0 + c) * T + i];
