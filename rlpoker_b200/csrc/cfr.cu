@@ -407,7 +407,7 @@ int enqueue_pipelined(rlp_cfr *c, cudaStream_t s, int iters, int *count) {
     return RLP_OK;
 }
 
-constexpr int kGraphUnroll = 8;
+constexpr int kGraphUnroll = 10;     // = the evaluation cadence of cfr() (cfr.py:125), so a 10-iteration call is one graph launch
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------
@@ -461,7 +461,12 @@ extern "C" int rlp_cfr_create(rlp_tree *t, void *stream_, rlp_cfr **out) {
     if (!t->zero_sum) RLP_CUDA(c->val2.alloc(N));
     RLP_CUDA(c->contrib_r.alloc((size_t)t->NC)); RLP_CUDA(c->contrib_o.alloc((size_t)t->ND));
     RLP_CUDA(c->astar.alloc((size_t)t->I));
-    RLP_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    {
+        // the side branch (bulk accumulate) yields to the main chain, which is the critical path
+        int lo = 0, hi = 0;
+        RLP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        RLP_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, lo));
+    }
     RLP_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     RLP_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     RLP_CUDA(c->iter.alloc(2));    // [1] stays {t=0, linear=0}: weight 1.0 for metric sweeps

@@ -56,7 +56,7 @@ Nvrtc g_nvrtc;
 // Resident CTAs per SM requested for the micro kernel (caps registers: 8 -> 64 regs, one wave for Leduc-13).
 int micro_min_blocks() {
     const char *e = getenv("RLP_MICRO_MINBLOCKS");
-    int v = e ? atoi(e) : 8;
+    int v = e ? atoi(e) : 5;
     return v < 1 ? 1 : (v > 16 ? 16 : v);
 }
 
