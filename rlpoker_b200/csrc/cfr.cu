@@ -161,16 +161,23 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
                  const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
                  const double *__restrict__ contrib_r, const double *__restrict__ contrib_o, double *R, double *S,
                  double *sigma, uint8_t *flags, IterState *iter, int advance, const int *__restrict__ list, int count) {
+    constexpr int kTab = 128;                      // diagonals whose offsets are staged in shared memory
+    __shared__ int64_t s_kc[kTab], s_ki[kTab];
     rlp::pdl_launch_dependents();
     const int gid = blockIdx.x * kBlock + threadIdx.x;
     const int g = gid >> 2, a = gid & 3;
     const bool valid = g < count;
     const int s = valid ? (list ? list[g] : g) : 0;
+    if (threadIdx.x < kTab) {                      // the offset tables are tiny and shared by every thread
+        const int kmax = iset_size[0];             // sizes are sorted descending
+        if ((int)threadIdx.x < kmax) { s_kc[threadIdx.x] = koff_col[threadIdx.x]; s_ki[threadIdx.x] = koff_iset[threadIdx.x]; }
+    }
     const int size = valid ? iset_size[s] : 0;
     const int64_t c0 = valid ? col_off[s] : 0;
     const int na = valid ? (int)(col_off[s + 1] - c0) : 0;
     const bool active = a < na;
     double r = 0.0, sa = 0.0, sg = 0.0;
+    __syncthreads();
     // Only static tables above: under programmatic launch this block may start while ANY earlier kernel of the
     // chain is still running, so regrets / sums / strategy / contributions are read after the wait.
     rlp::pdl_wait();
@@ -183,10 +190,11 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
         const double *co = contrib_o + s;
         // batches of 8 diagonals: 16 independent loads in flight, then the ordered adds
         int k = 0;
-        for (; k + 8 <= size; k += 8) {
+        const int fast = size < kTab ? size : kTab;
+        for (; k + 8 <= fast; k += 8) {
             double x[8], y[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { x[j] = cr[koff_col[k + j]]; y[j] = co[koff_iset[k + j]]; }
+            for (int j = 0; j < 8; ++j) { x[j] = cr[s_kc[k + j]]; y[j] = co[s_ki[k + j]]; }
 #pragma unroll
             for (int j = 0; j < 8; ++j) { r = r + x[j]; sa = sa + y[j] * sg; }
         }
