@@ -166,7 +166,9 @@ int rlp_expected_value(rlp_tree *tree, const double *sigma, double *out2, void *
  * this rank's nodes and leaves the per-pair deltas (regret || strategy-sum, 2*Q doubles, canonical
  * order) in a device buffer whose address `rlp_cfr_delta_ptr` returns; the caller all-reduces
  * that buffer in place (NCCL via torch.distributed) on the same stream; `rlp_cfr_apply_delta`
- * adds it and runs regret matching.  weight as in rlp_cfr_vanilla_iters.
+ * adds it and runs regret matching.  weight as in rlp_cfr_vanilla_iters.  t < 0 keeps the device-side iteration
+ * counter (which rlp_cfr_apply_delta advances), so a sweep / all-reduce / apply sequence can be captured once in a
+ * CUDA graph and replayed.
  */
 int rlp_cfr_local_sweep(rlp_cfr *cfr, int64_t t, int linear_weight, void *stream);
 void *rlp_cfr_delta_ptr(rlp_cfr *cfr);

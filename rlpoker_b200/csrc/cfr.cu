@@ -569,8 +569,10 @@ extern "C" int rlp_cfr_local_sweep(rlp_cfr *c, int64_t t_iter, int linear_weight
     if (!c) return fail(RLP_ERR_INVALID, "null solver");
     cudaStream_t s = (cudaStream_t)stream_;
     rlp_tree *t = c->tree;
-    k_set_iter<<<1, 1, 0, s>>>(c->iter.p, (long long)t_iter, linear_weight);
-    RLP_LAUNCH_CHECK();
+    if (t_iter >= 0) {          // t < 0: keep the device-side counter (lets the caller capture the call in a CUDA graph)
+        k_set_iter<<<1, 1, 0, s>>>(c->iter.p, (long long)t_iter, linear_weight);
+        RLP_LAUNCH_CHECK();
+    }
     int n = 0;
     int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n) : enqueue_sweep<false>(c, s, &n);
     if (rc) return rc;

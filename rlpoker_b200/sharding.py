@@ -148,11 +148,47 @@ class ShardedCFR:
         self.solver = DeviceCFR(self.tree, stream=stream)
         self.delta = torch.as_tensor(_DeviceArray(self.solver.delta_ptr(), 2 * flat_tree.num_pairs), device='cuda')
         self.nodes_touched = 0
+        self._cuda_graph = None
+        self._last_linear = None
 
-    def iterate(self, n_iters, linear_weight=False):
-        for _ in range(int(n_iters)):
-            self.solver.local_sweep(linear_weight=linear_weight)
-            if self.world > 1:
-                allreduce_delta(self.delta, self.group)
-            self.solver.apply_delta()
-        self.nodes_touched += 2 * self.full.num_nodes * int(n_iters)
+    GRAPH_ITERS = 10
+
+    def _one(self, linear_weight, keep_counter):
+        self.solver.local_sweep(linear_weight=linear_weight, keep_counter=keep_counter)
+        if self.world > 1:
+            allreduce_delta(self.delta, self.group)
+        self.solver.apply_delta()
+
+    def _graph(self):
+        """CUDA graph of GRAPH_ITERS iterations (local sweep, NCCL all-reduce, apply) -- without it the loop is
+        bound by host launch latency, not by the GPUs.  The graph continues from the device-side iteration counter
+        and weighting flag, which every eager iteration sets."""
+        import torch
+        if self._cuda_graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            t_before = self.solver.t
+            with torch.cuda.graph(g):
+                for _ in range(self.GRAPH_ITERS):
+                    self._one(False, keep_counter=True)
+            self.solver.t = t_before                              # capture records, it does not run
+            self._cuda_graph = g
+        return self._cuda_graph
+
+    def iterate(self, n_iters, linear_weight=False, use_graph=True):
+        n = int(n_iters)
+        done = 0
+        if use_graph and n >= self.GRAPH_ITERS:
+            if self._last_linear != bool(linear_weight):          # (re)sets counter + flag on the device; warms NCCL up
+                self._one(linear_weight, keep_counter=False)
+                self._last_linear = bool(linear_weight)
+                done += 1
+            g = self._graph()
+            while n - done >= self.GRAPH_ITERS:
+                g.replay()
+                self.solver.t += self.GRAPH_ITERS
+                done += self.GRAPH_ITERS
+        for _ in range(n - done):
+            self._one(linear_weight, keep_counter=False)
+            self._last_linear = bool(linear_weight)
+        self.nodes_touched += 2 * self.full.num_nodes * n

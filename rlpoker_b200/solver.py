@@ -200,8 +200,9 @@ class DeviceCFR:
         return out.value
 
     # multi-GPU split
-    def local_sweep(self, linear_weight=False, stream=None):
-        check(_lib.load().rlp_cfr_local_sweep(self.handle, self.t, int(bool(linear_weight)), _stream_ptr(stream)))
+    def local_sweep(self, linear_weight=False, stream=None, keep_counter=False):
+        check(_lib.load().rlp_cfr_local_sweep(self.handle, -1 if keep_counter else self.t, int(bool(linear_weight)),
+                                              _stream_ptr(stream)))
 
     def delta_ptr(self):
         return _lib.load().rlp_cfr_delta_ptr(self.handle)

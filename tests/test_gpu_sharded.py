@@ -46,3 +46,20 @@ def test_world_one_split_path_equals_fused_path():
     b.vanilla(9)
     np.testing.assert_allclose(a.solver.regrets, b.regrets, rtol=0, atol=1e-11)
     assert a.nodes_touched == b.nodes_touched
+
+
+def test_world_one_graph_replay_path():
+    """iterate() >= 10 iterations replays a CUDA graph of (local sweep, all-reduce, apply) x 10."""
+    from rlpoker_b200.flatten import flatten
+    from rlpoker_b200.sharding import ShardedCFR
+    from rlpoker_b200.solver import DeviceCFR, device_tree
+    ft = flatten(make_game('leduc3'))
+    a = ShardedCFR(ft, 0, 1)
+    a.iterate(25)
+    a.iterate(10, linear_weight=True)
+    b = DeviceCFR(device_tree(make_game('leduc3')))
+    b.vanilla(25)
+    b.vanilla(10, linear_weight=True)
+    np.testing.assert_allclose(a.solver.regrets, b.regrets, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(a.solver.strategy_sum, b.strategy_sum, rtol=0, atol=1e-9)
+    assert a.solver.t == 35 and a._cuda_graph is not None
