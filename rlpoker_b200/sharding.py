@@ -6,6 +6,8 @@ subtrees plus their ancestors; information-set numbering stays GLOBAL so the per
 line up and one sum-allreduce per iteration (2*Q doubles) completes the update.  Reach probabilities of the
 kept nodes are unchanged because chance probabilities are kept as they are.
 """
+import os
+
 import numpy as np
 
 from rlpoker_b200.flatten import FlatTree
@@ -175,7 +177,12 @@ class ShardedCFR:
             self._cuda_graph = g
         return self._cuda_graph
 
-    def iterate(self, n_iters, linear_weight=False, use_graph=True):
+    def iterate(self, n_iters, linear_weight=False, use_graph=None):
+        # Graph replay is validated single-process only (tests/test_gpu_sharded.py); a 2-rank run with the NCCL
+        # all-reduce captured inside torch.cuda.graph hung in round 1, so multi-rank runs stay eager unless
+        # RLP_SHARD_GRAPH=1 asks for it.
+        if use_graph is None:
+            use_graph = self.world == 1 or os.environ.get('RLP_SHARD_GRAPH') == '1'
         n = int(n_iters)
         done = 0
         if use_graph and n >= self.GRAPH_ITERS:
