@@ -171,6 +171,13 @@ int rlp_expected_value(rlp_tree *tree, const double *sigma, double *out2, void *
  * CUDA graph and replayed.
  */
 int rlp_cfr_local_sweep(rlp_cfr *cfr, int64_t t, int linear_weight, void *stream);
+/* The same loop entirely in C: rank 0 calls rlp_comm_unique_id, shares the 128 bytes (e.g. torch.distributed
+ * broadcast), every rank calls rlp_comm_init (ncclCommInitRank), then rlp_cfr_sharded_iters runs n iterations of
+ * sweep -> ncclAllReduce(sum, in place, caller's stream) -> apply without returning to the host language. */
+int rlp_comm_unique_id(unsigned char *out128);
+int rlp_comm_init(rlp_cfr *cfr, int rank, int nranks, const unsigned char *id128);
+void rlp_comm_destroy(rlp_cfr *cfr);
+int rlp_cfr_sharded_iters(rlp_cfr *cfr, int64_t t0, int64_t n_iters, int linear_weight, void *stream);
 void *rlp_cfr_delta_ptr(rlp_cfr *cfr);
 int rlp_cfr_apply_delta(rlp_cfr *cfr, void *stream);
 

@@ -64,6 +64,10 @@ SYMBOLS = {
     'rlp_expected_value': (C.c_int, [_vp, _dp, _dp, _vp]),
     'rlp_cfr_local_sweep': (C.c_int, [_vp, C.c_int64, C.c_int, _vp]),
     'rlp_cfr_delta_ptr': (_vp, [_vp]),
+    'rlp_comm_unique_id': (C.c_int, [_u8p]),
+    'rlp_comm_init': (C.c_int, [_vp, C.c_int, C.c_int, _u8p]),
+    'rlp_comm_destroy': (None, [_vp]),
+    'rlp_cfr_sharded_iters': (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, _vp]),
     'rlp_cfr_apply_delta': (C.c_int, [_vp, _vp]),
 }
 

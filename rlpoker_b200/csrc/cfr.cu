@@ -435,7 +435,11 @@ int permute(rlp_tree *t, const double *src, double *dst, int to_internal, cudaSt
 }
 }  // namespace rlp
 
-extern "C" void rlp_cfr_free(rlp_cfr *c) { delete c; }
+extern "C" void rlp_comm_destroy(rlp_cfr *c);
+extern "C" void rlp_cfr_free(rlp_cfr *c) {
+    rlp_comm_destroy(c);
+    delete c;
+}
 
 extern "C" int rlp_cfr_reset(rlp_cfr *c, void *stream_) {
     if (!c) return fail(RLP_ERR_INVALID, "null solver");

@@ -51,6 +51,8 @@ struct rlp_cfr {
     int graph_kernels = 0;
     // side stream + events for the two-branch iteration pipeline (accumulate of the micro-only information sets
     // overlaps the upper-tile kernels)
+    void *nccl_comm = nullptr;               // ncclComm_t of the deal-sharded solve (comm.cu)
+    int nccl_ranks = 1;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ~rlp_cfr() {

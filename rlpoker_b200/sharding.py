@@ -152,6 +152,42 @@ class ShardedCFR:
         self.nodes_touched = 0
         self._cuda_graph = None
         self._last_linear = None
+        self._native = False
+        if os.environ.get('RLP_SHARD_NATIVE', '1') == '1':
+            self._init_native_comm()
+
+    def _init_native_comm(self):
+        """NCCL communicator owned by the library: the whole loop then runs in C (rlp_cfr_sharded_iters)."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from rlpoker_b200 import _lib
+        lib = _lib.load()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        ok = torch.ones(1, dtype=torch.int32)
+        if self.world > 1:
+            if not dist.is_initialized():
+                return
+            if self.rank == 0:
+                buf = (C.c_uint8 * 128)()
+                if lib.rlp_comm_unique_id(buf) != 0:
+                    ok[0] = 0
+                ident = torch.tensor(list(buf), dtype=torch.uint8)
+            dev = torch.device('cuda', torch.cuda.current_device())
+            ident_d, ok_d = ident.to(dev), ok.to(dev)
+            dist.broadcast(ident_d, src=0, group=self.group)
+            dist.broadcast(ok_d, src=0, group=self.group)
+            if int(ok_d.item()) == 0:
+                return
+            ident = ident_d.cpu()
+        else:
+            buf = (C.c_uint8 * 128)()
+            if lib.rlp_comm_unique_id(buf) != 0:
+                return
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        arr = (C.c_uint8 * 128)(*ident.tolist())
+        rc = lib.rlp_comm_init(self.solver.handle, self.rank, self.world, arr)
+        self._native = rc == 0
 
     GRAPH_ITERS = 10
 
@@ -181,9 +217,18 @@ class ShardedCFR:
         # Graph replay is validated single-process only (tests/test_gpu_sharded.py); a 2-rank run with the NCCL
         # all-reduce captured inside torch.cuda.graph hung in round 1, so multi-rank runs stay eager unless
         # RLP_SHARD_GRAPH=1 asks for it.
-        if use_graph is None:
-            use_graph = self.world == 1 or os.environ.get('RLP_SHARD_GRAPH') == '1'
         n = int(n_iters)
+        if self._native and use_graph is None:
+            from rlpoker_b200 import _lib
+            from rlpoker_b200.solver import _stream_ptr
+            _lib.check(_lib.load().rlp_cfr_sharded_iters(self.solver.handle, self.solver.t, n, int(bool(linear_weight)),
+                                                         _stream_ptr(None)))
+            self.solver.t += n
+            self._last_linear = None
+            self.nodes_touched += 2 * self.full.num_nodes * n
+            return
+        if use_graph is None:
+            use_graph = self.world == 1 or os.environ.get('RLP_SHARD_GRAPH') == '1' 
         done = 0
         if use_graph and n >= self.GRAPH_ITERS:
             if self._last_linear != bool(linear_weight):          # (re)sets counter + flag on the device; warms NCCL up

@@ -55,11 +55,28 @@ def test_world_one_graph_replay_path():
     from rlpoker_b200.solver import DeviceCFR, device_tree
     ft = flatten(make_game('leduc3'))
     a = ShardedCFR(ft, 0, 1)
-    a.iterate(25)
-    a.iterate(10, linear_weight=True)
+    a.iterate(25, use_graph=True)
+    a.iterate(10, linear_weight=True, use_graph=True)
     b = DeviceCFR(device_tree(make_game('leduc3')))
     b.vanilla(25)
     b.vanilla(10, linear_weight=True)
     np.testing.assert_allclose(a.solver.regrets, b.regrets, rtol=0, atol=1e-9)
     np.testing.assert_allclose(a.solver.strategy_sum, b.strategy_sum, rtol=0, atol=1e-9)
     assert a.solver.t == 35 and a._cuda_graph is not None
+
+
+def test_world_one_native_nccl_loop():
+    """rlp_cfr_sharded_iters: the sweep / ncclAllReduce / apply loop in C (a 1-rank communicator here)."""
+    from rlpoker_b200.flatten import flatten
+    from rlpoker_b200.sharding import ShardedCFR
+    from rlpoker_b200.solver import DeviceCFR, device_tree
+    ft = flatten(make_game('leduc3'))
+    a = ShardedCFR(ft, 0, 1)
+    assert a._native
+    a.iterate(12)
+    a.iterate(5, linear_weight=True)
+    b = DeviceCFR(device_tree(make_game('leduc3')))
+    b.vanilla(12)
+    b.vanilla(5, linear_weight=True)
+    np.testing.assert_allclose(a.solver.regrets, b.regrets, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(a.solver.strategy_sum, b.strategy_sum, rtol=0, atol=1e-9)
