@@ -104,3 +104,20 @@ def test_write_read_roundtrip_and_reset():
     assert np.array_equal(s.read(0), x)
     s.reset()
     assert not s.read(0).any() and s.nodes_touched == 0
+
+
+def test_long_horizon_parity_leduc3():
+    """BASELINE config 2 at test scale: 20 000 vanilla iterations on Leduc-3, CUDA vs the CPU oracle (which
+    tests/test_oracle_golden.py pins to the reference at T <= 100).  north_star tolerance: average strategy within
+    1e-9 abs, exploitability within 1e-7; the single-GPU path is expected to be bit-identical."""
+    from oracle import oracle as orc
+    o = orc.Oracle(oracle_tree('leduc3'))
+    s = _solver('leduc3')
+    T = 20000
+    s.vanilla(T)
+    o.vanilla_levels(T, threads=4)
+    assert np.array_equal(s.regrets, o.R) and np.array_equal(s.strategy_sum, o.S)
+    avg = o.average_strategy()[0]
+    assert np.abs(s.average - avg).max() <= 1e-9
+    assert abs(s.exploitability()[0] - o.exploitability(avg)) <= 1e-7
+    assert s.nodes_touched == 2 * 25537 * T
