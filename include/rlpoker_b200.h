@@ -88,6 +88,13 @@ int rlp_leduc_generate(int32_t num_values, int32_t num_suits, int32_t max_raises
                        int32_t *parent, int8_t *player, int32_t *infoset, double *cprob,
                        double *u1, double *u2, int32_t *label, uint8_t *hidden);
 
+/* Host-only planning (no GPU needed): runs the validation, layout derivation, two-tier tiling and NVRTC compilation
+ * that rlp_tree_upload performs and reports stats16 = {tiled, upper tiles, micro subtrees, micro shapes, nodes and
+ * decision nodes and leaves of the largest micro shape, information sets only in micro subtrees, the rest, nodes and
+ * non-terminals of the largest upper tile, its shared memory, kernels compiled, kernels that failed to compile,
+ * largest information set, zero-sum}. */
+int rlp_tree_plan(const rlp_tree_desc *desc, int64_t *stats16);
+
 /* ---- solver --------------------------------------------------------------------------- */
 typedef enum { RLP_REGRET = 0, RLP_STRAT_SUM = 1, RLP_SIGMA = 2, RLP_AVERAGE = 3, RLP_CUM_IMM_REGRET = 4 } rlp_which;
 typedef enum { RLP_CHANCE_SAMPLED = 0, RLP_EXTERNAL_SAMPLED = 1 } rlp_variant;

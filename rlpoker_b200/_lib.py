@@ -43,6 +43,7 @@ SYMBOLS = {
     'rlp_tree_free': (None, [_vp]),
     'rlp_tree_bytes': (C.c_int64, [_vp]),
     'rlp_tree_stat': (C.c_int64, [_vp, C.c_int]),
+    'rlp_tree_plan': (C.c_int, [C.POINTER(TreeDesc), _i64p]),
     'rlp_leduc_generate': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _i8p, _i32p,
                                      _dp, _dp, _dp, _i32p, _u8p]),
     'rlp_cfr_create': (C.c_int, [_vp, _vp, C.POINTER(_vp)]),

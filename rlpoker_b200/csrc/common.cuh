@@ -16,6 +16,8 @@ namespace rlp {
 
 extern thread_local char g_error[512];
 extern std::atomic<uint64_t> g_launches;
+// Planning mode (rlp_tree_plan): derive the whole device layout on the host without touching a GPU.
+extern thread_local bool g_dry_run;
 
 int fail(int code, const char *fmt, ...);
 
@@ -53,11 +55,12 @@ struct DevBuf {
     cudaError_t alloc(size_t count) {
         release();
         n = count;
+        if (g_dry_run) return cudaSuccess;
         return cudaMalloc(&p, sizeof(T) * (count ? count : 1));
     }
     cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
         cudaError_t e = alloc(h.size());
-        if (e != cudaSuccess || h.empty()) return e;
+        if (e != cudaSuccess || h.empty() || g_dry_run) return e;
         return cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, s);
     }
     size_t bytes() const { return sizeof(T) * n; }
@@ -68,6 +71,7 @@ struct DevBuf {
 // never writes (static topology).  pdl_wait() returns once the predecessor has completed and flushed.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline cudaError_t sync_stream(cudaStream_t s) { return g_dry_run ? cudaSuccess : cudaStreamSynchronize(s); }
 bool pdl_enabled();
 void pdl_disable();
 

@@ -17,6 +17,8 @@
 
 using rlp::fail;
 
+namespace rlp { thread_local int g_jit_compiled = 0, g_jit_failed = 0; }
+
 namespace {
 
 struct Nvrtc {
@@ -164,8 +166,15 @@ static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std:
         std::string log(n, '\0');
         if (n) g_nvrtc.log(prog, &log[0]);
         if (log_out) *log_out = log;
+        rlp::g_jit_failed++;
+        snprintf(rlp::g_error, sizeof(rlp::g_error), "NVRTC: %.400s", log.c_str());
         g_nvrtc.destroy(&prog);
         return RLP_OK;                          // fall back to the interpreter
+    }
+    rlp::g_jit_compiled++;
+    if (rlp::g_dry_run) {                        // planning mode: the source compiled; nothing to load without a GPU
+        g_nvrtc.destroy(&prog);
+        return RLP_OK;
     }
     size_t sz = 0;
     g_nvrtc.cubin_size(prog, &sz);

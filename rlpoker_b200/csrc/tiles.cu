@@ -476,6 +476,8 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
             uint8_t ps = v == 0 ? 0 : status[parent[v]];
             if (ps != 0) { status[v] = 2; continue; }
             if (kind[v] == 1) { status[v] = 0; continue; }      // a portal hanging off the trunk
+            if (pl[v] == 0) { status[v] = 0; continue; }         // chance nodes below the trunk extend it: the cut goes
+                                                                // as deep as it can, giving more and smaller tiles
             if (fits(v)) { status[v] = 1; roots.push_back((int32_t)v); continue; }
             status[v] = 0;
             if (pl[v] > 0) ok = false;            // a decision node above the cut: not handled by the tiled path
@@ -692,12 +694,12 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
     RLP_CUDA(ts.m_ridx.upload(ridx, stream));
     RLP_CUDA(ts.portal_p1.alloc((size_t)portal_len)); RLP_CUDA(ts.portal_p2.alloc((size_t)portal_len));
     RLP_CUDA(ts.portal_v1.alloc((size_t)portal_len)); RLP_CUDA(ts.portal_v2.alloc(zs ? 0 : (size_t)portal_len));
-    if (portal_len > 0) {
+    if (portal_len > 0 && !rlp::g_dry_run) {
         unsigned g = (unsigned)((portal_len + 255) / 256);
         k_fill<<<g, 256, 0, stream>>>(ts.portal_p1.p, portal_len, 1.0); RLP_LAUNCH_CHECK();
         k_fill<<<g, 256, 0, stream>>>(ts.portal_p2.p, portal_len, 1.0); RLP_LAUNCH_CHECK();
     }
-    RLP_CUDA(cudaStreamSynchronize(stream));
+    RLP_CUDA(rlp::sync_stream(stream));
     // ---- shape-specialised kernels (jit.cu): all classes or none ------------------------------------------------
     ts.jit.clear();
     if (P > 0 && tmpl.size() <= 8) {
@@ -710,7 +712,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
             std::string log;
             int rc = jit_micro_kernel(tmpl[c], zs, &jc->lib, &jc->kernel, &log);
             if (rc) return rc;
-            if (!jc->kernel) { all = false; break; }
+            if (!jc->kernel) { all = false; if (!rlp::g_dry_run) break; else continue; }
             if (tmpl.size() > 1) {
                 jc->count = (int)members[c].size();
                 RLP_CUDA(jc->inst.upload(members[c], stream));
@@ -720,7 +722,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
             ts.jit.push_back(std::move(jc));
         }
         if (!all) ts.jit.clear();
-        RLP_CUDA(cudaStreamSynchronize(stream));
+        RLP_CUDA(rlp::sync_stream(stream));
     }
     // ---- information sets by where their nodes live: A = only inside micro subtrees, B = the rest ----------------
     {
@@ -733,11 +735,11 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
         ts.acc_b_count = (int)lb.size();
         RLP_CUDA(ts.acc_list_a.upload(la, stream));
         RLP_CUDA(ts.acc_list_b.upload(lb, stream));
-        RLP_CUDA(cudaStreamSynchronize(stream));
+        RLP_CUDA(rlp::sync_stream(stream));
     }
     // ---- upper tiles of ONE shape: straight-line kernels, one thread per tile ---------------------------------------
     ts.upper_jit.reset();
-    if (T > 0 && max_nodes <= 640 && !ts.jit.empty()) {
+    if (T > 0 && max_nodes <= 640 && (!ts.jit.empty() || rlp::g_dry_run)) {
         UpperShape sh;
         std::vector<std::vector<int32_t>> locals(T);
         bool same = true;
@@ -845,7 +847,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
                 RLP_CUDA(uj->slot_o.upload(uso, stream)); RLP_CUDA(uj->pcs.upload(upc, stream));
                 RLP_CUDA(uj->cprob.upload(ucp, stream)); RLP_CUDA(uj->pay1.upload(up1, stream));
                 RLP_CUDA(uj->pay2.upload(up2, stream)); RLP_CUDA(uj->poff.upload(upo, stream));
-                RLP_CUDA(cudaStreamSynchronize(stream));
+                RLP_CUDA(rlp::sync_stream(stream));
                 ts.upper_jit = std::move(uj);
             }
         }

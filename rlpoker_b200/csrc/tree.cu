@@ -10,6 +10,7 @@
 namespace rlp {
 thread_local char g_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
+thread_local bool g_dry_run = false;
 
 static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
@@ -206,7 +207,7 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
     if (!zs) {
         std::vector<double> p2(d->u2, d->u2 + N);
         RLP_CUDA(t->pay2.upload(p2, stream));
-        RLP_CUDA(cudaStreamSynchronize(stream));
+        RLP_CUDA(rlp::sync_stream(stream));
     }
     RLP_CUDA(t->koff_col.upload(koff_col, stream));
     RLP_CUDA(t->koff_iset.upload(koff_iset, stream));
@@ -217,7 +218,7 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
     RLP_CUDA(t->iset_node_off.upload(node_off, stream));
     RLP_CUDA(t->iset_nodes.upload(nodes, stream));
     RLP_CUDA(t->d_canon_of_col.upload(t->canon_of_col, stream));
-    RLP_CUDA(cudaStreamSynchronize(stream));     // host vectors die at scope exit
+    RLP_CUDA(rlp::sync_stream(stream));     // host vectors die at scope exit
     {
         const char *no_tiles = getenv("RLP_NO_TILES");
         if (!(no_tiles && no_tiles[0] == '1')) {
@@ -226,5 +227,25 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
         }
     }
     *out = t.release();
+    return RLP_OK;
+}
+
+// Host-only planning: everything rlp_tree_upload derives (validation, information-set layout, two-tier tiling, shape
+// classes, generated kernel sources compiled with NVRTC) without a GPU.  Lets the CPU test-suite cover the host logic.
+namespace rlp { extern thread_local int g_jit_compiled, g_jit_failed; }
+extern "C" int rlp_tree_plan(const rlp_tree_desc *d, int64_t *stats16) {
+    if (!d || !stats16) return fail(RLP_ERR_INVALID, "null argument");
+    rlp::g_dry_run = true;
+    rlp::g_jit_compiled = rlp::g_jit_failed = 0;
+    rlp_tree *t = nullptr;
+    int rc = rlp_tree_upload(d, nullptr, &t);
+    rlp::g_dry_run = false;
+    if (rc) return rc;
+    const TileSet &ts = t->tiles;
+    int64_t v[16] = {ts.enabled ? 1 : 0, ts.num_tiles, ts.num_micro, ts.num_classes, ts.micro_nodes, ts.micro_nt,
+                     ts.micro_term, ts.acc_a_count, ts.acc_b_count, ts.max_nodes, ts.max_nt, (int64_t)ts.smem_bytes,
+                     rlp::g_jit_compiled, rlp::g_jit_failed, t->Kmax, t->zero_sum ? 1 : 0};
+    for (int k = 0; k < 16; ++k) stats16[k] = v[k];
+    delete t;
     return RLP_OK;
 }

@@ -29,6 +29,30 @@ def _stream_ptr(stream):
     return C.c_void_p(int(stream))
 
 
+def _tree_desc(ft):
+    keep = [np.ascontiguousarray(ft.first_child, np.int32), np.ascontiguousarray(ft.player, np.int8),
+            np.ascontiguousarray(ft.infoset, np.int32), np.ascontiguousarray(ft.cprob, np.float64),
+            np.ascontiguousarray(ft.u1, np.float64), np.ascontiguousarray(ft.u2, np.float64),
+            np.ascontiguousarray(ft.act_off, np.int64), np.ascontiguousarray(ft.level_off, np.int64)]
+    desc = _lib.TreeDesc(
+        num_nodes=ft.num_nodes, num_infosets=ft.num_infosets, num_levels=ft.num_levels,
+        first_child=ptr(keep[0], _lib._i32p), player=ptr(keep[1], _lib._i8p), infoset=ptr(keep[2], _lib._i32p),
+        cprob=ptr(keep[3], _lib._dp), u1=ptr(keep[4], _lib._dp), u2=ptr(keep[5], _lib._dp),
+        act_off=ptr(keep[6], _lib._i64p), level_off=ptr(keep[7], _lib._i64p))
+    return desc, keep
+
+
+def plan_tree(flat_tree):
+    """Host-only dry run of the device layout (rlp_tree_plan): works without a GPU."""
+    desc, keep = _tree_desc(flat_tree)
+    out = np.zeros(16, np.int64)
+    check(_lib.load().rlp_tree_plan(C.byref(desc), ptr(out, _lib._i64p)))
+    names = ['tiled', 'upper_tiles', 'micro_subtrees', 'micro_shapes', 'micro_nodes', 'micro_decisions', 'micro_leaves',
+             'infosets_micro_only', 'infosets_upper', 'tile_nodes', 'tile_nonterminals', 'tile_smem', 'kernels_compiled',
+             'kernels_failed', 'largest_infoset', 'zero_sum']
+    return dict(zip(names, (int(x) for x in out)))
+
+
 class DeviceTree:
     def __init__(self, flat_tree, stream=None):
         _lib.require_device()
