@@ -138,8 +138,45 @@ BrView make_view(rlp_cfr *c, const double *sigma_int, int responder) {
 namespace rlp {
 int permute(rlp_tree *t, const double *src, double *dst, int to_internal, cudaStream_t s);
 
-// value of the best response of `player` against sigma_int (internal pair order) -> *value_dev
+static int enqueue_best_response(rlp_cfr *c, const double *sigma_int, int player, cudaStream_t s);
+
+// value of the best response of `player` against sigma_int (internal pair order) -> *value_dev.
+// The ~4 L launches are captured once per (strategy buffer, responder) and replayed as a CUDA graph.
 int launch_best_response(rlp_cfr *c, const double *sigma_int, int player, double *value_dev, cudaStream_t s) {
+    rlp_cfr::BrGraph *hit = nullptr;
+    for (auto &b : c->br_graphs) if (b.sigma == sigma_int && b.player == player) hit = &b;
+    if (!hit) {
+        cudaStream_t cap;
+        RLP_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        uint64_t before = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        int rc = e == cudaSuccess ? enqueue_best_response(c, sigma_int, player, cap) : RLP_ERR_CUDA;
+        int kernels = (int)(g_launches.load() - before);
+        if (e == cudaSuccess) e = cudaStreamEndCapture(cap, &graph);
+        g_launches.store(before);
+        cudaStreamDestroy(cap);
+        if (rc == RLP_OK && e == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+            c->br_graphs.push_back({sigma_int, player, exec, graph, kernels});
+            hit = &c->br_graphs.back();
+        } else {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+        }
+    }
+    if (hit) {
+        RLP_CUDA(cudaGraphLaunch(hit->exec, s));
+        g_launches.fetch_add(hit->kernels, std::memory_order_relaxed);
+    } else {
+        int rc = enqueue_best_response(c, sigma_int, player, s);
+        if (rc) return rc;
+    }
+    RLP_CUDA(cudaMemcpyAsync(value_dev, c->vbr.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return RLP_OK;
+}
+
+static int enqueue_best_response(rlp_cfr *c, const double *sigma_int, int player, cudaStream_t s) {
     rlp_tree *t = c->tree;
     BrView v = make_view(c, sigma_int, player);
     // pc[0] is 1.0 and never overwritten (rlp_cfr_create); a single terminal root is degenerate
@@ -157,7 +194,6 @@ int launch_best_response(rlp_cfr *c, const double *sigma_int, int player, double
                                                     c->contrib_r.p, c->vbr.p, c->astar.p);
         RLP_LAUNCH_CHECK();
     }
-    RLP_CUDA(cudaMemcpyAsync(value_dev, c->vbr.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
     return RLP_OK;
 }
 }  // namespace rlp
@@ -188,16 +224,10 @@ extern "C" int rlp_cfr_exploitability(rlp_cfr *c, int which, double *out3, void 
     return RLP_OK;
 }
 
-// Stand-alone entry points keep a scratch solver per tree (allocated on first use).
-struct rlp_tree_scratch { rlp_cfr *c = nullptr; };
+// Stand-alone entry points use a scratch solver owned by the tree (allocated on first use, freed with the tree).
 static rlp_cfr *scratch_solver(rlp_tree *t, void *stream_) {
-    // stored in a side table keyed by tree pointer; trees are few
-    static thread_local std::vector<std::pair<rlp_tree *, rlp_cfr *>> table;
-    for (auto &e : table) if (e.first == t) return e.second;
-    rlp_cfr *c = nullptr;
-    if (rlp_cfr_create(t, stream_, &c) != RLP_OK) return nullptr;
-    table.emplace_back(t, c);
-    return c;
+    if (!t->scratch && rlp_cfr_create(t, stream_, &t->scratch) != RLP_OK) t->scratch = nullptr;
+    return t->scratch;
 }
 
 extern "C" int rlp_best_response(rlp_tree *t, const double *sigma, int player, double *value_out,

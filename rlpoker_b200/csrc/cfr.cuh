@@ -51,6 +51,9 @@ struct rlp_cfr {
     int graph_kernels = 0;
     // side stream + events for the two-branch iteration pipeline (accumulate of the micro-only information sets
     // overlaps the upper-tile kernels)
+    // best-response sweeps captured as CUDA graphs, keyed by (strategy buffer, responder)
+    struct BrGraph { const double *sigma; int player; cudaGraphExec_t exec; cudaGraph_t graph; int kernels; };
+    std::vector<BrGraph> br_graphs;
     void *nccl_comm = nullptr;               // ncclComm_t of the deal-sharded solve (comm.cu)
     int nccl_ranks = 1;
     cudaStream_t side = nullptr;
@@ -58,6 +61,7 @@ struct rlp_cfr {
     ~rlp_cfr() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
+        for (auto &b : br_graphs) { if (b.exec) cudaGraphExecDestroy(b.exec); if (b.graph) cudaGraphDestroy(b.graph); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (side) cudaStreamDestroy(side);

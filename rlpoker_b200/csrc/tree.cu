@@ -59,7 +59,12 @@ extern "C" int rlp_device_count(void) {
     return n;
 }
 
-extern "C" void rlp_tree_free(rlp_tree *t) { delete t; }
+extern "C" void rlp_cfr_free(rlp_cfr *c);
+extern "C" void rlp_tree_free(rlp_tree *t) {
+    if (!t) return;
+    if (t->scratch) rlp_cfr_free(t->scratch);
+    delete t;
+}
 extern "C" int64_t rlp_tree_bytes(const rlp_tree *t) { return t ? t->bytes() : 0; }
 
 extern "C" int64_t rlp_tree_stat(const rlp_tree *t, int which) {

@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "tiles.cuh"
 
+struct rlp_cfr;
+
 struct rlp_tree {
     int64_t N = 0;
     int32_t I = 0;
@@ -45,6 +47,7 @@ struct rlp_tree {
     rlp::DevBuf<int64_t> iset_node_off;           // [I+1] internal order
     rlp::DevBuf<int32_t> iset_nodes;              // [ND]
     rlp::DevBuf<int64_t> d_canon_of_col;          // [Q]
+    rlp_cfr *scratch = nullptr;                   // solver used by the stand-alone entry points (rlp_best_response ...)
     TileSet tiles;                                // subtree tiles for the shared-memory sweep (may be disabled)
 
     int64_t bytes() const;

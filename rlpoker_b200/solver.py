@@ -102,8 +102,10 @@ class DeviceTree:
         return float(out[0]), float(out[1])
 
     def close(self):
-        # scratch solvers created by rlp_best_response keep a pointer to the tree; trees are long-lived
-        self.handle = None
+        """Free the device copy (solvers created on this tree must be gone first)."""
+        h, self.handle = self.handle, None
+        if h:
+            _lib.load().rlp_tree_free(h)
 
 
 def device_tree(game_or_flat, stream=None):
@@ -127,7 +129,7 @@ def device_tree(game_or_flat, stream=None):
 
 class DeviceCFR:
     def __init__(self, tree, stream=None):
-        self.tree = tree
+        self.tree = tree            # keeps the tree (and its device memory) alive as long as the solver
         self.handle = C.c_void_p()
         check(_lib.load().rlp_cfr_create(tree.handle, _stream_ptr(stream), C.byref(self.handle)))
         self.t = 0

@@ -60,3 +60,23 @@ print('fallback ok')
     env = dict(os.environ, RLP_NO_TILES='1')
     out = subprocess.check_output([sys.executable, '-c', code], env=env, text=True)
     assert 'fallback ok' in out
+
+
+def test_interpreter_kernels_path():
+    """RLP_NO_JIT=1: the hand-written interpreter kernels (k_micro, k_tile_sweep) instead of the NVRTC ones."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import make_game, oracle_tree
+from oracle import oracle as orc
+from rlpoker_b200.solver import DeviceCFR, device_tree
+for name in ('leduc3', 'ocp4', 'rps'):
+    o = orc.Oracle(oracle_tree(name)); s = DeviceCFR(device_tree(make_game(name)))
+    assert s.tree.layout['jit_shapes'] == 0 and s.tree.layout['upper_jit'] == 0 and s.tree.layout['tiled'] == 1
+    o.vanilla_levels(23); s.vanilla(23)
+    assert np.array_equal(s.regrets, o.R) and np.array_equal(s.strategy_sum, o.S) and np.array_equal(s.sigma, o.sigma)
+print('interpreter ok')
+''' % (ROOT, os.path.join(ROOT, 'tests'))
+    env = dict(os.environ, RLP_NO_JIT='1')
+    out = subprocess.check_output([sys.executable, '-c', code], env=env, text=True)
+    assert 'interpreter ok' in out
