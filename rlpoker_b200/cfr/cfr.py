@@ -20,7 +20,7 @@ import numpy as np
 
 from rlpoker_b200 import _lib
 from rlpoker_b200._lib import RLP_AVERAGE, RLP_CHANCE_SAMPLED, RLP_SIGMA, RLP_STRAT_SUM
-from rlpoker_b200.experiment import Experiment, StrategySaver
+from rlpoker_b200.experiment import Experiment, SolverCheckpoint, StrategySaver
 from rlpoker_b200.extensive_game import ActionFloat, Strategy
 from rlpoker_b200.flatten import array_to_strategy_dict, flatten, postorder_infoset_order
 from rlpoker_b200.solver import DeviceCFR, device_tree
@@ -146,7 +146,9 @@ def cfr(*args, **kwargs):
     Extra keyword arguments (all optional): ``seed`` (Philox seed for chance sampling; default drawn from
     numpy's global RNG so ``np.random.seed`` makes runs repeatable), ``lanes`` (sampled traversal pairs per
     iteration), ``immediate_regret`` (default True: maintain and report cfr_metrics' immediate regret),
-    ``keep_strategies`` (byte budget of the returned per-iteration history, default 1 GiB), ``verbose``.
+    ``keep_strategies`` (byte budget of the returned per-iteration history, default 1 GiB), ``verbose``,
+    ``checkpoint`` (save the solver state into the experiment directory at every evaluation) and ``resume`` (continue
+    from that state; ``num_iters`` stays the total iteration count).
     """
     bound, extra = _unpack(args, kwargs)
     experiment, game = bound['experiment'], bound['game']
@@ -157,13 +159,18 @@ def cfr(*args, **kwargs):
     want_imm = bool(extra.pop('immediate_regret', True))
     keep = extra.pop('keep_strategies', 1 << 30)
     verbose = bool(extra.pop('verbose', True))
+    checkpoint = bool(extra.pop('checkpoint', False))
+    resume = bool(extra.pop('resume', False))
     if extra:
         raise TypeError("cfr() got unexpected keyword arguments %s" % sorted(extra))
-    if sampling and seed is None:
-        seed = int(np.random.randint(0, 2 ** 31 - 1))
-
     ft = flatten(game)
     solver = DeviceCFR(device_tree(game))
+    ckpt = SolverCheckpoint(experiment) if experiment is not None and (checkpoint or resume) else None
+    if resume and ckpt is not None and ckpt.exists():
+        saved_seed, _ = ckpt.load(solver)
+        seed = saved_seed if seed is None else seed
+    if sampling and seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
     saver = CFRStrategySaver(experiment=experiment) if experiment is not None else None
     order = postorder_infoset_order(ft) if want_imm else None
     history = StrategyHistory(ft, limit_bytes=int(keep) if keep else 0)
@@ -184,7 +191,8 @@ def cfr(*args, **kwargs):
         return DeviceStrategy(ft, solver.read(RLP_AVERAGE), present, plain_dicts=True)
 
     start = time.time()
-    t = 0
+    t = solver.t
+    history._count = t                         # iterations before a resume point are not part of the history
     while t < num_iters:
         n = 1 if every_iter else min(num_iters - t, 10 - t % 10 if t % 10 else 1)
         advance(n)
@@ -218,6 +226,8 @@ def cfr(*args, **kwargs):
             if saver is not None:
                 average_strategy = current_average()
                 saver.save_best_strategy(average_strategy, t_last, exploitability)
+            if checkpoint and ckpt is not None:
+                ckpt.save(solver, seed=seed, use_chance_sampling=sampling, linear_weight=linear_weight)
         t += n
     if num_iters > 0:
         average_strategy = current_average()

@@ -135,3 +135,51 @@ def test_average_strategy_object_and_metrics(golden):
     order = flat.postorder_infoset_order(t)
     want = [o2.immediate_regret_step(sigma, 0, order), o2.immediate_regret_step(o.uniform(), 1, order)]
     assert series == want and imm == want[-1]
+
+
+def test_flat_game_drop_in(golden):
+    """A natively generated Leduc (no node objects) through the same driver, keys rebuilt from the arrays."""
+    from rlpoker_b200.cfr.cfr import cfr
+    from rlpoker_b200.best_response import compute_exploitability
+    from rlpoker_b200.games.card import Card
+    from rlpoker_b200.games.leduc_native import create_leduc
+    want = golden['cfr_driver_leduc3']
+    game = create_leduc(3)
+    strategy, expl, _ = cfr(game, num_iters=11, use_chance_sampling=False, verbose=False, immediate_regret=False,
+                            keep_strategies=0)
+    assert abs(expl[-1][1] - want['exploitabilities'][-1][1]) < 1e-12
+    key = (Card(0, 0), -1, 1, 1, Card(1, 0), 1, 2, 2)
+    assert {str(a): p for a, p in strategy[key].items()} == want['sample_entry']['value']
+    assert abs(compute_exploitability(game, strategy) - expl[-1][1]) < 1e-12
+
+
+def test_checkpoint_and_resume(tmp_path):
+    from rlpoker_b200.cfr.cfr import cfr
+    from rlpoker_b200.experiment import Experiment, SolverCheckpoint
+    game = make_game('leduc2')
+    full, _, _ = cfr(Experiment('full', base_save_path=str(tmp_path)), game, num_iters=41, use_chance_sampling=False,
+                     verbose=False, immediate_regret=False, keep_strategies=0)
+    exp = Experiment('parts', base_save_path=str(tmp_path))
+    cfr(exp, game, num_iters=21, use_chance_sampling=False, verbose=False, immediate_regret=False, keep_strategies=0,
+        checkpoint=True)
+    assert SolverCheckpoint(exp).exists()
+    resumed, expl, hist = cfr(exp, game, num_iters=41, use_chance_sampling=False, verbose=False, immediate_regret=False,
+                              keep_strategies=0, resume=True)
+    assert np.array_equal(resumed.sigma_array, full.sigma_array)          # bit-identical continuation
+    assert [t for t, _ in expl] == [30, 40] and len(hist) == 41
+
+
+def test_command_line_front_end(tmp_path):
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.check_output(
+        [sys.executable, os.path.join(ROOT, 'examples', 'cfr.py'), '--exp_name', 'cli', '--cfr_algorithm', 'vanilla',
+         '--num_iters', '11', '--game_specifier', 'Leduc:values_2:suits_2'], cwd=str(tmp_path), text=True)
+    assert 't: 10, nodes touched:' in out and 'Immediate regret:' in out and 'Exploitability of saved strategy:' in out
+    assert os.path.exists(os.path.join(str(tmp_path), 'experiments', 'cli', 'best_strategy.pkl'))
+    assert os.path.exists(os.path.join(str(tmp_path), 'experiments', 'cli', 'metrics.jsonl'))
+    out = subprocess.check_output(
+        [sys.executable, os.path.join(ROOT, 'examples', 'cfr.py'), '--exp_name', 'cli2', '--cfr_algorithm', 'external',
+         '--num_iters', '201', '--lanes', '64', '--seed', '1', '--no_immediate_regret'], cwd=str(tmp_path), text=True)
+    assert 't: 200, nodes touched:' in out
