@@ -258,6 +258,38 @@ k_local_delta(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, const
     }
 }
 
+// Four lanes per information set (<= 4 actions): the deltas of one action per lane, loads batched like
+// k_accumulate_rm4.  delta[q] (regret) and delta[Q + q] (strategy sum) in canonical pair order.
+__global__ void __launch_bounds__(kBlock)
+k_local_delta4(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
+               const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
+               const int64_t *__restrict__ canon_of_col, const double *__restrict__ contrib_r,
+               const double *__restrict__ contrib_o, const double *__restrict__ sigma, double *delta) {
+    const int gid = blockIdx.x * kBlock + threadIdx.x;
+    const int s = gid >> 2, a = gid & 3;
+    if (s >= I) return;
+    const int size = iset_size[s];
+    const int64_t c0 = col_off[s];
+    const int na = (int)(col_off[s + 1] - c0);
+    if (a >= na) return;
+    const double sg = sigma[c0 + a];
+    const double *cr = contrib_r + c0 + a;
+    const double *co = contrib_o + s;
+    double r = 0.0, sa = 0.0;
+    int k = 0;
+    for (; k + 8 <= size; k += 8) {
+        double x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { x[j] = cr[koff_col[k + j]]; y[j] = co[koff_iset[k + j]]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { r = r + x[j]; sa = sa + y[j] * sg; }
+    }
+    for (; k < size; ++k) { r = r + cr[koff_col[k]]; sa = sa + co[koff_iset[k]] * sg; }
+    const int64_t q = canon_of_col[c0 + a];
+    delta[q] = r;
+    delta[Q + q] = sa;
+}
+
 __global__ void __launch_bounds__(kBlock)
 k_apply_delta(int32_t I, int64_t Q, const int64_t *__restrict__ col_off, const int64_t *__restrict__ canon_of_col,
               const double *__restrict__ delta, double *R, double *S, double *sigma, uint8_t *flags, IterState *iter) {
@@ -581,9 +613,14 @@ extern "C" int rlp_cfr_local_sweep(rlp_cfr *c, int64_t t_iter, int linear_weight
     int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n) : enqueue_sweep<false>(c, s, &n);
     if (rc) return rc;
     if (t->I > 0) {
-        k_local_delta<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->Q, t->iset_size.p, t->col_off.p, t->koff_col.p,
-                                                      t->koff_iset.p, t->d_canon_of_col.p, c->contrib_r.p,
-                                                      c->contrib_o.p, c->sigma.p, c->delta.p);
+        if (t->max_act <= 4)
+            k_local_delta4<<<grid_for(4 * (int64_t)t->I), kBlock, 0, s>>>(t->I, t->Q, t->iset_size.p, t->col_off.p,
+                                                                     t->koff_col.p, t->koff_iset.p, t->d_canon_of_col.p,
+                                                                     c->contrib_r.p, c->contrib_o.p, c->sigma.p, c->delta.p);
+        else
+            k_local_delta<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->Q, t->iset_size.p, t->col_off.p, t->koff_col.p,
+                                                          t->koff_iset.p, t->d_canon_of_col.p, c->contrib_r.p,
+                                                          c->contrib_o.p, c->sigma.p, c->delta.p);
         RLP_LAUNCH_CHECK();
     }
     return RLP_OK;

@@ -54,6 +54,9 @@ struct rlp_cfr {
     // best-response sweeps captured as CUDA graphs, keyed by (strategy buffer, responder)
     struct BrGraph { const double *sigma; int player; cudaGraphExec_t exec; cudaGraph_t graph; int kernels; };
     std::vector<BrGraph> br_graphs;
+    cudaGraph_t shard_graph = nullptr;          // 10 iterations of sweep -> ncclAllReduce -> apply (comm.cu)
+    cudaGraphExec_t shard_exec = nullptr;
+    int shard_graph_kernels = 0;
     void *nccl_comm = nullptr;               // ncclComm_t of the deal-sharded solve (comm.cu)
     int nccl_ranks = 1;
     cudaStream_t side = nullptr;
@@ -61,6 +64,8 @@ struct rlp_cfr {
     ~rlp_cfr() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
+        if (shard_exec) cudaGraphExecDestroy(shard_exec);
+        if (shard_graph) cudaGraphDestroy(shard_graph);
         for (auto &b : br_graphs) { if (b.exec) cudaGraphExecDestroy(b.exec); if (b.graph) cudaGraphDestroy(b.graph); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);

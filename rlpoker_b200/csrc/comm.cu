@@ -70,19 +70,67 @@ extern "C" void rlp_comm_destroy(rlp_cfr *c) {
     if (c) c->nccl_comm = nullptr;
 }
 
+namespace {
+constexpr int kShardGraphIters = 10;
+
+int one_sharded_iteration(rlp_cfr *c, int64_t t, int linear_weight, cudaStream_t s) {
+    const size_t count = 2 * (size_t)c->tree->Q;
+    int rc = rlp_cfr_local_sweep(c, t, linear_weight, (void *)s);
+    if (rc) return rc;
+    if (c->nccl_ranks > 1) {
+        int r = g_nccl.all_reduce(c->delta.p, c->delta.p, count, kNcclDouble, kNcclSum, (NcclComm)c->nccl_comm, s);
+        if (r != 0) return fail(RLP_ERR_CUDA, "ncclAllReduce: %s", g_nccl.error_string(r));
+    }
+    return rlp_cfr_apply_delta(c, (void *)s);
+}
+
+// Capture kShardGraphIters iterations (NCCL collectives are capturable) so that the loop is not paced by host
+// launches.  Every rank captures the same sequence.  Opt-in (RLP_SHARD_CGRAPH=1) until validated on 8 GPUs.
+int ensure_shard_graph(rlp_cfr *c) {
+    if (c->shard_exec) return RLP_OK;
+    cudaStream_t cap;
+    RLP_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    uint64_t before = rlp::g_launches.load();
+    uint64_t touched = c->nodes_touched;
+    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    int rc = e == cudaSuccess ? RLP_OK : RLP_ERR_CUDA;
+    for (int u = 0; u < kShardGraphIters && rc == RLP_OK; ++u) rc = one_sharded_iteration(c, -1, 0, cap);
+    int kernels = (int)(rlp::g_launches.load() - before);
+    if (e == cudaSuccess) e = cudaStreamEndCapture(cap, &c->shard_graph);
+    rlp::g_launches.store(before);
+    c->nodes_touched = touched;                      // capture records, it does not run
+    cudaStreamDestroy(cap);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(RLP_ERR_CUDA, "capture of the sharded loop: %s", cudaGetErrorString(e));
+    RLP_CUDA(cudaGraphInstantiate(&c->shard_exec, c->shard_graph, 0));
+    c->shard_graph_kernels = kernels;
+    return RLP_OK;
+}
+}  // namespace
+
 extern "C" int rlp_cfr_sharded_iters(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, void *stream_) {
     if (!c || n_iters < 0) return fail(RLP_ERR_INVALID, "bad argument");
     if (!c->nccl_comm) return fail(RLP_ERR_INVALID, "rlp_comm_init has not been called on this solver");
     cudaStream_t s = (cudaStream_t)stream_;
-    const size_t count = 2 * (size_t)c->tree->Q;
-    for (int64_t it = 0; it < n_iters; ++it) {
-        int rc = rlp_cfr_local_sweep(c, it == 0 ? t0 : -1, linear_weight, stream_);
+    const char *env = getenv("RLP_SHARD_CGRAPH");
+    const bool use_graph = env && env[0] == '1';
+    int64_t done = 0;
+    if (n_iters > 0) {                                // the first iteration is eager: it sets counter + weighting flag
+        int rc = one_sharded_iteration(c, t0, linear_weight, s);
         if (rc) return rc;
-        if (c->nccl_ranks > 1) {
-            int r = g_nccl.all_reduce(c->delta.p, c->delta.p, count, kNcclDouble, kNcclSum, (NcclComm)c->nccl_comm, s);
-            if (r != 0) return fail(RLP_ERR_CUDA, "ncclAllReduce: %s", g_nccl.error_string(r));
+        done = 1;
+    }
+    if (use_graph && n_iters - done >= kShardGraphIters) {
+        int rc = ensure_shard_graph(c);
+        if (rc) return rc;
+        for (; n_iters - done >= kShardGraphIters; done += kShardGraphIters) {
+            RLP_CUDA(cudaGraphLaunch(c->shard_exec, s));
+            rlp::g_launches.fetch_add(c->shard_graph_kernels, std::memory_order_relaxed);
+            c->nodes_touched += 2ull * (uint64_t)c->tree->N * kShardGraphIters;
         }
-        rc = rlp_cfr_apply_delta(c, stream_);
+    }
+    for (; done < n_iters; ++done) {
+        int rc = one_sharded_iteration(c, -1, linear_weight, s);
         if (rc) return rc;
     }
     return RLP_OK;

@@ -80,3 +80,28 @@ def test_world_one_native_nccl_loop():
     b.vanilla(5, linear_weight=True)
     np.testing.assert_allclose(a.solver.regrets, b.regrets, rtol=0, atol=1e-9)
     np.testing.assert_allclose(a.solver.strategy_sum, b.strategy_sum, rtol=0, atol=1e-9)
+
+
+def test_world_one_native_loop_as_cuda_graph():
+    """RLP_SHARD_CGRAPH=1: the C loop (sweep, ncclAllReduce, apply) captured as a CUDA graph of 10 iterations."""
+    import os, subprocess, sys
+    from conftest import ROOT
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import make_game
+from rlpoker_b200.flatten import flatten
+from rlpoker_b200.sharding import ShardedCFR
+from rlpoker_b200.solver import DeviceCFR, device_tree
+ft = flatten(make_game('leduc3'))
+a = ShardedCFR(ft, 0, 1)
+assert a._native
+a.iterate(34); a.iterate(12, linear_weight=True)
+b = DeviceCFR(device_tree(make_game('leduc3')))
+b.vanilla(34); b.vanilla(12, linear_weight=True)
+np.testing.assert_allclose(a.solver.regrets, b.regrets, rtol=0, atol=1e-9)
+np.testing.assert_allclose(a.solver.strategy_sum, b.strategy_sum, rtol=0, atol=1e-9)
+print('cgraph ok')
+''' % (ROOT, os.path.join(ROOT, 'tests'))
+    out = subprocess.check_output([sys.executable, '-c', code], env=dict(os.environ, RLP_SHARD_CGRAPH='1'), text=True)
+    assert 'cgraph ok' in out
