@@ -486,6 +486,7 @@ extern "C" int rlp_cfr_reset(rlp_cfr *c, void *stream_) {
     c->nodes_touched = 0;
     c->touched_dirty = false;
     c->external_state = false;
+    c->dev_t = -1;
     return RLP_OK;
 }
 
@@ -573,6 +574,7 @@ extern "C" int rlp_cfr_vanilla_iters(rlp_cfr *c, int64_t t0, int64_t n_iters, in
     cudaStream_t s = (cudaStream_t)stream_;
     k_set_iter<<<1, 1, 0, s>>>(c->iter.p, (long long)t0, linear_weight);
     RLP_LAUNCH_CHECK();
+    c->dev_t = -1;
     int64_t left = n_iters;
     if (left >= kGraphUnroll) {
         int rc = ensure_graph(c);
@@ -608,6 +610,7 @@ extern "C" int rlp_cfr_local_sweep(rlp_cfr *c, int64_t t_iter, int linear_weight
     if (t_iter >= 0) {          // t < 0: keep the device-side counter (lets the caller capture the call in a CUDA graph)
         k_set_iter<<<1, 1, 0, s>>>(c->iter.p, (long long)t_iter, linear_weight);
         RLP_LAUNCH_CHECK();
+        c->dev_t = -1;          // callers that track the counter (comm.cu) set it again themselves
     }
     int n = 0;
     int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n) : enqueue_sweep<false>(c, s, &n);

@@ -54,6 +54,8 @@ struct rlp_cfr {
     // best-response sweeps captured as CUDA graphs, keyed by (strategy buffer, responder)
     struct BrGraph { const double *sigma; int player; cudaGraphExec_t exec; cudaGraph_t graph; int kernels; };
     std::vector<BrGraph> br_graphs;
+    long long dev_t = -1;                       // iteration counter / weighting flag known to be on the device
+    int dev_linear = -1;                        // (-1: unknown); lets rlp_cfr_sharded_iters skip its eager sync step
     cudaGraph_t shard_graph = nullptr;          // 10 iterations of sweep -> ncclAllReduce -> apply (comm.cu)
     cudaGraphExec_t shard_exec = nullptr;
     int shard_graph_kernels = 0;

@@ -115,7 +115,8 @@ extern "C" int rlp_cfr_sharded_iters(rlp_cfr *c, int64_t t0, int64_t n_iters, in
     const char *env = getenv("RLP_SHARD_CGRAPH");
     const bool use_graph = env && env[0] == '1';
     int64_t done = 0;
-    if (n_iters > 0) {                                // the first iteration is eager: it sets counter + weighting flag
+    const bool in_sync = c->dev_t == (long long)t0 && c->dev_linear == (linear_weight ? 1 : 0);
+    if (n_iters > 0 && !in_sync) {                    // an eager iteration sets counter + weighting flag on the device
         int rc = one_sharded_iteration(c, t0, linear_weight, s);
         if (rc) return rc;
         done = 1;
@@ -133,5 +134,7 @@ extern "C" int rlp_cfr_sharded_iters(rlp_cfr *c, int64_t t0, int64_t n_iters, in
         int rc = one_sharded_iteration(c, -1, linear_weight, s);
         if (rc) return rc;
     }
+    c->dev_t = (long long)(t0 + n_iters);
+    c->dev_linear = linear_weight ? 1 : 0;
     return RLP_OK;
 }

@@ -289,5 +289,6 @@ extern "C" int rlp_cfr_sampled_iters(rlp_cfr *c, int variant, int64_t lanes, uin
         }
     }
     c->touched_dirty = true;
+    c->dev_t = -1;
     return RLP_OK;
 }
