@@ -30,6 +30,7 @@ struct View {
     const int64_t *koff_col, *koff_iset;
     double *pc, *p1, *p2, *val1, *val2, *contrib_r, *contrib_o;
     const IterState *iter;
+    long long ND;       // contrib_r is action-major: [action][ND], indexed like contrib_o
 };
 
 // ---- forward: reach of the children of node i (cfr.py:180,208,217) -----------------------------
@@ -70,12 +71,12 @@ __device__ __forceinline__ void bwd_node(const View &v, int64_t i, double w) {
     double own = pl == 1 ? x1 : x2;
     double vp = pl == 1 ? a1 : (ZS ? -a1 : a2);
     int kk = v.krank[i];
-    double *dst = v.contrib_r + v.koff_col[kk] + v.colbase[i];
+    const long long slot = v.koff_iset[kk] + v.srank[i];
     for (int k = 0; k < n; ++k) {
         double va = pl == 1 ? v.val1[fc + k] : (ZS ? -v.val1[fc + k] : v.val2[fc + k]);
-        dst[k] = w * (va - vp) * opp;                 // weight * (v_a - v) * pi_minus_i
+        v.contrib_r[(long long)k * v.ND + slot] = w * (va - vp) * opp;      // weight * (v_a - v) * pi_minus_i
     }
-    v.contrib_o[v.koff_iset[kk] + v.srank[i]] = w * own;   // (weight * pi_i), times sigma in accumulate
+    v.contrib_o[slot] = w * own;                      // (weight * pi_i), times sigma in accumulate
 }
 
 __device__ __forceinline__ double iter_weight(const IterState *it) { return it->linear ? (double)it->t : 1.0; }
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kBlock)
 k_accumulate_rm(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
                 const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
                 const double *__restrict__ contrib_r, const double *__restrict__ contrib_o, double *R, double *S,
-                double *sigma, uint8_t *flags, IterState *iter, int advance) {
+                double *sigma, uint8_t *flags, IterState *iter, int advance, int64_t ND, double *sigma_am) {
     int s = blockIdx.x * kBlock + threadIdx.x;
     if (s == 0 && advance) iter->t += 1;       // every reader of iter->t ran in an earlier kernel
     if (s >= I) return;
@@ -130,11 +131,11 @@ k_accumulate_rm(int32_t I, const int32_t *__restrict__ iset_size, const int64_t 
         for (int a = 0; a < 4; ++a)
             if (a < na) { r[a] = R[c0 + a]; sa[a] = S[c0 + a]; sg[a] = sigma[c0 + a]; }
         for (int k = 0; k < size; ++k) {
-            const double *cr = contrib_r + koff_col[k] + c0;
-            double wo = contrib_o[koff_iset[k] + s];
+            const int64_t slot = koff_iset[k] + s;
+            double wo = contrib_o[slot];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
-                if (a < na) { r[a] = r[a] + cr[a]; sa[a] = sa[a] + wo * sg[a]; }
+                if (a < na) { r[a] = r[a] + contrib_r[(int64_t)a * ND + slot]; sa[a] = sa[a] + wo * sg[a]; }
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -143,7 +144,7 @@ k_accumulate_rm(int32_t I, const int32_t *__restrict__ iset_size, const int64_t 
         for (int a = 0; a < na; ++a) {
             double r = R[c0 + a], sa = S[c0 + a], sg = sigma[c0 + a];
             for (int k = 0; k < size; ++k) {
-                r = r + contrib_r[koff_col[k] + c0 + a];
+                r = r + contrib_r[(int64_t)a * ND + koff_iset[k] + s];
                 sa = sa + contrib_o[koff_iset[k] + s] * sg;
             }
             R[c0 + a] = r;
@@ -151,6 +152,7 @@ k_accumulate_rm(int32_t I, const int32_t *__restrict__ iset_size, const int64_t 
         }
     }
     rlp::regret_matching(R + c0, na, sigma + c0);
+    for (int a = 0; a < na; ++a) sigma_am[(int64_t)a * I + s] = sigma[c0 + a];
     flags[s] = 1; flags[I + s] = 1; flags[2 * I + s] = 1;
 }
 
@@ -160,7 +162,8 @@ __global__ void __launch_bounds__(kBlock)
 k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
                  const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
                  const double *__restrict__ contrib_r, const double *__restrict__ contrib_o, double *R, double *S,
-                 double *sigma, uint8_t *flags, IterState *iter, int advance, const int *__restrict__ list, int count) {
+                 double *sigma, uint8_t *flags, IterState *iter, int advance, const int *__restrict__ list, int count,
+                 int64_t ND, double *sigma_am) {
     constexpr int kTab = 128;                      // diagonals whose offsets are staged in shared memory
     __shared__ int64_t s_kc[kTab], s_ki[kTab];
     rlp::pdl_launch_dependents();
@@ -191,15 +194,21 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
         // batches of 8 diagonals: 16 independent loads in flight, then the ordered adds
         int k = 0;
         const int fast = size < kTab ? size : kTab;
-        for (; k + 8 <= fast; k += 8) {
+        // batches of 8 diagonals, the last one predicated: all of a batch's loads are in flight before the ordered adds
+        for (; k < fast; k += 8) {
             double x[8], y[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { x[j] = cr[s_kc[k + j]]; y[j] = co[s_ki[k + j]]; }
+            for (int j = 0; j < 8; ++j) {
+                const bool in = k + j < fast;
+                x[j] = in ? cr[s_ki[k + j]] : 0.0;
+                y[j] = in ? co[s_ki[k + j]] : 0.0;
+            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { r = r + x[j]; sa = sa + y[j] * sg; }
+            for (int j = 0; j < 8; ++j)
+                if (k + j < fast) { r = r + x[j]; sa = sa + y[j] * sg; }
         }
-        for (; k < size; ++k) {
-            r = r + cr[koff_col[k]];
+        for (k = fast; k < size; ++k) {
+            r = r + cr[koff_iset[k]];
             sa = sa + co[koff_iset[k]] * sg;
         }
         R[c0 + a] = r;
@@ -232,6 +241,7 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
         out = mine / acc.total();
     }
     sigma[c0 + a] = out;
+    sigma_am[(int64_t)a * I + s] = out;
     if (a == 0) { flags[s] = 1; flags[I + s] = 1; flags[2 * I + s] = 1; }
 }
 
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(kBlock)
 k_local_delta(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
               const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
               const int64_t *__restrict__ canon_of_col, const double *__restrict__ contrib_r,
-              const double *__restrict__ contrib_o, const double *__restrict__ sigma, double *delta) {
+              const double *__restrict__ contrib_o, const double *__restrict__ sigma, double *delta, int64_t ND) {
     int s = blockIdx.x * kBlock + threadIdx.x;
     if (s >= I) return;
     int size = iset_size[s];
@@ -249,7 +259,7 @@ k_local_delta(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, const
     for (int a = 0; a < na; ++a) {
         double r = 0.0, sa = 0.0, sg = sigma[c0 + a];
         for (int k = 0; k < size; ++k) {
-            r = r + contrib_r[koff_col[k] + c0 + a];
+            r = r + contrib_r[(int64_t)a * ND + koff_iset[k] + s];
             sa = sa + contrib_o[koff_iset[k] + s] * sg;
         }
         int64_t q = canon_of_col[c0 + a];
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(kBlock)
 k_local_delta4(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
                const int64_t *__restrict__ koff_col, const int64_t *__restrict__ koff_iset,
                const int64_t *__restrict__ canon_of_col, const double *__restrict__ contrib_r,
-               const double *__restrict__ contrib_o, const double *__restrict__ sigma, double *delta) {
+               const double *__restrict__ contrib_o, const double *__restrict__ sigma, double *delta, int64_t ND) {
     const int gid = blockIdx.x * kBlock + threadIdx.x;
     const int s = gid >> 2, a = gid & 3;
     if (s >= I) return;
@@ -273,18 +283,18 @@ k_local_delta4(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, cons
     const int na = (int)(col_off[s + 1] - c0);
     if (a >= na) return;
     const double sg = sigma[c0 + a];
-    const double *cr = contrib_r + c0 + a;
+    const double *cr = contrib_r + (int64_t)a * ND + s;
     const double *co = contrib_o + s;
     double r = 0.0, sa = 0.0;
     int k = 0;
     for (; k + 8 <= size; k += 8) {
         double x[8], y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { x[j] = cr[koff_col[k + j]]; y[j] = co[koff_iset[k + j]]; }
+        for (int j = 0; j < 8; ++j) { x[j] = cr[koff_iset[k + j]]; y[j] = co[koff_iset[k + j]]; }
 #pragma unroll
         for (int j = 0; j < 8; ++j) { r = r + x[j]; sa = sa + y[j] * sg; }
     }
-    for (; k < size; ++k) { r = r + cr[koff_col[k]]; sa = sa + co[koff_iset[k]] * sg; }
+    for (; k < size; ++k) { r = r + cr[koff_iset[k]]; sa = sa + co[koff_iset[k]] * sg; }
     const int64_t q = canon_of_col[c0 + a];
     delta[q] = r;
     delta[Q + q] = sa;
@@ -292,7 +302,8 @@ k_local_delta4(int32_t I, int64_t Q, const int32_t *__restrict__ iset_size, cons
 
 __global__ void __launch_bounds__(kBlock)
 k_apply_delta(int32_t I, int64_t Q, const int64_t *__restrict__ col_off, const int64_t *__restrict__ canon_of_col,
-              const double *__restrict__ delta, double *R, double *S, double *sigma, uint8_t *flags, IterState *iter) {
+              const double *__restrict__ delta, double *R, double *S, double *sigma, uint8_t *flags, IterState *iter,
+              double *sigma_am) {
     int s = blockIdx.x * kBlock + threadIdx.x;
     if (s == 0) iter->t += 1;
     if (s >= I) return;
@@ -304,6 +315,7 @@ k_apply_delta(int32_t I, int64_t Q, const int64_t *__restrict__ col_off, const i
         S[c0 + a] = S[c0 + a] + delta[Q + q];
     }
     rlp::regret_matching(R + c0, na, sigma + c0);
+    for (int a = 0; a < na; ++a) sigma_am[(int64_t)a * I + s] = sigma[c0 + a];
     flags[s] = 1; flags[I + s] = 1; flags[2 * I + s] = 1;
 }
 
@@ -328,6 +340,16 @@ __global__ void __launch_bounds__(kBlock) k_uniform(int32_t I, const int64_t *__
     for (int a = 0; a < na; ++a) sigma[c0 + a] = 1.0 / (double)na;
 }
 
+// sigma_am[action][set] <- sigma[set][action]
+__global__ void __launch_bounds__(kBlock)
+k_sigma_am(int32_t I, const int64_t *__restrict__ col_off, const double *__restrict__ sigma, double *sigma_am) {
+    int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= I) return;
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    for (int a = 0; a < na; ++a) sigma_am[(int64_t)a * I + s] = sigma[c0 + a];
+}
+
 __global__ void k_set_iter(IterState *it, long long t, int linear) {
     it->t = t;
     it->linear = linear;
@@ -350,6 +372,7 @@ View make_view(rlp_cfr *c) {
     v.koff_col = t->koff_col.p; v.koff_iset = t->koff_iset.p;
     v.pc = c->pc.p; v.p1 = c->p1.p; v.p2 = c->p2.p; v.val1 = c->val1.p; v.val2 = c->val2.p;
     v.contrib_r = c->contrib_r.p; v.contrib_o = c->contrib_o.p; v.iter = c->iter.p;
+    v.ND = t->ND;
     return v;
 }
 
@@ -394,11 +417,12 @@ int enqueue_iteration(rlp_cfr *c, cudaStream_t s, int *count, cudaEvent_t *marks
             RLP_CUDA(rlp::launch_pdl(k_accumulate_rm4, dim3(grid_for(4 * (int64_t)t->I)), dim3(kBlock), 0, s, t->I,
                                      t->iset_size.p, t->col_off.p, t->koff_col.p, t->koff_iset.p, c->contrib_r.p,
                                      c->contrib_o.p, c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, 1,
-                                     (const int *)nullptr, (int)t->I));
+                                     (const int *)nullptr, (int)t->I, (int64_t)t->ND, c->sigma_am.p));
         else
             k_accumulate_rm<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_col.p,
                                                             t->koff_iset.p, c->contrib_r.p, c->contrib_o.p, c->R.p,
-                                                            c->S.p, c->sigma.p, c->flags.p, c->iter.p, 1);
+                                                            c->S.p, c->sigma.p, c->flags.p, c->iter.p, 1, (int64_t)t->ND,
+                                                            c->sigma_am.p);
         RLP_LAUNCH_CHECK(); ++n;
     }
     if (marks) RLP_CUDA(cudaEventRecord(marks[4], s));
@@ -421,7 +445,8 @@ int launch_acc(rlp_cfr *c, cudaStream_t s, const int *list, int count, int advan
     rlp_tree *t = c->tree;
     RLP_CUDA(rlp::launch_pdl(k_accumulate_rm4, dim3(grid_for(4 * (int64_t)count)), dim3(kBlock), 0, s, t->I,
                              t->iset_size.p, t->col_off.p, t->koff_col.p, t->koff_iset.p, c->contrib_r.p, c->contrib_o.p,
-                             c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, advance, list, count));
+                             c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, advance, list, count, (int64_t)t->ND,
+                             c->sigma_am.p));
     rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
     return RLP_OK;
 }
@@ -483,6 +508,7 @@ extern "C" int rlp_cfr_reset(rlp_cfr *c, void *stream_) {
     RLP_CUDA(cudaMemsetAsync(c->flags.p, 0, c->flags.bytes(), s));
     RLP_CUDA(cudaMemsetAsync(c->iter.p, 0, 2 * sizeof(IterState), s));
     if (t->I > 0) { k_uniform<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->sigma.p); RLP_LAUNCH_CHECK(); }
+    c->sigma_am_dirty = true;
     c->nodes_touched = 0;
     c->touched_dirty = false;
     c->external_state = false;
@@ -504,7 +530,11 @@ extern "C" int rlp_cfr_create(rlp_tree *t, void *stream_, rlp_cfr **out) {
     RLP_CUDA(c->pc.alloc(N)); RLP_CUDA(c->p1.alloc(N)); RLP_CUDA(c->p2.alloc(N));
     RLP_CUDA(c->val1.alloc(N)); RLP_CUDA(c->vbr.alloc(N));
     if (!t->zero_sum) RLP_CUDA(c->val2.alloc(N));
-    RLP_CUDA(c->contrib_r.alloc((size_t)t->NC)); RLP_CUDA(c->contrib_o.alloc((size_t)t->ND));
+    // regret contributions are action-major [max_act][ND]; the best-response sweep reuses the buffer with its own
+    // [diagonal][column] indexing (NC entries)
+    RLP_CUDA(c->contrib_r.alloc(std::max((size_t)t->NC, (size_t)t->max_act * (size_t)t->ND)));
+    RLP_CUDA(c->contrib_o.alloc((size_t)t->ND));
+    RLP_CUDA(c->sigma_am.alloc((size_t)std::max(1, t->max_act) * (size_t)t->I));
     RLP_CUDA(c->astar.alloc((size_t)t->I));
     {
         // the side branch (bulk accumulate) yields to the main chain, which is the critical path
@@ -529,6 +559,18 @@ extern "C" int rlp_cfr_create(rlp_tree *t, void *stream_, rlp_cfr **out) {
     *out = c.release();
     return RLP_OK;
 }
+
+namespace rlp {
+// Bring the action-major strategy copy up to date (after a reset, a host write or the sampled variants; the vanilla
+// kernels keep it current themselves).
+int ensure_sigma_am(rlp_cfr *c, cudaStream_t s) {
+    if (!c->sigma_am_dirty) return RLP_OK;
+    rlp_tree *t = c->tree;
+    if (t->I > 0) { k_sigma_am<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->sigma.p, c->sigma_am.p); RLP_LAUNCH_CHECK(); }
+    c->sigma_am_dirty = false;
+    return RLP_OK;
+}
+}  // namespace rlp
 
 static int build_graph(rlp_cfr *c);
 static int ensure_graph(rlp_cfr *c) {
@@ -575,6 +617,7 @@ extern "C" int rlp_cfr_vanilla_iters(rlp_cfr *c, int64_t t0, int64_t n_iters, in
     k_set_iter<<<1, 1, 0, s>>>(c->iter.p, (long long)t0, linear_weight);
     RLP_LAUNCH_CHECK();
     c->dev_t = -1;
+    { int rc = rlp::ensure_sigma_am(c, s); if (rc) return rc; }
     int64_t left = n_iters;
     if (left >= kGraphUnroll) {
         int rc = ensure_graph(c);
@@ -612,6 +655,7 @@ extern "C" int rlp_cfr_local_sweep(rlp_cfr *c, int64_t t_iter, int linear_weight
         RLP_LAUNCH_CHECK();
         c->dev_t = -1;          // callers that track the counter (comm.cu) set it again themselves
     }
+    if (c->sigma_am_dirty) { int rc0 = rlp::ensure_sigma_am(c, s); if (rc0) return rc0; }
     int n = 0;
     int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n) : enqueue_sweep<false>(c, s, &n);
     if (rc) return rc;
@@ -619,11 +663,12 @@ extern "C" int rlp_cfr_local_sweep(rlp_cfr *c, int64_t t_iter, int linear_weight
         if (t->max_act <= 4)
             k_local_delta4<<<grid_for(4 * (int64_t)t->I), kBlock, 0, s>>>(t->I, t->Q, t->iset_size.p, t->col_off.p,
                                                                      t->koff_col.p, t->koff_iset.p, t->d_canon_of_col.p,
-                                                                     c->contrib_r.p, c->contrib_o.p, c->sigma.p, c->delta.p);
+                                                                     c->contrib_r.p, c->contrib_o.p, c->sigma.p, c->delta.p,
+                                                                     (int64_t)t->ND);
         else
             k_local_delta<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->Q, t->iset_size.p, t->col_off.p, t->koff_col.p,
                                                           t->koff_iset.p, t->d_canon_of_col.p, c->contrib_r.p,
-                                                          c->contrib_o.p, c->sigma.p, c->delta.p);
+                                                          c->contrib_o.p, c->sigma.p, c->delta.p, (int64_t)t->ND);
         RLP_LAUNCH_CHECK();
     }
     return RLP_OK;
@@ -637,7 +682,7 @@ extern "C" int rlp_cfr_apply_delta(rlp_cfr *c, void *stream_) {
     rlp_tree *t = c->tree;
     if (t->I > 0) {
         k_apply_delta<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->Q, t->col_off.p, t->d_canon_of_col.p, c->delta.p,
-                                                      c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p);
+                                                      c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, c->sigma_am.p);
         RLP_LAUNCH_CHECK();
     }
     c->nodes_touched += 2ull * (uint64_t)t->N;
@@ -679,6 +724,7 @@ extern "C" int rlp_cfr_write(rlp_cfr *c, int which, const double *src, void *str
     RLP_CUDA(cudaMemcpyAsync(c->tmpQ.p, src, sizeof(double) * (size_t)c->tree->Q, cudaMemcpyHostToDevice, s));
     int rc = rlp::permute(c->tree, c->tmpQ.p, dst, 1, s);
     if (rc) return rc;
+    if (which == RLP_SIGMA) c->sigma_am_dirty = true;
     RLP_CUDA(cudaStreamSynchronize(s));
     return RLP_OK;
 }
@@ -700,8 +746,8 @@ extern "C" int rlp_cfr_read_flags(rlp_cfr *c, uint8_t *dst, void *stream_) {
 namespace {
 __global__ void __launch_bounds__(kBlock)
 k_imm_regret(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
-             const int64_t *__restrict__ koff_col, const double *__restrict__ contrib_r, double *cum, double *per_iset,
-             double inv_steps) {
+             const int64_t *__restrict__ koff_iset, const double *__restrict__ contrib_r, double *cum, double *per_iset,
+             double inv_steps, int64_t ND) {
     int s = blockIdx.x * kBlock + threadIdx.x;
     if (s >= I) return;
     int size = iset_size[s];
@@ -710,7 +756,7 @@ k_imm_regret(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__
     double mx = 0.0;
     for (int a = 0; a < na; ++a) {
         double r = 0.0;
-        for (int k = 0; k < size; ++k) r = r + contrib_r[koff_col[k] + c0 + a];
+        for (int k = 0; k < size; ++k) r = r + contrib_r[(int64_t)a * ND + koff_iset[k] + s];
         double cu = cum[c0 + a] + r;
         cum[c0 + a] = cu;
         mx = (a == 0 || cu > mx) ? cu : mx;
@@ -724,14 +770,15 @@ extern "C" int rlp_cfr_immediate_regret_step(rlp_cfr *c, int64_t step, const int
     cudaStream_t s = (cudaStream_t)stream_;
     rlp_tree *t = c->tree;
     int n = 0;
+    { int rc0 = rlp::ensure_sigma_am(c, s); if (rc0) return rc0; }
     int rc = t->zero_sum ? enqueue_sweep<true>(c, s, &n, c->iter.p + 1) : enqueue_sweep<false>(c, s, &n, c->iter.p + 1);
     if (rc) return rc;
     double inv = 1.0 / (double)(1 + step);
     // per-information-set values land in the (otherwise idle) own-reach scratch: ND >= I doubles
     double *per_iset = c->contrib_o.p;
     if (t->I > 0) {
-        k_imm_regret<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_col.p, c->contrib_r.p,
-                                                     c->cum_imm.p, per_iset, inv);
+        k_imm_regret<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->iset_size.p, t->col_off.p, t->koff_iset.p, c->contrib_r.p,
+                                                     c->cum_imm.p, per_iset, inv, (int64_t)t->ND);
         RLP_LAUNCH_CHECK();
     }
     std::vector<double> h((size_t)t->I);
@@ -767,7 +814,8 @@ extern "C" int rlp_cfr_profile_stages(rlp_cfr *c, int reps, float *out_ms4, void
     cudaEvent_t ev[5];
     for (auto &e : ev) RLP_CUDA(cudaEventCreate(&e));
     for (int k = 0; k < 4; ++k) out_ms4[k] = 0.f;
-    int rc = RLP_OK;
+    int rc = rlp::ensure_sigma_am(c, s);
+    if (rc) return rc;
     for (int r = 0; r < reps + 2 && rc == RLP_OK; ++r) {
         int n = 0;
         rc = enqueue_iteration(c, s, &n, ev);

@@ -34,6 +34,10 @@ struct rlp_cfr {
     rlp_tree *tree = nullptr;
     // [Q] internal pair order
     rlp::DevBuf<double> R, S, sigma, avg, cum_imm, tmpQ, delta;
+    // action-major copy of sigma, [action][internal information set]: consecutive micro subtrees read consecutive
+    // words (the [set][action] layout costs 3x the L2 sectors in the micro kernel)
+    rlp::DevBuf<double> sigma_am;
+    bool sigma_am_dirty = true;
     rlp::DevBuf<uint8_t> flags;              // [3][I] internal order: in_R | in_S (or alpha) | in_sigma dict membership
     // per-node scratch
     rlp::DevBuf<double> pc, p1, p2, val1, val2, vbr;

@@ -85,15 +85,14 @@ std::string generate(const MicroTmpl &tm, bool zs) {
          "    const double* __restrict__ sigma, const double* __restrict__ portal_p1, const double* __restrict__ portal_p2,\n"
          "    double* __restrict__ portal_v1, double* __restrict__ portal_v2, double* __restrict__ contrib_r,\n"
          "    double* __restrict__ contrib_o, const IterState* __restrict__ iter, long long P,\n"
-         "    const int* __restrict__ inst, int count) {\n"
+         "    const int* __restrict__ inst, int count, long long ND, long long NI) {\n"
          "  const int i = blockIdx.x * blockDim.x + threadIdx.x;\n"
          "  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
          "  if (i >= count) { asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); return; }\n"
          "  const long long p = inst ? (long long)inst[i] : (long long)i;\n";
     const int n = tm.n, n_nt = tm.n_nt;
     for (int r = 0; r < n_nt; ++r)
-        o << "  const int cb" << r << " = colbase[" << r << " * P + p], sr" << r << " = slot_r[" << r << " * P + p], so"
-          << r << " = slot_o[" << r << " * P + p];\n";
+        o << "  const int sk" << r << " = colbase[" << r << " * P + p], so" << r << " = slot_o[" << r << " * P + p];\n";
     o << "  const double pcv = pc[p];\n  const int pi = pidx[p], ri = ridx[p];\n";
     for (int j = 0; j < n; ++j)
         if (tm.rank[j] & 0x80) {
@@ -107,7 +106,7 @@ std::string generate(const MicroTmpl &tm, bool zs) {
       << "  const double w = iter->linear ? (double)iter->t : 1.0;\n"
          "  const double q1_0 = portal_p1[ri], q2_0 = portal_p2[ri];\n";
     for (int j = 1; j < n; ++j)
-        o << "  const double s" << j << " = sigma[cb" << (int)tm.par_rank[j] << " + " << (int)tm.par_slot[j] << "];\n";
+        o << "  const double s" << j << " = sigma[" << (int)tm.par_slot[j] << " * NI + sk" << (int)tm.par_rank[j] << "];\n";
     // forward
     for (int r = 0; r < n_nt; ++r) {
         int j = tm.nt_node[r], pl = tm.player[j];
@@ -135,7 +134,7 @@ std::string generate(const MicroTmpl &tm, bool zs) {
           << "    const double vp = " << (pl == 1 ? "x" + std::to_string(j) : (zs ? "-x" + std::to_string(j) : "y" + std::to_string(j))) << ";\n";
         for (int k = 0; k < nc; ++k) {
             std::string va = pl == 1 ? "x" + std::to_string(fc + k) : (zs ? "-x" + std::to_string(fc + k) : "y" + std::to_string(fc + k));
-            o << "    contrib_r[sr" << r << " + " << k << "] = w * (" << va << " - vp) * opp;\n";
+            o << "    contrib_r[" << k << " * ND + so" << r << "] = w * (" << va << " - vp) * opp;\n";
         }
         o << "    contrib_o[so" << r << "] = w * own;\n  }\n";
     }
@@ -241,7 +240,7 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
              "    double* __restrict__ portal_p1, double* __restrict__ portal_p2, const double* __restrict__ portal_v1,\n"
              "    const double* __restrict__ portal_v2, double* __restrict__ contrib_r, double* __restrict__ contrib_o,\n"
              "    double* __restrict__ root_val, const IterState* __restrict__ iter, long long T,\n"
-             "    const double* __restrict__ fan_v1, const double* __restrict__ fan_v2) {\n"
+             "    const double* __restrict__ fan_v1, const double* __restrict__ fan_v2, long long ND) {\n"
              "  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n"
              "  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
              "  if (i >= T) { asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); return; }\n"
@@ -251,7 +250,7 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
                 int d = dec_idx[j];
                 o << "  const int cb" << j << " = colbase[" << d << " * T + i];\n";
                 if (phase == 1)
-                    o << "  const int sr" << j << " = slot_r[" << d << " * T + i], so" << j << " = slot_o[" << d << " * T + i];\n"
+                    o << "  const int so" << j << " = slot_o[" << d << " * T + i];\n"
                       << "  const double pc" << j << " = pcs[" << d << " * T + i];\n";
             }
         if (phase == 1) {
@@ -326,7 +325,7 @@ static std::string generate_upper(const UpperShape &sh, bool zs) {
               << "    const double vp = " << (kd == 1 ? S("x", j) : (zs ? "-" + S("x", j) : S("y", j))) << ";\n";
             for (int k = 0; k < nc; ++k) {
                 std::string va = kd == 1 ? S("x", fc + k) : (zs ? "-" + S("x", fc + k) : S("y", fc + k));
-                o << "    contrib_r[sr" << j << " + " << k << "] = w * (" << va << " - vp) * opp;\n";
+                o << "    contrib_r[" << k << " * ND + so" << j << "] = w * (" << va << " - vp) * opp;\n";
             }
             o << "    contrib_o[so" << j << "] = w * own;\n  }\n";
         }

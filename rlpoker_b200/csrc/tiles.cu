@@ -38,6 +38,7 @@ struct TileView {
     const double *portal_v1, *portal_v2;
     const IterState *iter;
     int max_nodes, max_nt, max_cp;
+    long long nd;           // contrib_r is action-major [action][nd], indexed by the contrib_o slot
 };
 
 // One CTA sweeps one upper tile.  Ownership is static: non-terminal rank i belongs to thread i % blockDim, slot
@@ -214,16 +215,16 @@ __global__ void __launch_bounds__(1024) k_tile_sweep(TileView v) {
             double opp = pl == 1 ? c * x2 : c * x1;
             double own = pl == 1 ? x1 : x2;
             double vp = pl == 1 ? a1 : (ZS ? -a1 : a2);
-            double *dst = v.contrib_r + ax.slot_r;
+            double *dst = v.contrib_r + ax.slot_o;
             if constexpr (WIDE) {
                 for (int k = 0; k < n; ++k) {
                     double x = pl == 1 ? val1[fc + k] : (ZS ? -val1[fc + k] : val2[fc + k]);
-                    dst[k] = w * (x - vp) * opp;
+                    dst[(long long)k * v.nd] = w * (x - vp) * opp;
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < kRegAct; ++k)
-                    if (k < n) dst[k] = w * (va[k] - vp) * opp;
+                    if (k < n) dst[(long long)k * v.nd] = w * (va[k] - vp) * opp;
             }
             v.contrib_o[ax.slot_o] = w * own;
         }
@@ -249,12 +250,13 @@ struct MicroView {
     const int *pidx;                           // [P] where this instance's portal lives ([portal rank][tile] layout)
     const int *ridx;                           // [P] where its root reach is (its chance parent's slot, if any)
     const double *pay1, *pay2;                 // [micro_term][P]
-    const double *pc, *sigma;
+    const double *pc, *sigma;               // sigma here is the ACTION-MAJOR copy [action][internal set]
     const double *portal_p1, *portal_p2;
     double *portal_v1, *portal_v2;
     double *contrib_r, *contrib_o;
     const IterState *iter;
     int P, num_classes, mn, mnt;
+    long long nd, num_isets;
 };
 
 template <bool ZS>
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
     AT(sq2, 0) = v.portal_p2[ri];
     // batch 2: strategy probability of every edge, payoff of every leaf (independent loads)
 #pragma unroll 4
-    for (int j = 1; j < n; ++j) AT(ssig, j) = v.sigma[AT(scb, tm->par_rank[j]) + tm->par_slot[j]];
+    for (int j = 1; j < n; ++j) AT(ssig, j) = v.sigma[(long long)tm->par_slot[j] * v.num_isets + AT(scb, tm->par_rank[j])];
     // forward (cfr.py:208,217)
     for (int r = 0; r + 1 < n_nt; ++r) {
         const int j = tm->nt_node[r];
@@ -339,10 +341,10 @@ __global__ void __launch_bounds__(kMicroBlock) k_micro(MicroView v) {
         const double opp = pl == 1 ? pcv * x2 : pcv * x1;
         const double own = pl == 1 ? x1 : x2;
         const double vp = pl == 1 ? a1 : (ZS ? -a1 : a2);
-        double *dst = v.contrib_r + AT(ssr, r);
+        double *dst = v.contrib_r + AT(sso, r);
         for (int k = 0; k < nc; ++k) {
             const double x = pl == 1 ? AT(sv1, fc + k) : (ZS ? -AT(sv1, fc + k) : AT(sv2, fc + k));
-            dst[k] = w * (x - vp) * opp;
+            dst[(long long)k * v.nd] = w * (x - vp) * opp;
         }
         v.contrib_o[AT(sso, r)] = w * own;
     }
@@ -647,7 +649,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
                 if (!zs) m_pay2[(size_t)term * P + p] = d->u2[g];
                 ++term;
             } else {
-                m_colbase[(size_t)nt * P + p] = colbase[g];
+                m_colbase[(size_t)nt * P + p] = srank[g];          // internal information-set id (sigma is read action-major)
                 m_slot_r[(size_t)nt * P + p] = (int)(koff_col[krank[g]] + colbase[g]);
                 m_slot_o[(size_t)nt * P + p] = (int)(koff_iset[krank[g]] + srank[g]);
                 ++nt;
@@ -858,10 +860,10 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
 
 static int launch_upper_jit(rlp_cfr *c, TileSet &ts, int phase, const IterState *it, cudaStream_t s) {
     UpperJit &u = *ts.upper_jit;
-    long long T = u.T;
+    long long T = u.T, nd = c->tree->ND;
     void *args[] = {&u.colbase.p, &u.slot_r.p, &u.slot_o.p, &u.pcs.p, &u.cprob.p, &u.pay1.p, &u.pay2.p, &u.poff.p,
                     &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
-                    &c->contrib_r.p, &c->contrib_o.p, &ts.root_val.p, &it, &T, &u.fan_v1.p, &u.fan_v2.p};
+                    &c->contrib_r.p, &c->contrib_o.p, &ts.root_val.p, &it, &T, &u.fan_v1.p, &u.fan_v2.p, &nd};
     if (phase == 1 && u.num_fan > 0) {
         long long total = (long long)u.num_fan * T;
         unsigned g = (unsigned)((total + 127) / 128);
@@ -936,6 +938,7 @@ int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int sta
     v.contrib_r = c->contrib_r.p; v.contrib_o = c->contrib_o.p; v.root_val = ts.root_val.p;
     v.portal_p1 = ts.portal_p1.p; v.portal_p2 = ts.portal_p2.p; v.portal_v1 = ts.portal_v1.p; v.portal_v2 = ts.portal_v2.p;
     v.iter = iter ? iter : c->iter.p; v.max_nodes = ts.max_nodes; v.max_nt = ts.max_nt; v.max_cp = ts.max_cp;
+    v.nd = t->ND;
     int n = 0;
     if (stage == 0 && ts.num_tiles > 0 && ts.num_micro > 0) {
         int rc = ts.upper_jit ? launch_upper_jit(c, ts, 0, v.iter, s) : launch_upper<0>(t, ts, v, s);
@@ -949,9 +952,10 @@ int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int sta
             if (jc->count == 0) continue;
             const int *inst = jc->inst.n ? jc->inst.p : nullptr;
             int count = jc->count;
+            long long nd = t->ND, ni = t->I;
             void *args[] = {&ts.m_colbase.p, &ts.m_slot_r.p, &ts.m_slot_o.p, &ts.m_pidx.p, &ts.m_ridx.p, &ts.m_pay1.p, &ts.m_pay2.p, &ts.m_pc.p,
-                            &c->sigma.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
-                            &c->contrib_r.p, &c->contrib_o.p, &it, &P, &inst, &count};
+                            &c->sigma_am.p, &ts.portal_p1.p, &ts.portal_p2.p, &ts.portal_v1.p, &ts.portal_v2.p,
+                            &c->contrib_r.p, &c->contrib_o.p, &it, &P, &inst, &count, &nd, &ni};
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)((count + 127) / 128)); cfg.blockDim = dim3(128); cfg.stream = s;
             cudaLaunchAttribute attr[1];
@@ -965,7 +969,7 @@ int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int sta
     } else if (stage == 1 && ts.num_micro > 0) {
         MicroView m;
         m.tmpl = ts.tmpl.p; m.cls = ts.m_class.p; m.colbase = ts.m_colbase.p; m.slot_r = ts.m_slot_r.p;
-        m.slot_o = ts.m_slot_o.p; m.pidx = ts.m_pidx.p; m.ridx = ts.m_ridx.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma.p;
+        m.slot_o = ts.m_slot_o.p; m.pidx = ts.m_pidx.p; m.ridx = ts.m_ridx.p; m.pay1 = ts.m_pay1.p; m.pay2 = ts.m_pay2.p; m.pc = ts.m_pc.p; m.sigma = c->sigma_am.p; m.nd = t->ND; m.num_isets = t->I;
         m.portal_p1 = ts.portal_p1.p; m.portal_p2 = ts.portal_p2.p; m.portal_v1 = ts.portal_v1.p;
         m.portal_v2 = ts.portal_v2.p; m.contrib_r = c->contrib_r.p; m.contrib_o = c->contrib_o.p;
         m.iter = v.iter; m.P = ts.num_micro; m.num_classes = ts.num_classes; m.mn = ts.micro_nodes; m.mnt = ts.micro_nt;
