@@ -189,9 +189,8 @@ k_accumulate_rm4(int32_t I, const int32_t *__restrict__ iset_size, const int64_t
     if (active) {
         r = R[c0 + a]; sa = S[c0 + a];
         sg = sigma[c0 + a];
-        const double *cr = contrib_r + c0 + a;
+        const double *cr = contrib_r + (int64_t)a * ND + s;      // action-major: same slots as contrib_o
         const double *co = contrib_o + s;
-        // batches of 8 diagonals: 16 independent loads in flight, then the ordered adds
         int k = 0;
         const int fast = size < kTab ? size : kTab;
         // batches of 8 diagonals, the last one predicated: all of a batch's loads are in flight before the ordered adds
