@@ -15,6 +15,17 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+def pytest_sessionstart(session):
+    """Build the native pieces when they are missing (a fresh checkout): the CUDA library cross-compiles without a
+    GPU, the oracle needs gcc only.  Up-to-date builds are left alone."""
+    import subprocess
+    lib = os.path.join(ROOT, 'rlpoker_b200', 'librlpoker_b200.so')
+    if not os.path.exists(lib):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'rlpoker_b200', 'csrc')])
+    if not os.path.exists(os.path.join(ROOT, 'oracle', '_build', 'libcfr_oracle.so')):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle')])
+
+
 @pytest.fixture(scope='session')
 def golden():
     with open(os.path.join(GOLDEN_DIR, 'reference_golden.json')) as f:
