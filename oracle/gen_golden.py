@@ -322,6 +322,14 @@ def main():
                                   experiment_writer=Writer())
         J['external_driver_leduc3'] = {'seed': 0, 'exploitabilities': [[int(a), b] for a, b in expl]}
 
+    # 10. the chance-sampled driver end to end (cfr.py:64-152 with use_chance_sampling=True)
+    if not args.quick:
+        np.random.seed(0)
+        exp = ref.Experiment('g_chance', base_save_path=tmp)
+        (avg, expl, _), _ = quiet(ref.cfr.cfr, exp, games['leduc3'], num_iters=101, use_chance_sampling=True,
+                                  experiment_writer=Writer())
+        J['chance_driver_leduc3'] = {'seed': 0, 'exploitabilities': [[int(a), b] for a, b in expl]}
+
     with open(os.path.join(OUT, 'reference_golden.json'), 'w') as f:
         json.dump(J, f, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(OUT, 'reference_arrays.npz'), **arrays)

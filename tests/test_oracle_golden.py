@@ -171,3 +171,37 @@ def test_philox_reference_vector():
     u = orc.philox_uniform(0, 0, 0, 0, 0)
     a, b = 0x6627e8d5 >> 5, 0xe169c58d >> 6
     assert u == (a * 67108864.0 + b) / 9007199254740992.0
+
+
+def test_external_driver_exploitability_trace(golden, otrees):
+    """external_sampling_cfr(experiment, game, num_iters=401) after np.random.seed(0): exploitability of
+    AverageStrategy.compute_strategy() at t = 0, 200, 400 (external_cfr.py:59-63)."""
+    if 'external_driver_leduc3' not in golden:
+        pytest.skip('quick golden set')
+    want = golden['external_driver_leduc3']
+    o = orc.Oracle(otrees('leduc3'))
+    np.random.seed(want['seed'])
+    rng = orc.rng_stream(np.random.random_sample(401 * 200))
+    got = []
+    for t in range(401):
+        o.external(1, rng)
+        if t % 200 == 0:
+            got.append([t, o.exploitability(o.alpha_strategy())])
+    assert got == want['exploitabilities']
+
+
+def test_chance_sampled_driver_exploitability_trace(golden, otrees):
+    """cfr(experiment, game, num_iters=101, use_chance_sampling=True) after np.random.seed(0): exploitability of the
+    average strategy every 10 iterations (cfr.py:125-129)."""
+    if 'chance_driver_leduc3' not in golden:
+        pytest.skip('quick golden set')
+    want = golden['chance_driver_leduc3']
+    o = orc.Oracle(otrees('leduc3'))
+    np.random.seed(want['seed'])
+    rng = orc.rng_stream(np.random.random_sample(101 * 2 * 16))
+    got = []
+    for t in range(101):
+        o.cfr_recursive(1, sampling=True, rng=rng)
+        if t % 10 == 0:
+            got.append([t, o.exploitability(o.average_strategy()[0])])
+    assert got == want['exploitabilities']

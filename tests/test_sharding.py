@@ -106,3 +106,19 @@ def test_two_rank_gloo_run_matches_single_process():
     np.testing.assert_allclose(got['S'], o.S, rtol=0, atol=1e-12)
     np.testing.assert_allclose(got['sigma'], o.sigma, rtol=0, atol=1e-10)
     os.remove(out)
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_every_shard_plans_and_compiles(world):
+    """The device layout of every rank's subtree (tiling, shapes, NVRTC compilation) derived on the host."""
+    from rlpoker_b200.games.leduc_native import leduc_flat_tree
+    from rlpoker_b200.sharding import shard_flat_tree
+    from rlpoker_b200.solver import plan_tree
+    ft = leduc_flat_tree(5)
+    deals = 0
+    for r in range(world):
+        p = plan_tree(shard_flat_tree(ft, r, world))
+        assert p['tiled'] == 1 and p['micro_shapes'] == 1 and p['kernels_failed'] == 0 and p['kernels_compiled'] == 2
+        assert p['micro_subtrees'] == 9 * 8 * p['upper_tiles']
+        deals += p['upper_tiles']
+    assert deals == 10 * 9
