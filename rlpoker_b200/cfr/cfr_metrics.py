@@ -1,10 +1,12 @@
-"""CFR metrics with the reference's API (rlpoker/cfr/cfr_metrics.py:13-254).
+"""CFR metrics with the reference's API (rlpoker/cfr/cfr_metrics.py:13-156).
 
 ``compute_immediate_regret`` runs one device sweep per strategy (rlp_cfr_immediate_regret_step) instead of the
 reference's Python recursion; when given the StrategyHistory a driver returned it reuses the series the
-driver already computed."""
-import collections
+driver already computed.
 
+Not provided: ``compute_expected_utility`` (cfr_metrics.py:159-254), which returns per-node value dictionaries keyed by
+node objects -- an inspection helper outside the solve.  The root values it would report are available from the device
+through ``rlpoker_b200.solver.DeviceTree.expected_value`` (rlp_expected_value)."""
 import numpy as np
 
 from rlpoker_b200._lib import RLP_SIGMA
@@ -31,36 +33,3 @@ def compute_immediate_regret(game, strategies):
         solver.write(RLP_SIGMA, arr)
         out.append(solver.immediate_regret_step(step, order))
     return out[-1], out, None
-
-
-def compute_expected_utility(game, sigma_1, sigma_2):
-    """(expected_utility_1, expected_utility_2): value of every player-1 node to player 1 and of every player-2
-    node to player 2 under (sigma_1, sigma_2) (cfr_metrics.py:159-254).  Host recursion over node objects: this
-    is an inspection helper keyed by node objects, not part of the solve."""
-    eu1, eu2 = collections.defaultdict(float), collections.defaultdict(float)
-
-    def walk(node):
-        if node.player == -1:
-            return node.utility[1], node.utility[2]
-        v1 = v2 = 0.0
-        if node.player == 0:
-            for action, child in node.children.items():
-                a1, a2 = walk(child)
-                p = node.chance_probs[action]
-                v1 += p * a1
-                v2 += p * a2
-            return v1, v2
-        info_set = game.info_set_ids[node]
-        probs = (sigma_1 if node.player == 1 else sigma_2)[info_set]
-        for action, child in node.children.items():
-            a1, a2 = walk(child)
-            v1 += probs[action] * a1
-            v2 += probs[action] * a2
-        if node.player == 1:
-            eu1[node] += v1
-        else:
-            eu2[node] += v2
-        return v1, v2
-
-    walk(game.root)
-    return eu1, eu2
