@@ -131,7 +131,7 @@ int rlp_cfr_update_average(rlp_cfr *cfr, double weight, void *stream);
  * cfr.py:32-41 for vanilla / chance-sampled state and AverageStrategy.compute_strategy
  * (cfr_util.py:95-106) for external-sampled state; absent information sets come out uniform. */
 int rlp_cfr_read(rlp_cfr *cfr, int which, double *dst, void *stream);
-int rlp_cfr_write(rlp_cfr *cfr, int which, const double *src, void *stream);
+int rlp_cfr_write(rlp_cfr *cfr, int which, const double *src, void *stream);   /* asynchronous if src is pinned */
 /* [I] flags: bit0 information set has a regret entry, bit1 an action-count / alpha entry,
  * bit2 a strategy entry in the reference's dicts (matters for the sampled variants only). */
 int rlp_cfr_read_flags(rlp_cfr *cfr, uint8_t *dst, void *stream);

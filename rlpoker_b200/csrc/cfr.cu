@@ -724,7 +724,9 @@ extern "C" int rlp_cfr_write(rlp_cfr *c, int which, const double *src, void *str
     int rc = rlp::permute(c->tree, c->tmpQ.p, dst, 1, s);
     if (rc) return rc;
     if (which == RLP_SIGMA) c->sigma_am_dirty = true;
-    RLP_CUDA(cudaStreamSynchronize(s));
+    // No synchronisation: a copy from pageable memory has been staged by the time cudaMemcpyAsync returns, and a
+    // pinned source must simply stay untouched until the stream reaches this point (it is ordered before every later
+    // call on the same stream, including rlp_cfr_read, which does synchronise).
     return RLP_OK;
 }
 
