@@ -37,8 +37,17 @@ class Leduc(ExtensiveGame):
         super().__init__(Leduc.create_tree(cards, max_raises=max_raises, raise_amount=raise_amount))
 
     @classmethod
-    def create_game(cls, num_values, num_suits=2, **kwargs):
-        """``Leduc.create_game(n)`` of the reference README (README.md:6): n ranks x 2 suits."""
+    def create_game(cls, num_values, num_suits=2, native=None, **kwargs):
+        """``Leduc.create_game(n)`` of the reference README (README.md:6): n ranks x 2 suits.
+
+        ``native=True`` (default from 8 ranks up, where node objects cost gigabytes) returns a
+        ``rlpoker_b200.games.leduc_native.FlatGame``: the same tree as flat arrays straight from the native generator,
+        accepted by every solver entry point but without ``root`` / node objects."""
+        if native is None:
+            native = num_values >= 8
+        if native:
+            from rlpoker_b200.games.leduc_native import create_leduc
+            return create_leduc(num_values, num_suits, **kwargs)
         return cls(get_deck(num_values, num_suits), **kwargs)
 
     # ------------------------------------------------------------------ tree

@@ -44,3 +44,14 @@ def test_other_rules():
     b = leduc_flat_tree(3, 1, max_raises=2, raise_amount=3)
     for name in ('parent', 'player', 'infoset', 'cprob', 'u1', 'u2', 'hidden'):
         assert np.array_equal(getattr(a, name), getattr(b, name)), name
+
+
+def test_create_game_switches_to_the_native_generator():
+    from rlpoker_b200.games.leduc import Leduc
+    from rlpoker_b200.games.leduc_native import FlatGame
+    small = Leduc.create_game(2)
+    assert isinstance(small, Leduc) and small.root.player == 0
+    big = Leduc.create_game(8)
+    assert isinstance(big, FlatGame) and big.flat.num_nodes == 1 + 16 + 23 * 240 + 207 * 240 * 14
+    forced = Leduc.create_game(3, native=True)
+    assert isinstance(forced, FlatGame) and forced.flat.num_infosets == 2208
