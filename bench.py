@@ -158,6 +158,22 @@ def run_reference(args, rank, world):
     }))
 
 
+def arm_watchdog(seconds):
+    """A hung collective must not hang the box: after `seconds` of wall clock the process reports and exits non-zero
+    (torchrun then tears the other ranks down)."""
+    import threading
+
+    def fire():
+        sys.stderr.write('bench.py: watchdog fired after %.0f s, aborting\n' % seconds)
+        sys.stderr.flush()
+        os._exit(3)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -167,7 +183,10 @@ def main():
     ap.add_argument('--iters-per-step', type=int, default=10)
     ap.add_argument('--cpu-budget-s', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--watchdog-s', type=float, default=float(os.environ.get('RLP_BENCH_WATCHDOG_S', '900')))
     args = ap.parse_args()
+    if args.watchdog_s > 0:
+        arm_watchdog(args.watchdog_s)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
