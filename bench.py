@@ -183,7 +183,7 @@ def main():
     ap.add_argument('--iters-per-step', type=int, default=10)
     ap.add_argument('--cpu-budget-s', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--watchdog-s', type=float, default=float(os.environ.get('RLP_BENCH_WATCHDOG_S', '900')))
+    ap.add_argument('--watchdog-s', type=float, default=float(os.environ.get('RLP_BENCH_WATCHDOG_S', '480')))
     args = ap.parse_args()
     if args.watchdog_s > 0:
         arm_watchdog(args.watchdog_s)
