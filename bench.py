@@ -64,6 +64,42 @@ def traffic_per_iteration():
         return None
 
 
+# One Leduc micro subtree = the 23-node betting round after the board card: 8 decision nodes, 15 leaves, 22 edges.
+# Bytes one `micro_k` thread moves for it (the generated source, csrc/jit.cu generate()): per decision node its
+# information-set column and its contribution slot (2 x i32), one f64 payoff per leaf, static chance reach (f64),
+# portal and reach indices (2 x i32), the two players' reaches in (2 x f64); out: the subtree value (f64), 22 regret
+# terms and 8 own-reach terms (f64).  The 22 strategy probabilities come from the 1 MB strategy table shared by all
+# subtrees; it is charged once per launch.
+MICRO_BYTES_IN = 8 * 2 * 4 + 15 * 8 + 8 + 2 * 4 + 2 * 8
+MICRO_BYTES_OUT = 8 + (22 + 8) * 8
+
+
+def dominant_kernel_roofline(layout, stages, peak, strategy_bytes):
+    """Roofline of the single longest kernel of the iteration (`micro_k`): algorithmic bytes of one launch over
+    its live CUDA-event duration.  None when the tree is not tiled or the stage times are missing."""
+    try:
+        n = int(layout['micro_subtrees'])
+        us = float(stages['micro'])
+        if n <= 0 or us <= 0:
+            return None
+        nbytes = n * (MICRO_BYTES_IN + MICRO_BYTES_OUT) + strategy_bytes
+        achieved = nbytes / (us * 1e-6) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+                k = json.load(f)['kernels']['micro_k']
+            traffic = (float(k['dram_read_MB']) + float(k['dram_write_MB'])) * 1e6
+        except Exception:
+            pass
+        return {'kernel': 'micro_k', 'units': n, 'bytes_per_unit': MICRO_BYTES_IN + MICRO_BYTES_OUT,
+                'algorithmic_bytes_per_launch': nbytes, 'us_per_launch': us, 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                'note': 'stores of one launch stay in the 126 MB L2 for the accumulate kernel, so DRAM traffic is '
+                        'below the algorithmic bytes'}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
@@ -306,6 +342,7 @@ def main():
                          'algorithmic_bytes_per_iteration': bytes_iter,
                          'bytes_per_node_update': bytes_iter / (2.0 * N), 'us_per_iteration': iter_ms * 1e3,
                          'stage_us_serialised': stages, 'layout': layout,
+                         'dominant_kernel': dominant_kernel_roofline(layout, stages, peak, 8 * Q),
                          'note': 'algorithmic bytes = SURVEY 8d formula (level sweep with reach/value arrays in HBM); the '
                                  'tiled sweep keeps those on chip, so DRAM traffic (ncu) is ~4x lower than the formula'},
         }
