@@ -78,13 +78,17 @@ def otrees():
     return oracle_tree
 
 
-def random_game(seed, depth=6, zero_sum=False, max_act=5):
+def random_game(seed, depth=6, zero_sum=False, max_act=5, classes=None):
     """A random extensive game with perfect recall: the acting player, #actions and hidden_from depend only on
     the depth, so nodes of one information set agree on their actions; where an action is visible to both
     players its first child may be a leaf (so leaves sit at several depths while every set of nodes a player
     cannot tell apart is all-terminal or all-internal, which the reference's br() assumes); random chance
-    probabilities, float payoffs."""
-    from rlpoker_b200.extensive_game import ExtensiveGame, ExtensiveGameNode
+    probabilities, float payoffs.  `classes` = (ExtensiveGame, ExtensiveGameNode) of another implementation
+    (oracle/gen_golden_random.py passes the reference's to build the identical tree there)."""
+    if classes is None:
+        from rlpoker_b200.extensive_game import ExtensiveGame, ExtensiveGameNode
+    else:
+        ExtensiveGame, ExtensiveGameNode = classes
     rng = np.random.RandomState(seed)
     who = [int(rng.randint(0, 3)) for _ in range(depth)]
     who[0] = 0 if seed % 2 == 0 else 1
