@@ -16,10 +16,11 @@ import sys
 import numpy as np
 
 from oracle import flat
-from oracle.gen_golden import OUT, import_reference, run_vanilla, sha, tree_record
+from oracle.gen_golden import OUT, import_reference, run_external, run_vanilla, sha, tree_record
 
 SEEDS = list(range(8))
 CFR_T = 5
+SAMPLED_T = 80           # iterations of the numpy-seeded chance-sampled / external-sampled runs (util.py:6-27 sampler)
 
 
 def zero_sum(seed):
@@ -44,6 +45,18 @@ def main():
                       'sha_R': sha(sn['R']), 'sha_S': sha(sn['S']), 'sha_avg': sha(sn['avg'])}
         for k in ('R', 'S', 'avg', 'avg_present', 'sigma'):
             arrays['seed%d_%s' % (seed, k)] = sn[k]
+        np.random.seed(1000 + seed)
+        cs = run_vanilla(ref, game, t, [SAMPLED_T], sampling=True)[SAMPLED_T]
+        rec['chance_sampled'] = {'seed': 1000 + seed, 'T': SAMPLED_T, 'nodes_touched': cs['nodes_touched'],
+                                 'exploitability': cs['exploitability']}
+        for k in ('R', 'S', 'in_R', 'in_S'):
+            arrays['seed%d_cs_%s' % (seed, k)] = cs[k]
+        np.random.seed(2000 + seed)
+        ex = run_external(ref, game, t, SAMPLED_T)
+        rec['external'] = {'seed': 2000 + seed, 'T': SAMPLED_T, 'nodes_touched': ex['nodes_touched'],
+                           'exploitability': ex['exploitability']}
+        for k in ('R', 'alpha', 'in_R', 'in_alpha'):
+            arrays['seed%d_ex_%s' % (seed, k)] = ex[k]
         J['games'][str(seed)] = rec
         print(seed, t.num_nodes, t.num_infosets, rec['uniform_br'], sn['exploitability'], flush=True)
     with open(os.path.join(OUT, 'reference_random.json'), 'w') as f:

@@ -49,3 +49,27 @@ def test_random_tree_against_reference(want, arrays, seed):
         assert np.array_equal(np.where(np.repeat(present, t.nact), avg, 0.0), arrays['seed%d_avg' % seed])
         assert o.exploitability(avg) == w['cfr']['exploitability']
         assert o.nodes_touched == w['cfr']['nodes_touched']
+
+
+@pytest.mark.parametrize('seed', SEEDS)
+def test_random_tree_sampled_variants_numpy_stream(want, arrays, seed):
+    """Chance-sampled (cfr.py:167-175) and external-sampling (external_cfr.py:82-173) runs of the reference driven by
+    numpy's seeded legacy generator; the oracle consumes the same MT19937 doubles through the restated sampler."""
+    w = want['games'][str(seed)]
+    t = flat.flatten_game(random_game(seed, zero_sum=zero_sum(seed)))
+    cs = w['chance_sampled']
+    o = orc.Oracle(t)
+    np.random.seed(cs['seed'])
+    o.cfr_recursive(cs['T'], sampling=True, rng=orc.rng_stream(np.random.random_sample(cs['T'] * 2 * 4000)))
+    assert o.nodes_touched == cs['nodes_touched']
+    assert np.array_equal(o.R, arrays['seed%d_cs_R' % seed]) and np.array_equal(o.S, arrays['seed%d_cs_S' % seed])
+    assert np.array_equal(o.in_R, arrays['seed%d_cs_in_R' % seed]) and np.array_equal(o.in_S, arrays['seed%d_cs_in_S' % seed])
+    assert o.exploitability(o.average_strategy()[0]) == cs['exploitability']
+    ex = w['external']
+    o = orc.Oracle(t)
+    np.random.seed(ex['seed'])
+    o.external(ex['T'], orc.rng_stream(np.random.random_sample(ex['T'] * 2 * 4000)))
+    assert o.nodes_touched == ex['nodes_touched']
+    assert np.array_equal(o.R, arrays['seed%d_ex_R' % seed]) and np.array_equal(o.S, arrays['seed%d_ex_alpha' % seed])
+    assert np.array_equal(o.in_R, arrays['seed%d_ex_in_R' % seed]) and np.array_equal(o.in_S, arrays['seed%d_ex_in_alpha' % seed])
+    assert o.exploitability(o.alpha_strategy()) == ex['exploitability']
