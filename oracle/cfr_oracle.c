@@ -251,13 +251,6 @@ static double cfr_rec(cfr_ctx *c, int32_t node, int i, double pi_c, double pi_1,
     return value;
 }
 
-static void set_uniform(const orc_tree *t, double *sigma) {
-    for (int32_t i = 0; i < t->num_infosets; ++i) {
-        int n = (int)(t->act_off[i + 1] - t->act_off[i]);
-        for (int a = 0; a < n; ++a) sigma[t->act_off[i] + a] = 1.0 / n;
-    }
-}
-
 /*
  * cfr.py:105-122 for iterations t0 .. t0+n_iters-1 by the reference's own recursion.
  * sigma holds strategy_t (complete; pass uniform at t0 == 0).  flags[3*I]: in_R | in_S | in_next.
