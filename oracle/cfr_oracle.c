@@ -15,7 +15,7 @@
  *   rlpoker/extensive_game.py:382-423        (expected_value_exact)
  *
  * Parity is PINNED: tests/test_oracle_golden.py checks this file bit-for-bit against
- * tests/golden/*.json, which oracle/gen_golden.py produced by running the reference itself.
+ * the JSON / npz files under tests/golden, which oracle/gen_golden.py produced by running the reference itself.
  *
  * Floating point: compile with -ffp-contract=off (no FMA); the two normaliser sums use
  * Neumaier compensation because CPython >= 3.12's builtin sum() does.
