@@ -1,0 +1,61 @@
+"""Statistical parity of the sampled variants (BASELINE.json: "the exploitability-vs-iteration curve must match within
+a stated statistical tolerance over fixed seeds").
+
+tests/golden/reference_seed_curves.json holds the reference's own curves on Leduc-3 for numpy seeds 0..15
+(oracle/gen_golden_curves.py).  The Philox-driven traversals this repo runs (oracle restatement here; the CUDA lanes are
+bit-identical to it for one lane per iteration, tests/test_gpu_sampled.py) use a different random stream, so they are
+compared as distributions: at every checkpoint the mean over 16 Philox seeds must lie within 3 standard errors (Welch:
+sqrt(sd_ref^2 / 16 + sd_ours^2 / 16)) of the reference's mean.  Stated tolerance: 3 s.e.; deterministic given the seeds."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+from oracle import oracle as orc
+
+
+@pytest.fixture(scope='module')
+def curves():
+    with open(os.path.join(GOLDEN_DIR, 'reference_seed_curves.json')) as f:
+        return json.load(f)
+
+
+def _welch_ok(ref, ours):
+    ref, ours = np.asarray(ref), np.asarray(ours)
+    se = np.sqrt(ref.var(0, ddof=1) / len(ref) + ours.var(0, ddof=1) / len(ours))
+    z = (ours.mean(0) - ref.mean(0)) / se
+    return z, bool(np.all(np.abs(z) < 3.0))
+
+
+def test_chance_sampled_curve_distribution(curves, otrees):
+    want = curves['chance_sampled']
+    t = otrees('leduc3')
+    ours = []
+    for seed in curves['seeds']:
+        o = orc.Oracle(t)
+        row, done = [], 0
+        for T in want['T']:
+            o.cfr_recursive(T - done, sampling=True, rng=orc.rng_philox(seed))
+            done = T
+            row.append(o.exploitability(o.average_strategy()[0]))
+        ours.append(row)
+    z, ok = _welch_ok(want['exploitability'], ours)
+    assert ok, (z, np.mean(ours, 0), np.mean(want['exploitability'], 0))
+
+
+def test_external_sampling_curve_distribution(curves, otrees):
+    want = curves['external']
+    t = otrees('leduc3')
+    ours = []
+    for seed in curves['seeds']:
+        o = orc.Oracle(t)
+        row, done = [], 0
+        for T in want['T']:
+            o.external(T - done, orc.rng_philox(seed))
+            done = T
+            row.append(o.exploitability(o.alpha_strategy()))
+        ours.append(row)
+    z, ok = _welch_ok(want['exploitability'], ours)
+    assert ok, (z, np.mean(ours, 0), np.mean(want['exploitability'], 0))
