@@ -59,3 +59,24 @@ def test_external_sampling_curve_distribution(curves, otrees):
         ours.append(row)
     z, ok = _welch_ok(want['exploitability'], ours)
     assert ok, (z, np.mean(ours, 0), np.mean(want['exploitability'], 0))
+
+
+@pytest.mark.parametrize('lanes', [4, 16])
+def test_batched_lanes_at_matched_traversal_counts(curves, otrees, lanes):
+    """Batched lanes (several traversals per iteration against one frozen strategy -- what the 2^20-lane configuration
+    does) compared with the reference at the same TOTAL number of traversals: 2000 chance-sampled and 400
+    external traversal pairs.  Equivalent within 3 s.e. up to 16 lanes at these horizons; with 64 lanes only 31
+    iterations remain and the exploitability is visibly higher (1.61 vs 1.23), which is the expected price of batching."""
+    t = otrees('leduc3')
+    ch, ex = [], []
+    for seed in curves['seeds']:
+        o = orc.Oracle(t)
+        o.cfr_recursive(2000 // lanes, sampling=True, lanes=lanes, rng=orc.rng_philox(seed))
+        ch.append([o.exploitability(o.average_strategy()[0])])
+        o = orc.Oracle(t)
+        o.external(400 // lanes, orc.rng_philox(seed), lanes=lanes)
+        ex.append([o.exploitability(o.alpha_strategy())])
+    z, ok = _welch_ok(np.array(curves['chance_sampled']['exploitability'])[:, 3:4], ch)
+    assert ok, z
+    z, ok = _welch_ok(np.array(curves['external']['exploitability'])[:, 2:3], ex)
+    assert ok, z
