@@ -205,3 +205,18 @@ def test_chance_sampled_driver_exploitability_trace(golden, otrees):
         if t % 10 == 0:
             got.append([t, o.exploitability(o.average_strategy()[0])])
     assert got == want['exploitabilities']
+
+
+def test_vanilla_leduc3_300_iterations_survey_values(otrees):
+    """SURVEY.md section 8(c) lists what the reference itself produced at T = 200 and 300 on Leduc-3 (an 8 minute
+    run in the survey session): exploitability, nodes_touched and the first 16 hex digits of the SHA-256 of the
+    average strategy.  The committed golden set stops at T = 100; this pins the longer horizon."""
+    o = orc.Oracle(otrees('leduc3'))
+    o.vanilla_levels(200, threads=4)
+    assert o.exploitability(o.average_strategy()[0]) == 0.2504793684655993
+    o.vanilla_levels(100, threads=4)
+    avg, present = o.average_strategy()
+    assert present.all()
+    assert o.exploitability(avg) == 0.1813807003021225
+    assert sha(avg)[:16] == '95ae4634f6f5513c'
+    assert o.nodes_touched == 15322200
