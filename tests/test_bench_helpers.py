@@ -23,3 +23,14 @@ def test_dominant_kernel_roofline_from_the_committed_run():
     assert d['traffic'] is not None and d['traffic'] < d['algorithmic_bytes_per_launch']
     assert bench.dominant_kernel_roofline(None, None, 1.0, 0) is None
     assert bench.dominant_kernel_roofline({'micro_subtrees': 0}, {'micro': 1.0}, 1.0, 0) is None
+
+
+def test_traffic_json_is_reproducible_from_the_committed_capture():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import ncu_summary
+    got = ncu_summary.summarise(os.path.join(ROOT, 'profiles', 'r1_v5_full_raw.csv'))
+    with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+        want = json.load(f)
+    assert got['dram_bytes_per_iteration'] == want['dram_bytes_per_iteration'] == bench.traffic_per_iteration()
+    assert got['kernels'] == want['kernels']
