@@ -148,15 +148,23 @@ def build_tree():
 
 
 def oracle_for(ft):
-    """The CPU port (oracle/) on the same arrays -- used only as the reported CPU baseline."""
+    """The CPU port (oracle/) on the product's arrays -- the checker of the parity block."""
     from oracle import flat, oracle as orc
     t = flat.from_arrays(ft.num_nodes, ft.parent, ft.first_child, ft.player, ft.infoset, ft.label, ft.hidden,
                          ft.cprob, ft.u1, ft.u2)
     return orc.Oracle(t)
 
 
-def time_cpu(ft, budget_s, threads):
-    o = oracle_for(ft)
+def oracle_own_tree():
+    """The CPU port on a Leduc-13 tree built by the oracle's OWN generator (oracle/leduc_oracle.c): the CPU arms do not
+    touch the product package."""
+    from oracle import oracle as orc
+    return orc.Oracle(orc.leduc_tree(RANKS))
+
+
+def time_cpu(budget_s, threads, o=None):
+    o = o or oracle_own_tree()
+    N = o.t.num_nodes
     t0 = time.perf_counter()
     o.vanilla_levels(1, threads=threads)
     one = time.perf_counter() - t0
@@ -164,30 +172,34 @@ def time_cpu(ft, budget_s, threads):
     t0 = time.perf_counter()
     o.vanilla_levels(n, threads=threads)
     dt = time.perf_counter() - t0
-    return 2.0 * ft.num_nodes * n / dt, n, dt
+    return 2.0 * N * n / dt, n, dt
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm's CPU port on all host cores, same tree / metric."""
+    """--impl reference: the reference algorithm's CPU port on all host cores, same tree / metric / step (the
+    reference itself is Python and cannot travel to the GPU box; BASELINE.md has its container figure).  One step =
+    ``iters_per_step`` iterations in ONE call, exactly like the GPU arm."""
     if rank != 0:
         return
-    ft = build_tree()
     threads = os.cpu_count() or 1
-    o = oracle_for(ft)
+    o = oracle_own_tree()
+    N, I = o.t.num_nodes, o.t.num_infosets
+    ipS = args.iters_per_step
     for _ in range(args.warmup):
-        o.vanilla_levels(1, threads=threads)
+        o.vanilla_levels(ipS, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.vanilla_levels(1, threads=threads)
+        o.vanilla_levels(ipS, threads=threads)
     dt = time.perf_counter() - t0
-    value = 2.0 * ft.num_nodes * args.steps / dt
-    sample = '1 CFR iteration per step (of the %d the GPU arm runs per step), %d steps' % (args.iters_per_step, args.steps)
+    value = 2.0 * N * ipS * args.steps / dt
+    sample = '%d steps of %d Leduc-13 CFR iterations on %d threads (C port of the reference algorithm)' % (
+        args.steps, ipS, threads)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'leduc13-vanilla-cfr', 'nodes': ft.num_nodes, 'infosets': ft.num_infosets,
-                   'iters_per_step': 1},
+        'config': {'workload': 'leduc13-vanilla-cfr', 'game': 'Leduc(get_deck(13, 2))', 'nodes': N, 'infosets': I,
+                   'pairs': int(o.Q), 'iters_per_step': ipS},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -213,14 +225,19 @@ def arm_watchdog(seconds):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--iters-per-step', type=int, default=10)
     ap.add_argument('--cpu-budget-s', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--watchdog-s', type=float, default=float(os.environ.get('RLP_BENCH_WATCHDOG_S', '480')))
+    ap.add_argument('--repeats', type=int, default=10, help='extra repeats of the K-step block for the spread')
+    ap.add_argument('--parity-iters', type=int, default=23)
+    ap.add_argument('--no-extras', action='store_true', help='skip the e2e_api / extra.* legs')
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 50 if args.impl == 'b200' else 5
     if args.watchdog_s > 0:
         arm_watchdog(args.watchdog_s)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -248,11 +265,17 @@ def main():
         solver = DeviceCFR(DeviceTree(ft))
         step = lambda: solver.vanilla(ipS)
         core = solver
+        run_iters = solver.vanilla
     else:
         from rlpoker_b200.sharding import ShardedCFR
         sh = ShardedCFR(ft, rank, world)
         step = lambda: sh.iterate(ipS)
         core = sh.solver
+        run_iters = sh.iterate
+    layout = core.tree.layout
+    if os.environ.get('RLP_NO_JIT') != '1' and os.environ.get('RLP_NO_TILES') != '1':
+        # the numbers below are those of the straight-line NVRTC kernels; anything else is a different program
+        assert layout['tiled'] == 1 and layout['jit_shapes'] >= 1 and layout['upper_jit'] == 1, layout
 
     def barrier():
         if world > 1:
@@ -285,9 +308,11 @@ def main():
     launches0 = _lib.load().rlp_kernel_launches()
     ms = timed(step, args.steps, flush=True)
     launches = _lib.load().rlp_kernel_launches() - launches0
-    clocks = sampler.stop() if sampler else None
     updates = 2.0 * N * ipS * args.steps
     value = updates / (ms * 1e-3)
+    # the same K-step block again, `repeats` times: spread of the headline number
+    rep = [updates / (timed(step, args.steps, flush=True) * 1e-3) for _ in range(max(0, args.repeats))]
+    clocks = sampler.stop() if sampler else None
     ms_warm = timed(step, args.steps, flush=False)           # back-to-back steps, L2 left alone (how a solve runs)
 
     # ---- end to end with host buffers ----------------------------------------------------------------
@@ -309,11 +334,41 @@ def main():
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps, flush=True)
     e2e_value = updates / (ms_e2e * 1e-3)
+    e2e_rep = [updates / (timed(e2e_step, args.steps, flush=True) * 1e-3) for _ in range(min(5, max(0, args.repeats)))]
 
     # ---- per-stage device time, live (CUDA events between the stages; serialised, so their sum exceeds the
     # pipelined iteration time -- shares are what matters) -------------------------------------------------
     stages = core.profile_stages(30) if world == 1 else None
-    layout = core.tree.layout
+
+    # ---- parity: the program that was just timed, against the CPU oracle on the same tree ------------------
+    # single GPU: regrets / action counts / strategy bit for bit; N > 1 (all-reduce changes the association): 1e-9.
+    T = args.parity_iters
+    core.reset()
+    if world > 1:
+        sh.solver.t = 0
+    run_iters(T)
+    torch.cuda.synchronize()
+    got_R, got_S, got_avg = core.read(RLP_REGRET), core.read(RLP_STRAT_SUM), core.read(RLP_AVERAGE)
+    got_expl = core.exploitability()[0]
+    parity = None
+    if rank == 0:
+        o = oracle_for(ft)
+        o.vanilla_levels(T, threads=os.cpu_count() or 1)
+        want_avg = o.average_strategy()[0]
+        want_expl = o.exploitability(want_avg)
+        bit = bool(np.array_equal(got_R, o.R) and np.array_equal(got_S, o.S))
+        parity = {'iterations': T, 'game': 'Leduc(get_deck(13, 2))', 'oracle': 'oracle/cfr_oracle.c level sweep',
+                  'bit_exact': bit, 'max_abs_regret': float(np.abs(got_R - o.R).max()),
+                  'max_abs_avg': float(np.abs(got_avg - want_avg).max()),
+                  'abs_exploitability': abs(got_expl - want_expl), 'exploitability': got_expl,
+                  'tolerance': {'avg': 1e-9, 'exploitability': 1e-7, 'bit_exact_required': world == 1}}
+        parity['ok'] = bool(parity['max_abs_avg'] <= 1e-9 and parity['abs_exploitability'] <= 1e-7 and
+                            (bit or world > 1) and parity['max_abs_regret'] <= 1e-9)
+
+    # ---- the public Python API, wall clock (cfr() as a user calls it, FlatGame = no node objects) -----------
+    e2e_api = None
+    if world == 1 and not args.no_extras:
+        e2e_api = time_python_api(ft, N)
 
     # ---- report -------------------------------------------------------------------------------------------
     if rank == 0:
@@ -330,14 +385,21 @@ def main():
                        'parallelism': 'deal-sharded x%d + allreduce' % world if world > 1 else 'single GPU',
                        'l2_policy': 'L2 flushed (512 MB write) between timed steps, outside the timed intervals; one '
                                     'iteration touches ~76 MB of HBM-resident state (ncu), less than the 126 MB L2'},
+            'spread': ({'repeats': len(rep), 'median': statistics.median(rep), 'min': min(rep), 'max': max(rep),
+                        'note': 'the K-step timed block repeated; `value` is the first block'} if rep else None),
             'steady_state': {'value': updates / (ms_warm * 1e-3), 'us_per_iteration': 1e3 * ms_warm / (args.steps * ipS),
                              'note': 'same K steps without the L2 flush between steps'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 16 * Q, 'd2h_bytes_per_step': 8 * Q,
-                    'ms_per_step': ms_e2e / args.steps},
+                    'ms_per_step': ms_e2e / args.steps,
+                    'spread': ({'repeats': len(e2e_rep), 'median': statistics.median(e2e_rep), 'min': min(e2e_rep),
+                                'max': max(e2e_rep)} if e2e_rep else None),
+                    'path': 'C ABI with pinned host buffers: rlp_cfr_write x2 -> rlp_cfr_vanilla_iters -> rlp_cfr_read'},
+            'e2e_api': e2e_api,
             'gpu_launches': int(launches),
             'clocks': clocks,
+            'parity': parity,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic_per_iteration(), 'peak_source': peak_src,
+                         'traffic': traffic_per_iteration() if world == 1 else None, 'peak_source': peak_src,
                          'kernel': 'whole CFR iteration (upper_k0 -> micro_k -> k_fanin -> upper_k1 -> k_accumulate_rm4 x2)',
                          'algorithmic_bytes_per_iteration': bytes_iter,
                          'bytes_per_node_update': bytes_iter / (2.0 * N), 'us_per_iteration': iter_ms * 1e3,
@@ -348,15 +410,40 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v1, n1, d1 = time_cpu(ft, args.cpu_budget_s / 2, 1)
-            vN, nN, dN = time_cpu(ft, args.cpu_budget_s / 2, threads)
+            v1, n1, d1 = time_cpu(args.cpu_budget_s / 2, 1)
+            vN, nN, dN = time_cpu(args.cpu_budget_s / 2, threads)
             line['cpu_baseline'] = {'value': vN, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                     'sample': '%d Leduc-13 CFR iterations in %.1f s on %d threads (C port of the '
                                               'reference algorithm, oracle/cfr_oracle.c)' % (nN, dN, threads),
                                     'single_thread_value': v1}
         print(json.dumps(line))
+        if not parity['ok']:
+            sys.stderr.write('bench.py: PARITY FAILED: %s\n' % json.dumps(parity))
+            sys.stderr.flush()
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(4)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_python_api(ft, N):
+    """Wall clock of the reference-shaped call ``cfr(game, num_iters=100, use_chance_sampling=False)`` on Leduc-13, with
+    the driver's default keyword arguments (immediate regret + the per-iteration strategy history, i.e. one Python
+    trip with two device->host reads per iteration) and with the lean ones (no history, no immediate regret: the
+    iterations run in blocks of 10 between the evaluations)."""
+    from rlpoker_b200.cfr.cfr import cfr
+    from rlpoker_b200.games.leduc_native import FlatGame
+    game = FlatGame(ft, 'Leduc values=13 suits=2')
+    out = {'call': 'cfr(game, num_iters=100, use_chance_sampling=False)', 'unit': UNIT}
+    cfr(game, num_iters=1, use_chance_sampling=False, verbose=False)          # upload + tiling + NVRTC: not timed
+    for name, kw in (('default', {}), ('lean', {'immediate_regret': False, 'keep_strategies': 0})):
+        t0 = time.perf_counter()
+        avg, expl, hist = cfr(game, num_iters=100, use_chance_sampling=False, verbose=False, **kw)
+        dt = time.perf_counter() - t0
+        out[name] = {'seconds': dt, 'value': 2.0 * N * 100 / dt, 'evaluations': len(expl),
+                     'final_exploitability': expl[-1][1], 'kwargs': kw}
+    return out
 
 
 if __name__ == '__main__':

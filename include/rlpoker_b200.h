@@ -155,6 +155,10 @@ int rlp_cfr_exploitability(rlp_cfr *cfr, int which, double *out3, void *stream);
  * sum_I max_a total[I,a] / (step+1), the I terms added in `order` (canonical information-set ids;
  * NULL = canonical order) with the compensated sum CPython's sum() uses. */
 int rlp_cfr_immediate_regret_step(rlp_cfr *cfr, int64_t step, const int32_t *order, double *out, void *stream);
+/* Same, and the per-information-set terms 1/(1+step) * max_a total[I,a] -- the step-th dictionary of the third value
+ * compute_immediate_regret returns (cfr_metrics.py:68-73,78) -- into per_iset[I] (canonical ids; nullable). */
+int rlp_cfr_immediate_regret_detail(rlp_cfr *cfr, int64_t step, const int32_t *order, double *out, double *per_iset,
+                                    void *stream);
 
 /*
  * Best response of `player` against `sigma` ([Q], host, canonical, complete):
@@ -166,6 +170,11 @@ int rlp_best_response(rlp_tree *tree, const double *sigma, int player, double *v
 
 /* (u1, u2) expected under `sigma` for both players: extensive_game.py:382-423. out2 = {u1, u2}. */
 int rlp_expected_value(rlp_tree *tree, const double *sigma, double *out2, void *stream);
+
+/* Value of every node for both players under `sigma` ([Q], host, canonical, complete; player-p rows are used at
+ * player-p nodes): cfr_metrics.py:159-254 compute_expected_utility(_recursive).  v1_out / v2_out: host [N] in
+ * breadth-first node order (terminals hold their utilities); either may be NULL. */
+int rlp_node_values(rlp_tree *tree, const double *sigma, double *v1_out, double *v2_out, void *stream);
 
 /* ---- multi-GPU (deal-sharded trees; one process per GPU) ---------------------------------- */
 /*

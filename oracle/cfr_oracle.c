@@ -654,8 +654,16 @@ static void node_regret_rec(const orc_tree *t, int32_t node, const double *sigma
  * Returns sum_I 1/(1+t) * max_a cumulative[I,a] with the builtin-sum (Neumaier) outer sum taken
  * in `order` (the reference's dict order; canonical when NULL).
  */
+double orc_immediate_regret_detail(const orc_tree *t, const double *sigma, double *cumulative, double *scratch,
+                                   int64_t step, const int32_t *order, double *per_iset);
 double orc_immediate_regret_step(const orc_tree *t, const double *sigma, double *cumulative, double *scratch,
                                  int64_t step, const int32_t *order) {
+    return orc_immediate_regret_detail(t, sigma, cumulative, scratch, step, order, NULL);
+}
+
+/* Same; per_iset[I] (nullable) receives the step's dictionary of cfr_metrics.py:68-73 in canonical order. */
+double orc_immediate_regret_detail(const orc_tree *t, const double *sigma, double *cumulative, double *scratch,
+                                   int64_t step, const int32_t *order, double *per_iset) {
     int64_t Q = t->act_off[t->num_infosets];
     memset(scratch, 0, sizeof(double) * Q);
     double a1, a2;
@@ -669,9 +677,34 @@ double orc_immediate_regret_step(const orc_tree *t, const double *sigma, double 
         double mx = cu[0];
         for (int a = 1; a < n; ++a) if (cu[a] > mx) mx = cu[a];
         double x = 1.0 / (double)(1 + step) * mx;
+        if (per_iset) per_iset[I] = x;
         double tt = s + x;
         if (fabs(s) >= fabs(x)) comp += (s - tt) + x; else comp += (x - tt) + s;
         s = tt;
     }
     return s + comp;
+}
+
+/* ------------------------------ node values (cfr_metrics.py:159-254) */
+
+/* compute_expected_utility_recursive: v_i(h) = sum over children, in child order from 0.0, of (chance probability or
+ * the actor's strategy) * v_i(child); terminals return their utilities.  sigma[Q] holds player-1 rows at player-1
+ * information sets and player-2 rows at player-2 ones.  v1 / v2: [N]. */
+static void node_value_rec(const orc_tree *t, int32_t node, const double *sigma, double *v1, double *v2) {
+    int pl = t->player[node];
+    if (pl == -1) { v1[node] = t->u1[node]; v2[node] = t->u2[node]; return; }
+    int32_t fc = t->first_child[node];
+    int n = t->first_child[node + 1] - fc;
+    double a1 = 0.0, a2 = 0.0;
+    for (int a = 0; a < n; ++a) {
+        node_value_rec(t, fc + a, sigma, v1, v2);
+        double p = pl == 0 ? t->cprob[fc + a] : sigma[t->act_off[t->infoset[node]] + a];
+        a1 += p * v1[fc + a];
+        a2 += p * v2[fc + a];
+    }
+    v1[node] = a1; v2[node] = a2;
+}
+
+void orc_node_values(const orc_tree *t, const double *sigma, double *v1, double *v2) {
+    node_value_rec(t, 0, sigma, v1, v2);
 }

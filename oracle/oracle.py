@@ -36,8 +36,8 @@ class _Rng(C.Structure):
 
 
 def build(force=False):
-    src = os.path.join(_HERE, 'cfr_oracle.c')
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ('cfr_oracle.c', 'leduc_oracle.c')]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(['make', '-s', '-C', _HERE, '-B'])
     return _SO
 
@@ -52,9 +52,11 @@ def lib():
         _lib.orc_philox_uniform.restype = C.c_double
         _lib.orc_philox_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         _lib.orc_immediate_regret_step.restype = C.c_double
+        _lib.orc_immediate_regret_detail.restype = C.c_double
         _lib.orc_cfr_recursive_iters.restype = C.c_int64
         _lib.orc_vanilla_level_iters.restype = C.c_int64
         _lib.orc_external_iters.restype = C.c_int64
+        _lib.orc_leduc_build.restype = C.c_int64
     return _lib
 
 
@@ -180,12 +182,21 @@ class Oracle:
         lib().orc_expected_value_exact(C.byref(self.c), _p(sigma, _dp), _p(out, _dp))
         return float(out[0]), float(out[1])
 
-    def immediate_regret_step(self, sigma, step, order=None):
+    def immediate_regret_step(self, sigma, step, order=None, detail=False):
         sigma = np.ascontiguousarray(sigma, np.float64)
         scratch = np.zeros(self.Q)
-        return lib().orc_immediate_regret_step(
+        per_iset = np.zeros(self.t.num_infosets) if detail else None
+        v = lib().orc_immediate_regret_detail(
             C.byref(self.c), _p(sigma, _dp), _p(self.cum_regret, _dp), _p(scratch, _dp), C.c_int64(step),
-            _p(order, _i32p) if order is not None else None)
+            _p(order, _i32p) if order is not None else None, _p(per_iset, _dp) if detail else None)
+        return (v, per_iset) if detail else v
+
+    def node_values(self, sigma):
+        """(v1[N], v2[N]) per cfr_metrics.py:159-254."""
+        sigma = np.ascontiguousarray(sigma, np.float64)
+        v1, v2 = np.zeros(self.t.num_nodes), np.zeros(self.t.num_nodes)
+        lib().orc_node_values(C.byref(self.c), _p(sigma, _dp), _p(v1, _dp), _p(v2, _dp))
+        return v1, v2
 
 
 def regret_matching(r, eps=1e-7, highest_regret=False):
@@ -209,3 +220,24 @@ def draw(p, u):
 
 def philox_uniform(seed, iteration, lane, trav, draw_idx):
     return lib().orc_philox_uniform(seed, iteration, lane, trav, draw_idx)
+
+
+def leduc_tree(num_values, num_suits=2, max_raises=4, raise_amount=2):
+    """Leduc(get_deck(num_values, num_suits)) as an OracleTree, built by the oracle's own C generator
+    (leduc_oracle.c) -- no product code involved."""
+    from oracle import flat
+    ni = C.c_int32(0)
+    n = lib().orc_leduc_build(int(num_values), int(num_suits), int(max_raises), int(raise_amount), C.byref(ni))
+    if n < 0:
+        raise ValueError('cannot build Leduc(%d, %d)' % (num_values, num_suits))
+    parent, infoset, label = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.int32)
+    first_child = np.empty(n + 1, np.int32)
+    player, hidden = np.empty(n, np.int8), np.empty(n, np.uint8)
+    cprob, u1, u2 = np.empty(n), np.empty(n), np.empty(n)
+    rc = lib().orc_leduc_fetch(_p(parent, _i32p), _p(first_child, _i32p), _p(player, C.POINTER(C.c_int8)),
+                               _p(infoset, _i32p), _p(label, _i32p), _p(hidden, _u8p), _p(cprob, _dp), _p(u1, _dp),
+                               _p(u2, _dp))
+    assert rc == 0
+    t = flat.from_arrays(n, parent, first_child, player, infoset, label, hidden, cprob, u1, u2)
+    assert t.num_infosets == ni.value
+    return t

@@ -61,6 +61,8 @@ SYMBOLS = {
     'rlp_nodes_touched': (C.c_uint64, [_vp]),
     'rlp_cfr_exploitability': (C.c_int, [_vp, C.c_int, _dp, _vp]),
     'rlp_cfr_immediate_regret_step': (C.c_int, [_vp, C.c_int64, _i32p, _dp, _vp]),
+    'rlp_cfr_immediate_regret_detail': (C.c_int, [_vp, C.c_int64, _i32p, _dp, _dp, _vp]),
+    'rlp_node_values': (C.c_int, [_vp, _dp, _dp, _dp, _vp]),
     'rlp_best_response': (C.c_int, [_vp, _dp, C.c_int, _dp, _i32p, _vp]),
     'rlp_expected_value': (C.c_int, [_vp, _dp, _dp, _vp]),
     'rlp_cfr_local_sweep': (C.c_int, [_vp, C.c_int64, C.c_int, _vp]),

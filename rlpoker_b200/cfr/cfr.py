@@ -93,6 +93,7 @@ class StrategyHistory(Sequence):
         self._sigmas, self._present = [], []
         self._limit = limit_bytes
         self._count = 0
+        self._base = 0              # iterations before a resume point: counted, but their strategies are not here
         self.immediate_regrets = []
 
     def _append(self, sigma, present):
@@ -111,10 +112,13 @@ class StrategyHistory(Sequence):
             index += self._count
         if not 0 <= index < self._count:
             raise IndexError(index)
-        if index >= len(self._sigmas):
+        if index < self._base:
+            raise IndexError("strategy %d predates the resume point (iteration %d); only later strategies are held"
+                             % (index, self._base))
+        if index - self._base >= len(self._sigmas):
             raise IndexError("strategy %d was not kept (history limited to %d bytes; pass keep_strategies=...)"
                              % (index, self._limit))
-        return DeviceStrategy(self._flat, self._sigmas[index], self._present[index])
+        return DeviceStrategy(self._flat, self._sigmas[index - self._base], self._present[index - self._base])
 
 
 def _unpack(args, kwargs):
@@ -166,14 +170,24 @@ def cfr(*args, **kwargs):
     ft = flatten(game)
     solver = DeviceCFR(device_tree(game))
     ckpt = SolverCheckpoint(experiment) if experiment is not None and (checkpoint or resume) else None
+    resumed = {}
     if resume and ckpt is not None and ckpt.exists():
-        saved_seed, _ = ckpt.load(solver)
+        saved_seed, resumed = ckpt.load(solver)
         seed = saved_seed if seed is None else seed
     if sampling and seed is None:
         seed = int(np.random.randint(0, 2 ** 31 - 1))
     saver = CFRStrategySaver(experiment=experiment) if experiment is not None else None
+    if saver is not None and resumed.get('best_exploitability') is not None:      # never overwrite a better best_strategy.pkl
+        saver._best_exploitability = float(resumed['best_exploitability'])
+        saver._best_exploitability_t = int(resumed.get('best_exploitability_t', 0))
     order = postorder_infoset_order(ft) if want_imm else None
     history = StrategyHistory(ft, limit_bytes=int(keep) if keep else 0)
+    if want_imm and solver.t > 0:
+        series = resumed.get('immediate_regrets')
+        if series is None or len(series) != solver.t:
+            raise ValueError("cannot resume with immediate_regret=True: the checkpoint does not hold the immediate-regret "
+                             "series of its %d iterations (it was written with immediate_regret=False)" % solver.t)
+        history.immediate_regrets = [float(x) for x in series]
     exploitabilities = []
     average_strategy = None
     every_iter = want_imm or bool(keep)
@@ -192,7 +206,7 @@ def cfr(*args, **kwargs):
 
     start = time.time()
     t = solver.t
-    history._count = t                         # iterations before a resume point are not part of the history
+    history._count = history._base = t         # iterations before a resume point are counted, not held
     while t < num_iters:
         n = 1 if every_iter else min(num_iters - t, 10 - t % 10 if t % 10 else 1)
         advance(n)
@@ -227,7 +241,10 @@ def cfr(*args, **kwargs):
                 average_strategy = current_average()
                 saver.save_best_strategy(average_strategy, t_last, exploitability)
             if checkpoint and ckpt is not None:
-                ckpt.save(solver, seed=seed, use_chance_sampling=sampling, linear_weight=linear_weight)
+                ckpt.save(solver, seed=seed, use_chance_sampling=sampling, linear_weight=linear_weight,
+                          immediate_regrets=history.immediate_regrets if want_imm else None,
+                          best_exploitability=saver._best_exploitability if saver is not None else None,
+                          best_exploitability_t=saver._best_exploitability_t if saver is not None else None)
         t += n
     if num_iters > 0:
         average_strategy = current_average()

@@ -104,18 +104,54 @@ __global__ void __launch_bounds__(kBlock) k_ev_fwd(BrView v, int64_t lo, int64_t
     for (int k = 0; k < n; ++k) v.reach[fc + k] = r * (pl == 0 ? v.cprob[fc + k] : sg[k]);
 }
 
-// Sequential (one thread) ordered sum over terminals: exact reproduction of the reference's
-// accumulation order.  Only used by the expected_value API (not on the solver's hot path).
-__global__ void k_ev_sum(BrView v, int64_t N, double *out2) {
+// Ordered sum over terminals (extensive_game.py:404-406 adds reach * utility in breadth-first order into one running
+// double, so the association is fixed: no tree reduction can reproduce it).  One CTA: all threads stage a chunk of
+// products in shared memory with coalesced loads, thread 0 then adds the chunk's terminal terms in order.  The chain
+// of dependent adds is the floor (~2.1 M adds at Leduc-13); the loads are off it.
+constexpr int kEvChunk = 1024;
+__global__ void __launch_bounds__(kEvChunk) k_ev_sum(BrView v, int64_t N, double *out2) {
+    __shared__ double t1[kEvChunk], t2[kEvChunk];
+    __shared__ unsigned char term[kEvChunk];
     double e1 = 0.0, e2 = 0.0;
-    for (int64_t i = 0; i < N; ++i) {
-        if (v.player[i] >= 0) continue;
-        double u1 = v.pay1[i], u2 = v.zero_sum ? -u1 : v.pay2[i];
-        e1 += v.reach[i] * u1;
-        e2 += v.reach[i] * u2;
+    for (int64_t base = 0; base < N; base += kEvChunk) {
+        const int64_t i = base + threadIdx.x;
+        bool is_t = false;
+        if (i < N && v.player[i] < 0) {
+            is_t = true;
+            const double u1 = v.pay1[i], u2 = v.zero_sum ? -u1 : v.pay2[i], r = v.reach[i];
+            t1[threadIdx.x] = r * u1;
+            t2[threadIdx.x] = r * u2;
+        }
+        term[threadIdx.x] = is_t ? 1 : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int n = (int)(N - base < kEvChunk ? N - base : kEvChunk);
+            for (int k = 0; k < n; ++k)
+                if (term[k]) { e1 += t1[k]; e2 += t2[k]; }
+        }
+        __syncthreads();
     }
-    out2[0] = e1;
-    out2[1] = e2;
+    if (threadIdx.x == 0) { out2[0] = e1; out2[1] = e2; }
+}
+
+// Node values under a strategy profile (cfr_metrics.py:181-254 compute_expected_utility_recursive):
+// v(h) = ((0 + e_0 v(c_0)) + e_1 v(c_1)) + ... in child order, e = chance probability or the actor's strategy.
+template <bool ZS>
+__global__ void __launch_bounds__(kBlock) k_val_level(BrView v, double *val1, double *val2, int64_t lo, int64_t hi) {
+    int64_t i = lo + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= hi) return;
+    int pl = v.player[i];
+    if (pl < 0) return;
+    int fc = v.first_child[i], n = v.first_child[i + 1] - fc;
+    const double *sg = pl > 0 ? v.sigma + v.colbase[i] : nullptr;
+    double a1 = 0.0, a2 = 0.0;
+    for (int k = 0; k < n; ++k) {
+        double e = pl == 0 ? v.cprob[fc + k] : sg[k];
+        a1 = a1 + e * val1[fc + k];
+        if (!ZS) a2 = a2 + e * val2[fc + k];
+    }
+    val1[i] = a1;
+    if (!ZS) val2[i] = a2;
 }
 
 __global__ void k_set_one(double *p) { *p = 1.0; }
@@ -269,8 +305,37 @@ extern "C" int rlp_expected_value(rlp_tree *t, const double *sigma, double *out2
         int64_t lo = t->level_off[l], hi = t->level_off[l + 1];
         k_ev_fwd<<<grid_for(hi - lo), kBlock, 0, s>>>(v, lo, hi); RLP_LAUNCH_CHECK();
     }
-    k_ev_sum<<<1, 1, 0, s>>>(v, t->N, c->scalars.p + 2); RLP_LAUNCH_CHECK();
+    k_ev_sum<<<1, kEvChunk, 0, s>>>(v, t->N, c->scalars.p + 2); RLP_LAUNCH_CHECK();
     RLP_CUDA(cudaMemcpyAsync(out2, c->scalars.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     RLP_CUDA(cudaStreamSynchronize(s));
+    return RLP_OK;
+}
+
+// Value of EVERY node for both players under `sigma` (host, [Q], canonical; player-1 rows are read at player-1
+// nodes and player-2 rows at player-2 nodes, so sigma = sigma_1 merged with sigma_2):
+// cfr_metrics.py:159-254 compute_expected_utility / compute_expected_utility_recursive.  v1_out / v2_out are host
+// arrays [N] in breadth-first node order (terminals hold their utilities); either may be NULL.
+extern "C" int rlp_node_values(rlp_tree *t, const double *sigma, double *v1_out, double *v2_out, void *stream_) {
+    if (!t || !sigma) return fail(RLP_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    rlp_cfr *c = scratch_solver(t, stream_);
+    if (!c) return RLP_ERR_CUDA;
+    RLP_CUDA(cudaMemcpyAsync(c->tmpQ.p, sigma, sizeof(double) * (size_t)t->Q, cudaMemcpyHostToDevice, s));
+    int rc = rlp::permute(t, c->tmpQ.p, c->avg.p, 1, s);
+    if (rc) return rc;
+    BrView v = make_view(c, c->avg.p, 0);
+    // val1 / val2 hold the payoffs at terminals permanently (rlp_cfr_create); interior nodes are rewritten here
+    for (int l = t->L - 2; l >= 0; --l) {
+        int64_t lo = t->level_off[l], hi = t->level_off[l + 1];
+        if (t->zero_sum) k_val_level<true><<<grid_for(hi - lo), kBlock, 0, s>>>(v, c->val1.p, c->val2.p, lo, hi);
+        else k_val_level<false><<<grid_for(hi - lo), kBlock, 0, s>>>(v, c->val1.p, c->val2.p, lo, hi);
+        RLP_LAUNCH_CHECK();
+    }
+    const size_t bytes = sizeof(double) * (size_t)t->N;
+    if (v1_out) RLP_CUDA(cudaMemcpyAsync(v1_out, c->val1.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (v2_out) RLP_CUDA(cudaMemcpyAsync(v2_out, t->zero_sum ? c->val1.p : c->val2.p, bytes, cudaMemcpyDeviceToHost, s));
+    RLP_CUDA(cudaStreamSynchronize(s));
+    if (v2_out && t->zero_sum)                       // v2 = -v1 exactly (negation commutes with rounding)
+        for (int64_t i = 0; i < t->N; ++i) v2_out[i] = -v2_out[i];
     return RLP_OK;
 }

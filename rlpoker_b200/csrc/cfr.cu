@@ -744,6 +744,8 @@ extern "C" int rlp_cfr_read_flags(rlp_cfr *c, uint8_t *dst, void *stream_) {
 }
 
 // ---- immediate regret (cfr_metrics.py:13-78), one strategy per call ------------------------------------
+extern "C" int rlp_cfr_immediate_regret_detail(rlp_cfr *c, int64_t step, const int32_t *order, double *out,
+                                               double *per_iset_out, void *stream_);
 namespace {
 __global__ void __launch_bounds__(kBlock)
 k_imm_regret(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__restrict__ col_off,
@@ -767,6 +769,13 @@ k_imm_regret(int32_t I, const int32_t *__restrict__ iset_size, const int64_t *__
 }  // namespace
 
 extern "C" int rlp_cfr_immediate_regret_step(rlp_cfr *c, int64_t step, const int32_t *order, double *out, void *stream_) {
+    return rlp_cfr_immediate_regret_detail(c, step, order, out, nullptr, stream_);
+}
+
+// Same, and additionally the per-information-set terms 1/(1+step) * max_a total[I,a] (the t-th dictionary of
+// cfr_metrics.compute_immediate_regret's third return value, cfr_metrics.py:68-73) into per_iset[I] (canonical ids).
+extern "C" int rlp_cfr_immediate_regret_detail(rlp_cfr *c, int64_t step, const int32_t *order, double *out,
+                                               double *per_iset_out, void *stream_) {
     if (!c || !out || step < 0) return fail(RLP_ERR_INVALID, "bad argument");
     cudaStream_t s = (cudaStream_t)stream_;
     rlp_tree *t = c->tree;
@@ -789,6 +798,8 @@ extern "C" int rlp_cfr_immediate_regret_step(rlp_cfr *c, int64_t step, const int
     rlp::Neumaier acc;
     for (int32_t k = 0; k < t->I; ++k) acc.add(h[t->srank_of_iset[order ? order[k] : k]]);
     *out = acc.total();
+    if (per_iset_out)
+        for (int32_t k = 0; k < t->I; ++k) per_iset_out[k] = h[t->srank_of_iset[k]];
     return RLP_OK;
 }
 

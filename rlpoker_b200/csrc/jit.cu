@@ -6,7 +6,8 @@
 // literal, every intermediate a named double -- and compiles it for sm_100a with NVRTC (--fmad=false, like the rest
 // of the library).  The result keeps the whole subtree in registers, issues all of its loads up front, and runs
 // ~6x fewer instructions.  The arithmetic, operand for operand, is that of k_micro / cfr.cu / the reference's
-// cfr_recursive (rlpoker/cfr/cfr.py:158-255).  If NVRTC is unavailable (or RLP_NO_JIT=1) the interpreter is used.
+// cfr_recursive (rlpoker/cfr/cfr.py:158-255).  RLP_NO_JIT=1 selects the interpreter kernels instead; a missing NVRTC or
+// a failed compile is a hard error (no silent fallback).
 #include <dlfcn.h>
 #include <nvrtc.h>
 
@@ -148,15 +149,18 @@ std::string generate(const MicroTmpl &tm, bool zs) {
 
 namespace rlp {
 
-// Compile the straight-line kernel of `tm`; returns RLP_OK with *kernel == nullptr when JIT is unavailable.
-// Compile `src` for sm_100a and load it; *lib_out stays null when JIT is unavailable or the compile fails.
+// Compile `src` for sm_100a and load it; *lib_out stays null only under RLP_NO_JIT=1 (or in planning mode).
 static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std::string *log_out) {
     *lib_out = nullptr;
+    // RLP_NO_JIT=1 is the ONLY way onto the interpreter kernels for a tree whose shapes qualify for straight-line
+    // code: a missing libnvrtc or a failed compile is an error, not a silent 3x slowdown.
     const char *no_jit = getenv("RLP_NO_JIT");
     if (no_jit && no_jit[0] == '1') return RLP_OK;
-    if (!g_nvrtc.load()) return RLP_OK;
+    if (!g_nvrtc.load())
+        return fail(RLP_ERR_UNSUPPORTED, "libnvrtc.so.12 could not be loaded (set RLP_NO_JIT=1 to run the interpreter kernels)");
     nvrtcProgram prog;
-    if (g_nvrtc.create(&prog, src.c_str(), "micro_k.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return RLP_OK;
+    if (g_nvrtc.create(&prog, src.c_str(), "micro_k.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(RLP_ERR_CUDA, "nvrtcCreateProgram failed");
     const char *opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17"};
     nvrtcResult res = g_nvrtc.compile(prog, 4, opts);
     if (res != NVRTC_SUCCESS) {
@@ -166,9 +170,8 @@ static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std:
         if (n) g_nvrtc.log(prog, &log[0]);
         if (log_out) *log_out = log;
         rlp::g_jit_failed++;
-        snprintf(rlp::g_error, sizeof(rlp::g_error), "NVRTC: %.400s", log.c_str());
         g_nvrtc.destroy(&prog);
-        return RLP_OK;                          // fall back to the interpreter
+        return fail(RLP_ERR_CUDA, "NVRTC compile failed: %.400s", log.c_str());
     }
     rlp::g_jit_compiled++;
     if (rlp::g_dry_run) {                        // planning mode: the source compiled; nothing to load without a GPU
@@ -181,9 +184,10 @@ static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std:
     g_nvrtc.cubin(prog, cubin.data());
     g_nvrtc.destroy(&prog);
     cudaLibrary_t lib;
-    if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+    cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) {
         cudaGetLastError();
-        return RLP_OK;
+        return fail(RLP_ERR_CUDA, "cudaLibraryLoadData of a generated kernel: %s", cudaGetErrorString(e));
     }
     *lib_out = lib;
     return RLP_OK;
@@ -199,6 +203,7 @@ int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaK
         cudaLibraryUnload(*lib_out);
         *lib_out = nullptr;
         *kernel = nullptr;
+        return fail(RLP_ERR_CUDA, "generated library has no micro_k");
     }
     return RLP_OK;
 }
@@ -343,6 +348,7 @@ int jit_upper_kernels(const UpperShape &sh, bool zs, cudaLibrary_t *lib_out, cud
         cudaLibraryUnload(*lib_out);
         *lib_out = nullptr;
         *k0 = *k1 = nullptr;
+        return fail(RLP_ERR_CUDA, "generated library has no upper_k0 / upper_k1");
     }
     return RLP_OK;
 }

@@ -886,10 +886,13 @@ static int launch_upper_jit(rlp_cfr *c, TileSet &ts, int phase, const IterState 
 
 template <bool ZS, int R, bool WIDE, int PHASE>
 static int launch_variant(const TileSet &ts, const TileView &v, cudaStream_t s) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device (context), not per thread: one bit per device ordinal
+    static std::atomic<uint64_t> attr_set{0};
+    int dev = 0;
+    RLP_CUDA(cudaGetDevice(&dev));
+    if (!(attr_set.load() >> (dev & 63) & 1)) {
         RLP_CUDA(cudaFuncSetAttribute(k_tile_sweep<ZS, R, WIDE, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_set = true;
+        attr_set.fetch_or(1ull << (dev & 63));
     }
     RLP_CUDA(rlp::launch_pdl(k_tile_sweep<ZS, R, WIDE, PHASE>, dim3(ts.num_tiles), dim3(ts.block), ts.smem_bytes, s, v));
     rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -974,11 +977,13 @@ int launch_tile_stage(rlp_cfr *c, cudaStream_t s, const IterState *iter, int sta
         m.portal_v2 = ts.portal_v2.p; m.contrib_r = c->contrib_r.p; m.contrib_o = c->contrib_o.p;
         m.iter = v.iter; m.P = ts.num_micro; m.num_classes = ts.num_classes; m.mn = ts.micro_nodes; m.mnt = ts.micro_nt;
         unsigned g = (unsigned)((ts.num_micro + kMicroBlock - 1) / kMicroBlock);
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<uint64_t> attr_set{0};      // per device ordinal (the attribute is per context)
+        int dev = 0;
+        RLP_CUDA(cudaGetDevice(&dev));
+        if (!(attr_set.load() >> (dev & 63) & 1)) {
             RLP_CUDA(cudaFuncSetAttribute(k_micro<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             RLP_CUDA(cudaFuncSetAttribute(k_micro<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
+            attr_set.fetch_or(1ull << (dev & 63));
         }
         if (t->zero_sum) RLP_CUDA(rlp::launch_pdl(k_micro<true>, dim3(g), dim3(kMicroBlock), ts.micro_smem, s, m));
         else RLP_CUDA(rlp::launch_pdl(k_micro<false>, dim3(g), dim3(kMicroBlock), ts.micro_smem, s, m));

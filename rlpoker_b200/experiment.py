@@ -126,9 +126,10 @@ class StrategySaver:
 
 
 class SolverCheckpoint:
-    """Stop / resume for a device solver: regrets, strategy sums, current strategy, membership flags, iteration
-    counter and the sampler seed in one ``.npz`` (flat arrays in canonical pair order, so the file is independent of the
-    device layout)."""
+    """Stop / resume for a device solver: regrets, strategy sums, current strategy, the running immediate-regret totals
+    (cfr_metrics.py:71-76), membership flags, iteration counter, nodes touched and the sampler seed in one ``.npz``
+    (flat arrays in canonical pair order, so the file is independent of the device layout).  ``extra`` carries what the
+    driver needs to continue its own series (best exploitability so far, the immediate-regret series)."""
 
     FILE = 'solver_state.npz'
 
@@ -137,10 +138,11 @@ class SolverCheckpoint:
         self.path = os.path.join(root, self.FILE)
 
     def save(self, solver, seed=None, **extra):
-        from rlpoker_b200._lib import RLP_REGRET, RLP_SIGMA, RLP_STRAT_SUM
+        from rlpoker_b200._lib import RLP_CUM_IMM_REGRET, RLP_REGRET, RLP_SIGMA, RLP_STRAT_SUM
         tmp = self.path + '.tmp.npz'
         np.savez(tmp, regrets=solver.read(RLP_REGRET), sums=solver.read(RLP_STRAT_SUM), sigma=solver.read(RLP_SIGMA),
-                 flags=solver.flags(), t=np.int64(solver.t), seed=np.int64(-1 if seed is None else seed),
+                 cum_imm=solver.read(RLP_CUM_IMM_REGRET), flags=solver.flags(), t=np.int64(solver.t),
+                 nodes_touched=np.uint64(solver.nodes_touched), seed=np.int64(-1 if seed is None else seed),
                  extra=json.dumps(extra))
         os.replace(tmp, self.path)
         return self.path
@@ -150,7 +152,7 @@ class SolverCheckpoint:
 
     def load(self, solver):
         """Restore ``solver`` in place; returns (seed or None, extra dict)."""
-        from rlpoker_b200._lib import RLP_REGRET, RLP_SIGMA, RLP_STRAT_SUM
+        from rlpoker_b200._lib import RLP_CUM_IMM_REGRET, RLP_REGRET, RLP_SIGMA, RLP_STRAT_SUM
         with np.load(self.path) as state:
             if state['regrets'].shape != (solver.tree.num_pairs,):
                 raise ValueError("checkpoint is for a different game (%d pairs, solver has %d)"
@@ -159,6 +161,10 @@ class SolverCheckpoint:
             solver.write(RLP_STRAT_SUM, state['sums'])
             solver.write(RLP_SIGMA, state['sigma'])
             solver.write_flags(state['flags'])
+            if 'cum_imm' in state:
+                solver.write(RLP_CUM_IMM_REGRET, state['cum_imm'])
+            if 'nodes_touched' in state:
+                solver.set_nodes_touched(int(state['nodes_touched']))
             solver.t = int(state['t'])
             seed = int(state['seed'])
             extra = json.loads(str(state['extra']))

@@ -187,7 +187,28 @@ class ShardedCFR:
             ident = torch.tensor(list(buf), dtype=torch.uint8)
         arr = (C.c_uint8 * 128)(*ident.tolist())
         rc = lib.rlp_comm_init(self.solver.handle, self.rank, self.world, arr)
-        self._native = rc == 0
+        ok_all = rc == 0
+        if self.world > 1:
+            # every rank must take the same path: agree on the outcome before anyone enters a collective
+            flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=torch.device('cuda', torch.cuda.current_device()))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            ok_all = int(flag.item()) == 1
+            if not ok_all:
+                lib.rlp_comm_destroy(self.solver.handle)
+                raise _lib.RlpError("rlp_comm_init failed on at least one rank (this rank: status %d, %s)"
+                                    % (rc, lib.rlp_last_error().decode()))
+        self._native = ok_all
+
+    def close(self):
+        """Free the solver, its communicator and the rank-local device tree."""
+        self.delta = None
+        self._cuda_graph = None
+        solver, self.solver = self.solver, None
+        if solver is not None:
+            solver.close()
+        tree, self.tree = self.tree, None
+        if tree is not None:
+            tree.close()
 
     GRAPH_ITERS = 10
 

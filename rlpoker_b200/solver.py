@@ -107,6 +107,13 @@ class DeviceTree:
         if h:
             _lib.load().rlp_tree_free(h)
 
+    def __del__(self):
+        # Safe: every DeviceCFR holds a reference to its tree, so all solvers are freed before the tree is.
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 def device_tree(game_or_flat, stream=None):
     """Flatten (once) and upload (once per game object)."""
@@ -133,18 +140,23 @@ class DeviceCFR:
         self.handle = C.c_void_p()
         check(_lib.load().rlp_cfr_create(tree.handle, _stream_ptr(stream), C.byref(self.handle)))
         self.t = 0
+        self._touched_base = 0      # nodes touched before a resume point (SolverCheckpoint.load)
 
-    def __del__(self):
+    def close(self):
         h, self.handle = getattr(self, 'handle', None), None
         if h:
-            try:
-                _lib.load().rlp_cfr_free(h)
-            except Exception:
-                pass
+            _lib.load().rlp_cfr_free(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def reset(self, stream=None):
         check(_lib.load().rlp_cfr_reset(self.handle, _stream_ptr(stream)))
         self.t = 0
+        self._touched_base = 0
 
     def vanilla(self, n_iters, linear_weight=False, stream=None):
         check(_lib.load().rlp_cfr_vanilla_iters(self.handle, self.t, int(n_iters), int(bool(linear_weight)),
@@ -208,7 +220,11 @@ class DeviceCFR:
 
     @property
     def nodes_touched(self):
-        return int(_lib.load().rlp_nodes_touched(self.handle))
+        return self._touched_base + int(_lib.load().rlp_nodes_touched(self.handle))
+
+    def set_nodes_touched(self, total):
+        """Make ``nodes_touched`` continue from ``total`` (resume from a checkpoint)."""
+        self._touched_base = int(total) - int(_lib.load().rlp_nodes_touched(self.handle))
 
     def exploitability(self, which=RLP_AVERAGE, stream=None):
         """(total, BR1, BR2) of the average (default) or current strategy, computed on the device."""
@@ -216,14 +232,18 @@ class DeviceCFR:
         check(_lib.load().rlp_cfr_exploitability(self.handle, which, ptr(out, _lib._dp), _stream_ptr(stream)))
         return float(out[0]), float(out[1]), float(out[2])
 
-    def immediate_regret_step(self, step, order=None, stream=None):
+    def immediate_regret_step(self, step, order=None, stream=None, detail=False):
+        """One step of cfr_metrics.compute_immediate_regret for the current strategy; with ``detail`` also the [I]
+        per-information-set terms (canonical order)."""
         out = C.c_double()
         if order is not None:
             order = np.ascontiguousarray(order, np.int32)
-        check(_lib.load().rlp_cfr_immediate_regret_step(self.handle, int(step),
-                                                        ptr(order, _lib._i32p) if order is not None else None,
-                                                        C.byref(out), _stream_ptr(stream)))
-        return out.value
+        per_iset = np.empty(self.tree.flat.num_infosets, np.float64) if detail else None
+        check(_lib.load().rlp_cfr_immediate_regret_detail(self.handle, int(step),
+                                                          ptr(order, _lib._i32p) if order is not None else None,
+                                                          C.byref(out), ptr(per_iset, _lib._dp) if detail else None,
+                                                          _stream_ptr(stream)))
+        return (out.value, per_iset) if detail else out.value
 
     # multi-GPU split
     def local_sweep(self, linear_weight=False, stream=None, keep_counter=False):

@@ -169,6 +169,44 @@ def test_checkpoint_and_resume(tmp_path):
     assert [t for t, _ in expl] == [30, 40] and len(hist) == 41
 
 
+def test_resume_with_default_arguments(tmp_path):
+    """Resume with immediate_regret=True and the strategy history on (the defaults): the immediate-regret series, the
+    nodes-touched counter, the history indexing and best_strategy.pkl must continue as if never interrupted."""
+    import pickle
+    from rlpoker_b200.cfr.cfr import cfr
+    from rlpoker_b200.cfr.cfr_metrics import compute_immediate_regret
+    from rlpoker_b200.experiment import Experiment
+
+    class Log:
+        def __init__(self):
+            self.rows = []
+
+        def log(self, data, global_step=None):
+            self.rows.append((global_step, dict(data)))
+
+    game = make_game('leduc2')
+    w_full, w_a, w_b = Log(), Log(), Log()
+    full, expl_full, hist_full = cfr(Experiment('full', base_save_path=str(tmp_path)), game, num_iters=41,
+                                     use_chance_sampling=False, verbose=False, experiment_writer=w_full)
+    exp = Experiment('parts', base_save_path=str(tmp_path))
+    cfr(exp, game, num_iters=21, use_chance_sampling=False, verbose=False, checkpoint=True, experiment_writer=w_a)
+    with open(os.path.join(exp.save_path, 'best_strategy.pkl'), 'rb') as f:
+        best_before = pickle.load(f)
+    resumed, expl, hist = cfr(exp, game, num_iters=41, use_chance_sampling=False, verbose=False, resume=True,
+                              experiment_writer=w_b)
+    assert np.array_equal(resumed.sigma_array, full.sigma_array)
+    assert hist.immediate_regrets == hist_full.immediate_regrets
+    assert w_a.rows + w_b.rows == w_full.rows                 # nodes_touched, exploitability, immediate_regret per step
+    assert len(hist) == 41 and hist[40] == hist_full[40] and hist[-1] == hist_full[-1] and hist[21] == hist_full[21]
+    with pytest.raises(IndexError, match='resume point'):
+        hist[0]
+    assert compute_immediate_regret(game, hist)[:2] == compute_immediate_regret(game, hist_full)[:2]
+    # exploitability falls over this horizon, so the resumed run must have replaced the pickle with a better strategy
+    with open(os.path.join(exp.save_path, 'best_strategy.pkl'), 'rb') as f:
+        best_after = pickle.load(f)
+    assert expl[-1][1] < expl_full[2][1] and best_after != best_before
+
+
 def test_command_line_front_end(tmp_path):
     import subprocess
     import sys

@@ -1,0 +1,35 @@
+"""Real multi-process runs: one process per GPU, launched with torch.distributed.run on 127.0.0.1.  Skipped on
+boxes with fewer than two GPUs (the single-GPU emulation of the same logic is tests/test_gpu_sharded.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _torchrun(world, script, args, env=None, timeout=420):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+           '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 2000),
+           os.path.join(ROOT, 'tests', 'workers', script)] + [str(a) for a in args]
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run(cmd, env=e, text=True, capture_output=True, timeout=timeout)
+    assert out.returncode == 0, out.stdout[-3000:] + '\n' + out.stderr[-3000:]
+    return out.stdout
+
+
+@pytest.mark.parametrize('graph', ['0', '1'])
+def test_two_rank_nccl_deal_sharded_vs_oracle(graph):
+    if _gpus() < 2:
+        pytest.skip('needs 2 GPUs')
+    out = _torchrun(2, 'nccl_sharded_worker.py', [5, 23], env={'RLP_SHARD_CGRAPH': graph})
+    assert 'nccl sharded ok' in out

@@ -1,19 +1,15 @@
 """CUDA path against the second golden set (Leduc with other betting rules / suit counts, other OneCardPoker sizes;
 tests/golden/reference_variants.*): regrets and average strategy bit for bit, best responses to 1e-12.
 
-Written after the round-1 GPU budget was spent, so it has never run on a B200: it is skipped unless
-RLP_TEST_VARIANTS=1 until it has been seen green once.  The same trees are covered on the
-CPU by tests/test_oracle_variants.py (layout, oracle vs reference, device layout planning + NVRTC compilation)."""
-import os
-
+The same trees are covered on the CPU by tests/test_oracle_variants.py (layout, oracle vs reference, device layout
+planning + NVRTC compilation)."""
 import numpy as np
 import pytest
 
 from test_oracle_variants import build, variant_arrays, variants  # noqa: F401  (fixtures)
 from oracle.gen_golden_variants import VARIANTS
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('RLP_TEST_VARIANTS') != '1', reason='not yet validated on a GPU')]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('name', sorted(VARIANTS))

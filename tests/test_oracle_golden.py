@@ -220,3 +220,26 @@ def test_vanilla_leduc3_300_iterations_survey_values(otrees):
     assert o.exploitability(avg) == 0.1813807003021225
     assert sha(avg)[:16] == '95ae4634f6f5513c'
     assert o.nodes_touched == 15322200
+
+
+@pytest.mark.parametrize('n', [2, 3, 4])
+def test_oracle_leduc_generator_matches_reference_layout(golden, otrees, n):
+    """oracle/leduc_oracle.c (the generator behind bench.py's CPU arms) against the layout hashes the reference
+    itself produced, and array for array against the flattened object tree."""
+    from oracle.gen_golden import sha
+    name = 'leduc%d' % n
+    t = orc.leduc_tree(n)
+    if name in golden['trees']:
+        want = golden['trees'][name]
+        assert t.num_nodes == want['num_nodes'] and t.num_infosets == want['num_infosets']
+        assert [int(x) for x in t.level_off] == want['level_off']
+        for k in ('parent', 'player', 'infoset', 'cprob', 'u1', 'u2', 'hidden', 'first_child'):
+            assert sha(getattr(t, k)) == want['sha_' + k], (name, k)
+    a = otrees(name)
+    for k in ('parent', 'first_child', 'player', 'infoset', 'hidden', 'cprob', 'u1', 'u2', 'act_off', 'iset_nodes'):
+        assert np.array_equal(getattr(a, k), getattr(t, k)), (name, k)
+    # labels: 0 fold, 1 call, 2 bet, 16 + deck index for cards
+    for i in range(1, a.num_nodes):
+        lab = a.labels[a.label[i]]
+        code = int(t.label[i])
+        assert (code == lab) if isinstance(lab, int) else (code == 16 + lab.value * 2 + lab.suit), i
