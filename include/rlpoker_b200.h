@@ -73,7 +73,9 @@ void rlp_tree_free(rlp_tree *tree);
 /* Device bytes held by the tree. */
 int64_t rlp_tree_bytes(const rlp_tree *tree);
 /* Layout facts: which = 0 tiled sweep in use, 1 #upper tiles, 2 #micro subtrees, 3 #micro shapes, 4 #shapes with a
- * compiled straight-line kernel, 5 zero-sum, 6 largest information set, 7 upper-tile block size, 8 its shared memory. */
+ * compiled straight-line kernel, 5 zero-sum, 6 largest information set, 7 upper-tile block size, 8 its shared memory,
+ * 9 upper tiles compiled to straight-line code, 10 group-fused persistent iteration kernel in use, 11 its micro batches
+ * per iteration, 12 its upper groups, 13 its grid (co-resident CTAs), 14 public-state components (the sharding unit). */
 int64_t rlp_tree_stat(const rlp_tree *tree, int which);
 
 /*
@@ -94,6 +96,9 @@ int rlp_leduc_generate(int32_t num_values, int32_t num_suits, int32_t max_raises
  * non-terminals of the largest upper tile, its shared memory, kernels compiled, kernels that failed to compile,
  * largest information set, zero-sum}. */
 int rlp_tree_plan(const rlp_tree_desc *desc, int64_t *stats16);
+/* The same dry run, returning also the CUDA C++ source generated for the group-fused persistent iteration kernel
+ * (empty string when the tree does not qualify): *len = bytes needed incl. NUL; buf (nullable) gets up to cap bytes. */
+int rlp_tree_plan_fused_source(const rlp_tree_desc *desc, int64_t *stats16, char *buf, int64_t cap, int64_t *len);
 
 /* ---- solver --------------------------------------------------------------------------- */
 typedef enum { RLP_REGRET = 0, RLP_STRAT_SUM = 1, RLP_SIGMA = 2, RLP_AVERAGE = 3, RLP_CUM_IMM_REGRET = 4 } rlp_which;
@@ -143,6 +148,10 @@ int rlp_cfr_profile_stages(rlp_cfr *cfr, int reps, float *out_ms4, void *stream)
 /* Debug aid: runs `iters` vanilla iterations while block 0 of every sweep kernel logs {kind, start ns, end ns}
  * (kind 0 upper phase 0, 1 micro, 2 upper phase 1, 3 accumulate A, 4 accumulate B / all) -- the in-graph schedule. */
 int rlp_cfr_timeline(rlp_cfr *cfr, int iters, unsigned long long *out, int cap_records, int *n_out, void *stream);
+/* Measurement aid for the group-fused persistent kernel (one cooperative launch per rlp_cfr_vanilla_iters call): runs
+ * `iters` unit-weight iterations continuing at t0 while CTA 0 stamps %globaltimer {iteration start, its micro phase done,
+ * grid barrier passed, its upper phase done}; out_ns receives 4 * iters stamps.  RLP_ERR_UNSUPPORTED when not in use. */
+int rlp_cfr_fused_timeline(rlp_cfr *cfr, int64_t t0, int iters, unsigned long long *out_ns, void *stream);
 /* CFRState.nodes_touched (rlpoker/cfr/cfr_util.py:5-11). */
 uint64_t rlp_nodes_touched(rlp_cfr *cfr);
 

@@ -10,6 +10,7 @@
 #include <memory>
 
 #include "cfr.cuh"
+#include "fused.cuh"
 
 using rlp::fail;
 
@@ -508,6 +509,7 @@ extern "C" int rlp_cfr_reset(rlp_cfr *c, void *stream_) {
     RLP_CUDA(cudaMemsetAsync(c->iter.p, 0, 2 * sizeof(IterState), s));
     if (t->I > 0) { k_uniform<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->sigma.p); RLP_LAUNCH_CHECK(); }
     c->sigma_am_dirty = true;
+    c->sigF_dirty = true;
     c->nodes_touched = 0;
     c->touched_dirty = false;
     c->external_state = false;
@@ -613,9 +615,16 @@ static int build_graph(rlp_cfr *c) {
 extern "C" int rlp_cfr_vanilla_iters(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, void *stream_) {
     if (!c || n_iters < 0) return fail(RLP_ERR_INVALID, "bad argument");
     cudaStream_t s = (cudaStream_t)stream_;
+    if (rlp::fused_available(c)) {          // one cooperative launch runs all n_iters iterations (fused.cu)
+        c->dev_t = -1;
+        if (n_iters > 0) { int rc = rlp::fused_run(c, t0, n_iters, linear_weight, s, nullptr, 0); if (rc) return rc; }
+        c->nodes_touched += 2ull * (uint64_t)c->tree->N * (uint64_t)n_iters;
+        return RLP_OK;
+    }
     k_set_iter<<<1, 1, 0, s>>>(c->iter.p, (long long)t0, linear_weight);
     RLP_LAUNCH_CHECK();
     c->dev_t = -1;
+    c->sigF_dirty = true;
     { int rc = rlp::ensure_sigma_am(c, s); if (rc) return rc; }
     int64_t left = n_iters;
     if (left >= kGraphUnroll) {
@@ -684,6 +693,7 @@ extern "C" int rlp_cfr_apply_delta(rlp_cfr *c, void *stream_) {
                                                       c->R.p, c->S.p, c->sigma.p, c->flags.p, c->iter.p, c->sigma_am.p);
         RLP_LAUNCH_CHECK();
     }
+    c->sigF_dirty = true;
     c->nodes_touched += 2ull * (uint64_t)t->N;
     return RLP_OK;
 }
@@ -723,7 +733,7 @@ extern "C" int rlp_cfr_write(rlp_cfr *c, int which, const double *src, void *str
     RLP_CUDA(cudaMemcpyAsync(c->tmpQ.p, src, sizeof(double) * (size_t)c->tree->Q, cudaMemcpyHostToDevice, s));
     int rc = rlp::permute(c->tree, c->tmpQ.p, dst, 1, s);
     if (rc) return rc;
-    if (which == RLP_SIGMA) c->sigma_am_dirty = true;
+    if (which == RLP_SIGMA) { c->sigma_am_dirty = true; c->sigF_dirty = true; }
     // No synchronisation: a copy from pageable memory has been staged by the time cudaMemcpyAsync returns, and a
     // pinned source must simply stay untouched until the stream reaches this point (it is ordered before every later
     // call on the same stream, including rlp_cfr_read, which does synchronise).
@@ -826,6 +836,7 @@ extern "C" int rlp_cfr_profile_stages(rlp_cfr *c, int reps, float *out_ms4, void
     cudaEvent_t ev[5];
     for (auto &e : ev) RLP_CUDA(cudaEventCreate(&e));
     for (int k = 0; k < 4; ++k) out_ms4[k] = 0.f;
+    c->sigF_dirty = true;
     int rc = rlp::ensure_sigma_am(c, s);
     if (rc) return rc;
     for (int r = 0; r < reps + 2 && rc == RLP_OK; ++r) {
@@ -867,4 +878,21 @@ extern "C" int rlp_cfr_timeline(rlp_cfr *c, int iters, unsigned long long *out, 
     RLP_CUDA(cudaMemcpy(c->iter.p, &h2, sizeof(h2), cudaMemcpyHostToDevice));
     *n_out = n;
     return rc;
+}
+
+// Measurement aid for the group-fused persistent kernel: runs `iters` iterations (continuing at iteration t0 with unit
+// weights) in one launch while CTA 0 stamps %globaltimer {iteration start, its phase A done, first grid barrier passed,
+// its phase B done}; out_ns receives 4 * iters nanosecond stamps.  RLP_ERR_UNSUPPORTED when the tree does not qualify.
+extern "C" int rlp_cfr_fused_timeline(rlp_cfr *c, int64_t t0, int iters, unsigned long long *out_ns, void *stream_) {
+    if (!c || !out_ns || iters < 1) return fail(RLP_ERR_INVALID, "bad argument");
+    if (!rlp::fused_available(c)) return fail(RLP_ERR_UNSUPPORTED, "the fused iteration kernel is not in use for this tree");
+    cudaStream_t s = (cudaStream_t)stream_;
+    RLP_CUDA(c->timeline.alloc(4 * (size_t)iters));
+    RLP_CUDA(cudaMemsetAsync(c->timeline.p, 0, c->timeline.bytes(), s));
+    int rc = rlp::fused_run(c, t0, iters, 0, s, c->timeline.p, 4ll * iters);
+    if (rc) return rc;
+    RLP_CUDA(cudaMemcpyAsync(out_ns, c->timeline.p, c->timeline.bytes(), cudaMemcpyDeviceToHost, s));
+    RLP_CUDA(cudaStreamSynchronize(s));
+    c->nodes_touched += 2ull * (uint64_t)c->tree->N * (uint64_t)iters;
+    return RLP_OK;
 }

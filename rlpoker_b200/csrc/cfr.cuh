@@ -38,6 +38,12 @@ struct rlp_cfr {
     // words (the [set][action] layout costs 3x the L2 sectors in the micro kernel)
     rlp::DevBuf<double> sigma_am;
     bool sigma_am_dirty = true;
+    // group-fused persistent kernel (fused.cu): strategy in the fused numbering, [2 buffers][action][fused id]
+    rlp::DevBuf<double> sigF;
+    int sigF_cur = 0;                        // buffer holding the current strategy
+    bool sigF_dirty = true;                  // c->sigma was changed by something other than the fused kernel
+    rlp::DevBuf<unsigned char> fused_params; // device copy of FusedParams for this solver
+    void *fused_params_tl = nullptr;
     rlp::DevBuf<uint8_t> flags;              // [3][I] internal order: in_R | in_S (or alpha) | in_sigma dict membership
     // per-node scratch
     rlp::DevBuf<double> pc, p1, p2, val1, val2, vbr;

@@ -1,0 +1,940 @@
+// Group-fused persistent CFR iteration (replaces, for trees that qualify, the five-kernel pipeline of cfr.cu /
+// tiles.cu: upper_k0 -> micro_k -> k_fanin -> upper_k1 -> k_accumulate_rm4 x2).  Same arithmetic, operand for
+// operand, as those kernels and therefore as the reference's cfr_recursive (rlpoker/cfr/cfr.py:158-255) and
+// compute_regret_matching (rlpoker/cfr/cfr_util.py:14-58): regrets, action counts and strategies stay bit-identical.
+//
+// Idea.  All nodes of an information set of player p inside the micro subtrees differ only in what p cannot see, so
+// the micro subtrees fall into GROUPS per player: the G subtrees of a group share ALL of p's information sets, and the
+// position of a subtree inside the group is the rank of its nodes inside those information sets (ascending node id =
+// the order in which the reference's recursion visits them).  One thread evaluates one subtree (straight-line code
+// generated for the shape, NVRTC), the G threads of a group leave p's regret terms in shared memory, and one thread
+// per (information set, action) adds them IN MEMBER ORDER onto the regret and applies regret matching -- no
+// contribution scratch in HBM/L2, no separate accumulate kernel, no atomics.  Every subtree is evaluated twice (once
+// in a player-1 group, once in a player-2 group); that costs ~1.3x the arithmetic and removes ~100 MB of traffic per
+// iteration at Leduc-13.  The upper tiles (round-1 betting of one deal) are grouped the same way.
+//
+// One cooperative persistent kernel runs all iterations of a call:
+//     prologue  reach of both players from the tile roots to the portals            | grid barrier
+//     phase A   micro groups of both players: evaluate, accumulate, regret matching | grid barrier
+//     phase B   upper groups: fan-in of the portal values, evaluate the tile, accumulate + regret matching of the
+//               round-1 information sets, then the reach of the group's player to the portals for the NEXT
+//               iteration (it depends only on that player's own new strategy)      | grid barrier
+// The strategy is double buffered by iteration parity (a group rewrites its player's strategy while groups of the
+// other player still read the old one) in a "fused" information-set numbering chosen so that the opponent-strategy
+// gathers of a group hit consecutive words.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <map>
+#include <numeric>
+#include <sstream>
+#include <string>
+
+#include "cfr.cuh"
+#include "fused.cuh"
+
+using rlp::fail;
+
+namespace rlp {
+int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std::string *log_out);
+}
+
+// ---- parameter block shared with the generated source (every field is 8 bytes: no padding questions) ----------
+#define RLP_FUSED_FIELDS(X)                                                                                        \
+    X(const int *, mem_opp0) X(const int *, mem_opp1)         /* [opp decision][slot] fused ids of the opponent's sets */ \
+    X(const int *, mem_pat0) X(const int *, mem_pat1)         /* [slot] payoff pattern */                          \
+    X(const int *, mem_ridx0) X(const int *, mem_ridx1)       /* [slot] where the subtree root's reach lives */      \
+    X(const int *, mem_pidx0) X(const int *, mem_pidx1)       /* [slot] where its value goes (tile * KP + portal rank) */ \
+    X(const double *, mem_pc0) X(const double *, mem_pc1)     /* [slot] static chance reach */                      \
+    X(const int *, grp_fid0) X(const int *, grp_fid1)         /* [group][own decision] fused id */                   \
+    X(const int *, grp_col0) X(const int *, grp_col1)         /* [group][own decision] first internal pair */        \
+    X(const int *, grp_iset0) X(const int *, grp_iset1)       /* [group][own decision] internal information set */   \
+    X(const double *, paytab)                                 /* [pattern][leaf] */                                 \
+    X(const int *, tg_tile0) X(const int *, tg_tile1)         /* [upper group][member] tile */                      \
+    X(const int *, tg_fid0) X(const int *, tg_fid1)           /* [upper group][own decision] */                     \
+    X(const int *, tg_col0) X(const int *, tg_col1)                                                                \
+    X(const int *, tg_iset0) X(const int *, tg_iset1)                                                              \
+    X(const int *, u_fid)                                     /* [decision][tile] fused id */                       \
+    X(const double *, u_pcs) X(const double *, u_cprob) X(const double *, u_pay1)                                   \
+    X(const int *, fan_desc) X(const double *, fan_cp)        /* FanDesc[num_fan] as 4 ints; [fan edge][tile] */     \
+    X(double *, R) X(double *, S) X(double *, sigma_row)      /* solver state, internal pair order */               \
+    X(double *, sigF0) X(double *, sigF1)                     /* strategy, [action][fused id], two buffers */        \
+    X(double *, portal_p1) X(double *, portal_p2) X(double *, portal_v)                                             \
+    X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
+    X(long long, num_isets) X(long long, first_batch0) X(long long, end_batch0) X(long long, first_batch1)          \
+    X(long long, end_batch1) X(long long, tl_cap)
+
+struct FusedParams {
+#define X(type, name) type name;
+    RLP_FUSED_FIELDS(X)
+#undef X
+};
+static_assert(sizeof(FusedParams) % 8 == 0, "8-byte fields only");
+
+#define RLP_STR2(x) #x
+#define X(type, name) RLP_STR2(type) " " #name ";\n"
+static const char *kFusedFieldsText = RLP_FUSED_FIELDS(X);
+#undef X
+
+struct FusedPlan {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    FusedParams host{};                 // tree part filled; solver part (R, S, ...) filled per solver
+    rlp::DevBuf<int> mem_opp[2], mem_pat[2], mem_ridx[2], mem_pidx[2], grp_fid[2], grp_col[2], grp_iset[2];
+    rlp::DevBuf<double> mem_pc[2], paytab;
+    rlp::DevBuf<int> tg_tile[2], tg_fid[2], tg_col[2], tg_iset[2], u_fid;
+    rlp::DevBuf<int> fid_of_iset;       // [I] internal -> fused
+    rlp::DevBuf<unsigned int> bar;
+    long long NF = 0;
+    int n_batches[2] = {0, 0}, n_ugroups[2] = {0, 0};
+    int max_act = 0;
+    int grid = 0, block = 256;
+    int num_components = 0;
+    std::vector<int> batch_comp[2];     // component of every batch (multi-GPU sharding by public state)
+    std::string source;
+    ~FusedPlan() { if (lib) cudaLibraryUnload(lib); }
+};
+void fused_plan_free(FusedPlan *p) { delete p; }
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// ------------------------------------------------------------------------------------------------ source generator
+struct Shape {
+    // micro
+    const MicroTmpl *tm;
+    std::vector<int> dec[2];            // decision ranks of player 1 / 2
+    // upper
+    const UpperShape *sh;
+    std::vector<int> udec[2];           // decision indices (shape order among decision nodes) of player 1 / 2
+    std::vector<int> dec_idx, term_idx, edge_idx, parent, slot;
+    int n_udec = 0, n_uterm = 0, n_uedge = 0;
+};
+
+struct Consts {
+    int G[2], GPC[2], NG[2], GB[2], NUG[2];
+    long long NS[2];                    // slots = NG * G
+    long long NF, T;
+    int NT, KP, F;
+};
+
+std::string S_(const char *p, int j) { return std::string(p) + std::to_string(j); }
+
+// (own decision jj, action a) enumeration of a player's regret terms
+struct Terms { std::vector<int> cj, ca, coff, na; int kr = 0; };
+
+Terms micro_terms(const Shape &s, int pl) {
+    Terms t;
+    for (size_t jj = 0; jj < s.dec[pl].size(); ++jj) {
+        int node = s.tm->nt_node[s.dec[pl][jj]];
+        t.coff.push_back(t.kr);
+        t.na.push_back(s.tm->nchild[node]);
+        for (int a = 0; a < s.tm->nchild[node]; ++a) { t.cj.push_back((int)jj); t.ca.push_back(a); ++t.kr; }
+    }
+    return t;
+}
+
+Terms upper_terms(const Shape &s, int pl) {
+    Terms t;
+    const UpperShape &sh = *s.sh;
+    std::vector<int> node_of_dec;
+    for (size_t j = 0; j < sh.kind.size(); ++j) if (sh.kind[j] == 1 || sh.kind[j] == 2) node_of_dec.push_back((int)j);
+    for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) {
+        int node = node_of_dec[s.udec[pl][jj]];
+        t.coff.push_back(t.kr);
+        t.na.push_back(sh.nchild[node]);
+        for (int a = 0; a < sh.nchild[node]; ++a) { t.cj.push_back((int)jj); t.ca.push_back(a); ++t.kr; }
+    }
+    return t;
+}
+
+void emit_table(std::ostringstream &o, const char *name, int pl, const std::vector<int> &v) {
+    o << "__constant__ int " << name << pl << "[" << std::max<size_t>(1, v.size()) << "] = {";
+    for (size_t i = 0; i < v.size(); ++i) o << (i ? "," : "") << v[i];
+    if (v.empty()) o << "0";
+    o << "};\n";
+}
+
+// One micro subtree, evaluated by one thread for the groups of player `pl` (0-based).
+void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int pl) {
+    const MicroTmpl &tm = *s.tm;
+    const int n = tm.n, n_nt = tm.n_nt;
+    const int opp = 1 - pl;
+    std::vector<int> own_j(n_nt, -1), opp_j(n_nt, -1);
+    for (size_t j = 0; j < s.dec[pl].size(); ++j) own_j[s.dec[pl][j]] = (int)j;
+    for (size_t j = 0; j < s.dec[opp].size(); ++j) opp_j[s.dec[opp][j]] = (int)j;
+    Terms t = micro_terms(s, pl);
+    o << "__device__ __forceinline__ void micro_eval" << pl << "(const FusedParams* __restrict__ P, long long g, int k, int tid, double w,\n"
+         "    const double* sig_in, double* sm_r, double* sm_o) {\n"
+         "  const long long slot = g * " << c.G[pl] << " + k;\n"
+         "  const int pat = P->mem_pat" << pl << "[slot], ri = P->mem_ridx" << pl << "[slot];\n"
+         "  const double pcv = P->mem_pc" << pl << "[slot];\n";
+    if (pl == 0) o << "  const int pi = P->mem_pidx0[slot];\n";
+    for (int r = 0; r < n_nt; ++r) {
+        if (own_j[r] >= 0)
+            o << "  const int f" << r << " = P->grp_fid" << pl << "[g * " << s.dec[pl].size() << " + " << own_j[r] << "];\n";
+        else
+            o << "  const int f" << r << " = P->mem_opp" << pl << "[" << opp_j[r] << "LL * " << c.NS[pl] << "LL + slot];\n";
+    }
+    o << "  const double* pp = P->paytab + (long long)pat * " << c.NT << ";\n";
+    for (int j = 0; j < n; ++j)
+        if (tm.rank[j] & 0x80) o << "  const double x" << j << " = pp[" << (tm.rank[j] & 0x7F) << "];\n";
+    o << "  const double q1_0 = __ldcg(P->portal_p1 + ri), q2_0 = __ldcg(P->portal_p2 + ri);\n";
+    for (int j = 1; j < n; ++j)
+        o << "  const double s" << j << " = __ldcg(sig_in + " << (int)tm.par_slot[j] << "LL * " << c.NF << "LL + f" << (int)tm.par_rank[j] << ");\n";
+    for (int r = 0; r < n_nt; ++r) {                    // forward (cfr.py:208,217)
+        int j = tm.nt_node[r], p = tm.player[j];
+        for (int k = 0; k < tm.nchild[j]; ++k) {
+            int ch = tm.first_child[j] + k;
+            if (tm.rank[ch] & 0x80) continue;
+            int rc = tm.rank[ch];
+            o << "  const double q1_" << rc << " = " << (p == 1 ? S_("s", ch) + " * " : std::string()) << "q1_" << r << ";\n";
+            o << "  const double q2_" << rc << " = " << (p == 2 ? S_("s", ch) + " * " : std::string()) << "q2_" << r << ";\n";
+        }
+    }
+    for (int r = n_nt - 1; r >= 0; --r) {               // backward (cfr.py:204-242)
+        int j = tm.nt_node[r], p = tm.player[j], fc = tm.first_child[j], nc = tm.nchild[j];
+        o << "  double a" << j << " = 0.0;\n";
+        for (int k = 0; k < nc; ++k) o << "  a" << j << " = a" << j << " + s" << (fc + k) << " * x" << (fc + k) << ";\n";
+        o << "  const double x" << j << " = a" << j << ";\n";
+        if (p != pl + 1) continue;
+        int jj = own_j[r];
+        o << "  {\n    const double opp = " << (p == 1 ? "pcv * q2_" : "pcv * q1_") << r << ";\n"
+          << "    const double own = " << (p == 1 ? "q1_" : "q2_") << r << ";\n"
+          << "    const double vp = " << (p == 1 ? S_("x", j) : "-" + S_("x", j)) << ";\n";
+        for (int k = 0; k < nc; ++k) {
+            std::string va = p == 1 ? S_("x", fc + k) : "-" + S_("x", fc + k);
+            o << "    sm_r[" << (t.coff[jj] + k) << " * " << kBlock << " + tid] = w * (" << va << " - vp) * opp;\n";
+        }
+        o << "    sm_o[" << jj << " * " << kBlock << " + tid] = w * own;\n  }\n";
+    }
+    if (pl == 0) o << "  P->portal_v[pi] = x0;\n";
+    o << "}\n";
+}
+
+// One upper tile, evaluated by one thread for the upper groups of player `pl`: values up from the portals / fan-in
+// sums, contributions of pl's decision nodes into shared memory.
+void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int pl) {
+    const UpperShape &sh = *s.sh;
+    const int n = (int)sh.kind.size();
+    Terms t = upper_terms(s, pl);
+    std::vector<int> own_jj(s.n_udec, -1);
+    for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) own_jj[s.udec[pl][jj]] = (int)jj;
+    o << "__device__ __forceinline__ void upper_eval" << pl << "(const FusedParams* __restrict__ P, long long i, int m, double w,\n"
+         "    const double* sig_in, const double* sm_fan, double* sm_r, double* sm_o) {\n";
+    for (int j = 0; j < n; ++j)
+        if (s.dec_idx[j] >= 0) {
+            o << "  const int f" << j << " = P->u_fid[" << s.dec_idx[j] << "LL * " << c.T << "LL + i];\n";
+            if (sh.kind[j] == pl + 1) o << "  const double pc" << j << " = P->u_pcs[" << s.dec_idx[j] << "LL * " << c.T << "LL + i];\n";
+        }
+    for (int j = 0; j < n; ++j) {
+        if (s.edge_idx[j] >= 0) o << "  const double e" << j << " = P->u_cprob[" << s.edge_idx[j] << "LL * " << c.T << "LL + i];\n";
+        if (s.term_idx[j] >= 0) o << "  const double x" << j << " = P->u_pay1[" << s.term_idx[j] << "LL * " << c.T << "LL + i];\n";
+    }
+    for (int j = 1; j < n; ++j)
+        if (s.parent[j] >= 0 && s.dec_idx[s.parent[j]] >= 0)
+            o << "  const double s" << j << " = __ldcg(sig_in + " << s.slot[j] << "LL * " << c.NF << "LL + f" << s.parent[j] << ");\n";
+    for (int j = 0; j < n; ++j) {
+        if (sh.kind[j] == 4) o << "  const double x" << j << " = sm_fan[m * " << c.F << " + " << sh.fan_index[j] << "];\n";
+        if (sh.kind[j] == 3) o << "  const double x" << j << " = __ldcg(P->portal_v + i * " << c.KP << "LL + " << sh.portal_rank[j] << ");\n";
+    }
+    o << "  const double q1_0 = 1.0, q2_0 = 1.0;\n";
+    for (int j = 0; j < n; ++j) {                       // forward: reach of the tile's own decision nodes
+        int kd = sh.kind[j];
+        if (kd == -1 || kd == 3 || kd == 4) continue;
+        for (int k = 0; k < sh.nchild[j]; ++k) {
+            int ch = sh.first_child[j] + k;
+            if (sh.kind[ch] == -1 || sh.kind[ch] == 3 || sh.kind[ch] == 4) continue;
+            o << "  const double q1_" << ch << " = " << (kd == 1 ? S_("s", ch) + " * " : std::string()) << S_("q1_", j) << ";\n"
+              << "  const double q2_" << ch << " = " << (kd == 2 ? S_("s", ch) + " * " : std::string()) << S_("q2_", j) << ";\n";
+        }
+    }
+    for (int j = n - 1; j >= 0; --j) {                  // backward
+        int kd = sh.kind[j];
+        if (kd == -1 || kd == 3 || kd == 4) continue;
+        int fc = sh.first_child[j], nc = sh.nchild[j];
+        o << "  double a" << j << " = 0.0;\n";
+        for (int k = 0; k < nc; ++k)
+            o << "  a" << j << " = a" << j << " + " << (kd == 0 ? S_("e", fc + k) : S_("s", fc + k)) << " * x" << (fc + k) << ";\n";
+        o << "  const double x" << j << " = a" << j << ";\n";
+        if (kd != pl + 1) continue;
+        int jj = own_jj[s.dec_idx[j]];
+        o << "  {\n    const double opp = pc" << j << (kd == 1 ? " * q2_" : " * q1_") << j << ";\n"
+          << "    const double own = " << (kd == 1 ? "q1_" : "q2_") << j << ";\n"
+          << "    const double vp = " << (kd == 1 ? S_("x", j) : "-" + S_("x", j)) << ";\n";
+        for (int k = 0; k < nc; ++k) {
+            std::string va = kd == 1 ? S_("x", fc + k) : "-" + S_("x", fc + k);
+            o << "    sm_r[" << (t.coff[jj] + k) << " * " << c.GB[pl] << " + m] = w * (" << va << " - vp) * opp;\n";
+        }
+        o << "    sm_o[" << jj << " * " << c.GB[pl] << " + m] = w * own;\n  }\n";
+    }
+    o << "  (void)x0;\n}\n";
+}
+
+// Reach of player `pl` from the tile root to every portal / fan-in node of one tile, from pl's strategy rows in
+// shared memory (sm_s[term index] = probability of that (own decision, action)).
+void gen_upper_reach(std::ostringstream &o, const Shape &s, const Consts &c, int pl) {
+    const UpperShape &sh = *s.sh;
+    const int n = (int)sh.kind.size();
+    Terms t = upper_terms(s, pl);
+    std::vector<int> own_jj(s.n_udec, -1);
+    for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) own_jj[s.udec[pl][jj]] = (int)jj;
+    o << "__device__ __forceinline__ void upper_reach" << pl << "(const FusedParams* __restrict__ P, long long i, const double* sm_s) {\n"
+         "  double* out = P->portal_p" << (pl + 1) << ";\n  const double q_0 = 1.0;\n";
+    for (int j = 0; j < n; ++j) {
+        int kd = sh.kind[j];
+        if (kd == -1 || kd == 3 || kd == 4) continue;
+        for (int k = 0; k < sh.nchild[j]; ++k) {
+            int ch = sh.first_child[j] + k;
+            if (sh.kind[ch] == -1) continue;
+            std::string v = kd == pl + 1 ? "sm_s[" + std::to_string(t.coff[own_jj[s.dec_idx[j]]] + k) + "] * " + S_("q_", j) : S_("q_", j);
+            if (sh.kind[ch] == 4) o << "  out[" << sh.fan_k0[ch] << "LL * " << c.T << "LL + i] = " << v << ";\n";
+            else if (sh.kind[ch] == 3) o << "  out[" << sh.portal_rank[ch] << "LL * " << c.T << "LL + i] = " << v << ";\n";
+            else o << "  const double q_" << ch << " = " << v << ";\n";
+        }
+    }
+    o << "}\n";
+}
+
+std::string generate_source(const Shape &s, const Consts &c) {
+    std::ostringstream o;
+    o.precision(17);
+    o << "struct FusedParams {\n" << kFusedFieldsText << "};\n"
+      << "#define BLOCK " << kBlock << "\n"
+      << R"(
+__device__ __forceinline__ unsigned long long now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// All CTAs are co-resident (cooperative launch).  `target` = arrivals expected so far on the monotone counter.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int v;
+    do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+// compute_regret_matching + normalise_probs (cfr_util.py:14-58) for action `a` of a set whose regrets are r[0..na)
+__device__ __forceinline__ double rm_one(const double* r, int na, int a) {
+  double mx = r[0];
+  for (int b = 1; b < na; ++b) mx = r[b] > mx ? r[b] : mx;
+  if (mx <= 0.0) return 1.0 / (double)na;
+  double s = 0.0, c = 0.0, mine = 0.0;
+  for (int b = 0; b < na; ++b) {
+    double p = r[b] > 0.0 ? r[b] : 0.0;
+    p = p > 1e-7 ? p : 1e-7;
+    double t = s + p;
+    if (fabs(s) >= fabs(p)) c += (s - t) + p; else c += (p - t) + s;
+    s = t;
+    if (b == a) mine = p;
+  }
+  return mine / (s + c);
+}
+)";
+    for (int pl = 0; pl < 2; ++pl) {
+        Terms mt = micro_terms(s, pl), ut = upper_terms(s, pl);
+        emit_table(o, "MCJ", pl, mt.cj); emit_table(o, "MCA", pl, mt.ca); emit_table(o, "MCOFF", pl, mt.coff); emit_table(o, "MNA", pl, mt.na);
+        emit_table(o, "UCJ", pl, ut.cj); emit_table(o, "UCA", pl, ut.ca); emit_table(o, "UCOFF", pl, ut.coff); emit_table(o, "UNA", pl, ut.na);
+        gen_micro_eval(o, s, c, pl);
+        gen_upper_eval(o, s, c, pl);
+        gen_upper_reach(o, s, c, pl);
+    }
+    // ---- per-player batch / unit drivers (same text, different literals) ------------------------------------------
+    for (int pl = 0; pl < 2; ++pl) {
+        Terms mt = micro_terms(s, pl), ut = upper_terms(s, pl);
+        const int G = c.G[pl], GPC = c.GPC[pl], KR = mt.kr, MO = (int)s.dec[pl].size();
+        o << "__device__ __forceinline__ void micro_batch" << pl << "(const FusedParams* __restrict__ P, long long batch, double w, const double* sig_in,\n"
+             "    double* sig_out, double* sm_r, double* sm_o, double* sm_rn) {\n"
+             "  const int tid = threadIdx.x;\n"
+             "  const int gl = tid / " << G << ", k = tid - gl * " << G << ";\n"
+             "  const long long g = batch * " << GPC << " + gl;\n"
+             "  if (gl < " << GPC << " && g < " << c.NG[pl] << "LL) micro_eval" << pl << "(P, g, k, tid, w, sig_in, sm_r, sm_o);\n"
+             "  __syncthreads();\n"
+             "  for (int x = tid; x < " << GPC * KR << "; x += BLOCK) {\n"
+             "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
+             "    const long long ag = batch * " << GPC << " + agl;\n"
+             "    if (ag >= " << c.NG[pl] << "LL) continue;\n"
+             "    const int j = MCJ" << pl << "[ci], a = MCA" << pl << "[ci];\n"
+             "    const int col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
+             "    const int fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
+             "    double r = __ldcg(P->R + col), sa = __ldcg(P->S + col);\n"
+             "    const double sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
+             "    const double* cr = sm_r + ci * BLOCK + agl * " << G << ";\n"
+             "    const double* co = sm_o + j * BLOCK + agl * " << G << ";\n"
+             "#pragma unroll 8\n"
+             "    for (int m = 0; m < " << G << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
+             "    P->R[col] = r; P->S[col] = sa;\n"
+             "    sm_rn[x] = r;\n"
+             "  }\n"
+             "  __syncthreads();\n"
+             "  for (int x = tid; x < " << GPC * KR << "; x += BLOCK) {\n"
+             "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
+             "    const long long ag = batch * " << GPC << " + agl;\n"
+             "    if (ag >= " << c.NG[pl] << "LL) continue;\n"
+             "    const int j = MCJ" << pl << "[ci], a = MCA" << pl << "[ci];\n"
+             "    const int col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
+             "    const int fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
+             "    const double out = rm_one(sm_rn + agl * " << KR << " + MCOFF" << pl << "[j], MNA" << pl << "[j], a);\n"
+             "    P->sigma_row[col] = out;\n"
+             "    sig_out[(long long)a * " << c.NF << "LL + fid] = out;\n"
+             "    if (a == 0) { const int is = P->grp_iset" << pl << "[ag * " << MO << " + j]; const long long I = P->num_isets;\n"
+             "      P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
+             "  }\n"
+             "  __syncthreads();\n"
+             "}\n";
+        const int GB = c.GB[pl], KRB = ut.kr, MB = (int)s.udec[pl].size();
+        // mode 0: full unit (fan-in, evaluate, accumulate, regret matching, reach); mode 1: reach only (prologue)
+        o << "__device__ __forceinline__ void upper_unit" << pl << "(const FusedParams* __restrict__ P, int u, double w, const double* sig_in,\n"
+             "    double* sig_out, int reach_only, double* sm_fan, double* sm_r, double* sm_o, double* sm_rn, double* sm_s) {\n"
+             "  const int tid = threadIdx.x;\n"
+             "  const int* tiles = P->tg_tile" << pl << " + (long long)u * " << GB << ";\n"
+             "  if (reach_only) {\n"
+             "    for (int x = tid; x < " << KRB << "; x += BLOCK) {\n"
+             "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
+             "      sm_s[x] = __ldcg(sig_in + (long long)a * " << c.NF << "LL + P->tg_fid" << pl << "[u * " << MB << " + j]);\n"
+             "    }\n"
+             "  } else {\n"
+             "    const int* fd = P->fan_desc;\n"
+             "    for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
+             "      const int m = x / " << std::max(1, c.F) << ", f = x - m * " << std::max(1, c.F) << ";\n"
+             "      const long long i = tiles[m];\n"
+             "      const int k0 = fd[4 * f], nch = fd[4 * f + 1], e0 = fd[4 * f + 2];\n"
+             "      const double* pv = P->portal_v + i * " << c.KP << "LL + k0;\n"
+             "      const double* cp = P->fan_cp + (long long)e0 * " << c.T << "LL + i;\n"
+             "      double acc = 0.0;\n"
+             "      int ch = 0;\n"
+             "      for (; ch + 8 <= nch; ch += 8) {\n"
+             "        double e[8], v[8];\n"
+             "#pragma unroll\n"
+             "        for (int q = 0; q < 8; ++q) { e[q] = cp[(long long)(ch + q) * " << c.T << "LL]; v[q] = __ldcg(pv + ch + q); }\n"
+             "#pragma unroll\n"
+             "        for (int q = 0; q < 8; ++q) acc = acc + e[q] * v[q];\n"
+             "      }\n"
+             "      for (; ch < nch; ++ch) acc = acc + cp[(long long)ch * " << c.T << "LL] * __ldcg(pv + ch);\n"
+             "      sm_fan[x] = acc;\n"
+             "    }\n"
+             "    __syncthreads();\n"
+             "    if (tid < " << GB << ") upper_eval" << pl << "(P, tiles[tid], tid, w, sig_in, sm_fan, sm_r, sm_o);\n"
+             "    __syncthreads();\n"
+             "    for (int x = tid; x < " << KRB << "; x += BLOCK) {\n"
+             "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
+             "      const int col = P->tg_col" << pl << "[u * " << MB << " + j] + a;\n"
+             "      const int fid = P->tg_fid" << pl << "[u * " << MB << " + j];\n"
+             "      double r = __ldcg(P->R + col), sa = __ldcg(P->S + col);\n"
+             "      const double sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
+             "      const double* cr = sm_r + x * " << GB << ";\n"
+             "      const double* co = sm_o + j * " << GB << ";\n"
+             "      for (int m = 0; m < " << GB << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
+             "      P->R[col] = r; P->S[col] = sa;\n"
+             "      sm_rn[x] = r;\n"
+             "    }\n"
+             "    __syncthreads();\n"
+             "    for (int x = tid; x < " << KRB << "; x += BLOCK) {\n"
+             "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
+             "      const int col = P->tg_col" << pl << "[u * " << MB << " + j] + a;\n"
+             "      const int fid = P->tg_fid" << pl << "[u * " << MB << " + j];\n"
+             "      const double out = rm_one(sm_rn + UCOFF" << pl << "[j], UNA" << pl << "[j], a);\n"
+             "      P->sigma_row[col] = out;\n"
+             "      sig_out[(long long)a * " << c.NF << "LL + fid] = out;\n"
+             "      sm_s[x] = out;\n"
+             "      if (a == 0) { const int is = P->tg_iset" << pl << "[u * " << MB << " + j]; const long long I = P->num_isets;\n"
+             "        P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
+             "    }\n"
+             "  }\n"
+             "  __syncthreads();\n"
+             "  if (tid < " << GB << ") upper_reach" << pl << "(P, tiles[tid], sm_s);\n"
+             "  __syncthreads();\n"
+             "}\n";
+    }
+    Terms m0 = micro_terms(s, 0), m1 = micro_terms(s, 1), u0 = upper_terms(s, 0), u1 = upper_terms(s, 1);
+    const int KRmax = std::max(m0.kr, m1.kr), MOmax = (int)std::max(s.dec[0].size(), s.dec[1].size());
+    const int rn_a = std::max(c.GPC[0] * m0.kr, c.GPC[1] * m1.kr);
+    const int fan_n = std::max(1, std::max(c.GB[0], c.GB[1]) * c.F);
+    const int ur_n = std::max(1, std::max(u0.kr * c.GB[0], u1.kr * c.GB[1]));
+    const int uo_n = std::max(1, std::max((int)s.udec[0].size() * c.GB[0], (int)s.udec[1].size() * c.GB[1]));
+    const int us_n = std::max(1, std::max(u0.kr, u1.kr));
+    const int sm_r_n = std::max(KRmax * kBlock, ur_n), sm_o_n = std::max(MOmax * kBlock, uo_n);
+    const int sm_rn_n = std::max(std::max(1, rn_a), us_n);
+    o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, 2) cfr_fused_k(const FusedParams* __restrict__ P, long long t0, int iters,\n"
+         "    int linear, int cur0) {\n"
+         "  __shared__ double sm_r[" << sm_r_n << "];\n"
+         "  __shared__ double sm_o[" << sm_o_n << "];\n"
+         "  __shared__ double sm_rn[" << sm_rn_n << "];\n"
+         "  __shared__ double sm_fan[" << fan_n << "];\n"
+         "  __shared__ double sm_s[" << us_n << "];\n"
+         "  const unsigned int nb = gridDim.x;\n"
+         "  unsigned int arrivals = 0;\n"
+         "  const bool log = P->tl != 0 && blockIdx.x == 0 && threadIdx.x == 0;\n"
+         "  long long tlc = 0;\n"
+         "  const int NU0 = " << c.NUG[0] << ", NU1 = " << c.NUG[1] << ";\n"
+         "  // prologue: reach of both players to the portals from the current strategy\n"
+         "  {\n"
+         "    const double* sig_in = cur0 ? P->sigF1 : P->sigF0;\n"
+         "    for (int u = blockIdx.x; u < NU0 + NU1; u += nb) {\n"
+         "      if (u < NU0) upper_unit0(P, u, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "      else upper_unit1(P, u - NU0, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "    }\n"
+         "    arrivals += nb; grid_barrier(P->bar, arrivals);\n"
+         "  }\n"
+         "  for (int it = 0; it < iters; ++it) {\n"
+         "    const int cur = (cur0 + it) & 1;\n"
+         "    const double* sig_in = cur ? P->sigF1 : P->sigF0;\n"
+         "    double* sig_out = cur ? P->sigF0 : P->sigF1;\n"
+         "    const double w = linear ? (double)(t0 + it) : 1.0;\n"
+         "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
+         "    // phase A: micro groups of player 1, then of player 2 (one list of batches)\n"
+         "    const long long nb0 = P->end_batch0 - P->first_batch0, nb1 = P->end_batch1 - P->first_batch1;\n"
+         "    for (long long b = blockIdx.x; b < nb0 + nb1; b += nb) {\n"
+         "      if (b < nb0) micro_batch0(P, P->first_batch0 + b, w, sig_in, sig_out, sm_r, sm_o, sm_rn);\n"
+         "      else micro_batch1(P, P->first_batch1 + (b - nb0), w, sig_in, sig_out, sm_r, sm_o, sm_rn);\n"
+         "    }\n"
+         "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
+         "    arrivals += nb; grid_barrier(P->bar, arrivals);\n"
+         "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
+         "    // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)\n"
+         "    for (int u = blockIdx.x; u < NU0 + NU1; u += nb) {\n"
+         "      if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "      else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "    }\n"
+         "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
+         "    arrivals += nb; grid_barrier(P->bar, arrivals);\n"
+         "  }\n"
+         "}\n";
+    return o.str();
+}
+
+__global__ void __launch_bounds__(256)
+k_sigma_fused(int32_t I, long long NF, const int64_t *__restrict__ col_off, const int *__restrict__ fid,
+              const double *__restrict__ sigma, double *sigF) {
+    int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= I) return;
+    int64_t c0 = col_off[s];
+    int na = (int)(col_off[s + 1] - c0);
+    for (int a = 0; a < na; ++a) sigF[(long long)a * NF + fid[s]] = sigma[c0 + a];
+}
+
+}  // namespace
+
+namespace rlp {
+
+// Called at the end of build_tiles when all micro subtrees share one shape and all upper tiles share one shape.
+// Leaves ts.fused null (the five-kernel pipeline stays in use) when the tree does not have the group structure.
+int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
+    rlp_tree *t = cx.t;
+    TileSet &ts = t->tiles;
+    ts.fused.reset();
+    const char *off = getenv("RLP_NO_FUSED");
+    if (off && off[0] == '1') return RLP_OK;
+    if (!t->zero_sum || t->max_act > 4 || ts.num_classes != 1 || !ts.upper_jit) return RLP_OK;
+    const rlp_tree_desc *d = cx.d;
+    const int32_t *fc = d->first_child;
+    const MicroTmpl &tm = *cx.tm;
+    const UpperShape &sh = *cx.sh;
+    const int64_t P = (int64_t)cx.portal_node->size();
+    const int64_t T = (int64_t)cx.desc->size();
+    const int32_t I = t->I;
+    if (P == 0 || T == 0) return RLP_OK;
+    {   // every portal must hang off a tile (no portals directly under the trunk)
+        const TileDesc &last = (*cx.desc)[T - 1];
+        if (last.portal_off + last.n_portal != P) return RLP_OK;
+    }
+    const std::vector<int32_t> &srank = *cx.srank, &krank = *cx.krank;
+    std::vector<int32_t> size(I, 0);
+    for (int64_t g = 0; g < d->num_nodes; ++g) if (d->player[g] > 0) size[srank[g]]++;
+
+    Shape s;
+    s.tm = &tm; s.sh = &sh;
+    for (int r = 0; r < tm.n_nt; ++r) {
+        int p = tm.player[tm.nt_node[r]];
+        if (p != 1 && p != 2) return RLP_OK;
+        s.dec[p - 1].push_back(r);
+    }
+    if (s.dec[0].empty() || s.dec[1].empty()) return RLP_OK;
+    const int n_up = (int)sh.kind.size();
+    s.dec_idx.assign(n_up, -1); s.term_idx.assign(n_up, -1); s.edge_idx.assign(n_up, -1); s.parent.assign(n_up, -1); s.slot.assign(n_up, 0);
+    for (int j = 0; j < n_up; ++j) {
+        if (sh.kind[j] == 1 || sh.kind[j] == 2) { s.udec[sh.kind[j] - 1].push_back(s.n_udec); s.dec_idx[j] = s.n_udec++; }
+        else if (sh.kind[j] == -1) s.term_idx[j] = s.n_uterm++;
+        for (int k = 0; k < sh.nchild[j]; ++k) {
+            int ch = sh.first_child[j] + k;
+            s.parent[ch] = j; s.slot[ch] = k;
+            if (sh.kind[j] == 0) s.edge_idx[ch] = s.n_uedge++;
+        }
+    }
+    if (s.udec[0].empty() || s.udec[1].empty()) return RLP_OK;
+
+    // ---- decision nodes of every micro instance (global node ids by non-terminal rank) --------------------------
+    const int n_nt = tm.n_nt;
+    std::vector<int32_t> inode((size_t)P * n_nt);
+    {
+        std::vector<int32_t> loc;
+        for (int64_t p = 0; p < P; ++p) {
+            loc.clear();
+            loc.push_back((*cx.portal_node)[p]);
+            for (size_t q = 0; q < loc.size(); ++q)
+                for (int32_t c = fc[loc[q]]; c < fc[loc[q] + 1]; ++c) loc.push_back(c);
+            for (int r = 0; r < n_nt; ++r) inode[(size_t)p * n_nt + r] = loc[tm.nt_node[r]];
+        }
+    }
+    std::vector<uint8_t> covered(I, 0);
+    // ---- micro groups per player ---------------------------------------------------------------------------------
+    struct Groups { int G = 0; std::vector<int32_t> key; std::vector<int64_t> members; };   // members[g * G + k]
+    Groups mg[2];
+    std::vector<int32_t> group_of[2];
+    for (int pl = 0; pl < 2; ++pl) {
+        Groups &gr = mg[pl];
+        const int r0 = s.dec[pl][0];
+        gr.G = size[srank[inode[r0]]];
+        if (gr.G < 1 || gr.G > kBlock) return RLP_OK;
+        std::vector<int32_t> gid_of_iset(I, -1);
+        group_of[pl].assign(P, -1);
+        for (int64_t p = 0; p < P; ++p) {
+            int32_t key = srank[inode[(size_t)p * n_nt + r0]];
+            int32_t k = krank[inode[(size_t)p * n_nt + r0]];
+            int32_t g = gid_of_iset[key];
+            if (g < 0) {
+                g = gid_of_iset[key] = (int32_t)gr.key.size();
+                gr.key.push_back(key);
+                gr.members.resize(gr.members.size() + gr.G, -1);
+            }
+            if (size[key] != gr.G || k >= gr.G || gr.members[(size_t)g * gr.G + k] >= 0) return RLP_OK;
+            gr.members[(size_t)g * gr.G + k] = p;
+            group_of[pl][p] = g;
+        }
+        for (int64_t m : gr.members) if (m < 0) return RLP_OK;           // incomplete group (e.g. a deal shard)
+        const size_t NG = gr.key.size();
+        for (size_t g = 0; g < NG; ++g) {
+            const int64_t p0 = gr.members[g * gr.G];
+            for (size_t jj = 0; jj < s.dec[pl].size(); ++jj) {
+                const int r = s.dec[pl][jj];
+                const int32_t is = srank[inode[(size_t)p0 * n_nt + r]];
+                if (size[is] != gr.G || covered[is]) return RLP_OK;       // shared with another group / rank
+                covered[is] = 1;
+                for (int k = 0; k < gr.G; ++k) {
+                    const int64_t p = gr.members[g * gr.G + k];
+                    const int32_t node = inode[(size_t)p * n_nt + r];
+                    if (srank[node] != is || krank[node] != k) return RLP_OK;
+                }
+            }
+        }
+    }
+    // ---- upper groups per player ---------------------------------------------------------------------------------
+    std::vector<int> dec_nodes;       // shape index of the d-th decision node
+    for (int j = 0; j < n_up; ++j) if (s.dec_idx[j] >= 0) dec_nodes.push_back(j);
+    auto tile_node = [&](int64_t tile, int d_idx) { return (*cx.locals)[tile][dec_nodes[d_idx]]; };
+    Groups ug[2];
+    for (int pl = 0; pl < 2; ++pl) {
+        Groups &gr = ug[pl];
+        const int d0 = s.udec[pl][0];
+        gr.G = size[srank[tile_node(0, d0)]];
+        if (gr.G < 1 || gr.G > kBlock) return RLP_OK;
+        std::vector<int32_t> gid_of_iset(I, -1);
+        for (int64_t k = 0; k < T; ++k) {
+            int32_t node = tile_node(k, d0);
+            int32_t key = srank[node], kr = krank[node];
+            int32_t g = gid_of_iset[key];
+            if (g < 0) {
+                g = gid_of_iset[key] = (int32_t)gr.key.size();
+                gr.key.push_back(key);
+                gr.members.resize(gr.members.size() + gr.G, -1);
+            }
+            if (size[key] != gr.G || kr >= gr.G || gr.members[(size_t)g * gr.G + kr] >= 0) return RLP_OK;
+            gr.members[(size_t)g * gr.G + kr] = k;
+        }
+        for (int64_t m : gr.members) if (m < 0) return RLP_OK;
+        for (size_t g = 0; g < gr.key.size(); ++g)
+            for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) {
+                const int dd = s.udec[pl][jj];
+                const int32_t is = srank[tile_node(gr.members[g * gr.G], dd)];
+                if (size[is] != gr.G || covered[is]) return RLP_OK;
+                covered[is] = 1;
+                for (int k = 0; k < gr.G; ++k) {
+                    const int32_t node = tile_node(gr.members[g * gr.G + k], dd);
+                    if (srank[node] != is || krank[node] != k) return RLP_OK;
+                }
+            }
+    }
+    for (int32_t is = 0; is < I; ++is) if (!covered[is] && size[is] > 0) return RLP_OK;
+
+    // ---- components (instances linked through groups of either player); groups ordered by component -------------
+    std::vector<int64_t> uf(P);
+    std::iota(uf.begin(), uf.end(), 0);
+    auto find = [&](int64_t x) { while (uf[x] != x) { uf[x] = uf[uf[x]]; x = uf[x]; } return x; };
+    for (int pl = 0; pl < 2; ++pl)
+        for (size_t g = 0; g < mg[pl].key.size(); ++g)
+            for (int k = 1; k < mg[pl].G; ++k) {
+                int64_t a = find(mg[pl].members[g * mg[pl].G]), b = find(mg[pl].members[g * mg[pl].G + k]);
+                if (a != b) uf[std::max(a, b)] = std::min(a, b);
+            }
+    std::vector<int32_t> comp_of(P, -1);
+    int ncomp = 0;
+    for (int64_t p = 0; p < P; ++p) { int64_t r = find(p); if (comp_of[r] < 0) comp_of[r] = ncomp++; comp_of[p] = comp_of[r]; }
+    std::vector<int32_t> order[2];
+    for (int pl = 0; pl < 2; ++pl) {
+        const size_t NG = mg[pl].key.size();
+        order[pl].resize(NG);
+        std::iota(order[pl].begin(), order[pl].end(), 0);
+        std::stable_sort(order[pl].begin(), order[pl].end(), [&](int32_t a, int32_t b) {
+            return comp_of[mg[pl].members[(size_t)a * mg[pl].G]] < comp_of[mg[pl].members[(size_t)b * mg[pl].G]];
+        });
+    }
+
+    // ---- fused numbering of the information sets: opponent gathers of a group should hit consecutive words ---------
+    std::vector<int> fid(I, -1);
+    int next = 0;
+    for (int pl = 0; pl < 2; ++pl) {
+        const int opp = 1 - pl;
+        for (int32_t g : order[pl])
+            for (size_t jj = 0; jj < s.dec[opp].size(); ++jj)
+                for (int k = 0; k < mg[pl].G; ++k) {
+                    const int64_t p = mg[pl].members[(size_t)g * mg[pl].G + k];
+                    const int32_t is = srank[inode[(size_t)p * n_nt + s.dec[opp][jj]]];
+                    if (fid[is] < 0) fid[is] = next++;
+                }
+    }
+    for (int pl = 0; pl < 2; ++pl) {
+        const int opp = 1 - pl;
+        for (size_t g = 0; g < ug[pl].key.size(); ++g)
+            for (size_t jj = 0; jj < s.udec[opp].size(); ++jj)
+                for (int k = 0; k < ug[pl].G; ++k) {
+                    const int32_t is = srank[tile_node(ug[pl].members[g * ug[pl].G + k], s.udec[opp][jj])];
+                    if (fid[is] < 0) fid[is] = next++;
+                }
+    }
+    for (int32_t is = 0; is < I; ++is) if (fid[is] < 0) fid[is] = next++;
+    const long long NF = I;
+
+    // ---- payoff patterns --------------------------------------------------------------------------------------------
+    const int NT = tm.n_term;
+    std::vector<int> pat(P);
+    std::vector<double> paytab;
+    {
+        std::map<std::string, int> seen;
+        std::string key((size_t)NT * sizeof(double), '\0');
+        for (int64_t p = 0; p < P; ++p) {
+            for (int tr = 0; tr < NT; ++tr) memcpy(&key[(size_t)tr * sizeof(double)], &(*cx.m_pay1)[(size_t)tr * P + p], sizeof(double));
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(key, (int)seen.size()).first;
+                for (int tr = 0; tr < NT; ++tr) paytab.push_back((*cx.m_pay1)[(size_t)tr * P + p]);
+            }
+            pat[p] = it->second;
+            if (seen.size() > 65536) return RLP_OK;
+        }
+    }
+
+    // ---- shared-memory budget of the generated kernel (static shared memory only: 48 KB) -----------------------------
+    Consts c;
+    Terms mt[2] = {micro_terms(s, 0), micro_terms(s, 1)}, ut[2] = {upper_terms(s, 0), upper_terms(s, 1)};
+    for (int pl = 0; pl < 2; ++pl) {
+        c.G[pl] = mg[pl].G; c.GPC[pl] = std::max(1, kBlock / mg[pl].G); c.NG[pl] = (int)mg[pl].key.size();
+        c.NS[pl] = (long long)c.NG[pl] * c.G[pl];
+        c.GB[pl] = ug[pl].G; c.NUG[pl] = (int)ug[pl].key.size();
+    }
+    c.NF = NF; c.T = T; c.NT = NT; c.KP = cx.kp; c.F = (int)cx.fans->size();
+    {
+        size_t kr = std::max(mt[0].kr, mt[1].kr), mo = std::max(s.dec[0].size(), s.dec[1].size());
+        size_t ur = std::max(ut[0].kr * c.GB[0], ut[1].kr * c.GB[1]), uo = std::max(s.udec[0].size() * c.GB[0], s.udec[1].size() * c.GB[1]);
+        size_t rn = std::max(c.GPC[0] * mt[0].kr, c.GPC[1] * mt[1].kr);
+        size_t bytes = 8 * (std::max(kr * kBlock, ur) + std::max(mo * kBlock, uo) + rn + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 64);
+        if (bytes > 46 * 1024) return RLP_OK;
+    }
+
+    // ---- tables -----------------------------------------------------------------------------------------------------
+    std::unique_ptr<FusedPlan, FusedPlanDeleter> fp(new FusedPlan);
+    fp->NF = NF; fp->max_act = t->max_act; fp->num_components = ncomp;
+    const std::vector<int> &ridx = *cx.ridx;
+    std::vector<int> tile_of_portal(P), rank_of_portal(P);
+    for (int64_t k = 0; k < T; ++k)
+        for (int q = 0; q < (*cx.desc)[k].n_portal; ++q) {
+            tile_of_portal[(*cx.desc)[k].portal_off + q] = (int)k;
+            rank_of_portal[(*cx.desc)[k].portal_off + q] = q;
+        }
+    if ((long long)T * cx.kp >= (long long)INT32_MAX) return RLP_OK;
+    for (int pl = 0; pl < 2; ++pl) {
+        const int opp = 1 - pl, G = mg[pl].G, MO = (int)s.dec[pl].size(), MP = (int)s.dec[opp].size();
+        const size_t NG = mg[pl].key.size(), NS = NG * G;
+        std::vector<int> h_opp((size_t)MP * NS), h_pat(NS), h_ridx(NS), h_pidx(NS), h_fid(NG * MO), h_col(NG * MO), h_iset(NG * MO);
+        std::vector<double> h_pc(NS);
+        fp->batch_comp[pl].assign((NG + c.GPC[pl] - 1) / c.GPC[pl], 0);
+        for (size_t gi = 0; gi < NG; ++gi) {
+            const int32_t g = order[pl][gi];
+            for (int k = 0; k < G; ++k) {
+                const int64_t p = mg[pl].members[(size_t)g * G + k];
+                const size_t slot = gi * G + k;
+                for (int jj = 0; jj < MP; ++jj) h_opp[(size_t)jj * NS + slot] = fid[srank[inode[(size_t)p * n_nt + s.dec[opp][jj]]]];
+                h_pat[slot] = pat[p];
+                h_ridx[slot] = ridx[p];
+                h_pidx[slot] = tile_of_portal[p] * cx.kp + rank_of_portal[p];
+                h_pc[slot] = (*cx.pcs)[(*cx.portal_node)[p]];
+            }
+            const int64_t p0 = mg[pl].members[(size_t)g * G];
+            for (int jj = 0; jj < MO; ++jj) {
+                const int32_t is = srank[inode[(size_t)p0 * n_nt + s.dec[pl][jj]]];
+                h_fid[gi * MO + jj] = fid[is];
+                h_col[gi * MO + jj] = (int)t->col_off_h[is];
+                h_iset[gi * MO + jj] = is;
+            }
+            fp->batch_comp[pl][gi / c.GPC[pl]] = comp_of[p0];     // (the last group of a batch wins; only used for sharding)
+        }
+        RLP_CUDA(fp->mem_opp[pl].upload(h_opp, stream)); RLP_CUDA(fp->mem_pat[pl].upload(h_pat, stream));
+        RLP_CUDA(fp->mem_ridx[pl].upload(h_ridx, stream)); RLP_CUDA(fp->mem_pidx[pl].upload(h_pidx, stream));
+        RLP_CUDA(fp->mem_pc[pl].upload(h_pc, stream)); RLP_CUDA(fp->grp_fid[pl].upload(h_fid, stream));
+        RLP_CUDA(fp->grp_col[pl].upload(h_col, stream)); RLP_CUDA(fp->grp_iset[pl].upload(h_iset, stream));
+        fp->n_batches[pl] = (int)((NG + c.GPC[pl] - 1) / c.GPC[pl]);
+        // upper groups
+        const int GB = ug[pl].G, MB = (int)s.udec[pl].size();
+        const size_t NU = ug[pl].key.size();
+        std::vector<int> h_tile(NU * GB), h_ufid(NU * MB), h_ucol(NU * MB), h_uiset(NU * MB);
+        for (size_t g = 0; g < NU; ++g) {
+            for (int k = 0; k < GB; ++k) h_tile[g * GB + k] = (int)ug[pl].members[g * GB + k];
+            for (int jj = 0; jj < MB; ++jj) {
+                const int32_t is = srank[tile_node(ug[pl].members[g * GB], s.udec[pl][jj])];
+                h_ufid[g * MB + jj] = fid[is]; h_ucol[g * MB + jj] = (int)t->col_off_h[is]; h_uiset[g * MB + jj] = is;
+            }
+        }
+        RLP_CUDA(fp->tg_tile[pl].upload(h_tile, stream)); RLP_CUDA(fp->tg_fid[pl].upload(h_ufid, stream));
+        RLP_CUDA(fp->tg_col[pl].upload(h_ucol, stream)); RLP_CUDA(fp->tg_iset[pl].upload(h_uiset, stream));
+        fp->n_ugroups[pl] = (int)NU;
+        RLP_CUDA(rlp::sync_stream(stream));
+    }
+    {
+        std::vector<int> h_ufid((size_t)s.n_udec * T);
+        for (int64_t k = 0; k < T; ++k)
+            for (int dd = 0; dd < s.n_udec; ++dd) h_ufid[(size_t)dd * T + k] = fid[srank[tile_node(k, dd)]];
+        RLP_CUDA(fp->u_fid.upload(h_ufid, stream));
+        RLP_CUDA(fp->paytab.upload(paytab, stream));
+        RLP_CUDA(fp->fid_of_iset.upload(fid, stream));
+        RLP_CUDA(fp->bar.alloc(4));
+        RLP_CUDA(rlp::sync_stream(stream));
+    }
+    // ---- generate, compile, load -----------------------------------------------------------------------------------------
+    fp->source = generate_source(s, c);
+    std::string log;
+    int rc = compile_and_load_source(fp->source, &fp->lib, &log);
+    if (rc) return rc;
+    FusedParams &h = fp->host;
+    UpperJit &uj = *ts.upper_jit;
+    h.mem_opp0 = fp->mem_opp[0].p; h.mem_opp1 = fp->mem_opp[1].p; h.mem_pat0 = fp->mem_pat[0].p; h.mem_pat1 = fp->mem_pat[1].p;
+    h.mem_ridx0 = fp->mem_ridx[0].p; h.mem_ridx1 = fp->mem_ridx[1].p; h.mem_pidx0 = fp->mem_pidx[0].p; h.mem_pidx1 = fp->mem_pidx[1].p;
+    h.mem_pc0 = fp->mem_pc[0].p; h.mem_pc1 = fp->mem_pc[1].p; h.grp_fid0 = fp->grp_fid[0].p; h.grp_fid1 = fp->grp_fid[1].p;
+    h.grp_col0 = fp->grp_col[0].p; h.grp_col1 = fp->grp_col[1].p; h.grp_iset0 = fp->grp_iset[0].p; h.grp_iset1 = fp->grp_iset[1].p;
+    h.paytab = fp->paytab.p;
+    h.tg_tile0 = fp->tg_tile[0].p; h.tg_tile1 = fp->tg_tile[1].p; h.tg_fid0 = fp->tg_fid[0].p; h.tg_fid1 = fp->tg_fid[1].p;
+    h.tg_col0 = fp->tg_col[0].p; h.tg_col1 = fp->tg_col[1].p; h.tg_iset0 = fp->tg_iset[0].p; h.tg_iset1 = fp->tg_iset[1].p;
+    h.u_fid = fp->u_fid.p; h.u_pcs = uj.pcs.p; h.u_cprob = uj.cprob.p; h.u_pay1 = uj.pay1.p;
+    h.fan_desc = reinterpret_cast<const int *>(uj.fan.p); h.fan_cp = uj.fan_cp.p;
+    h.portal_p1 = ts.portal_p1.p; h.portal_p2 = ts.portal_p2.p; h.portal_v = ts.portal_v1.p;
+    h.bar = fp->bar.p; h.tl = nullptr; h.tl_cap = 0;
+    h.num_isets = I;
+    h.first_batch0 = 0; h.end_batch0 = fp->n_batches[0]; h.first_batch1 = 0; h.end_batch1 = fp->n_batches[1];
+    if (!rlp::g_dry_run) {
+        if (!fp->lib) return RLP_OK;                       // RLP_NO_JIT=1
+        if (cudaLibraryGetKernel(&fp->kernel, fp->lib, "cfr_fused_k") != cudaSuccess) {
+            cudaGetLastError();
+            return fail(RLP_ERR_CUDA, "generated library has no cfr_fused_k");
+        }
+        int dev = 0, sms = 0, per_sm = 0;
+        RLP_CUDA(cudaGetDevice(&dev));
+        RLP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fp->kernel, kBlock, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+        const char *e = getenv("RLP_FUSED_CTAS_PER_SM");
+        if (e && atoi(e) >= 1) per_sm = std::min(per_sm, atoi(e));
+        fp->grid = sms * std::min(per_sm, 2);
+    } else {
+        fp->grid = 296;
+    }
+    ts.fused = std::move(fp);
+    return RLP_OK;
+}
+
+bool fused_available(const rlp_cfr *c) {
+    const TileSet &ts = c->tree->tiles;
+    if (!ts.enabled || !ts.fused || !ts.fused->kernel) return false;
+    const char *off = getenv("RLP_NO_FUSED");
+    return !(off && off[0] == '1');
+}
+
+int fused_stat(const rlp_tree *t, int which) {
+    const FusedPlan *f = t->tiles.fused.get();
+    if (!f) return which == 0 ? 0 : -1;
+    switch (which) {
+        case 0: return f->kernel ? 1 : 0;
+        case 1: return f->n_batches[0] + f->n_batches[1];
+        case 2: return f->n_ugroups[0] + f->n_ugroups[1];
+        case 3: return f->grid;
+        case 4: return f->num_components;
+        default: return -1;
+    }
+}
+
+const std::string *fused_source(const rlp_tree *t) { return t->tiles.fused ? &t->tiles.fused->source : nullptr; }
+
+// n iterations t0 .. t0+n-1 in ONE cooperative launch.  `tl` (device, nullable) receives globaltimer stamps of CTA 0:
+// per iteration {start, phase A done, barrier passed, phase B done}.
+int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaStream_t s, unsigned long long *tl, long long tl_cap) {
+    rlp_tree *t = c->tree;
+    FusedPlan &f = *t->tiles.fused;
+    const size_t plane = (size_t)f.NF * (size_t)std::max(1, f.max_act);
+    if (!c->sigF.p) {
+        RLP_CUDA(c->sigF.alloc(2 * plane));
+        RLP_CUDA(cudaMemsetAsync(c->sigF.p, 0, c->sigF.bytes(), s));
+        RLP_CUDA(c->fused_params.alloc(sizeof(FusedParams)));
+        c->sigF_dirty = true;
+        c->fused_params_tl = (void *)-1;
+    }
+    if (c->sigF_dirty) {
+        if (t->I > 0) {
+            k_sigma_fused<<<(unsigned)((t->I + 255) / 256), 256, 0, s>>>(t->I, f.NF, t->col_off.p, f.fid_of_iset.p, c->sigma.p, c->sigF.p);
+            RLP_LAUNCH_CHECK();
+        }
+        c->sigF_cur = 0;
+        c->sigF_dirty = false;
+    }
+    if (c->fused_params_tl != (void *)tl) {
+        FusedParams h = f.host;
+        h.R = c->R.p; h.S = c->S.p; h.sigma_row = c->sigma.p; h.sigF0 = c->sigF.p; h.sigF1 = c->sigF.p + plane;
+        h.flags = c->flags.p; h.tl = tl; h.tl_cap = tl_cap;
+        RLP_CUDA(cudaMemcpyAsync(c->fused_params.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+        RLP_CUDA(cudaStreamSynchronize(s));              // `h` is a stack object
+        c->fused_params_tl = (void *)tl;
+    }
+    int64_t left = n_iters, tt = t0;
+    while (left > 0) {
+        const int chunk = (int)std::min<int64_t>(left, 1 << 20);
+        RLP_CUDA(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), s));
+        const FusedParams *pp = reinterpret_cast<const FusedParams *>(c->fused_params.p);
+        long long t_arg = tt;
+        int iters = chunk, lin = linear_weight ? 1 : 0, cur0 = c->sigF_cur;
+        void *args[] = {&pp, &t_arg, &iters, &lin, &cur0};
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)f.grid); cfg.blockDim = dim3(kBlock); cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)f.kernel, args);
+        if (e == cudaErrorCooperativeLaunchTooLarge && f.grid > 1) {
+            cudaGetLastError();
+            int dev = 0, sms = 0;
+            RLP_CUDA(cudaGetDevice(&dev));
+            RLP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            if (f.grid <= sms) return fail(RLP_ERR_CUDA, "cooperative launch of %d CTAs refused", f.grid);
+            f.grid = sms;
+            continue;
+        }
+        if (e != cudaSuccess) return fail(RLP_ERR_CUDA, "launch of the fused iteration kernel: %s", cudaGetErrorString(e));
+        rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
+        c->sigF_cur = (c->sigF_cur + chunk) & 1;
+        left -= chunk; tt += chunk;
+    }
+    c->sigma_am_dirty = true;            // the five-kernel pipeline's action-major copy is stale now
+    return RLP_OK;
+}
+
+}  // namespace rlp

@@ -194,6 +194,10 @@ static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std:
 }
 
 // Compile the straight-line kernel of `tm`; returns RLP_OK with *kernel == nullptr when JIT is unavailable.
+int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std::string *log_out) {
+    return compile_and_load(src, lib_out, log_out);
+}
+
 int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *kernel, std::string *log_out) {
     *kernel = nullptr;
     int rc = compile_and_load(generate(tm, zs), lib_out, log_out);

@@ -290,6 +290,7 @@ extern "C" int rlp_cfr_sampled_iters(rlp_cfr *c, int variant, int64_t lanes, uin
     }
     c->touched_dirty = true;
     c->sigma_am_dirty = true;
+    c->sigF_dirty = true;
     c->dev_t = -1;
     return RLP_OK;
 }

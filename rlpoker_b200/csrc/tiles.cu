@@ -6,6 +6,7 @@
 #include <string>
 
 #include "cfr.cuh"
+#include "fused.cuh"
 
 using rlp::fail;
 
@@ -782,7 +783,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
             std::string log;
             int rc = jit_upper_kernels(sh, zs, &uj->lib, &uj->k0, &uj->k1, &log);
             if (rc) return rc;
-            if (uj->k0 && uj->k1) {
+            if ((uj->k0 && uj->k1) || rlp::g_dry_run) {
                 const int n = (int)sh.kind.size();
                 int nd = 0, ne = 0, ntm = 0;
                 for (int j = 0; j < n; ++j) {
@@ -851,6 +852,13 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
                 RLP_CUDA(uj->pay2.upload(up2, stream)); RLP_CUDA(uj->poff.upload(upo, stream));
                 RLP_CUDA(rlp::sync_stream(stream));
                 ts.upper_jit = std::move(uj);
+                // group-fused persistent kernel (fused.cu) when the tree has the group structure
+                if (tmpl.size() == 1 && (!ts.jit.empty() || rlp::g_dry_run)) {
+                    rlp::FusedCtx cx{d, t, &srank, &krank, &portal_node, &desc, &locals, &sh, &fans, &tmpl[0], &m_pay1,
+                                     &pcs, &ridx, kp};
+                    int frc = rlp::plan_fused(cx, stream);
+                    if (frc) return frc;
+                }
             }
         }
     }

@@ -98,8 +98,14 @@ struct JitClass {
     ~JitClass() { if (lib) cudaLibraryUnload(lib); }
 };
 
+// Group-fused persistent iteration kernel (fused.cu): device tables + the compiled kernel.
+struct FusedPlan;
+void fused_plan_free(FusedPlan *);
+struct FusedPlanDeleter { void operator()(FusedPlan *p) const { fused_plan_free(p); } };
+
 struct TileSet {
     bool enabled = false;
+    std::unique_ptr<FusedPlan, FusedPlanDeleter> fused;   // set when the tree qualifies (see fused.cu)
     // upper tiles
     int num_tiles = 0;
     int max_nodes = 0, max_nt = 0, max_cp = 0;

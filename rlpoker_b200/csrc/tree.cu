@@ -6,6 +6,7 @@
 #include <numeric>
 
 #include "tree.cuh"
+#include "fused.cuh"
 
 namespace rlp {
 thread_local char g_error[512] = "";
@@ -80,6 +81,11 @@ extern "C" int64_t rlp_tree_stat(const rlp_tree *t, int which) {
         case 6: return t->Kmax;
         case 7: return t->tiles.block;
         case 8: return (int64_t)t->tiles.smem_bytes;
+        case 10: return rlp::fused_stat(t, 0);            // group-fused persistent kernel in use
+        case 11: return rlp::fused_stat(t, 1);            // its micro batches per iteration
+        case 12: return rlp::fused_stat(t, 2);            // its upper groups per iteration
+        case 13: return rlp::fused_stat(t, 3);            // its grid (CTAs, all co-resident)
+        case 14: return rlp::fused_stat(t, 4);            // public-state components (sharding unit)
         default: return -1;
     }
 }
@@ -237,7 +243,27 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
 
 // Host-only planning: everything rlp_tree_upload derives (validation, information-set layout, two-tier tiling, shape
 // classes, generated kernel sources compiled with NVRTC) without a GPU.  Lets the CPU test-suite cover the host logic.
-namespace rlp { extern thread_local int g_jit_compiled, g_jit_failed; }
+namespace rlp { extern thread_local int g_jit_compiled, g_jit_failed; thread_local std::string *g_plan_source_out = nullptr; }
+
+// Planning mode plus the generated source of the group-fused kernel (empty when the tree does not qualify): the
+// number of bytes needed (incl. the terminating NUL) is returned in *len; buf (nullable) receives up to cap bytes.
+extern "C" int rlp_tree_plan_fused_source(const rlp_tree_desc *d, int64_t *stats16, char *buf, int64_t cap, int64_t *len) {
+    std::string src;
+    rlp::g_plan_source_out = &src;
+    int64_t tmp[16];
+    int rc = rlp_tree_plan(d, stats16 ? stats16 : tmp);
+    rlp::g_plan_source_out = nullptr;
+    if (rc) return rc;
+    if (len) *len = (int64_t)src.size() + 1;
+    if (buf && cap > 0) {
+        size_t n = std::min<size_t>((size_t)cap - 1, src.size());
+        memcpy(buf, src.data(), n);
+        buf[n] = 0;
+    }
+    return RLP_OK;
+}
+
+extern "C" int rlp_tree_plan(const rlp_tree_desc *d, int64_t *stats16);
 extern "C" int rlp_tree_plan(const rlp_tree_desc *d, int64_t *stats16) {
     if (!d || !stats16) return fail(RLP_ERR_INVALID, "null argument");
     rlp::g_dry_run = true;
@@ -247,6 +273,10 @@ extern "C" int rlp_tree_plan(const rlp_tree_desc *d, int64_t *stats16) {
     rlp::g_dry_run = false;
     if (rc) return rc;
     const TileSet &ts = t->tiles;
+    if (rlp::g_plan_source_out) {
+        const std::string *src = rlp::fused_source(t);
+        *rlp::g_plan_source_out = src ? *src : std::string();
+    }
     int64_t v[16] = {ts.enabled ? 1 : 0, ts.num_tiles, ts.num_micro, ts.num_classes, ts.micro_nodes, ts.micro_nt,
                      ts.micro_term, ts.acc_a_count, ts.acc_b_count, ts.max_nodes, ts.max_nt, (int64_t)ts.smem_bytes,
                      rlp::g_jit_compiled, rlp::g_jit_failed, t->Kmax, t->zero_sum ? 1 : 0};

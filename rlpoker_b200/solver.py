@@ -79,7 +79,8 @@ class DeviceTree:
     @property
     def layout(self):
         names = ['tiled', 'upper_tiles', 'micro_subtrees', 'micro_shapes', 'jit_shapes', 'zero_sum',
-                 'largest_infoset', 'tile_block', 'tile_smem', 'upper_jit']
+                 'largest_infoset', 'tile_block', 'tile_smem', 'upper_jit', 'fused', 'fused_batches',
+                 'fused_upper_groups', 'fused_grid', 'components']
         return {n: int(_lib.load().rlp_tree_stat(self.handle, i)) for i, n in enumerate(names)}
 
     def best_response(self, sigma, player, want_argmax=False, stream=None):
@@ -190,6 +191,20 @@ class DeviceCFR:
         self.t += reps + 2
         names = ['upper_phase0', 'micro', 'upper_phase1', 'accumulate_rm']
         return {n: 1e3 * out[i] / reps for i, n in enumerate(names)}
+
+    def fused_timeline(self, iters=20, stream=None):
+        """Per-iteration phase times (microseconds, as seen by CTA 0) of the group-fused persistent kernel:
+        micro phase, first grid barrier, upper phase, second barrier + loop turn-around.  Runs `iters` iterations."""
+        buf = (C.c_uint64 * (4 * iters))()
+        check(_lib.load().rlp_cfr_fused_timeline(self.handle, self.t, int(iters), buf, _stream_ptr(stream)))
+        self.t += iters
+        t = np.array(list(buf), np.float64).reshape(iters, 4) / 1e3
+        out = {'micro_phase': float(np.mean(t[:, 1] - t[:, 0])), 'barrier_1': float(np.mean(t[:, 2] - t[:, 1])),
+               'upper_phase': float(np.mean(t[:, 3] - t[:, 2]))}
+        if iters > 1:
+            out['barrier_2'] = float(np.mean(t[1:, 0] - t[:-1, 3]))
+            out['iteration'] = float((t[-1, 0] - t[0, 0]) / (iters - 1))
+        return out
 
     def timeline(self, iters=16, stream=None):
         """[(kind, start_us, end_us)] of block 0 of every sweep kernel over `iters` iterations, relative to the first."""
