@@ -98,7 +98,7 @@ void fused_plan_free(FusedPlan *p) { delete p; }
 
 namespace {
 
-constexpr int kBlock = 256;
+constexpr int kMaxBlock = 256;     // upper bound of the CTA size (shared-memory arrays are sized from the actual one)
 
 // ------------------------------------------------------------------------------------------------ source generator
 struct Shape {
@@ -113,10 +113,12 @@ struct Shape {
 };
 
 struct Consts {
+    int BLK, MINB;                      // CTA size, resident CTAs per SM asked of the compiler
     int G[2], GPC[2], NG[2], GB[2], NUG[2];
     long long NS[2];                    // slots = NG * G
     long long NF, T;
     int NT, KP, F;
+    int NCH;                            // children of every fan-in node when they all agree, else 0
 };
 
 std::string S_(const char *p, int j) { return std::string(p) + std::to_string(j); }
@@ -205,9 +207,9 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
           << "    const double vp = " << (p == 1 ? S_("x", j) : "-" + S_("x", j)) << ";\n";
         for (int k = 0; k < nc; ++k) {
             std::string va = p == 1 ? S_("x", fc + k) : "-" + S_("x", fc + k);
-            o << "    sm_r[" << (t.coff[jj] + k) << " * " << kBlock << " + tid] = w * (" << va << " - vp) * opp;\n";
+            o << "    sm_r[" << (t.coff[jj] + k) << " * " << c.BLK << " + tid] = w * (" << va << " - vp) * opp;\n";
         }
-        o << "    sm_o[" << jj << " * " << kBlock << " + tid] = w * own;\n  }\n";
+        o << "    sm_o[" << jj << " * " << c.BLK << " + tid] = w * own;\n  }\n";
     }
     if (pl == 0) o << "  P->portal_v[pi] = x0;\n";
     o << "}\n";
@@ -301,7 +303,7 @@ std::string generate_source(const Shape &s, const Consts &c) {
     std::ostringstream o;
     o.precision(17);
     o << "struct FusedParams {\n" << kFusedFieldsText << "};\n"
-      << "#define BLOCK " << kBlock << "\n"
+      << "#define BLOCK " << c.BLK << "\n"
       << R"(
 __device__ __forceinline__ unsigned long long now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // All CTAs are co-resident (cooperative launch).  `target` = arrivals expected so far on the monotone counter.
@@ -349,43 +351,82 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
              "    double* sig_out, double* sm_r, double* sm_o, double* sm_rn) {\n"
              "  const int tid = threadIdx.x;\n"
              "  const int gl = tid / " << G << ", k = tid - gl * " << G << ";\n"
-             "  const long long g = batch * " << GPC << " + gl;\n"
-             "  if (gl < " << GPC << " && g < " << c.NG[pl] << "LL) micro_eval" << pl << "(P, g, k, tid, w, sig_in, sm_r, sm_o);\n"
-             "  __syncthreads();\n"
-             "  for (int x = tid; x < " << GPC * KR << "; x += BLOCK) {\n"
-             "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
-             "    const long long ag = batch * " << GPC << " + agl;\n"
-             "    if (ag >= " << c.NG[pl] << "LL) continue;\n"
-             "    const int j = MCJ" << pl << "[ci], a = MCA" << pl << "[ci];\n"
-             "    const int col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
-             "    const int fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
-             "    double r = __ldcg(P->R + col), sa = __ldcg(P->S + col);\n"
-             "    const double sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
-             "    const double* cr = sm_r + ci * BLOCK + agl * " << G << ";\n"
-             "    const double* co = sm_o + j * BLOCK + agl * " << G << ";\n"
-             "#pragma unroll 8\n"
-             "    for (int m = 0; m < " << G << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
-             "    P->R[col] = r; P->S[col] = sa;\n"
-             "    sm_rn[x] = r;\n"
-             "  }\n"
-             "  __syncthreads();\n"
-             "  for (int x = tid; x < " << GPC * KR << "; x += BLOCK) {\n"
-             "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
-             "    const long long ag = batch * " << GPC << " + agl;\n"
-             "    if (ag >= " << c.NG[pl] << "LL) continue;\n"
-             "    const int j = MCJ" << pl << "[ci], a = MCA" << pl << "[ci];\n"
-             "    const int col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
-             "    const int fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
-             "    const double out = rm_one(sm_rn + agl * " << KR << " + MCOFF" << pl << "[j], MNA" << pl << "[j], a);\n"
-             "    P->sigma_row[col] = out;\n"
-             "    sig_out[(long long)a * " << c.NF << "LL + fid] = out;\n"
-             "    if (a == 0) { const int is = P->grp_iset" << pl << "[ag * " << MO << " + j]; const long long I = P->num_isets;\n"
-             "      P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
-             "  }\n"
-             "  __syncthreads();\n"
-             "}\n";
+             "  const long long g = batch * " << GPC << " + gl;\n";
+        const bool one_pass = GPC * KR <= c.BLK;       // every (set, action) of the batch has its own thread
+        if (one_pass) {
+            // the accumulating threads fetch regret, action count and strategy BEFORE the evaluation, so those loads
+            // overlap it instead of sitting behind the barrier
+            o << "  const int agl = tid / " << KR << ", ci = tid - agl * " << KR << ";\n"
+                 "  const long long ag = batch * " << GPC << " + agl;\n"
+                 "  const bool acc = tid < " << GPC * KR << " && ag < " << c.NG[pl] << "LL;\n"
+                 "  int j = 0, a = 0, col = 0, fid = 0;\n"
+                 "  double r = 0.0, sa = 0.0, sg = 0.0;\n"
+                 "  if (acc) {\n"
+                 "    j = MCJ" << pl << "[ci]; a = MCA" << pl << "[ci];\n"
+                 "    col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
+                 "    fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
+                 "    r = __ldcg(P->R + col); sa = __ldcg(P->S + col);\n"
+                 "    sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
+                 "  }\n"
+                 "  if (gl < " << GPC << " && g < " << c.NG[pl] << "LL) micro_eval" << pl << "(P, g, k, tid, w, sig_in, sm_r, sm_o);\n"
+                 "  __syncthreads();\n"
+                 "  if (acc) {\n"
+                 "    const double* cr = sm_r + ci * BLOCK + agl * " << G << ";\n"
+                 "    const double* co = sm_o + j * BLOCK + agl * " << G << ";\n"
+                 "#pragma unroll 8\n"
+                 "    for (int m = 0; m < " << G << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
+                 "    P->R[col] = r; P->S[col] = sa;\n"
+                 "    sm_rn[tid] = r;\n"
+                 "  }\n"
+                 "  __syncthreads();\n"
+                 "  if (acc) {\n"
+                 "    const double out = rm_one(sm_rn + agl * " << KR << " + MCOFF" << pl << "[j], MNA" << pl << "[j], a);\n"
+                 "    P->sigma_row[col] = out;\n"
+                 "    sig_out[(long long)a * " << c.NF << "LL + fid] = out;\n"
+                 "    if (a == 0) { const int is = P->grp_iset" << pl << "[ag * " << MO << " + j]; const long long I = P->num_isets;\n"
+                 "      P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
+                 "  }\n"
+                 "  __syncthreads();\n"
+                 "}\n";
+        } else {
+            o << "  if (gl < " << GPC << " && g < " << c.NG[pl] << "LL) micro_eval" << pl << "(P, g, k, tid, w, sig_in, sm_r, sm_o);\n"
+                 "  __syncthreads();\n"
+                 "  for (int x = tid; x < " << GPC * KR << "; x += BLOCK) {\n"
+                 "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
+                 "    const long long ag = batch * " << GPC << " + agl;\n"
+                 "    if (ag >= " << c.NG[pl] << "LL) continue;\n"
+                 "    const int j = MCJ" << pl << "[ci], a = MCA" << pl << "[ci];\n"
+                 "    const int col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
+                 "    const int fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
+                 "    double r = __ldcg(P->R + col), sa = __ldcg(P->S + col);\n"
+                 "    const double sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
+                 "    const double* cr = sm_r + ci * BLOCK + agl * " << G << ";\n"
+                 "    const double* co = sm_o + j * BLOCK + agl * " << G << ";\n"
+                 "#pragma unroll 8\n"
+                 "    for (int m = 0; m < " << G << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
+                 "    P->R[col] = r; P->S[col] = sa;\n"
+                 "    sm_rn[x] = r;\n"
+                 "  }\n"
+                 "  __syncthreads();\n"
+                 "  for (int x = tid; x < " << GPC * KR << "; x += BLOCK) {\n"
+                 "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
+                 "    const long long ag = batch * " << GPC << " + agl;\n"
+                 "    if (ag >= " << c.NG[pl] << "LL) continue;\n"
+                 "    const int j = MCJ" << pl << "[ci], a = MCA" << pl << "[ci];\n"
+                 "    const int col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
+                 "    const int fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
+                 "    const double out = rm_one(sm_rn + agl * " << KR << " + MCOFF" << pl << "[j], MNA" << pl << "[j], a);\n"
+                 "    P->sigma_row[col] = out;\n"
+                 "    sig_out[(long long)a * " << c.NF << "LL + fid] = out;\n"
+                 "    if (a == 0) { const int is = P->grp_iset" << pl << "[ag * " << MO << " + j]; const long long I = P->num_isets;\n"
+                 "      P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
+                 "  }\n"
+                 "  __syncthreads();\n"
+                 "}\n";
+        }
         const int GB = c.GB[pl], KRB = ut.kr, MB = (int)s.udec[pl].size();
         // mode 0: full unit (fan-in, evaluate, accumulate, regret matching, reach); mode 1: reach only (prologue)
+        const bool acc_one = KRB <= c.BLK;
         o << "__device__ __forceinline__ void upper_unit" << pl << "(const FusedParams* __restrict__ P, int u, double w, const double* sig_in,\n"
              "    double* sig_out, int reach_only, double* sm_fan, double* sm_r, double* sm_o, double* sm_rn, double* sm_s) {\n"
              "  const int tid = threadIdx.x;\n"
@@ -395,54 +436,92 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
              "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
              "      sm_s[x] = __ldcg(sig_in + (long long)a * " << c.NF << "LL + P->tg_fid" << pl << "[u * " << MB << " + j]);\n"
              "    }\n"
-             "  } else {\n"
-             "    const int* fd = P->fan_desc;\n"
+             "  } else {\n";
+        if (acc_one)        // regret / action count / strategy of the unit's (set, action) pairs: in flight during the fan-in
+            o << "    int aj = 0, aa = 0, acol = 0, afid = 0;\n"
+                 "    double ar = 0.0, asa = 0.0, asg = 0.0;\n"
+                 "    if (tid < " << KRB << ") {\n"
+                 "      aj = UCJ" << pl << "[tid]; aa = UCA" << pl << "[tid];\n"
+                 "      acol = P->tg_col" << pl << "[u * " << MB << " + aj] + aa;\n"
+                 "      afid = P->tg_fid" << pl << "[u * " << MB << " + aj];\n"
+                 "      ar = __ldcg(P->R + acol); asa = __ldcg(P->S + acol);\n"
+                 "      asg = __ldcg(sig_in + (long long)aa * " << c.NF << "LL + afid);\n"
+                 "    }\n";
+        o << "    const int* fd = P->fan_desc;\n"
              "    for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
              "      const int m = x / " << std::max(1, c.F) << ", f = x - m * " << std::max(1, c.F) << ";\n"
              "      const long long i = tiles[m];\n"
-             "      const int k0 = fd[4 * f], nch = fd[4 * f + 1], e0 = fd[4 * f + 2];\n"
+             "      const int k0 = fd[4 * f], e0 = fd[4 * f + 2];\n"
              "      const double* pv = P->portal_v + i * " << c.KP << "LL + k0;\n"
              "      const double* cp = P->fan_cp + (long long)e0 * " << c.T << "LL + i;\n"
-             "      double acc = 0.0;\n"
-             "      int ch = 0;\n"
-             "      for (; ch + 8 <= nch; ch += 8) {\n"
-             "        double e[8], v[8];\n"
-             "#pragma unroll\n"
-             "        for (int q = 0; q < 8; ++q) { e[q] = cp[(long long)(ch + q) * " << c.T << "LL]; v[q] = __ldcg(pv + ch + q); }\n"
-             "#pragma unroll\n"
-             "        for (int q = 0; q < 8; ++q) acc = acc + e[q] * v[q];\n"
-             "      }\n"
-             "      for (; ch < nch; ++ch) acc = acc + cp[(long long)ch * " << c.T << "LL] * __ldcg(pv + ch);\n"
-             "      sm_fan[x] = acc;\n"
+             "      double acc = 0.0;\n";
+        if (c.NCH > 0 && c.NCH <= 32) {     // every fan-in node has NCH children: all loads in flight, then the ordered adds
+            o << "      double e[" << c.NCH << "], v[" << c.NCH << "];\n"
+                 "#pragma unroll\n"
+                 "      for (int q = 0; q < " << c.NCH << "; ++q) { e[q] = cp[(long long)q * " << c.T << "LL]; v[q] = __ldcg(pv + q); }\n"
+                 "#pragma unroll\n"
+                 "      for (int q = 0; q < " << c.NCH << "; ++q) acc = acc + e[q] * v[q];\n";
+        } else {
+            o << "      const int nch = fd[4 * f + 1];\n"
+                 "      int ch = 0;\n"
+                 "      for (; ch + 8 <= nch; ch += 8) {\n"
+                 "        double e[8], v[8];\n"
+                 "#pragma unroll\n"
+                 "        for (int q = 0; q < 8; ++q) { e[q] = cp[(long long)(ch + q) * " << c.T << "LL]; v[q] = __ldcg(pv + ch + q); }\n"
+                 "#pragma unroll\n"
+                 "        for (int q = 0; q < 8; ++q) acc = acc + e[q] * v[q];\n"
+                 "      }\n"
+                 "      for (; ch < nch; ++ch) acc = acc + cp[(long long)ch * " << c.T << "LL] * __ldcg(pv + ch);\n";
+        }
+        o << "      sm_fan[x] = acc;\n"
              "    }\n"
              "    __syncthreads();\n"
              "    if (tid < " << GB << ") upper_eval" << pl << "(P, tiles[tid], tid, w, sig_in, sm_fan, sm_r, sm_o);\n"
-             "    __syncthreads();\n"
-             "    for (int x = tid; x < " << KRB << "; x += BLOCK) {\n"
-             "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
-             "      const int col = P->tg_col" << pl << "[u * " << MB << " + j] + a;\n"
-             "      const int fid = P->tg_fid" << pl << "[u * " << MB << " + j];\n"
-             "      double r = __ldcg(P->R + col), sa = __ldcg(P->S + col);\n"
-             "      const double sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
-             "      const double* cr = sm_r + x * " << GB << ";\n"
-             "      const double* co = sm_o + j * " << GB << ";\n"
-             "      for (int m = 0; m < " << GB << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
-             "      P->R[col] = r; P->S[col] = sa;\n"
-             "      sm_rn[x] = r;\n"
-             "    }\n"
-             "    __syncthreads();\n"
-             "    for (int x = tid; x < " << KRB << "; x += BLOCK) {\n"
-             "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
-             "      const int col = P->tg_col" << pl << "[u * " << MB << " + j] + a;\n"
-             "      const int fid = P->tg_fid" << pl << "[u * " << MB << " + j];\n"
-             "      const double out = rm_one(sm_rn + UCOFF" << pl << "[j], UNA" << pl << "[j], a);\n"
-             "      P->sigma_row[col] = out;\n"
-             "      sig_out[(long long)a * " << c.NF << "LL + fid] = out;\n"
-             "      sm_s[x] = out;\n"
-             "      if (a == 0) { const int is = P->tg_iset" << pl << "[u * " << MB << " + j]; const long long I = P->num_isets;\n"
-             "        P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
-             "    }\n"
-             "  }\n"
+             "    __syncthreads();\n";
+        if (acc_one) {
+            o << "    if (tid < " << KRB << ") {\n"
+                 "      const double* cr = sm_r + tid * " << GB << ";\n"
+                 "      const double* co = sm_o + aj * " << GB << ";\n"
+                 "      for (int m = 0; m < " << GB << "; ++m) { ar = ar + cr[m]; asa = asa + co[m] * asg; }\n"
+                 "      P->R[acol] = ar; P->S[acol] = asa;\n"
+                 "      sm_rn[tid] = ar;\n"
+                 "    }\n"
+                 "    __syncthreads();\n"
+                 "    if (tid < " << KRB << ") {\n"
+                 "      const double out = rm_one(sm_rn + UCOFF" << pl << "[aj], UNA" << pl << "[aj], aa);\n"
+                 "      P->sigma_row[acol] = out;\n"
+                 "      sig_out[(long long)aa * " << c.NF << "LL + afid] = out;\n"
+                 "      sm_s[tid] = out;\n"
+                 "      if (aa == 0) { const int is = P->tg_iset" << pl << "[u * " << MB << " + aj]; const long long I = P->num_isets;\n"
+                 "        P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
+                 "    }\n";
+        } else {
+            o << "    for (int x = tid; x < " << KRB << "; x += BLOCK) {\n"
+                 "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
+                 "      const int col = P->tg_col" << pl << "[u * " << MB << " + j] + a;\n"
+                 "      const int fid = P->tg_fid" << pl << "[u * " << MB << " + j];\n"
+                 "      double r = __ldcg(P->R + col), sa = __ldcg(P->S + col);\n"
+                 "      const double sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
+                 "      const double* cr = sm_r + x * " << GB << ";\n"
+                 "      const double* co = sm_o + j * " << GB << ";\n"
+                 "      for (int m = 0; m < " << GB << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
+                 "      P->R[col] = r; P->S[col] = sa;\n"
+                 "      sm_rn[x] = r;\n"
+                 "    }\n"
+                 "    __syncthreads();\n"
+                 "    for (int x = tid; x < " << KRB << "; x += BLOCK) {\n"
+                 "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
+                 "      const int col = P->tg_col" << pl << "[u * " << MB << " + j] + a;\n"
+                 "      const int fid = P->tg_fid" << pl << "[u * " << MB << " + j];\n"
+                 "      const double out = rm_one(sm_rn + UCOFF" << pl << "[j], UNA" << pl << "[j], a);\n"
+                 "      P->sigma_row[col] = out;\n"
+                 "      sig_out[(long long)a * " << c.NF << "LL + fid] = out;\n"
+                 "      sm_s[x] = out;\n"
+                 "      if (a == 0) { const int is = P->tg_iset" << pl << "[u * " << MB << " + j]; const long long I = P->num_isets;\n"
+                 "        P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
+                 "    }\n";
+        }
+        o << "  }\n"
              "  __syncthreads();\n"
              "  if (tid < " << GB << ") upper_reach" << pl << "(P, tiles[tid], sm_s);\n"
              "  __syncthreads();\n"
@@ -455,9 +534,9 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
     const int ur_n = std::max(1, std::max(u0.kr * c.GB[0], u1.kr * c.GB[1]));
     const int uo_n = std::max(1, std::max((int)s.udec[0].size() * c.GB[0], (int)s.udec[1].size() * c.GB[1]));
     const int us_n = std::max(1, std::max(u0.kr, u1.kr));
-    const int sm_r_n = std::max(KRmax * kBlock, ur_n), sm_o_n = std::max(MOmax * kBlock, uo_n);
+    const int sm_r_n = std::max(KRmax * c.BLK, ur_n), sm_o_n = std::max(MOmax * c.BLK, uo_n);
     const int sm_rn_n = std::max(std::max(1, rn_a), us_n);
-    o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, 2) cfr_fused_k(const FusedParams* __restrict__ P, long long t0, int iters,\n"
+    o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, " << c.MINB << ") cfr_fused_k(const FusedParams* __restrict__ P, long long t0, int iters,\n"
          "    int linear, int cur0) {\n"
          "  __shared__ double sm_r[" << sm_r_n << "];\n"
          "  __shared__ double sm_o[" << sm_o_n << "];\n"
@@ -540,6 +619,10 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         const TileDesc &last = (*cx.desc)[T - 1];
         if (last.portal_off + last.n_portal != P) return RLP_OK;
     }
+    // CTA shape: RLP_FUSED_BLOCK threads (default 256), RLP_FUSED_MINB resident CTAs per SM (default 2)
+    int blk = 256, minb = 2;
+    { const char *e = getenv("RLP_FUSED_BLOCK"); if (e && atoi(e) >= 32 && atoi(e) <= kMaxBlock && atoi(e) % 32 == 0) blk = atoi(e); }
+    { const char *e = getenv("RLP_FUSED_MINB"); if (e && atoi(e) >= 1 && atoi(e) <= 8) minb = atoi(e); }
     const std::vector<int32_t> &srank = *cx.srank, &krank = *cx.krank;
     std::vector<int32_t> size(I, 0);
     for (int64_t g = 0; g < d->num_nodes; ++g) if (d->player[g] > 0) size[srank[g]]++;
@@ -587,7 +670,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         Groups &gr = mg[pl];
         const int r0 = s.dec[pl][0];
         gr.G = size[srank[inode[r0]]];
-        if (gr.G < 1 || gr.G > kBlock) return RLP_OK;
+        if (gr.G < 1 || gr.G > blk) return RLP_OK;
         std::vector<int32_t> gid_of_iset(I, -1);
         group_of[pl].assign(P, -1);
         for (int64_t p = 0; p < P; ++p) {
@@ -629,7 +712,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         Groups &gr = ug[pl];
         const int d0 = s.udec[pl][0];
         gr.G = size[srank[tile_node(0, d0)]];
-        if (gr.G < 1 || gr.G > kBlock) return RLP_OK;
+        if (gr.G < 1 || gr.G > blk) return RLP_OK;
         std::vector<int32_t> gid_of_iset(I, -1);
         for (int64_t k = 0; k < T; ++k) {
             int32_t node = tile_node(k, d0);
@@ -727,24 +810,27 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
 
     // ---- shared-memory budget of the generated kernel (static shared memory only: 48 KB) -----------------------------
     Consts c;
+    c.BLK = blk; c.MINB = minb;
     Terms mt[2] = {micro_terms(s, 0), micro_terms(s, 1)}, ut[2] = {upper_terms(s, 0), upper_terms(s, 1)};
     for (int pl = 0; pl < 2; ++pl) {
-        c.G[pl] = mg[pl].G; c.GPC[pl] = std::max(1, kBlock / mg[pl].G); c.NG[pl] = (int)mg[pl].key.size();
+        c.G[pl] = mg[pl].G; c.GPC[pl] = std::max(1, blk / mg[pl].G); c.NG[pl] = (int)mg[pl].key.size();
         c.NS[pl] = (long long)c.NG[pl] * c.G[pl];
         c.GB[pl] = ug[pl].G; c.NUG[pl] = (int)ug[pl].key.size();
     }
     c.NF = NF; c.T = T; c.NT = NT; c.KP = cx.kp; c.F = (int)cx.fans->size();
+    c.NCH = cx.fans->empty() ? 0 : (*cx.fans)[0].nchild;
+    for (const FanDesc &fd : *cx.fans) if (fd.nchild != c.NCH) c.NCH = 0;
     {
         size_t kr = std::max(mt[0].kr, mt[1].kr), mo = std::max(s.dec[0].size(), s.dec[1].size());
         size_t ur = std::max(ut[0].kr * c.GB[0], ut[1].kr * c.GB[1]), uo = std::max(s.udec[0].size() * c.GB[0], s.udec[1].size() * c.GB[1]);
         size_t rn = std::max(c.GPC[0] * mt[0].kr, c.GPC[1] * mt[1].kr);
-        size_t bytes = 8 * (std::max(kr * kBlock, ur) + std::max(mo * kBlock, uo) + rn + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 64);
+        size_t bytes = 8 * (std::max(kr * blk, ur) + std::max(mo * blk, uo) + rn + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 64);
         if (bytes > 46 * 1024) return RLP_OK;
     }
 
     // ---- tables -----------------------------------------------------------------------------------------------------
     std::unique_ptr<FusedPlan, FusedPlanDeleter> fp(new FusedPlan);
-    fp->NF = NF; fp->max_act = t->max_act; fp->num_components = ncomp;
+    fp->NF = NF; fp->max_act = t->max_act; fp->num_components = ncomp; fp->block = blk;
     const std::vector<int> &ridx = *cx.ridx;
     std::vector<int> tile_of_portal(P), rank_of_portal(P);
     for (int64_t k = 0; k < T; ++k)
@@ -839,13 +925,13 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         int dev = 0, sms = 0, per_sm = 0;
         RLP_CUDA(cudaGetDevice(&dev));
         RLP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fp->kernel, kBlock, 0) != cudaSuccess || per_sm < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fp->kernel, blk, 0) != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
             per_sm = 1;
         }
         const char *e = getenv("RLP_FUSED_CTAS_PER_SM");
         if (e && atoi(e) >= 1) per_sm = std::min(per_sm, atoi(e));
-        fp->grid = sms * std::min(per_sm, 2);
+        fp->grid = sms * std::min(per_sm, minb);
     } else {
         fp->grid = 296;
     }
@@ -913,7 +999,7 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
         int iters = chunk, lin = linear_weight ? 1 : 0, cur0 = c->sigF_cur;
         void *args[] = {&pp, &t_arg, &iters, &lin, &cur0};
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)f.grid); cfg.blockDim = dim3(kBlock); cfg.stream = s;
+        cfg.gridDim = dim3((unsigned)f.grid); cfg.blockDim = dim3((unsigned)f.block); cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
