@@ -61,8 +61,8 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(double *, sigF0) X(double *, sigF1)                     /* strategy, [action][fused id], two buffers */        \
     X(double *, portal_p1) X(double *, portal_p2) X(double *, portal_v)                                             \
     X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
-    X(long long, num_isets) X(long long, first_batch0) X(long long, end_batch0) X(long long, first_batch1)          \
-    X(long long, end_batch1) X(long long, tl_cap)
+    X(long long, num_isets) X(long long, first_group0) X(long long, end_group0) X(long long, first_group1)          \
+    X(long long, end_group1) X(long long, tl_cap)
 
 struct FusedParams {
 #define X(type, name) type name;
@@ -90,7 +90,7 @@ struct FusedPlan {
     int max_act = 0;
     int grid = 0, block = 256;
     int num_components = 0;
-    std::vector<int> batch_comp[2];     // component of every batch (multi-GPU sharding by public state)
+    std::vector<int> group_comp[2];     // component of every group, fused order (multi-GPU sharding by public state)
     std::string source;
     ~FusedPlan() { if (lib) cudaLibraryUnload(lib); }
 };
@@ -114,6 +114,7 @@ struct Shape {
 
 struct Consts {
     int BLK, MINB;                      // CTA size, resident CTAs per SM asked of the compiler
+    int TEAM;                           // threads that work on one micro unit together: 32 (a warp, __syncwarp) or BLK
     int G[2], GPC[2], NG[2], GB[2], NUG[2];
     long long NS[2];                    // slots = NG * G
     long long NF, T;
@@ -167,7 +168,7 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
     for (size_t j = 0; j < s.dec[pl].size(); ++j) own_j[s.dec[pl][j]] = (int)j;
     for (size_t j = 0; j < s.dec[opp].size(); ++j) opp_j[s.dec[opp][j]] = (int)j;
     Terms t = micro_terms(s, pl);
-    o << "__device__ __forceinline__ void micro_eval" << pl << "(const FusedParams* __restrict__ P, long long g, int k, int tid, double w,\n"
+    o << "__device__ __forceinline__ void micro_eval" << pl << "(const FusedParams* __restrict__ P, long long g, int k, int tix, double w,\n"
          "    const double* sig_in, double* sm_r, double* sm_o) {\n"
          "  const long long slot = g * " << c.G[pl] << " + k;\n"
          "  const int pat = P->mem_pat" << pl << "[slot], ri = P->mem_ridx" << pl << "[slot];\n"
@@ -207,9 +208,9 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
           << "    const double vp = " << (p == 1 ? S_("x", j) : "-" + S_("x", j)) << ";\n";
         for (int k = 0; k < nc; ++k) {
             std::string va = p == 1 ? S_("x", fc + k) : "-" + S_("x", fc + k);
-            o << "    sm_r[" << (t.coff[jj] + k) << " * " << c.BLK << " + tid] = w * (" << va << " - vp) * opp;\n";
+            o << "    sm_r[" << (t.coff[jj] + k) << " * SMS + tix] = w * (" << va << " - vp) * opp;\n";
         }
-        o << "    sm_o[" << jj << " * " << c.BLK << " + tid] = w * own;\n  }\n";
+        o << "    sm_o[" << jj << " * SMS + tix] = w * own;\n  }\n";
     }
     if (pl == 0) o << "  P->portal_v[pi] = x0;\n";
     o << "}\n";
@@ -304,16 +305,38 @@ std::string generate_source(const Shape &s, const Consts &c) {
     o.precision(17);
     o << "struct FusedParams {\n" << kFusedFieldsText << "};\n"
       << "#define BLOCK " << c.BLK << "\n"
+      // row stride of the per-thread shared arrays: odd, so the (set, action) threads of the ordered sums -- which read
+      // different ROWS at the same column -- fall into different banks (a stride of BLOCK doubles is 11-way conflicted)
+      << "#define TEAM " << c.TEAM << "\n"
+      << "#define SMS " << (c.TEAM + 1) << "\n"
+      << (c.TEAM == 32 ? "#define TEAM_SYNC() __syncwarp()\n" : "#define TEAM_SYNC() __syncthreads()\n")
       << R"(
 __device__ __forceinline__ unsigned long long now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-// All CTAs are co-resident (cooperative launch).  `target` = arrivals expected so far on the monotone counter.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+// Grid barrier for co-resident CTAs (cooperative launch).  bar[0] counts arrivals (monotone over the launch); the LAST
+// arriver of barrier number `k` writes k into a private flag word of every CTA (bar[32 + 32 * cta], 128 bytes apart,
+// so spread over the L2 slices) and each waiting CTA polls only its own word: no address is polled by more than one
+// thread.  (Polling bar[0] from ~300 CTAs saturates its L2 slice and slows every load that maps to that slice.)
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int k, unsigned int nb) {
+  __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(bar, 1u);
+    const unsigned int prev = atomicAdd(bar, 1u);
+    s_last = prev + 1u == k * nb;
+    __threadfence();
+  }
+  __syncthreads();
+  if (s_last) {
+    for (unsigned int c = threadIdx.x; c < nb; c += BLOCK)
+      asm volatile("st.relaxed.gpu.u32 [%0], %1;" :: "l"(bar + 32 + 32 * c), "r"(k) : "memory");
+  } else if (threadIdx.x == 0) {
+    const unsigned int* mine = bar + 32 + 32 * blockIdx.x;
     unsigned int v;
-    do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v >= k) break;
+      __nanosleep(20);
+    }
     __threadfence();
   }
   __syncthreads();
@@ -347,18 +370,21 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
     for (int pl = 0; pl < 2; ++pl) {
         Terms mt = micro_terms(s, pl), ut = upper_terms(s, pl);
         const int G = c.G[pl], GPC = c.GPC[pl], KR = mt.kr, MO = (int)s.dec[pl].size();
-        o << "__device__ __forceinline__ void micro_batch" << pl << "(const FusedParams* __restrict__ P, long long batch, double w, const double* sig_in,\n"
+        const int GPT = GPC;                            // groups per team
+        const std::string gfirst = "P->first_group" + std::to_string(pl), gend = "P->end_group" + std::to_string(pl);
+        o << "__device__ __forceinline__ void micro_unit" << pl << "(const FusedParams* __restrict__ P, long long unit, double w, const double* sig_in,\n"
              "    double* sig_out, double* sm_r, double* sm_o, double* sm_rn) {\n"
-             "  const int tid = threadIdx.x;\n"
-             "  const int gl = tid / " << G << ", k = tid - gl * " << G << ";\n"
-             "  const long long g = batch * " << GPC << " + gl;\n";
-        const bool one_pass = GPC * KR <= c.BLK;       // every (set, action) of the batch has its own thread
+             "  const int tix = threadIdx.x % TEAM;\n"
+             "  const int gl = tix / " << G << ", k = tix - gl * " << G << ";\n"
+             "  const long long g0 = " << gfirst << " + unit * " << GPT << ", gend = " << gend << ";\n"
+             "  const long long g = g0 + gl;\n";
+        const bool one_pass = GPT * KR <= c.TEAM;      // every (set, action) of the unit has its own thread
         if (one_pass) {
             // the accumulating threads fetch regret, action count and strategy BEFORE the evaluation, so those loads
-            // overlap it instead of sitting behind the barrier
-            o << "  const int agl = tid / " << KR << ", ci = tid - agl * " << KR << ";\n"
-                 "  const long long ag = batch * " << GPC << " + agl;\n"
-                 "  const bool acc = tid < " << GPC * KR << " && ag < " << c.NG[pl] << "LL;\n"
+            // overlap it instead of sitting behind the team barrier
+            o << "  const int agl = tix / " << KR << ", ci = tix - agl * " << KR << ";\n"
+                 "  const long long ag = g0 + agl;\n"
+                 "  const bool acc = tix < " << GPT * KR << " && ag < gend;\n"
                  "  int j = 0, a = 0, col = 0, fid = 0;\n"
                  "  double r = 0.0, sa = 0.0, sg = 0.0;\n"
                  "  if (acc) {\n"
@@ -368,17 +394,17 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    r = __ldcg(P->R + col); sa = __ldcg(P->S + col);\n"
                  "    sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
                  "  }\n"
-                 "  if (gl < " << GPC << " && g < " << c.NG[pl] << "LL) micro_eval" << pl << "(P, g, k, tid, w, sig_in, sm_r, sm_o);\n"
-                 "  __syncthreads();\n"
+                 "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, g, k, tix, w, sig_in, sm_r, sm_o);\n"
+                 "  TEAM_SYNC();\n"
                  "  if (acc) {\n"
-                 "    const double* cr = sm_r + ci * BLOCK + agl * " << G << ";\n"
-                 "    const double* co = sm_o + j * BLOCK + agl * " << G << ";\n"
+                 "    const double* cr = sm_r + ci * SMS + agl * " << G << ";\n"
+                 "    const double* co = sm_o + j * SMS + agl * " << G << ";\n"
                  "#pragma unroll 8\n"
                  "    for (int m = 0; m < " << G << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
                  "    P->R[col] = r; P->S[col] = sa;\n"
-                 "    sm_rn[tid] = r;\n"
+                 "    sm_rn[tix] = r;\n"
                  "  }\n"
-                 "  __syncthreads();\n"
+                 "  TEAM_SYNC();\n"
                  "  if (acc) {\n"
                  "    const double out = rm_one(sm_rn + agl * " << KR << " + MCOFF" << pl << "[j], MNA" << pl << "[j], a);\n"
                  "    P->sigma_row[col] = out;\n"
@@ -386,32 +412,32 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    if (a == 0) { const int is = P->grp_iset" << pl << "[ag * " << MO << " + j]; const long long I = P->num_isets;\n"
                  "      P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
                  "  }\n"
-                 "  __syncthreads();\n"
+                 "  TEAM_SYNC();\n"
                  "}\n";
         } else {
-            o << "  if (gl < " << GPC << " && g < " << c.NG[pl] << "LL) micro_eval" << pl << "(P, g, k, tid, w, sig_in, sm_r, sm_o);\n"
-                 "  __syncthreads();\n"
-                 "  for (int x = tid; x < " << GPC * KR << "; x += BLOCK) {\n"
+            o << "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, g, k, tix, w, sig_in, sm_r, sm_o);\n"
+                 "  TEAM_SYNC();\n"
+                 "  for (int x = tix; x < " << GPT * KR << "; x += TEAM) {\n"
                  "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
-                 "    const long long ag = batch * " << GPC << " + agl;\n"
-                 "    if (ag >= " << c.NG[pl] << "LL) continue;\n"
+                 "    const long long ag = g0 + agl;\n"
+                 "    if (ag >= gend) continue;\n"
                  "    const int j = MCJ" << pl << "[ci], a = MCA" << pl << "[ci];\n"
                  "    const int col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
                  "    const int fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
                  "    double r = __ldcg(P->R + col), sa = __ldcg(P->S + col);\n"
                  "    const double sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
-                 "    const double* cr = sm_r + ci * BLOCK + agl * " << G << ";\n"
-                 "    const double* co = sm_o + j * BLOCK + agl * " << G << ";\n"
+                 "    const double* cr = sm_r + ci * SMS + agl * " << G << ";\n"
+                 "    const double* co = sm_o + j * SMS + agl * " << G << ";\n"
                  "#pragma unroll 8\n"
                  "    for (int m = 0; m < " << G << "; ++m) { r = r + cr[m]; sa = sa + co[m] * sg; }\n"
                  "    P->R[col] = r; P->S[col] = sa;\n"
                  "    sm_rn[x] = r;\n"
                  "  }\n"
-                 "  __syncthreads();\n"
-                 "  for (int x = tid; x < " << GPC * KR << "; x += BLOCK) {\n"
+                 "  TEAM_SYNC();\n"
+                 "  for (int x = tix; x < " << GPT * KR << "; x += TEAM) {\n"
                  "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
-                 "    const long long ag = batch * " << GPC << " + agl;\n"
-                 "    if (ag >= " << c.NG[pl] << "LL) continue;\n"
+                 "    const long long ag = g0 + agl;\n"
+                 "    if (ag >= gend) continue;\n"
                  "    const int j = MCJ" << pl << "[ci], a = MCA" << pl << "[ci];\n"
                  "    const int col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
                  "    const int fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
@@ -421,7 +447,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    if (a == 0) { const int is = P->grp_iset" << pl << "[ag * " << MO << " + j]; const long long I = P->num_isets;\n"
                  "      P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
                  "  }\n"
-                 "  __syncthreads();\n"
+                 "  TEAM_SYNC();\n"
                  "}\n";
         }
         const int GB = c.GB[pl], KRB = ut.kr, MB = (int)s.udec[pl].size();
@@ -534,8 +560,11 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
     const int ur_n = std::max(1, std::max(u0.kr * c.GB[0], u1.kr * c.GB[1]));
     const int uo_n = std::max(1, std::max((int)s.udec[0].size() * c.GB[0], (int)s.udec[1].size() * c.GB[1]));
     const int us_n = std::max(1, std::max(u0.kr, u1.kr));
-    const int sm_r_n = std::max(KRmax * c.BLK, ur_n), sm_o_n = std::max(MOmax * c.BLK, uo_n);
-    const int sm_rn_n = std::max(std::max(1, rn_a), us_n);
+    const int NT = c.BLK / c.TEAM;                      // teams per CTA
+    const int rn_team = std::max(1, std::max(c.GPC[0] * m0.kr, c.GPC[1] * m1.kr));
+    const int sm_r_n = std::max(NT * KRmax * (c.TEAM + 1), ur_n), sm_o_n = std::max(NT * MOmax * (c.TEAM + 1), uo_n);
+    const int sm_rn_n = std::max(NT * rn_team, us_n);
+    (void)rn_a;
     o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, " << c.MINB << ") cfr_fused_k(const FusedParams* __restrict__ P, long long t0, int iters,\n"
          "    int linear, int cur0) {\n"
          "  __shared__ double sm_r[" << sm_r_n << "];\n"
@@ -543,11 +572,21 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "  __shared__ double sm_rn[" << sm_rn_n << "];\n"
          "  __shared__ double sm_fan[" << fan_n << "];\n"
          "  __shared__ double sm_s[" << us_n << "];\n"
+         "  __shared__ int s_lead;\n"
          "  const unsigned int nb = gridDim.x;\n"
-         "  unsigned int arrivals = 0;\n"
+         "  unsigned int nbar = 0;\n"
          "  const bool log = P->tl != 0 && blockIdx.x == 0 && threadIdx.x == 0;\n"
          "  long long tlc = 0;\n"
          "  const int NU0 = " << c.NUG[0] << ", NU1 = " << c.NUG[1] << ";\n"
+         "  // The upper phase has far fewer units than there are CTAs.  Consecutive CTAs share an SM, so the units go to\n"
+         "  // one LEADER CTA per SM (the first CTA to register on its SM), spread over all SMs.\n"
+         "  if (threadIdx.x == 0) {\n"
+         "    unsigned int smid; asm volatile(\"mov.u32 %0, %%smid;\" : \"=r\"(smid));\n"
+         "    const unsigned int rank = atomicAdd(P->bar + 32 + 32 * nb + (smid & 1023u), 1u);\n"
+         "    s_lead = rank == 0 ? (int)atomicAdd(P->bar + 1, 1u) : -1;\n"
+         "  }\n"
+         "  __syncthreads();\n"
+         "  const int lead = s_lead;\n"
          "  // prologue: reach of both players to the portals from the current strategy\n"
          "  {\n"
          "    const double* sig_in = cur0 ? P->sigF1 : P->sigF0;\n"
@@ -555,30 +594,38 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "      if (u < NU0) upper_unit0(P, u, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
          "      else upper_unit1(P, u - NU0, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
          "    }\n"
-         "    arrivals += nb; grid_barrier(P->bar, arrivals);\n"
+         "    grid_barrier(P->bar, ++nbar, nb);\n"
          "  }\n"
+         "  const int n_lead = (int)__ldcg(P->bar + 1);\n"
+         "  const int team = threadIdx.x / TEAM;\n"
+         "  double* t_r = sm_r + team * " << KRmax * (c.TEAM + 1) << ";\n"
+         "  double* t_o = sm_o + team * " << MOmax * (c.TEAM + 1) << ";\n"
+         "  double* t_rn = sm_rn + team * " << rn_team << ";\n"
+         "  const long long nu0 = (P->end_group0 - P->first_group0 + " << c.GPC[0] - 1 << ") / " << c.GPC[0] << ";\n"
+         "  const long long nu1 = (P->end_group1 - P->first_group1 + " << c.GPC[1] - 1 << ") / " << c.GPC[1] << ";\n"
          "  for (int it = 0; it < iters; ++it) {\n"
          "    const int cur = (cur0 + it) & 1;\n"
          "    const double* sig_in = cur ? P->sigF1 : P->sigF0;\n"
          "    double* sig_out = cur ? P->sigF0 : P->sigF1;\n"
          "    const double w = linear ? (double)(t0 + it) : 1.0;\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
-         "    // phase A: micro groups of player 1, then of player 2 (one list of batches)\n"
-         "    const long long nb0 = P->end_batch0 - P->first_batch0, nb1 = P->end_batch1 - P->first_batch1;\n"
-         "    for (long long b = blockIdx.x; b < nb0 + nb1; b += nb) {\n"
-         "      if (b < nb0) micro_batch0(P, P->first_batch0 + b, w, sig_in, sig_out, sm_r, sm_o, sm_rn);\n"
-         "      else micro_batch1(P, P->first_batch1 + (b - nb0), w, sig_in, sig_out, sm_r, sm_o, sm_rn);\n"
+         "    // phase A: micro units of player 1, then of player 2 (one list), one unit per team at a time\n"
+         "    for (long long un = (long long)blockIdx.x * " << NT << " + team; un < nu0 + nu1; un += (long long)nb * " << NT << ") {\n"
+         "      if (un < nu0) micro_unit0(P, un, w, sig_in, sig_out, t_r, t_o, t_rn);\n"
+         "      else micro_unit1(P, un - nu0, w, sig_in, sig_out, t_r, t_o, t_rn);\n"
          "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
-         "    arrivals += nb; grid_barrier(P->bar, arrivals);\n"
+         "    grid_barrier(P->bar, ++nbar, nb);\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)\n"
-         "    for (int u = blockIdx.x; u < NU0 + NU1; u += nb) {\n"
-         "      if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
-         "      else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "    if (lead >= 0) {\n"
+         "      for (int u = lead; u < NU0 + NU1; u += n_lead) {\n"
+         "        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "      }\n"
          "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
-         "    arrivals += nb; grid_barrier(P->bar, arrivals);\n"
+         "    grid_barrier(P->bar, ++nbar, nb);\n"
          "  }\n"
          "}\n";
     return o.str();
@@ -811,9 +858,13 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     // ---- shared-memory budget of the generated kernel (static shared memory only: 48 KB) -----------------------------
     Consts c;
     c.BLK = blk; c.MINB = minb;
+    // a warp per micro unit (no CTA-wide barrier in the micro phase) when a group fits a warp; RLP_FUSED_TEAM=cta
+    // forces the CTA-wide variant
+    c.TEAM = (mg[0].G <= 32 && mg[1].G <= 32) ? 32 : blk;
+    { const char *e = getenv("RLP_FUSED_TEAM"); if (e && e[0] == 'c') c.TEAM = blk; }
     Terms mt[2] = {micro_terms(s, 0), micro_terms(s, 1)}, ut[2] = {upper_terms(s, 0), upper_terms(s, 1)};
     for (int pl = 0; pl < 2; ++pl) {
-        c.G[pl] = mg[pl].G; c.GPC[pl] = std::max(1, blk / mg[pl].G); c.NG[pl] = (int)mg[pl].key.size();
+        c.G[pl] = mg[pl].G; c.GPC[pl] = std::max(1, c.TEAM / mg[pl].G); c.NG[pl] = (int)mg[pl].key.size();
         c.NS[pl] = (long long)c.NG[pl] * c.G[pl];
         c.GB[pl] = ug[pl].G; c.NUG[pl] = (int)ug[pl].key.size();
     }
@@ -823,8 +874,9 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     {
         size_t kr = std::max(mt[0].kr, mt[1].kr), mo = std::max(s.dec[0].size(), s.dec[1].size());
         size_t ur = std::max(ut[0].kr * c.GB[0], ut[1].kr * c.GB[1]), uo = std::max(s.udec[0].size() * c.GB[0], s.udec[1].size() * c.GB[1]);
-        size_t rn = std::max(c.GPC[0] * mt[0].kr, c.GPC[1] * mt[1].kr);
-        size_t bytes = 8 * (std::max(kr * blk, ur) + std::max(mo * blk, uo) + rn + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 64);
+        size_t nt = (size_t)(blk / c.TEAM);
+        size_t rn = nt * std::max(c.GPC[0] * mt[0].kr, c.GPC[1] * mt[1].kr);
+        size_t bytes = 8 * (std::max(nt * kr * (c.TEAM + 1), ur) + std::max(nt * mo * (c.TEAM + 1), uo) + rn + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 64);
         if (bytes > 46 * 1024) return RLP_OK;
     }
 
@@ -844,7 +896,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         const size_t NG = mg[pl].key.size(), NS = NG * G;
         std::vector<int> h_opp((size_t)MP * NS), h_pat(NS), h_ridx(NS), h_pidx(NS), h_fid(NG * MO), h_col(NG * MO), h_iset(NG * MO);
         std::vector<double> h_pc(NS);
-        fp->batch_comp[pl].assign((NG + c.GPC[pl] - 1) / c.GPC[pl], 0);
+        fp->group_comp[pl].assign(NG, 0);
         for (size_t gi = 0; gi < NG; ++gi) {
             const int32_t g = order[pl][gi];
             for (int k = 0; k < G; ++k) {
@@ -863,7 +915,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
                 h_col[gi * MO + jj] = (int)t->col_off_h[is];
                 h_iset[gi * MO + jj] = is;
             }
-            fp->batch_comp[pl][gi / c.GPC[pl]] = comp_of[p0];     // (the last group of a batch wins; only used for sharding)
+            fp->group_comp[pl][gi] = comp_of[p0];
         }
         RLP_CUDA(fp->mem_opp[pl].upload(h_opp, stream)); RLP_CUDA(fp->mem_pat[pl].upload(h_pat, stream));
         RLP_CUDA(fp->mem_ridx[pl].upload(h_ridx, stream)); RLP_CUDA(fp->mem_pidx[pl].upload(h_pidx, stream));
@@ -893,7 +945,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         RLP_CUDA(fp->u_fid.upload(h_ufid, stream));
         RLP_CUDA(fp->paytab.upload(paytab, stream));
         RLP_CUDA(fp->fid_of_iset.upload(fid, stream));
-        RLP_CUDA(fp->bar.alloc(4));
+        RLP_CUDA(fp->bar.alloc(32 + 32 * 4096 + 1024));      // arrivals, leader count | one flag line per CTA | per-SM counters
         RLP_CUDA(rlp::sync_stream(stream));
     }
     // ---- generate, compile, load -----------------------------------------------------------------------------------------
@@ -915,7 +967,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.portal_p1 = ts.portal_p1.p; h.portal_p2 = ts.portal_p2.p; h.portal_v = ts.portal_v1.p;
     h.bar = fp->bar.p; h.tl = nullptr; h.tl_cap = 0;
     h.num_isets = I;
-    h.first_batch0 = 0; h.end_batch0 = fp->n_batches[0]; h.first_batch1 = 0; h.end_batch1 = fp->n_batches[1];
+    h.first_group0 = 0; h.end_group0 = c.NG[0]; h.first_group1 = 0; h.end_group1 = c.NG[1];
     if (!rlp::g_dry_run) {
         if (!fp->lib) return RLP_OK;                       // RLP_NO_JIT=1
         if (cudaLibraryGetKernel(&fp->kernel, fp->lib, "cfr_fused_k") != cudaSuccess) {
@@ -931,7 +983,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         }
         const char *e = getenv("RLP_FUSED_CTAS_PER_SM");
         if (e && atoi(e) >= 1) per_sm = std::min(per_sm, atoi(e));
-        fp->grid = sms * std::min(per_sm, minb);
+        fp->grid = std::min(4096, sms * std::min(per_sm, minb));
     } else {
         fp->grid = 296;
     }
@@ -993,7 +1045,7 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
     int64_t left = n_iters, tt = t0;
     while (left > 0) {
         const int chunk = (int)std::min<int64_t>(left, 1 << 20);
-        RLP_CUDA(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), s));
+        RLP_CUDA(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int) * (32 + 32 * (size_t)f.grid + 1024), s));
         const FusedParams *pp = reinterpret_cast<const FusedParams *>(c->fused_params.p);
         long long t_arg = tt;
         int iters = chunk, lin = linear_weight ? 1 : 0, cur0 = c->sigF_cur;

@@ -150,7 +150,8 @@ std::string generate(const MicroTmpl &tm, bool zs) {
 namespace rlp {
 
 // Compile `src` for sm_100a and load it; *lib_out stays null only under RLP_NO_JIT=1 (or in planning mode).
-static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std::string *log_out) {
+static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std::string *log_out,
+                            const char *program_name = "micro_k.cu") {
     *lib_out = nullptr;
     // RLP_NO_JIT=1 is the ONLY way onto the interpreter kernels for a tree whose shapes qualify for straight-line
     // code: a missing libnvrtc or a failed compile is an error, not a silent 3x slowdown.
@@ -159,7 +160,7 @@ static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std:
     if (!g_nvrtc.load())
         return fail(RLP_ERR_UNSUPPORTED, "libnvrtc.so.12 could not be loaded (set RLP_NO_JIT=1 to run the interpreter kernels)");
     nvrtcProgram prog;
-    if (g_nvrtc.create(&prog, src.c_str(), "micro_k.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    if (g_nvrtc.create(&prog, src.c_str(), program_name, 0, nullptr, nullptr) != NVRTC_SUCCESS)
         return fail(RLP_ERR_CUDA, "nvrtcCreateProgram failed");
     const char *opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17"};
     nvrtcResult res = g_nvrtc.compile(prog, 4, opts);
@@ -194,8 +195,15 @@ static int compile_and_load(const std::string &src, cudaLibrary_t *lib_out, std:
 }
 
 // Compile the straight-line kernel of `tm`; returns RLP_OK with *kernel == nullptr when JIT is unavailable.
+// RLP_FUSED_DUMP=<path>: the source is also written to <path> and compiled under that name, so that a profiler's
+// source view (ncu --import-source on, -lineinfo) can find it.
 int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std::string *log_out) {
-    return compile_and_load(src, lib_out, log_out);
+    const char *dump = getenv("RLP_FUSED_DUMP");
+    if (dump && dump[0]) {
+        if (FILE *f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+        return compile_and_load(src, lib_out, log_out, dump);
+    }
+    return compile_and_load(src, lib_out, log_out, "cfr_fused_k.cu");
 }
 
 int jit_micro_kernel(const MicroTmpl &tm, bool zs, cudaLibrary_t *lib_out, cudaKernel_t *kernel, std::string *log_out) {
