@@ -43,13 +43,15 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
 #define RLP_FUSED_FIELDS(X)                                                                                        \
     X(const int *, mem_opp0) X(const int *, mem_opp1)         /* [opp decision][slot] fused ids of the opponent's sets */ \
     X(const int *, mem_pat0) X(const int *, mem_pat1)         /* [slot] payoff pattern */                          \
-    X(const int *, mem_ridx0) X(const int *, mem_ridx1)       /* [slot] where the subtree root's reach lives */      \
+    X(const int *, mem_ridx0) X(const int *, mem_ridx1)       /* [slot] where the OPPONENT's reach of the subtree root lives */ \
+    X(const int *, grp_ridx0) X(const int *, grp_ridx1)       /* [group] where the group's own player's reach lives */   \
     X(const int *, mem_pidx0) X(const int *, mem_pidx1)       /* [slot] where its value goes (tile * KP + portal rank) */ \
     X(const double *, mem_pc0) X(const double *, mem_pc1)     /* [slot] static chance reach */                      \
     X(const int *, grp_fid0) X(const int *, grp_fid1)         /* [group][own decision] fused id */                   \
     X(const int *, grp_col0) X(const int *, grp_col1)         /* [group][own decision] first internal pair */        \
     X(const int *, grp_iset0) X(const int *, grp_iset1)       /* [group][own decision] internal information set */   \
     X(const double *, paytab)                                 /* [pattern][leaf] */                                 \
+    X(const signed char *, paytab8)                           /* [pattern][16-byte rows]: small integer payoffs */    \
     X(const int *, tg_tile0) X(const int *, tg_tile1)         /* [upper group][member] tile */                      \
     X(const int *, tg_fid0) X(const int *, tg_fid1)           /* [upper group][own decision] */                     \
     X(const int *, tg_col0) X(const int *, tg_col1)                                                                \
@@ -80,8 +82,9 @@ struct FusedPlan {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     FusedParams host{};                 // tree part filled; solver part (R, S, ...) filled per solver
-    rlp::DevBuf<int> mem_opp[2], mem_pat[2], mem_ridx[2], mem_pidx[2], grp_fid[2], grp_col[2], grp_iset[2];
-    rlp::DevBuf<double> mem_pc[2], paytab;
+    rlp::DevBuf<int> mem_opp[2], mem_pat[2], mem_ridx[2], mem_pidx[2], grp_fid[2], grp_col[2], grp_iset[2], grp_ridx[2];
+    rlp::DevBuf<double> mem_pc[2], paytab, reach[2];
+    rlp::DevBuf<signed char> paytab8;
     rlp::DevBuf<int> tg_tile[2], tg_fid[2], tg_col[2], tg_iset[2], u_fid;
     rlp::DevBuf<int> fid_of_iset;       // [I] internal -> fused
     rlp::DevBuf<unsigned int> bar;
@@ -120,6 +123,10 @@ struct Consts {
     long long NF, T;
     int NT, KP, F;
     int NCH;                            // children of every fan-in node when they all agree, else 0
+    int PAY8;                           // payoffs are integers in [-127, 127]: 1-byte pattern table, rows of PAYROW bytes
+    int PAYROW;
+    std::vector<double> fan_cps;        // one chance probability per fan-in node when it is the same for all edges / tiles
+    int sm_r_n;                         // doubles in the kernel's sm_r array (also the staging area of the fan-in)
 };
 
 std::string S_(const char *p, int j) { return std::string(p) + std::to_string(j); }
@@ -171,7 +178,7 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
     o << "__device__ __forceinline__ void micro_eval" << pl << "(const FusedParams* __restrict__ P, long long g, int k, int tix, double w,\n"
          "    const double* sig_in, double* sm_r, double* sm_o) {\n"
          "  const long long slot = g * " << c.G[pl] << " + k;\n"
-         "  const int pat = P->mem_pat" << pl << "[slot], ri = P->mem_ridx" << pl << "[slot];\n"
+         "  const int pat = P->mem_pat" << pl << "[slot], ri = P->mem_ridx" << pl << "[slot], ro = P->grp_ridx" << pl << "[g];\n"
          "  const double pcv = P->mem_pc" << pl << "[slot];\n";
     if (pl == 0) o << "  const int pi = P->mem_pidx0[slot];\n";
     for (int r = 0; r < n_nt; ++r) {
@@ -180,10 +187,22 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         else
             o << "  const int f" << r << " = P->mem_opp" << pl << "[" << opp_j[r] << "LL * " << c.NS[pl] << "LL + slot];\n";
     }
-    o << "  const double* pp = P->paytab + (long long)pat * " << c.NT << ";\n";
-    for (int j = 0; j < n; ++j)
-        if (tm.rank[j] & 0x80) o << "  const double x" << j << " = pp[" << (tm.rank[j] & 0x7F) << "];\n";
-    o << "  const double q1_0 = __ldcg(P->portal_p1 + ri), q2_0 = __ldcg(P->portal_p2 + ri);\n";
+    if (c.PAY8) {           // one or two 16-byte loads fetch all leaf payoffs of the subtree's pattern (exact: small integers)
+        o << "  const int4* pp = reinterpret_cast<const int4*>(P->paytab8 + (long long)pat * " << c.PAYROW << ");\n";
+        for (int q = 0; q < c.PAYROW / 16; ++q) o << "  const int4 pw" << q << " = __ldg(pp + " << q << ");\n";
+        for (int j = 0; j < n; ++j)
+            if (tm.rank[j] & 0x80) {
+                int tr = tm.rank[j] & 0x7F, q = tr / 16, wd = (tr % 16) / 4, by = tr % 4;
+                o << "  const double x" << j << " = (double)(int)(signed char)(pw" << q << "." << "xyzw"[wd] << " >> " << 8 * by << ");\n";
+            }
+    } else {
+        o << "  const double* pp = P->paytab + (long long)pat * " << c.NT << ";\n";
+        for (int j = 0; j < n; ++j)
+            if (tm.rank[j] & 0x80) o << "  const double x" << j << " = pp[" << (tm.rank[j] & 0x7F) << "];\n";
+    }
+    // a player's reach of a portal depends only on that player's own upper group: one value per (reach slot, group)
+    if (pl == 0) o << "  const double q1_0 = __ldcg(P->portal_p1 + ro), q2_0 = __ldcg(P->portal_p2 + ri);\n";
+    else o << "  const double q1_0 = __ldcg(P->portal_p1 + ri), q2_0 = __ldcg(P->portal_p2 + ro);\n";
     for (int j = 1; j < n; ++j)
         o << "  const double s" << j << " = __ldcg(sig_in + " << (int)tm.par_slot[j] << "LL * " << c.NF << "LL + f" << (int)tm.par_rank[j] << ");\n";
     for (int r = 0; r < n_nt; ++r) {                    // forward (cfr.py:208,217)
@@ -283,7 +302,7 @@ void gen_upper_reach(std::ostringstream &o, const Shape &s, const Consts &c, int
     Terms t = upper_terms(s, pl);
     std::vector<int> own_jj(s.n_udec, -1);
     for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) own_jj[s.udec[pl][jj]] = (int)jj;
-    o << "__device__ __forceinline__ void upper_reach" << pl << "(const FusedParams* __restrict__ P, long long i, const double* sm_s) {\n"
+    o << "__device__ __forceinline__ void upper_reach" << pl << "(const FusedParams* __restrict__ P, int u, const double* sm_s) {\n"
          "  double* out = P->portal_p" << (pl + 1) << ";\n  const double q_0 = 1.0;\n";
     for (int j = 0; j < n; ++j) {
         int kd = sh.kind[j];
@@ -292,8 +311,8 @@ void gen_upper_reach(std::ostringstream &o, const Shape &s, const Consts &c, int
             int ch = sh.first_child[j] + k;
             if (sh.kind[ch] == -1) continue;
             std::string v = kd == pl + 1 ? "sm_s[" + std::to_string(t.coff[own_jj[s.dec_idx[j]]] + k) + "] * " + S_("q_", j) : S_("q_", j);
-            if (sh.kind[ch] == 4) o << "  out[" << sh.fan_k0[ch] << "LL * " << c.T << "LL + i] = " << v << ";\n";
-            else if (sh.kind[ch] == 3) o << "  out[" << sh.portal_rank[ch] << "LL * " << c.T << "LL + i] = " << v << ";\n";
+            if (sh.kind[ch] == 4) o << "  out[" << sh.fan_k0[ch] * c.NUG[pl] << " + u] = " << v << ";\n";
+            else if (sh.kind[ch] == 3) o << "  out[" << sh.portal_rank[ch] * c.NUG[pl] << " + u] = " << v << ";\n";
             else o << "  const double q_" << ch << " = " << v << ";\n";
         }
     }
@@ -358,6 +377,11 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
   return mine / (s + c);
 }
 )";
+    if (!c.fan_cps.empty()) {
+        o << "__constant__ double FCP[" << c.fan_cps.size() << "] = {";
+        for (size_t f = 0; f < c.fan_cps.size(); ++f) o << (f ? "," : "") << c.fan_cps[f];
+        o << "};\n";
+    }
     for (int pl = 0; pl < 2; ++pl) {
         Terms mt = micro_terms(s, pl), ut = upper_terms(s, pl);
         emit_table(o, "MCJ", pl, mt.cj); emit_table(o, "MCA", pl, mt.ca); emit_table(o, "MCOFF", pl, mt.coff); emit_table(o, "MNA", pl, mt.na);
@@ -473,22 +497,41 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      ar = __ldcg(P->R + acol); asa = __ldcg(P->S + acol);\n"
                  "      asg = __ldcg(sig_in + (long long)aa * " << c.NF << "LL + afid);\n"
                  "    }\n";
-        o << "    const int* fd = P->fan_desc;\n"
-             "    for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
-             "      const int m = x / " << std::max(1, c.F) << ", f = x - m * " << std::max(1, c.F) << ";\n"
-             "      const long long i = tiles[m];\n"
-             "      const int k0 = fd[4 * f], e0 = fd[4 * f + 2];\n"
-             "      const double* pv = P->portal_v + i * " << c.KP << "LL + k0;\n"
-             "      const double* cp = P->fan_cp + (long long)e0 * " << c.T << "LL + i;\n"
-             "      double acc = 0.0;\n";
-        if (c.NCH > 0 && c.NCH <= 32) {     // every fan-in node has NCH children: all loads in flight, then the ordered adds
-            o << "      double e[" << c.NCH << "], v[" << c.NCH << "];\n"
-                 "#pragma unroll\n"
-                 "      for (int q = 0; q < " << c.NCH << "; ++q) { e[q] = cp[(long long)q * " << c.T << "LL]; v[q] = __ldcg(pv + q); }\n"
-                 "#pragma unroll\n"
-                 "      for (int q = 0; q < " << c.NCH << "; ++q) acc = acc + e[q] * v[q];\n";
+        o << "    const int* fd = P->fan_desc;\n";
+        const int pv_pad = c.NCH > 0 ? c.KP + c.KP / c.NCH + 1 : c.KP;   // padded row of one tile's portal values in shared memory
+        const int chunk = c.sm_r_n / std::max(1, pv_pad);                  // tiles per pass through the staging area (= sm_r)
+        if (!c.fan_cps.empty() && chunk >= 1) {
+            // The unit's portal values are staged through shared memory tile by tile (coalesced rows), then one thread per
+            // (tile, fan-in node) adds chance probability x value in child order.  Rows are padded by one word per fan-in
+            // node so that the threads of a warp (stride = one fan-in node) hit different banks.
+            o << "    for (int m0 = 0; m0 < " << GB << "; m0 += " << chunk << ") {\n"
+                 "      const int mc = " << GB << " - m0 < " << chunk << " ? " << GB << " - m0 : " << chunk << ";\n"
+                 "      for (int x = tid; x < mc * " << c.KP << "; x += BLOCK) {\n"
+                 "        const int mm = x / " << c.KP << ", q = x - mm * " << c.KP << ";\n"
+                 "        sm_r[mm * " << pv_pad << " + q" << (c.NCH > 0 ? " + q / " + std::to_string(c.NCH) : std::string()) << "] = "
+                 "__ldcg(P->portal_v + (long long)tiles[m0 + mm] * " << c.KP << "LL + q);\n"
+                 "      }\n"
+                 "      __syncthreads();\n"
+                 "      for (int x = tid; x < mc * " << c.F << "; x += BLOCK) {\n"
+                 "        const int mm = x / " << std::max(1, c.F) << ", f = x - mm * " << std::max(1, c.F) << ";\n"
+                 "        const int k0 = fd[4 * f], nch = fd[4 * f + 1];\n"
+                 "        const double e = FCP[f];\n"
+                 "        const double* pv = sm_r + mm * " << pv_pad << " + k0" << (c.NCH > 0 ? " + k0 / " + std::to_string(c.NCH) : std::string()) << ";\n"
+                 "        double acc = 0.0;\n"
+                 "        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch];\n"
+                 "        sm_fan[(m0 + mm) * " << std::max(1, c.F) << " + f] = acc;\n"
+                 "      }\n"
+                 "      __syncthreads();\n"
+                 "    }\n";
         } else {
-            o << "      const int nch = fd[4 * f + 1];\n"
+            o << "    for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
+                 "      const int m = x / " << std::max(1, c.F) << ", f = x - m * " << std::max(1, c.F) << ";\n"
+                 "      const long long i = tiles[m];\n"
+                 "      const int k0 = fd[4 * f], e0 = fd[4 * f + 2];\n"
+                 "      const double* pv = P->portal_v + i * " << c.KP << "LL + k0;\n"
+                 "      const double* cp = P->fan_cp + (long long)e0 * " << c.T << "LL + i;\n"
+                 "      double acc = 0.0;\n"
+                 "      const int nch = fd[4 * f + 1];\n"
                  "      int ch = 0;\n"
                  "      for (; ch + 8 <= nch; ch += 8) {\n"
                  "        double e[8], v[8];\n"
@@ -497,11 +540,12 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "#pragma unroll\n"
                  "        for (int q = 0; q < 8; ++q) acc = acc + e[q] * v[q];\n"
                  "      }\n"
-                 "      for (; ch < nch; ++ch) acc = acc + cp[(long long)ch * " << c.T << "LL] * __ldcg(pv + ch);\n";
+                 "      for (; ch < nch; ++ch) acc = acc + cp[(long long)ch * " << c.T << "LL] * __ldcg(pv + ch);\n"
+                 "      sm_fan[x] = acc;\n"
+                 "    }\n"
+                 "    __syncthreads();\n";
         }
-        o << "      sm_fan[x] = acc;\n"
-             "    }\n"
-             "    __syncthreads();\n"
+        o <<
              "    if (tid < " << GB << ") upper_eval" << pl << "(P, tiles[tid], tid, w, sig_in, sm_fan, sm_r, sm_o);\n"
              "    __syncthreads();\n";
         if (acc_one) {
@@ -549,7 +593,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
         }
         o << "  }\n"
              "  __syncthreads();\n"
-             "  if (tid < " << GB << ") upper_reach" << pl << "(P, tiles[tid], sm_s);\n"
+             "  if (tid == 0) upper_reach" << pl << "(P, u, sm_s);\n"
              "  __syncthreads();\n"
              "}\n";
     }
@@ -562,7 +606,8 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
     const int us_n = std::max(1, std::max(u0.kr, u1.kr));
     const int NT = c.BLK / c.TEAM;                      // teams per CTA
     const int rn_team = std::max(1, std::max(c.GPC[0] * m0.kr, c.GPC[1] * m1.kr));
-    const int sm_r_n = std::max(NT * KRmax * (c.TEAM + 1), ur_n), sm_o_n = std::max(NT * MOmax * (c.TEAM + 1), uo_n);
+    const int sm_r_n = c.sm_r_n, sm_o_n = std::max(NT * MOmax * (c.TEAM + 1), uo_n);
+    (void)ur_n;
     const int sm_rn_n = std::max(NT * rn_team, us_n);
     (void)rn_a;
     o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, " << c.MINB << ") cfr_fused_k(const FusedParams* __restrict__ P, long long t0, int iters,\n"
@@ -871,6 +916,25 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     c.NF = NF; c.T = T; c.NT = NT; c.KP = cx.kp; c.F = (int)cx.fans->size();
     c.NCH = cx.fans->empty() ? 0 : (*cx.fans)[0].nchild;
     for (const FanDesc &fd : *cx.fans) if (fd.nchild != c.NCH) c.NCH = 0;
+    // one chance probability per fan-in node when all its edges in all tiles agree (Leduc: 1 / #remaining cards)
+    for (const FanDesc &fd : *cx.fans) {
+        const double v0 = (*cx.fan_cp)[(size_t)fd.e0 * T];
+        bool same = true;
+        for (int ch = 0; ch < fd.nchild && same; ++ch)
+            for (int64_t k = 0; k < T && same; ++k) same = (*cx.fan_cp)[(size_t)(fd.e0 + ch) * T + k] == v0;
+        if (!same) { c.fan_cps.clear(); break; }
+        c.fan_cps.push_back(v0);
+    }
+    if (c.fan_cps.size() != cx.fans->size()) c.fan_cps.clear();
+    // small integer payoffs: a 1-byte pattern table (exact), rows padded to 16 bytes
+    c.PAY8 = 1;
+    for (double v : paytab) if (!(v == (double)(int)v && v >= -127.0 && v <= 127.0)) { c.PAY8 = 0; break; }
+    c.PAYROW = ((NT + 15) / 16) * 16;
+    if (c.PAYROW > 64) c.PAY8 = 0;
+    {
+        const int nt_ = blk / c.TEAM;
+        c.sm_r_n = std::max(nt_ * std::max(mt[0].kr, mt[1].kr) * (c.TEAM + 1), std::max(1, std::max(ut[0].kr * c.GB[0], ut[1].kr * c.GB[1])));
+    }
     {
         size_t kr = std::max(mt[0].kr, mt[1].kr), mo = std::max(s.dec[0].size(), s.dec[1].size());
         size_t ur = std::max(ut[0].kr * c.GB[0], ut[1].kr * c.GB[1]), uo = std::max(s.udec[0].size() * c.GB[0], s.udec[1].size() * c.GB[1]);
@@ -884,6 +948,13 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     std::unique_ptr<FusedPlan, FusedPlanDeleter> fp(new FusedPlan);
     fp->NF = NF; fp->max_act = t->max_act; fp->num_components = ncomp; fp->block = blk;
     const std::vector<int> &ridx = *cx.ridx;
+    // upper group of every tile, per player (a player's reach of a portal depends only on that player's upper group)
+    std::vector<int> tile_ug[2];
+    for (int pl = 0; pl < 2; ++pl) {
+        tile_ug[pl].assign(T, -1);
+        for (size_t g = 0; g < ug[pl].key.size(); ++g)
+            for (int k = 0; k < ug[pl].G; ++k) tile_ug[pl][ug[pl].members[g * ug[pl].G + k]] = (int)g;
+    }
     std::vector<int> tile_of_portal(P), rank_of_portal(P);
     for (int64_t k = 0; k < T; ++k)
         for (int q = 0; q < (*cx.desc)[k].n_portal; ++q) {
@@ -894,7 +965,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     for (int pl = 0; pl < 2; ++pl) {
         const int opp = 1 - pl, G = mg[pl].G, MO = (int)s.dec[pl].size(), MP = (int)s.dec[opp].size();
         const size_t NG = mg[pl].key.size(), NS = NG * G;
-        std::vector<int> h_opp((size_t)MP * NS), h_pat(NS), h_ridx(NS), h_pidx(NS), h_fid(NG * MO), h_col(NG * MO), h_iset(NG * MO);
+        std::vector<int> h_opp((size_t)MP * NS), h_pat(NS), h_ridx(NS), h_pidx(NS), h_fid(NG * MO), h_col(NG * MO), h_iset(NG * MO), h_gridx(NG);
         std::vector<double> h_pc(NS);
         fp->group_comp[pl].assign(NG, 0);
         for (size_t gi = 0; gi < NG; ++gi) {
@@ -904,7 +975,13 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
                 const size_t slot = gi * G + k;
                 for (int jj = 0; jj < MP; ++jj) h_opp[(size_t)jj * NS + slot] = fid[srank[inode[(size_t)p * n_nt + s.dec[opp][jj]]]];
                 h_pat[slot] = pat[p];
-                h_ridx[slot] = ridx[p];
+                {   // ridx[p] = reach slot * T + tile (tiles.cu); here: reach slot * #upper groups + the player's upper group
+                    const int rslot = (int)(ridx[p] / T), tile = tile_of_portal[p];
+                    h_ridx[slot] = rslot * c.NUG[opp] + tile_ug[opp][tile];
+                    const int own = rslot * c.NUG[pl] + tile_ug[pl][tile];
+                    if (k == 0) h_gridx[gi] = own;
+                    else if (h_gridx[gi] != own) return RLP_OK;      // members of a group must share their own reach
+                }
                 h_pidx[slot] = tile_of_portal[p] * cx.kp + rank_of_portal[p];
                 h_pc[slot] = (*cx.pcs)[(*cx.portal_node)[p]];
             }
@@ -919,6 +996,8 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         }
         RLP_CUDA(fp->mem_opp[pl].upload(h_opp, stream)); RLP_CUDA(fp->mem_pat[pl].upload(h_pat, stream));
         RLP_CUDA(fp->mem_ridx[pl].upload(h_ridx, stream)); RLP_CUDA(fp->mem_pidx[pl].upload(h_pidx, stream));
+        RLP_CUDA(fp->grp_ridx[pl].upload(h_gridx, stream));
+        RLP_CUDA(fp->reach[pl].alloc((size_t)cx.kp * (size_t)c.NUG[pl]));
         RLP_CUDA(fp->mem_pc[pl].upload(h_pc, stream)); RLP_CUDA(fp->grp_fid[pl].upload(h_fid, stream));
         RLP_CUDA(fp->grp_col[pl].upload(h_col, stream)); RLP_CUDA(fp->grp_iset[pl].upload(h_iset, stream));
         fp->n_batches[pl] = (int)((NG + c.GPC[pl] - 1) / c.GPC[pl]);
@@ -944,6 +1023,16 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
             for (int dd = 0; dd < s.n_udec; ++dd) h_ufid[(size_t)dd * T + k] = fid[srank[tile_node(k, dd)]];
         RLP_CUDA(fp->u_fid.upload(h_ufid, stream));
         RLP_CUDA(fp->paytab.upload(paytab, stream));
+        {
+            std::vector<signed char> p8;
+            if (c.PAY8) {
+                const size_t npat = paytab.size() / (size_t)NT;
+                p8.assign(npat * c.PAYROW, 0);
+                for (size_t q = 0; q < npat; ++q)
+                    for (int tr = 0; tr < NT; ++tr) p8[q * c.PAYROW + tr] = (signed char)(int)paytab[q * NT + tr];
+            }
+            RLP_CUDA(fp->paytab8.upload(p8, stream));
+        }
         RLP_CUDA(fp->fid_of_iset.upload(fid, stream));
         RLP_CUDA(fp->bar.alloc(32 + 32 * 4096 + 1024));      // arrivals, leader count | one flag line per CTA | per-SM counters
         RLP_CUDA(rlp::sync_stream(stream));
@@ -956,6 +1045,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     FusedParams &h = fp->host;
     UpperJit &uj = *ts.upper_jit;
     h.mem_opp0 = fp->mem_opp[0].p; h.mem_opp1 = fp->mem_opp[1].p; h.mem_pat0 = fp->mem_pat[0].p; h.mem_pat1 = fp->mem_pat[1].p;
+    h.grp_ridx0 = fp->grp_ridx[0].p; h.grp_ridx1 = fp->grp_ridx[1].p; h.paytab8 = fp->paytab8.p;
     h.mem_ridx0 = fp->mem_ridx[0].p; h.mem_ridx1 = fp->mem_ridx[1].p; h.mem_pidx0 = fp->mem_pidx[0].p; h.mem_pidx1 = fp->mem_pidx[1].p;
     h.mem_pc0 = fp->mem_pc[0].p; h.mem_pc1 = fp->mem_pc[1].p; h.grp_fid0 = fp->grp_fid[0].p; h.grp_fid1 = fp->grp_fid[1].p;
     h.grp_col0 = fp->grp_col[0].p; h.grp_col1 = fp->grp_col[1].p; h.grp_iset0 = fp->grp_iset[0].p; h.grp_iset1 = fp->grp_iset[1].p;
@@ -964,7 +1054,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.tg_col0 = fp->tg_col[0].p; h.tg_col1 = fp->tg_col[1].p; h.tg_iset0 = fp->tg_iset[0].p; h.tg_iset1 = fp->tg_iset[1].p;
     h.u_fid = fp->u_fid.p; h.u_pcs = uj.pcs.p; h.u_cprob = uj.cprob.p; h.u_pay1 = uj.pay1.p;
     h.fan_desc = reinterpret_cast<const int *>(uj.fan.p); h.fan_cp = uj.fan_cp.p;
-    h.portal_p1 = ts.portal_p1.p; h.portal_p2 = ts.portal_p2.p; h.portal_v = ts.portal_v1.p;
+    h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p; h.portal_v = ts.portal_v1.p;
     h.bar = fp->bar.p; h.tl = nullptr; h.tl_cap = 0;
     h.num_isets = I;
     h.first_group0 = 0; h.end_group0 = c.NG[0]; h.first_group1 = 0; h.end_group1 = c.NG[1];

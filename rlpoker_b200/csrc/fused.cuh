@@ -23,6 +23,7 @@ struct FusedCtx {
     const std::vector<double> *m_pay1;                     // [leaf][P]
     const std::vector<double> *pcs;                        // [N] static chance reach
     const std::vector<int> *ridx;                          // [P] index of the root reach in the portal reach arrays
+    const std::vector<double> *fan_cp;                     // [fan edge][T] chance probabilities of the fan-in nodes
     int kp;                                                // most portals of any tile
 };
 

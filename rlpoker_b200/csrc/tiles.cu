@@ -855,7 +855,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
                 // group-fused persistent kernel (fused.cu) when the tree has the group structure
                 if (tmpl.size() == 1 && (!ts.jit.empty() || rlp::g_dry_run)) {
                     rlp::FusedCtx cx{d, t, &srank, &krank, &portal_node, &desc, &locals, &sh, &fans, &tmpl[0], &m_pay1,
-                                     &pcs, &ridx, kp};
+                                     &pcs, &ridx, &fcp, kp};
                     int frc = rlp::plan_fused(cx, stream);
                     if (frc) return frc;
                 }
