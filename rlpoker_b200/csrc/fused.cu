@@ -243,23 +243,40 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
     Terms t = upper_terms(s, pl);
     std::vector<int> own_jj(s.n_udec, -1);
     for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) own_jj[s.udec[pl][jj]] = (int)jj;
-    o << "__device__ __forceinline__ void upper_eval" << pl << "(const FusedParams* __restrict__ P, long long i, int m, double w,\n"
-         "    const double* sig_in, const double* sm_fan, double* sm_r, double* sm_o) {\n";
+    // everything the tile needs from global memory EXCEPT the fan-in sums: loaded at the start of the unit so that the
+    // loads overlap the fan-in instead of following it
+    o << "struct UIn" << pl << " {\n";
+    for (int j = 0; j < n; ++j) {
+        if (s.dec_idx[j] >= 0 && sh.kind[j] == pl + 1) o << "  double pc" << j << ";\n";
+        if (s.edge_idx[j] >= 0) o << "  double e" << j << ";\n";
+        if (s.term_idx[j] >= 0) o << "  double x" << j << ";\n";
+        if (j >= 1 && s.parent[j] >= 0 && s.dec_idx[s.parent[j]] >= 0) o << "  double s" << j << ";\n";
+        if (sh.kind[j] == 3) o << "  double x" << j << ";\n";
+    }
+    o << "  double pad_;\n};\n"
+         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, const double* sig_in, UIn" << pl << "& in) {\n";
     for (int j = 0; j < n; ++j)
         if (s.dec_idx[j] >= 0) {
             o << "  const int f" << j << " = P->u_fid[" << s.dec_idx[j] << "LL * " << c.T << "LL + i];\n";
-            if (sh.kind[j] == pl + 1) o << "  const double pc" << j << " = P->u_pcs[" << s.dec_idx[j] << "LL * " << c.T << "LL + i];\n";
+            if (sh.kind[j] == pl + 1) o << "  in.pc" << j << " = P->u_pcs[" << s.dec_idx[j] << "LL * " << c.T << "LL + i];\n";
         }
     for (int j = 0; j < n; ++j) {
-        if (s.edge_idx[j] >= 0) o << "  const double e" << j << " = P->u_cprob[" << s.edge_idx[j] << "LL * " << c.T << "LL + i];\n";
-        if (s.term_idx[j] >= 0) o << "  const double x" << j << " = P->u_pay1[" << s.term_idx[j] << "LL * " << c.T << "LL + i];\n";
+        if (s.edge_idx[j] >= 0) o << "  in.e" << j << " = P->u_cprob[" << s.edge_idx[j] << "LL * " << c.T << "LL + i];\n";
+        if (s.term_idx[j] >= 0) o << "  in.x" << j << " = P->u_pay1[" << s.term_idx[j] << "LL * " << c.T << "LL + i];\n";
     }
     for (int j = 1; j < n; ++j)
         if (s.parent[j] >= 0 && s.dec_idx[s.parent[j]] >= 0)
-            o << "  const double s" << j << " = __ldcg(sig_in + " << s.slot[j] << "LL * " << c.NF << "LL + f" << s.parent[j] << ");\n";
+            o << "  in.s" << j << " = __ldcg(sig_in + " << s.slot[j] << "LL * " << c.NF << "LL + f" << s.parent[j] << ");\n";
+    for (int j = 0; j < n; ++j)
+        if (sh.kind[j] == 3) o << "  in.x" << j << " = __ldcg(P->portal_v + i * " << c.KP << "LL + " << sh.portal_rank[j] << ");\n";
+    o << "  in.pad_ = 0.0;\n}\n";
+    o << "__device__ __forceinline__ void upper_eval" << pl << "(int m, double w, const UIn" << pl << "& in, const double* sm_fan, double* sm_r, double* sm_o) {\n";
     for (int j = 0; j < n; ++j) {
+        if (s.dec_idx[j] >= 0 && sh.kind[j] == pl + 1) o << "  const double pc" << j << " = in.pc" << j << ";\n";
+        if (s.edge_idx[j] >= 0) o << "  const double e" << j << " = in.e" << j << ";\n";
+        if (s.term_idx[j] >= 0 || sh.kind[j] == 3) o << "  const double x" << j << " = in.x" << j << ";\n";
+        if (j >= 1 && s.parent[j] >= 0 && s.dec_idx[s.parent[j]] >= 0) o << "  const double s" << j << " = in.s" << j << ";\n";
         if (sh.kind[j] == 4) o << "  const double x" << j << " = sm_fan[m * " << c.F << " + " << sh.fan_index[j] << "];\n";
-        if (sh.kind[j] == 3) o << "  const double x" << j << " = __ldcg(P->portal_v + i * " << c.KP << "LL + " << sh.portal_rank[j] << ");\n";
     }
     o << "  const double q1_0 = 1.0, q2_0 = 1.0;\n";
     for (int j = 0; j < n; ++j) {                       // forward: reach of the tile's own decision nodes
@@ -291,7 +308,7 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         }
         o << "    sm_o[" << jj << " * " << c.GB[pl] << " + m] = w * own;\n  }\n";
     }
-    o << "  (void)x0;\n}\n";
+    o << "  (void)x0; (void)q1_0; (void)q2_0;\n}\n";
 }
 
 // Reach of player `pl` from the tile root to every portal / fan-in node of one tile, from pl's strategy rows in
@@ -497,21 +514,35 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      ar = __ldcg(P->R + acol); asa = __ldcg(P->S + acol);\n"
                  "      asg = __ldcg(sig_in + (long long)aa * " << c.NF << "LL + afid);\n"
                  "    }\n";
-        o << "    const int* fd = P->fan_desc;\n";
+        o << "    const int* fd = P->fan_desc;\n"
+             "    UIn" << pl << " uin;\n"
+             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], sig_in, uin);\n";
         const int pv_pad = c.NCH > 0 ? c.KP + c.KP / c.NCH + 1 : c.KP;   // padded row of one tile's portal values in shared memory
         const int chunk = c.sm_r_n / std::max(1, pv_pad);                  // tiles per pass through the staging area (= sm_r)
-        if (!c.fan_cps.empty() && chunk >= 1) {
-            // The unit's portal values are staged through shared memory tile by tile (coalesced rows), then one thread per
-            // (tile, fan-in node) adds chance probability x value in child order.  Rows are padded by one word per fan-in
-            // node so that the threads of a warp (stride = one fan-in node) hit different banks.
-            o << "    for (int m0 = 0; m0 < " << GB << "; m0 += " << chunk << ") {\n"
-                 "      const int mc = " << GB << " - m0 < " << chunk << " ? " << GB << " - m0 : " << chunk << ";\n"
-                 "      for (int x = tid; x < mc * " << c.KP << "; x += BLOCK) {\n"
-                 "        const int mm = x / " << c.KP << ", q = x - mm * " << c.KP << ";\n"
-                 "        sm_r[mm * " << pv_pad << " + q" << (c.NCH > 0 ? " + q / " + std::to_string(c.NCH) : std::string()) << "] = "
-                 "__ldcg(P->portal_v + (long long)tiles[m0 + mm] * " << c.KP << "LL + q);\n"
+        const int total_pv = GB * c.KP, NV = (total_pv + c.BLK - 1) / c.BLK;
+        if (!c.fan_cps.empty() && chunk >= 1 && NV <= 40) {
+            // The unit's portal values: every thread fetches its share with coalesced loads, ALL in flight at once (they stay
+            // in registers), then they pass through shared memory a few tiles at a time and one thread per (tile, fan-in
+            // node) adds chance probability x value in child order.  Rows are padded by one word per fan-in node so that the
+            // threads of a warp (stride = one fan-in node) hit different banks.
+            const int nchunk = (GB + chunk - 1) / chunk;
+            const std::string padq = c.NCH > 0 ? " + q / " + std::to_string(c.NCH) : std::string();
+            o << "    double fv[" << NV << "];\n"
+                 "#pragma unroll\n"
+                 "    for (int i = 0; i < " << NV << "; ++i) {\n"
+                 "      const int L = tid + i * BLOCK;\n"
+                 "      if (L < " << total_pv << ") { const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << "; fv[i] = __ldcg(P->portal_v + (long long)tiles[mm] * " << c.KP << "LL + q); }\n"
+                 "    }\n"
+                 "#pragma unroll\n"
+                 "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
+                 "#pragma unroll\n"
+                 "      for (int i = 0; i < " << NV << "; ++i) {\n"
+                 "        const int L = tid + i * BLOCK;\n"
+                 "        const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << ";\n"
+                 "        if (L < " << total_pv << " && mm / " << chunk << " == c0) sm_r[(mm - c0 * " << chunk << ") * " << pv_pad << " + q" << padq << "] = fv[i];\n"
                  "      }\n"
                  "      __syncthreads();\n"
+                 "      const int mc = " << GB << " - c0 * " << chunk << " < " << chunk << " ? " << GB << " - c0 * " << chunk << " : " << chunk << ";\n"
                  "      for (int x = tid; x < mc * " << c.F << "; x += BLOCK) {\n"
                  "        const int mm = x / " << std::max(1, c.F) << ", f = x - mm * " << std::max(1, c.F) << ";\n"
                  "        const int k0 = fd[4 * f], nch = fd[4 * f + 1];\n"
@@ -519,7 +550,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "        const double* pv = sm_r + mm * " << pv_pad << " + k0" << (c.NCH > 0 ? " + k0 / " + std::to_string(c.NCH) : std::string()) << ";\n"
                  "        double acc = 0.0;\n"
                  "        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch];\n"
-                 "        sm_fan[(m0 + mm) * " << std::max(1, c.F) << " + f] = acc;\n"
+                 "        sm_fan[(c0 * " << chunk << " + mm) * " << std::max(1, c.F) << " + f] = acc;\n"
                  "      }\n"
                  "      __syncthreads();\n"
                  "    }\n";
@@ -546,7 +577,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    __syncthreads();\n";
         }
         o <<
-             "    if (tid < " << GB << ") upper_eval" << pl << "(P, tiles[tid], tid, w, sig_in, sm_fan, sm_r, sm_o);\n"
+             "    if (tid < " << GB << ") upper_eval" << pl << "(tid, w, uin, sm_fan, sm_r, sm_o);\n"
              "    __syncthreads();\n";
         if (acc_one) {
             o << "    if (tid < " << KRB << ") {\n"
