@@ -149,8 +149,10 @@ int rlp_cfr_profile_stages(rlp_cfr *cfr, int reps, float *out_ms4, void *stream)
  * (kind 0 upper phase 0, 1 micro, 2 upper phase 1, 3 accumulate A, 4 accumulate B / all) -- the in-graph schedule. */
 int rlp_cfr_timeline(rlp_cfr *cfr, int iters, unsigned long long *out, int cap_records, int *n_out, void *stream);
 /* Measurement aid for the group-fused persistent kernel (one cooperative launch per rlp_cfr_vanilla_iters call): runs
- * `iters` unit-weight iterations continuing at t0 while CTA 0 stamps %globaltimer {iteration start, its micro phase done,
- * grid barrier passed, its upper phase done}; out_ns receives 4 * iters stamps.  RLP_ERR_UNSUPPORTED when not in use. */
+ * `iters` unit-weight iterations continuing at t0 while one CTA stamps %globaltimer {iteration start, its micro phase
+ * done, grid barrier passed, then inside its upper unit: loads issued, fan-in done, tile evaluated, accumulate + regret
+ * matching done, reach written, and its upper phase done}; out_ns receives 9 * iters stamps.  RLP_ERR_UNSUPPORTED when
+ * the kernel is not in use. */
 int rlp_cfr_fused_timeline(rlp_cfr *cfr, int64_t t0, int iters, unsigned long long *out_ns, void *stream);
 /* CFRState.nodes_touched (rlpoker/cfr/cfr_util.py:5-11). */
 uint64_t rlp_nodes_touched(rlp_cfr *cfr);

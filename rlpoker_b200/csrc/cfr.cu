@@ -881,15 +881,17 @@ extern "C" int rlp_cfr_timeline(rlp_cfr *c, int iters, unsigned long long *out, 
 }
 
 // Measurement aid for the group-fused persistent kernel: runs `iters` iterations (continuing at iteration t0 with unit
-// weights) in one launch while CTA 0 stamps %globaltimer {iteration start, its phase A done, first grid barrier passed,
-// its phase B done}; out_ns receives 4 * iters nanosecond stamps.  RLP_ERR_UNSUPPORTED when the tree does not qualify.
+// weights) in one launch while one CTA (the first "leader", which also owns upper unit 0) stamps %globaltimer
+// {iteration start, its micro phase done, first grid barrier passed, upper unit: loads issued, fan-in done, tile
+// evaluated, accumulate + regret matching done, reach written, its upper phase done}; out_ns receives 9 * iters
+// nanosecond stamps.  RLP_ERR_UNSUPPORTED when the tree does not qualify.
 extern "C" int rlp_cfr_fused_timeline(rlp_cfr *c, int64_t t0, int iters, unsigned long long *out_ns, void *stream_) {
     if (!c || !out_ns || iters < 1) return fail(RLP_ERR_INVALID, "bad argument");
     if (!rlp::fused_available(c)) return fail(RLP_ERR_UNSUPPORTED, "the fused iteration kernel is not in use for this tree");
     cudaStream_t s = (cudaStream_t)stream_;
-    RLP_CUDA(c->timeline.alloc(4 * (size_t)iters));
+    RLP_CUDA(c->timeline.alloc(9 * (size_t)iters));
     RLP_CUDA(cudaMemsetAsync(c->timeline.p, 0, c->timeline.bytes(), s));
-    int rc = rlp::fused_run(c, t0, iters, 0, s, c->timeline.p, 4ll * iters);
+    int rc = rlp::fused_run(c, t0, iters, 0, s, c->timeline.p, 9ll * iters);
     if (rc) return rc;
     RLP_CUDA(cudaMemcpyAsync(out_ns, c->timeline.p, c->timeline.bytes(), cudaMemcpyDeviceToHost, s));
     RLP_CUDA(cudaStreamSynchronize(s));

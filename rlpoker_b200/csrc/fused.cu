@@ -126,7 +126,8 @@ struct Consts {
     int PAY8;                           // payoffs are integers in [-127, 127]: 1-byte pattern table, rows of PAYROW bytes
     int PAYROW;
     std::vector<double> fan_cps;        // one chance probability per fan-in node when it is the same for all edges / tiles
-    int sm_r_n;                         // doubles in the kernel's sm_r array (also the staging area of the fan-in)
+    int sm_r_n, sm_o_n;                 // doubles in the kernel's sm_r / sm_o arrays (contiguous: the fan-in stages through both)
+    int GBS, MBS, UT_OWN, UT_N;         // layout of the cached per-unit tables (ints): strides and the offset of the own-decision part
 };
 
 std::string S_(const char *p, int j) { return std::string(p) + std::to_string(j); }
@@ -254,10 +255,10 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         if (sh.kind[j] == 3) o << "  double x" << j << ";\n";
     }
     o << "  double pad_;\n};\n"
-         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, const double* sig_in, UIn" << pl << "& in) {\n";
+         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, UIn" << pl << "& in) {\n";
     for (int j = 0; j < n; ++j)
         if (s.dec_idx[j] >= 0) {
-            o << "  const int f" << j << " = P->u_fid[" << s.dec_idx[j] << "LL * " << c.T << "LL + i];\n";
+            o << "  const int f" << j << " = sm_ut[" << c.GBS + s.dec_idx[j] * c.GBS << " + m];\n";
             if (sh.kind[j] == pl + 1) o << "  in.pc" << j << " = P->u_pcs[" << s.dec_idx[j] << "LL * " << c.T << "LL + i];\n";
         }
     for (int j = 0; j < n; ++j) {
@@ -494,14 +495,30 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
         const int GB = c.GB[pl], KRB = ut.kr, MB = (int)s.udec[pl].size();
         // mode 0: full unit (fan-in, evaluate, accumulate, regret matching, reach); mode 1: reach only (prologue)
         const bool acc_one = KRB <= c.BLK;
-        o << "__device__ __forceinline__ void upper_unit" << pl << "(const FusedParams* __restrict__ P, int u, double w, const double* sig_in,\n"
-             "    double* sig_out, int reach_only, double* sm_fan, double* sm_r, double* sm_o, double* sm_rn, double* sm_s) {\n"
+        // per-unit static tables cached in shared memory (sm_ut): [0, GBS) tiles | [GBS, GBS + n_udec * GBS) fused ids of the
+        // tiles' decision nodes | then own-decision first pairs, fused ids, information sets (MBS each)
+        o << "__device__ __noinline__ void upper_cache" << pl << "(const FusedParams* __restrict__ P, int u, int* sm_ut) {\n"
              "  const int tid = threadIdx.x;\n"
-             "  const int* tiles = P->tg_tile" << pl << " + (long long)u * " << GB << ";\n"
+             "  for (int x = tid; x < " << GB << "; x += BLOCK) sm_ut[x] = P->tg_tile" << pl << "[(long long)u * " << GB << " + x];\n"
+             "  for (int x = tid; x < " << s.n_udec * GB << "; x += BLOCK) {\n"
+             "    const int d = x / " << GB << ", m = x - d * " << GB << ";\n"
+             "    sm_ut[" << c.GBS << " + d * " << c.GBS << " + m] = P->u_fid[(long long)d * " << c.T << "LL + P->tg_tile" << pl << "[(long long)u * " << GB << " + m]];\n"
+             "  }\n"
+             "  for (int x = tid; x < " << MB << "; x += BLOCK) {\n"
+             "    sm_ut[" << c.UT_OWN << " + x] = P->tg_col" << pl << "[u * " << MB << " + x];\n"
+             "    sm_ut[" << c.UT_OWN + c.MBS << " + x] = P->tg_fid" << pl << "[u * " << MB << " + x];\n"
+             "    sm_ut[" << c.UT_OWN + 2 * c.MBS << " + x] = P->tg_iset" << pl << "[u * " << MB << " + x];\n"
+             "  }\n"
+             "}\n";
+        o << "__device__ __noinline__ void upper_unit" << pl << "(const FusedParams* __restrict__ P, int u, double w, const double* sig_in,\n"
+             "    double* sig_out, int reach_only, double* sm_fan, double* sm_r, double* sm_o, double* sm_rn, double* sm_s, const int* sm_ut,\n"
+             "    unsigned long long* st) {\n"
+             "  const int tid = threadIdx.x;\n"
+             "  const int* tiles = sm_ut;\n"
              "  if (reach_only) {\n"
              "    for (int x = tid; x < " << KRB << "; x += BLOCK) {\n"
              "      const int j = UCJ" << pl << "[x], a = UCA" << pl << "[x];\n"
-             "      sm_s[x] = __ldcg(sig_in + (long long)a * " << c.NF << "LL + P->tg_fid" << pl << "[u * " << MB << " + j]);\n"
+             "      sm_s[x] = __ldcg(sig_in + (long long)a * " << c.NF << "LL + sm_ut[" << c.UT_OWN + c.MBS << " + j]);\n"
              "    }\n"
              "  } else {\n";
         if (acc_one)        // regret / action count / strategy of the unit's (set, action) pairs: in flight during the fan-in
@@ -509,16 +526,17 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    double ar = 0.0, asa = 0.0, asg = 0.0;\n"
                  "    if (tid < " << KRB << ") {\n"
                  "      aj = UCJ" << pl << "[tid]; aa = UCA" << pl << "[tid];\n"
-                 "      acol = P->tg_col" << pl << "[u * " << MB << " + aj] + aa;\n"
-                 "      afid = P->tg_fid" << pl << "[u * " << MB << " + aj];\n"
+                 "      acol = sm_ut[" << c.UT_OWN << " + aj] + aa;\n"
+                 "      afid = sm_ut[" << c.UT_OWN + c.MBS << " + aj];\n"
                  "      ar = __ldcg(P->R + acol); asa = __ldcg(P->S + acol);\n"
                  "      asg = __ldcg(sig_in + (long long)aa * " << c.NF << "LL + afid);\n"
                  "    }\n";
         o << "    const int* fd = P->fan_desc;\n"
              "    UIn" << pl << " uin;\n"
-             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], sig_in, uin);\n";
+             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], tid, sm_ut, sig_in, uin);\n"
+             "    if (st && tid == 0) st[0] = now_ns();\n";
         const int pv_pad = c.NCH > 0 ? c.KP + c.KP / c.NCH + 1 : c.KP;   // padded row of one tile's portal values in shared memory
-        const int chunk = c.sm_r_n / std::max(1, pv_pad);                  // tiles per pass through the staging area (= sm_r)
+        const int chunk = (c.sm_r_n + c.sm_o_n) / std::max(1, pv_pad);     // tiles per pass through the staging area (sm_r + sm_o)
         const int total_pv = GB * c.KP, NV = (total_pv + c.BLK - 1) / c.BLK;
         if (!c.fan_cps.empty() && chunk >= 1 && NV <= 40) {
             // The unit's portal values: every thread fetches its share with coalesced loads, ALL in flight at once (they stay
@@ -577,8 +595,10 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    __syncthreads();\n";
         }
         o <<
+             "    if (st && tid == 0) st[1] = now_ns();\n"
              "    if (tid < " << GB << ") upper_eval" << pl << "(tid, w, uin, sm_fan, sm_r, sm_o);\n"
-             "    __syncthreads();\n";
+             "    __syncthreads();\n"
+             "    if (st && tid == 0) st[2] = now_ns();\n";
         if (acc_one) {
             o << "    if (tid < " << KRB << ") {\n"
                  "      const double* cr = sm_r + tid * " << GB << ";\n"
@@ -593,7 +613,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      P->sigma_row[acol] = out;\n"
                  "      sig_out[(long long)aa * " << c.NF << "LL + afid] = out;\n"
                  "      sm_s[tid] = out;\n"
-                 "      if (aa == 0) { const int is = P->tg_iset" << pl << "[u * " << MB << " + aj]; const long long I = P->num_isets;\n"
+                 "      if (aa == 0) { const int is = sm_ut[" << c.UT_OWN + 2 * c.MBS << " + aj]; const long long I = P->num_isets;\n"
                  "        P->flags[is] = 1; P->flags[I + is] = 1; P->flags[2 * I + is] = 1; }\n"
                  "    }\n";
         } else {
@@ -624,8 +644,10 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
         }
         o << "  }\n"
              "  __syncthreads();\n"
+             "  if (st && tid == 0) st[3] = now_ns();\n"
              "  if (tid == 0) upper_reach" << pl << "(P, u, sm_s);\n"
              "  __syncthreads();\n"
+             "  if (st && tid == 0) st[4] = now_ns();\n"
              "}\n";
     }
     Terms m0 = micro_terms(s, 0), m1 = micro_terms(s, 1), u0 = upper_terms(s, 0), u1 = upper_terms(s, 1);
@@ -637,21 +659,23 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
     const int us_n = std::max(1, std::max(u0.kr, u1.kr));
     const int NT = c.BLK / c.TEAM;                      // teams per CTA
     const int rn_team = std::max(1, std::max(c.GPC[0] * m0.kr, c.GPC[1] * m1.kr));
-    const int sm_r_n = c.sm_r_n, sm_o_n = std::max(NT * MOmax * (c.TEAM + 1), uo_n);
-    (void)ur_n;
+    const int sm_r_n = c.sm_r_n, sm_o_n = c.sm_o_n;
+    (void)ur_n; (void)uo_n; (void)MOmax;
     const int sm_rn_n = std::max(NT * rn_team, us_n);
     (void)rn_a;
     o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, " << c.MINB << ") cfr_fused_k(const FusedParams* __restrict__ P, long long t0, int iters,\n"
          "    int linear, int cur0) {\n"
-         "  __shared__ double sm_r[" << sm_r_n << "];\n"
-         "  __shared__ double sm_o[" << sm_o_n << "];\n"
+         "  __shared__ double sm_ro[" << sm_r_n + sm_o_n << "];\n"
+         "  __shared__ int sm_ut[" << c.UT_N << "];\n"
+         "  double* sm_r = sm_ro;\n"
+         "  double* sm_o = sm_ro + " << sm_r_n << ";\n"
+         "  int cached_u = -1;\n"
          "  __shared__ double sm_rn[" << sm_rn_n << "];\n"
          "  __shared__ double sm_fan[" << fan_n << "];\n"
          "  __shared__ double sm_s[" << us_n << "];\n"
          "  __shared__ int s_lead;\n"
          "  const unsigned int nb = gridDim.x;\n"
          "  unsigned int nbar = 0;\n"
-         "  const bool log = P->tl != 0 && blockIdx.x == 0 && threadIdx.x == 0;\n"
          "  long long tlc = 0;\n"
          "  const int NU0 = " << c.NUG[0] << ", NU1 = " << c.NUG[1] << ";\n"
          "  // The upper phase has far fewer units than there are CTAs.  Consecutive CTAs share an SM, so the units go to\n"
@@ -663,12 +687,16 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "  }\n"
          "  __syncthreads();\n"
          "  const int lead = s_lead;\n"
+         "  const bool logc = P->tl != 0 && lead == 0;            // the CTA whose view of the phases is recorded\n"
+         "  const bool log = logc && threadIdx.x == 0;\n"
          "  // prologue: reach of both players to the portals from the current strategy\n"
          "  {\n"
          "    const double* sig_in = cur0 ? P->sigF1 : P->sigF0;\n"
          "    for (int u = blockIdx.x; u < NU0 + NU1; u += nb) {\n"
-         "      if (u < NU0) upper_unit0(P, u, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
-         "      else upper_unit1(P, u - NU0, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "      if (u < NU0) upper_cache0(P, u, sm_ut); else upper_cache1(P, u - NU0, sm_ut);\n"
+         "      __syncthreads();\n"
+         "      if (u < NU0) upper_unit0(P, u, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, 0);\n"
+         "      else upper_unit1(P, u - NU0, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, 0);\n"
          "    }\n"
          "    grid_barrier(P->bar, ++nbar, nb);\n"
          "  }\n"
@@ -696,10 +724,17 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "    // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)\n"
          "    if (lead >= 0) {\n"
          "      for (int u = lead; u < NU0 + NU1; u += n_lead) {\n"
-         "        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
-         "        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s);\n"
+         "        unsigned long long* st = (logc && u == lead && tlc + 5 <= P->tl_cap) ? P->tl + tlc : 0;\n"
+         "        if (u != cached_u) {          // a leader keeps its unit's static tables across iterations\n"
+         "          if (u < NU0) upper_cache0(P, u, sm_ut); else upper_cache1(P, u - NU0, sm_ut);\n"
+         "          cached_u = u;\n"
+         "          __syncthreads();\n"
+         "        }\n"
+         "        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, st);\n"
+         "        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, st);\n"
          "      }\n"
          "    }\n"
+         "    tlc += 5;\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    grid_barrier(P->bar, ++nbar, nb);\n"
          "  }\n"
@@ -965,13 +1000,20 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     {
         const int nt_ = blk / c.TEAM;
         c.sm_r_n = std::max(nt_ * std::max(mt[0].kr, mt[1].kr) * (c.TEAM + 1), std::max(1, std::max(ut[0].kr * c.GB[0], ut[1].kr * c.GB[1])));
+        c.sm_o_n = std::max(nt_ * (int)std::max(s.dec[0].size(), s.dec[1].size()) * (c.TEAM + 1),
+                            std::max(1, std::max((int)s.udec[0].size() * c.GB[0], (int)s.udec[1].size() * c.GB[1])));
+        c.GBS = std::max(c.GB[0], c.GB[1]);
+        c.MBS = (int)std::max(s.udec[0].size(), s.udec[1].size());
+        c.UT_OWN = c.GBS + s.n_udec * c.GBS;
+        c.UT_N = c.UT_OWN + 3 * c.MBS;
     }
     {
         size_t kr = std::max(mt[0].kr, mt[1].kr), mo = std::max(s.dec[0].size(), s.dec[1].size());
         size_t ur = std::max(ut[0].kr * c.GB[0], ut[1].kr * c.GB[1]), uo = std::max(s.udec[0].size() * c.GB[0], s.udec[1].size() * c.GB[1]);
         size_t nt = (size_t)(blk / c.TEAM);
         size_t rn = nt * std::max(c.GPC[0] * mt[0].kr, c.GPC[1] * mt[1].kr);
-        size_t bytes = 8 * (std::max(nt * kr * (c.TEAM + 1), ur) + std::max(nt * mo * (c.TEAM + 1), uo) + rn + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 64);
+        size_t bytes = 4 * (size_t)(std::max(c.GB[0], c.GB[1]) * (1 + s.n_udec) + 16) +
+                       8 * (std::max(nt * kr * (c.TEAM + 1), ur) + std::max(nt * mo * (c.TEAM + 1), uo) + rn + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 64);
         if (bytes > 46 * 1024) return RLP_OK;
     }
 

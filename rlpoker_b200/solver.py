@@ -195,14 +195,18 @@ class DeviceCFR:
     def fused_timeline(self, iters=20, stream=None):
         """Per-iteration phase times (microseconds, as seen by CTA 0) of the group-fused persistent kernel:
         micro phase, first grid barrier, upper phase, second barrier + loop turn-around.  Runs `iters` iterations."""
-        buf = (C.c_uint64 * (4 * iters))()
+        buf = (C.c_uint64 * (9 * iters))()
         check(_lib.load().rlp_cfr_fused_timeline(self.handle, self.t, int(iters), buf, _stream_ptr(stream)))
         self.t += iters
-        t = np.array(list(buf), np.float64).reshape(iters, 4) / 1e3
+        t = np.array(list(buf), np.float64).reshape(iters, 9) / 1e3
         out = {'micro_phase': float(np.mean(t[:, 1] - t[:, 0])), 'barrier_1': float(np.mean(t[:, 2] - t[:, 1])),
-               'upper_phase': float(np.mean(t[:, 3] - t[:, 2]))}
+               'upper_phase': float(np.mean(t[:, 8] - t[:, 2]))}
+        if np.all(t[:, 3:8] > 0):          # the recording CTA owns an upper unit: split of that unit
+            out['upper_split'] = {'issue_loads': float(np.mean(t[:, 3] - t[:, 2])), 'fan_in': float(np.mean(t[:, 4] - t[:, 3])),
+                                  'tile': float(np.mean(t[:, 5] - t[:, 4])), 'accumulate_rm': float(np.mean(t[:, 6] - t[:, 5])),
+                                  'reach': float(np.mean(t[:, 7] - t[:, 6]))}
         if iters > 1:
-            out['barrier_2'] = float(np.mean(t[1:, 0] - t[:-1, 3]))
+            out['barrier_2'] = float(np.mean(t[1:, 0] - t[:-1, 8]))
             out['iteration'] = float((t[-1, 0] - t[0, 0]) / (iters - 1))
         return out
 

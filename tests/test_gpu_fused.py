@@ -97,8 +97,8 @@ def test_fused_timeline_reports_phases():
     s = DeviceCFR(dt)
     s.vanilla(3)
     tl = s.fused_timeline(12)
-    assert set(tl) == {'micro_phase', 'barrier_1', 'upper_phase', 'barrier_2', 'iteration'}
-    assert all(v >= 0 for v in tl.values()) and 0 < tl['iteration'] < 1000
+    assert {'micro_phase', 'barrier_1', 'upper_phase', 'barrier_2', 'iteration'} <= set(tl)
+    assert all(v >= 0 for k, v in tl.items() if k != 'upper_split') and 0 < tl['iteration'] < 1000
     assert s.t == 15
     del s
     dt.close()
