@@ -104,24 +104,25 @@ def dominant_kernel_roofline(layout, stages, peak, strategy_bytes):
 # Group-fused persistent kernel (csrc/fused.cu): bytes one iteration must move when every table element is charged
 # once per pass that reads or writes it (the storage format differs from SURVEY 8d's level sweep, so the formula is
 # restated here as the survey asks; both are reported).  Leduc shapes: 8 decision nodes / 15 leaves per micro
-# subtree and per upper tile, 9 board-deal chance nodes per tile.
+# subtree, 8 decision nodes and 9 board-deal chance nodes per upper tile.
 #   micro subtree, per pass (it is evaluated once per player): 4 opponent information-set ids (i32), payoff pattern id,
-#     reach index (i32), static chance reach (f64), the two players' reaches at its root (f64); the first pass also
-#     reads the value index (i32) and writes the subtree value (f64)
-#   upper tile, per pass: one (chance probability, portal value) pair per board card and betting line, 8 ids,
-#     4 chance reaches, 6 fold payoffs, 9 reach outputs
+#     opponent-reach index (i32), static chance reach (f64), the opponent's reach at its root (f64) [the own reach, the
+#     own ids and the 16-byte payoff pattern are per GROUP of 2n-2 subtrees]; the first pass also reads the value index
+#     (i32) and writes the subtree value (f64) -- once per rank when sharded
+#   upper tile, per pass: the values of its 9 x (2n-2) micro subtrees (f64) and 22 strategy probabilities
 #   (information set, action) pair: regret and action count read + written, strategy read, written twice
 #     (row-major for the API, fused numbering for the next iteration)
-FUSED_MICRO_BYTES = 2 * (4 * 4 + 4 + 4 + 8 + 16) + (4 + 8)
+FUSED_MICRO_BYTES_PER_PASS = 4 * 4 + 4 + 4 + 8 + 8
+FUSED_MICRO_BYTES = 2 * FUSED_MICRO_BYTES_PER_PASS + (4 + 8)
 FUSED_PAIR_BYTES = 4 * 8 + 8 + 2 * 8
 
 
-def fused_bytes_per_iteration(ft, layout):
-    C = RANKS * 2
-    boards = C - 2
-    tile = 2 * (9 * boards * 16 + 8 * 4 + 4 * 8 + 6 * 8 + 9 * 8)
-    return (layout['micro_subtrees'] * FUSED_MICRO_BYTES + layout['upper_tiles'] * tile +
-            ft.num_pairs * FUSED_PAIR_BYTES)
+def fused_bytes_per_iteration(ft, layout, world=1):
+    """Per GPU: the micro subtrees and their information sets are divided over the ranks, the upper tiles replicated."""
+    boards = RANKS * 2 - 2
+    tile = 2 * (9 * boards * 8 + 22 * 8)
+    micro = layout['micro_subtrees'] * (FUSED_MICRO_BYTES + 8 * (world - 1))
+    return micro / world + layout['upper_tiles'] * tile + ft.num_pairs * FUSED_PAIR_BYTES / world
 
 
 class ClockSampler:
@@ -291,15 +292,25 @@ def main():
         core = solver
         run_iters = solver.vanilla
     else:
-        from rlpoker_b200.sharding import ShardedCFR
-        sh = ShardedCFR(ft, rank, world)
+        # default: sharding by public state (peer stores inside the persistent kernel, bit-exact); RLP_BENCH_SHARDING=deal
+        # selects the deal-sharded solve with one NCCL all-reduce of the regret / action-count deltas per iteration
+        sharding = os.environ.get('RLP_BENCH_SHARDING', 'public')
+        if sharding == 'deal':
+            from rlpoker_b200.sharding import ShardedCFR
+            sh = ShardedCFR(ft, rank, world)
+        else:
+            from rlpoker_b200.sharding import PublicStateShardedCFR
+            sh = PublicStateShardedCFR(ft, rank, world)
         step = lambda: sh.iterate(ipS)
         core = sh.solver
         run_iters = sh.iterate
     layout = core.tree.layout
+    public = world > 1 and os.environ.get('RLP_BENCH_SHARDING', 'public') != 'deal'
     if os.environ.get('RLP_NO_JIT') != '1' and os.environ.get('RLP_NO_TILES') != '1':
         # the numbers below are those of the straight-line NVRTC kernels; anything else is a different program
         assert layout['tiled'] == 1 and layout['jit_shapes'] >= 1 and layout['upper_jit'] == 1, layout
+        if world == 1 and os.environ.get('RLP_NO_FUSED') != '1':
+            assert layout['fused'] == 1, layout
 
     def barrier():
         if world > 1:
@@ -363,7 +374,7 @@ def main():
     # ---- per-stage device time, live (CUDA events between the stages; serialised, so their sum exceeds the
     # pipelined iteration time -- shares are what matters) -------------------------------------------------
     fused = layout.get('fused') == 1 and os.environ.get('RLP_NO_FUSED') != '1'
-    if world > 1:
+    if world > 1 and not public:
         stages = None
     elif fused:
         stages = core.fused_timeline(40)          # CTA 0's view of the phases inside the persistent kernel
@@ -378,7 +389,13 @@ def main():
         sh.solver.t = 0
     run_iters(T)
     torch.cuda.synchronize()
-    got_R, got_S, got_avg = core.read(RLP_REGRET), core.read(RLP_STRAT_SUM), core.read(RLP_AVERAGE)
+    if public:
+        sh.check()
+        got_R, got_S = sh.merged(RLP_REGRET), sh.merged(RLP_STRAT_SUM)
+        sh.gather_state()
+    else:
+        got_R, got_S = core.read(RLP_REGRET), core.read(RLP_STRAT_SUM)
+    got_avg = core.read(RLP_AVERAGE)
     got_expl = core.exploitability()[0]
     parity = None
     if rank == 0:
@@ -391,9 +408,9 @@ def main():
                   'bit_exact': bit, 'max_abs_regret': float(np.abs(got_R - o.R).max()),
                   'max_abs_avg': float(np.abs(got_avg - want_avg).max()),
                   'abs_exploitability': abs(got_expl - want_expl), 'exploitability': got_expl,
-                  'tolerance': {'avg': 1e-9, 'exploitability': 1e-7, 'bit_exact_required': world == 1}}
+                  'tolerance': {'avg': 1e-9, 'exploitability': 1e-7, 'bit_exact_required': world == 1 or public}}
         parity['ok'] = bool(parity['max_abs_avg'] <= 1e-9 and parity['abs_exploitability'] <= 1e-7 and
-                            (bit or world > 1) and parity['max_abs_regret'] <= 1e-9)
+                            (bit or (world > 1 and not public)) and parity['max_abs_regret'] <= 1e-9)
 
     # ---- the public Python API, wall clock (cfr() as a user calls it, FlatGame = no node objects) -----------
     e2e_api = None
@@ -412,7 +429,9 @@ def main():
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': 'leduc13-vanilla-cfr', 'game': 'Leduc(get_deck(13, 2))', 'nodes': N,
                        'infosets': ft.num_infosets, 'pairs': Q, 'iters_per_step': ipS,
-                       'parallelism': 'deal-sharded x%d + allreduce' % world if world > 1 else 'single GPU',
+                       'parallelism': ('single GPU' if world == 1 else
+                                       'public-state components sharded x%d, subtree values exchanged by peer stores inside the '
+                                       'persistent kernel' % world if public else 'deal-sharded x%d + NCCL allreduce' % world),
                        'l2_policy': 'L2 flushed (512 MB write) between timed steps, outside the timed intervals; one '
                                     'iteration touches ~76 MB of HBM-resident state (ncu), less than the 126 MB L2'},
             'spread': ({'repeats': len(rep), 'median': statistics.median(rep), 'min': min(rep), 'max': max(rep),
@@ -456,7 +475,7 @@ def roofline_block(ft, layout, stages, fused, world, bytes_iter, iter_ms, achiev
          'algorithmic_bytes_per_iteration': bytes_iter, 'bytes_per_node_update': bytes_iter / (2.0 * N),
          'us_per_iteration': iter_ms * 1e3, 'layout': layout}
     if fused:
-        fb = fused_bytes_per_iteration(ft, layout)
+        fb = fused_bytes_per_iteration(ft, layout, world)
         r.update({
             'kernel': 'cfr_fused_k: ONE cooperative persistent launch per call; per iteration a micro phase (subtree '
                       'groups: evaluate + ordered accumulate + regret matching) and an upper phase (round-1 tiles), two '
@@ -464,7 +483,7 @@ def roofline_block(ft, layout, stages, fused, world, bytes_iter, iter_ms, achiev
             'stage_us': stages,
             'restated': {'algorithmic_bytes_per_iteration': fb, 'achieved': fb / (iter_ms * 1e-3) / 1e9,
                          'frac': fb / (iter_ms * 1e-3) / 1e9 / peak,
-                         'bytes_per_micro_subtree': FUSED_MICRO_BYTES, 'bytes_per_pair': FUSED_PAIR_BYTES,
+                         'bytes_per_micro_subtree': FUSED_MICRO_BYTES, 'bytes_per_pair': FUSED_PAIR_BYTES, 'per_gpu': True,
                          'note': 'bytes of the fused storage format (no reach / value / contribution arrays leave the '
                                  'SM); the ~30 MB working set is L2-resident, so the iteration is bound by FP64 issue, '
                                  'shared-memory ordered sums and two grid barriers, not by HBM'},

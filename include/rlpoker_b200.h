@@ -208,6 +208,24 @@ int rlp_cfr_sharded_iters(rlp_cfr *cfr, int64_t t0, int64_t n_iters, int linear_
 void *rlp_cfr_delta_ptr(rlp_cfr *cfr);
 int rlp_cfr_apply_delta(rlp_cfr *cfr, void *stream);
 
+
+/*
+ * Sharding by PUBLIC STATE (trees that run the group-fused kernel, e.g. every Leduc-n): the micro subtrees fall into
+ * components that share no information set (Leduc: one per board card and round-1 betting line); rank r sweeps its
+ * components and alone holds their regrets / action counts / strategy.  Per iteration the ranks exchange only the VALUE
+ * of every micro subtree (1.1 MB in total at Leduc-13), stored straight into every peer's buffer over NVLink by the
+ * micro phase of the one persistent kernel, with the phase's grid barrier doubling as the cross-GPU handshake.  All
+ * sums keep the single-GPU order: the result is bit-identical to one GPU and to the reference.
+ *   every rank: rlp_cfr_p2p_export -> 64-byte CUDA IPC handle of its exchange buffer; share the handles (e.g.
+ *   torch.distributed all_gather); every rank: rlp_cfr_p2p_connect with all handles in rank order (<= 8 ranks on one
+ *   node); then rlp_cfr_vanilla_iters with the SAME arguments on every rank.  rlp_cfr_read returns this rank's view:
+ *   merge with rlp_cfr_p2p_owned (1 = this rank's entry is the current one; every set is owned by exactly one rank).
+ */
+int rlp_cfr_p2p_export(rlp_cfr *cfr, unsigned char *handle64);
+int rlp_cfr_p2p_connect(rlp_cfr *cfr, int rank, int nranks, const unsigned char *handles);
+int rlp_cfr_p2p_owned(rlp_cfr *cfr, unsigned char *owned);
+int rlp_cfr_p2p_failed(rlp_cfr *cfr);
+
 #ifdef __cplusplus
 }
 #endif

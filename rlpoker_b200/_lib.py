@@ -67,6 +67,10 @@ SYMBOLS = {
     'rlp_node_values': (C.c_int, [_vp, _dp, _dp, _dp, _vp]),
     'rlp_best_response': (C.c_int, [_vp, _dp, C.c_int, _dp, _i32p, _vp]),
     'rlp_expected_value': (C.c_int, [_vp, _dp, _dp, _vp]),
+    'rlp_cfr_p2p_export': (C.c_int, [_vp, _u8p]),
+    'rlp_cfr_p2p_connect': (C.c_int, [_vp, C.c_int, C.c_int, _u8p]),
+    'rlp_cfr_p2p_owned': (C.c_int, [_vp, _u8p]),
+    'rlp_cfr_p2p_failed': (C.c_int, [_vp]),
     'rlp_cfr_local_sweep': (C.c_int, [_vp, C.c_int64, C.c_int, _vp]),
     'rlp_cfr_delta_ptr': (_vp, [_vp]),
     'rlp_comm_unique_id': (C.c_int, [_u8p]),

@@ -493,7 +493,9 @@ int permute(rlp_tree *t, const double *src, double *dst, int to_internal, cudaSt
 }  // namespace rlp
 
 extern "C" void rlp_comm_destroy(rlp_cfr *c);
+namespace rlp { void p2p_release(rlp_cfr *c); }
 extern "C" void rlp_cfr_free(rlp_cfr *c) {
+    if (c) rlp::p2p_release(c);
     rlp_comm_destroy(c);
     delete c;
 }

@@ -42,8 +42,7 @@ struct rlp_cfr {
     rlp::DevBuf<double> sigF;
     int sigF_cur = 0;                        // buffer holding the current strategy
     bool sigF_dirty = true;                  // c->sigma was changed by something other than the fused kernel
-    rlp::DevBuf<unsigned char> fused_params; // device copy of FusedParams for this solver
-    void *fused_params_tl = nullptr;
+
     rlp::DevBuf<uint8_t> flags;              // [3][I] internal order: in_R | in_S (or alpha) | in_sigma dict membership
     // per-node scratch
     rlp::DevBuf<double> pc, p1, p2, val1, val2, vbr;
@@ -69,6 +68,7 @@ struct rlp_cfr {
     cudaGraph_t shard_graph = nullptr;          // 10 iterations of sweep -> ncclAllReduce -> apply (comm.cu)
     cudaGraphExec_t shard_exec = nullptr;
     int shard_graph_kernels = 0;
+    void *p2p = nullptr;                     // rlp::P2P of the solve sharded by public state (fused.cu)
     void *nccl_comm = nullptr;               // ncclComm_t of the deal-sharded solve (comm.cu)
     int nccl_ranks = 1;
     cudaStream_t side = nullptr;

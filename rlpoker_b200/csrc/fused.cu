@@ -61,7 +61,17 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(const int *, fan_desc) X(const double *, fan_cp)        /* FanDesc[num_fan] as 4 ints; [fan edge][tile] */     \
     X(double *, R) X(double *, S) X(double *, sigma_row)      /* solver state, internal pair order */               \
     X(double *, sigF0) X(double *, sigF1)                     /* strategy, [action][fused id], two buffers */        \
-    X(double *, portal_p1) X(double *, portal_p2) X(double *, portal_v)                                             \
+    X(double *, portal_p1) X(double *, portal_p2)                                                                   \
+    X(double *, pvl0) X(double *, pvl1)                       /* portal values, this GPU, by iteration parity */     \
+    X(double *, pvA0) X(double *, pvA1) X(double *, pvA2) X(double *, pvA3) X(double *, pvA4) X(double *, pvA5)     \
+    X(double *, pvA6) X(double *, pvA7)                       /* even-iteration buffer of every rank (peer mapped) */ \
+    X(double *, pvB0) X(double *, pvB1) X(double *, pvB2) X(double *, pvB3) X(double *, pvB4) X(double *, pvB5)     \
+    X(double *, pvB6) X(double *, pvB7)                       /* odd-iteration buffer of every rank */               \
+    X(unsigned long long *, xfp0) X(unsigned long long *, xfp1) X(unsigned long long *, xfp2)                        \
+    X(unsigned long long *, xfp3) X(unsigned long long *, xfp4) X(unsigned long long *, xfp5)                        \
+    X(unsigned long long *, xfp6) X(unsigned long long *, xfp7) /* flag arrays of every rank (peer mapped) */        \
+    X(unsigned long long *, xfl)                              /* this rank's flag array: xfl[r] written by rank r */  \
+    X(long long, nranks) X(long long, rank) X(long long, xbase)                                                     \
     X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
     X(long long, num_isets) X(long long, first_group0) X(long long, end_group0) X(long long, first_group1)          \
     X(long long, end_group1) X(long long, tl_cap)
@@ -94,6 +104,9 @@ struct FusedPlan {
     int grid = 0, block = 256;
     int num_components = 0;
     std::vector<int> group_comp[2];     // component of every group, fused order (multi-GPU sharding by public state)
+    std::vector<int> h_grp_iset[2], h_tg_iset[2];   // host copies: internal information sets of the groups
+    int mo[2] = {0, 0};                 // own decisions per micro group
+    size_t pv_len = 0;                  // doubles in one portal-value buffer
     std::string source;
     ~FusedPlan() { if (lib) cudaLibraryUnload(lib); }
 };
@@ -177,7 +190,7 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
     for (size_t j = 0; j < s.dec[opp].size(); ++j) opp_j[s.dec[opp][j]] = (int)j;
     Terms t = micro_terms(s, pl);
     o << "__device__ __forceinline__ void micro_eval" << pl << "(const FusedParams* __restrict__ P, long long g, int k, int tix, double w,\n"
-         "    const double* sig_in, double* sm_r, double* sm_o) {\n"
+         "    const double* sig_in, double* sm_r, double* sm_o, int par) {\n"
          "  const long long slot = g * " << c.G[pl] << " + k;\n"
          "  const int pat = P->mem_pat" << pl << "[slot], ri = P->mem_ridx" << pl << "[slot], ro = P->grp_ridx" << pl << "[g];\n"
          "  const double pcv = P->mem_pc" << pl << "[slot];\n";
@@ -232,7 +245,10 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         }
         o << "    sm_o[" << jj << " * SMS + tix] = w * own;\n  }\n";
     }
-    if (pl == 0) o << "  P->portal_v[pi] = x0;\n";
+    if (pl == 0)        // the subtree value goes to EVERY rank's buffer of this iteration's parity (peer stores over NVLink)
+        o << "  { double* const* pvp = par ? &P->pvB0 : &P->pvA0; const int nr = (int)P->nranks;\n"
+             "    for (int r = 0; r < nr; ++r) pvp[r][pi] = x0; }\n";
+    else o << "  (void)par;\n";
     o << "}\n";
 }
 
@@ -255,7 +271,7 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         if (sh.kind[j] == 3) o << "  double x" << j << ";\n";
     }
     o << "  double pad_;\n};\n"
-         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, UIn" << pl << "& in) {\n";
+         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, const double* pvl, UIn" << pl << "& in) {\n";
     for (int j = 0; j < n; ++j)
         if (s.dec_idx[j] >= 0) {
             o << "  const int f" << j << " = sm_ut[" << c.GBS + s.dec_idx[j] * c.GBS << " + m];\n";
@@ -269,7 +285,7 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         if (s.parent[j] >= 0 && s.dec_idx[s.parent[j]] >= 0)
             o << "  in.s" << j << " = __ldcg(sig_in + " << s.slot[j] << "LL * " << c.NF << "LL + f" << s.parent[j] << ");\n";
     for (int j = 0; j < n; ++j)
-        if (sh.kind[j] == 3) o << "  in.x" << j << " = __ldcg(P->portal_v + i * " << c.KP << "LL + " << sh.portal_rank[j] << ");\n";
+        if (sh.kind[j] == 3) o << "  in.x" << j << " = __ldcg(pvl + i * " << c.KP << "LL + " << sh.portal_rank[j] << ");\n";
     o << "  in.pad_ = 0.0;\n}\n";
     o << "__device__ __forceinline__ void upper_eval" << pl << "(int m, double w, const UIn" << pl << "& in, const double* sm_fan, double* sm_r, double* sm_o) {\n";
     for (int j = 0; j < n; ++j) {
@@ -378,6 +394,56 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int k, 
   }
   __syncthreads();
 }
+// The same barrier with the exchange step of the multi-GPU solve folded in: the subtree values were stored straight
+// into every peer's buffer (NVLink peer stores) during the micro phase; the last CTA of this GPU to arrive publishes
+// `token` in every peer's flag array and waits until every peer has published it here, then releases the local CTAs.
+// System-scope fences order the peer stores of all local CTAs before the flag.  The wait is bounded: a lost peer
+// sets bar[2] (the host reports it) instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P, unsigned int k, unsigned int nb, unsigned long long token) {
+  __shared__ int s_last;
+  unsigned int* bar = P->bar;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int prev = atomicAdd(bar, 1u);
+    s_last = prev + 1u == k * nb;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) {
+      const int nr = (int)P->nranks, me = (int)P->rank;
+      unsigned long long* const* peers = &P->xfp0;
+      for (int r = 0; r < nr; ++r)
+        if (r != me) asm volatile("st.release.sys.u64 [%0], %1;" :: "l"(peers[r] + me), "l"(token) : "memory");
+      for (int r = 0; r < nr; ++r) {
+        if (r == me) continue;
+        unsigned long long v = 0;
+        long long spins = 0;
+        for (;;) {
+          asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(P->xfl + r) : "memory");
+          if (v >= token) break;
+          if (++spins > (1ll << 24)) { bar[2] = 1u; break; }      // ~seconds: give up, flag the error
+          __nanosleep(100);
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    for (unsigned int c = threadIdx.x; c < nb; c += BLOCK)
+      asm volatile("st.relaxed.gpu.u32 [%0], %1;" :: "l"(bar + 32 + 32 * c), "r"(k) : "memory");
+  } else if (threadIdx.x == 0) {
+    const unsigned int* mine = bar + 32 + 32 * blockIdx.x;
+    unsigned int v;
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v >= k) break;
+      __nanosleep(20);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
 // compute_regret_matching + normalise_probs (cfr_util.py:14-58) for action `a` of a set whose regrets are r[0..na)
 __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
   double mx = r[0];
@@ -415,7 +481,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
         const int GPT = GPC;                            // groups per team
         const std::string gfirst = "P->first_group" + std::to_string(pl), gend = "P->end_group" + std::to_string(pl);
         o << "__device__ __forceinline__ void micro_unit" << pl << "(const FusedParams* __restrict__ P, long long unit, double w, const double* sig_in,\n"
-             "    double* sig_out, double* sm_r, double* sm_o, double* sm_rn) {\n"
+             "    double* sig_out, double* sm_r, double* sm_o, double* sm_rn, int par) {\n"
              "  const int tix = threadIdx.x % TEAM;\n"
              "  const int gl = tix / " << G << ", k = tix - gl * " << G << ";\n"
              "  const long long g0 = " << gfirst << " + unit * " << GPT << ", gend = " << gend << ";\n"
@@ -436,7 +502,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    r = __ldcg(P->R + col); sa = __ldcg(P->S + col);\n"
                  "    sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
                  "  }\n"
-                 "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, g, k, tix, w, sig_in, sm_r, sm_o);\n"
+                 "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, g, k, tix, w, sig_in, sm_r, sm_o, par);\n"
                  "  TEAM_SYNC();\n"
                  "  if (acc) {\n"
                  "    const double* cr = sm_r + ci * SMS + agl * " << G << ";\n"
@@ -457,7 +523,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "  TEAM_SYNC();\n"
                  "}\n";
         } else {
-            o << "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, g, k, tix, w, sig_in, sm_r, sm_o);\n"
+            o << "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, g, k, tix, w, sig_in, sm_r, sm_o, par);\n"
                  "  TEAM_SYNC();\n"
                  "  for (int x = tix; x < " << GPT * KR << "; x += TEAM) {\n"
                  "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
@@ -512,7 +578,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
              "}\n";
         o << "__device__ __noinline__ void upper_unit" << pl << "(const FusedParams* __restrict__ P, int u, double w, const double* sig_in,\n"
              "    double* sig_out, int reach_only, double* sm_fan, double* sm_r, double* sm_o, double* sm_rn, double* sm_s, const int* sm_ut,\n"
-             "    unsigned long long* st) {\n"
+             "    const double* pvl, unsigned long long* st) {\n"
              "  const int tid = threadIdx.x;\n"
              "  const int* tiles = sm_ut;\n"
              "  if (reach_only) {\n"
@@ -533,7 +599,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    }\n";
         o << "    const int* fd = P->fan_desc;\n"
              "    UIn" << pl << " uin;\n"
-             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], tid, sm_ut, sig_in, uin);\n"
+             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], tid, sm_ut, sig_in, pvl, uin);\n"
              "    if (st && tid == 0) st[0] = now_ns();\n";
         const int pv_pad = c.NCH > 0 ? c.KP + c.KP / c.NCH + 1 : c.KP;   // padded row of one tile's portal values in shared memory
         const int chunk = (c.sm_r_n + c.sm_o_n) / std::max(1, pv_pad);     // tiles per pass through the staging area (sm_r + sm_o)
@@ -549,7 +615,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "#pragma unroll\n"
                  "    for (int i = 0; i < " << NV << "; ++i) {\n"
                  "      const int L = tid + i * BLOCK;\n"
-                 "      if (L < " << total_pv << ") { const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << "; fv[i] = __ldcg(P->portal_v + (long long)tiles[mm] * " << c.KP << "LL + q); }\n"
+                 "      if (L < " << total_pv << ") { const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << "; fv[i] = __ldcg(pvl + (long long)tiles[mm] * " << c.KP << "LL + q); }\n"
                  "    }\n"
                  "#pragma unroll\n"
                  "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
@@ -577,7 +643,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      const int m = x / " << std::max(1, c.F) << ", f = x - m * " << std::max(1, c.F) << ";\n"
                  "      const long long i = tiles[m];\n"
                  "      const int k0 = fd[4 * f], e0 = fd[4 * f + 2];\n"
-                 "      const double* pv = P->portal_v + i * " << c.KP << "LL + k0;\n"
+                 "      const double* pv = pvl + i * " << c.KP << "LL + k0;\n"
                  "      const double* cp = P->fan_cp + (long long)e0 * " << c.T << "LL + i;\n"
                  "      double acc = 0.0;\n"
                  "      const int nch = fd[4 * f + 1];\n"
@@ -663,8 +729,9 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
     (void)ur_n; (void)uo_n; (void)MOmax;
     const int sm_rn_n = std::max(NT * rn_team, us_n);
     (void)rn_a;
-    o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, " << c.MINB << ") cfr_fused_k(const FusedParams* __restrict__ P, long long t0, int iters,\n"
+    o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, " << c.MINB << ") cfr_fused_k(const __grid_constant__ FusedParams PV, long long t0, int iters,\n"
          "    int linear, int cur0) {\n"
+         "  const FusedParams* __restrict__ P = &PV;      // parameter (constant) space: no global load behind a field read\n"
          "  __shared__ double sm_ro[" << sm_r_n + sm_o_n << "];\n"
          "  __shared__ int sm_ut[" << c.UT_N << "];\n"
          "  double* sm_r = sm_ro;\n"
@@ -695,8 +762,8 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "    for (int u = blockIdx.x; u < NU0 + NU1; u += nb) {\n"
          "      if (u < NU0) upper_cache0(P, u, sm_ut); else upper_cache1(P, u - NU0, sm_ut);\n"
          "      __syncthreads();\n"
-         "      if (u < NU0) upper_unit0(P, u, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, 0);\n"
-         "      else upper_unit1(P, u - NU0, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, 0);\n"
+         "      if (u < NU0) upper_unit0(P, u, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, 0, 0);\n"
+         "      else upper_unit1(P, u - NU0, 1.0, sig_in, 0, 1, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, 0, 0);\n"
          "    }\n"
          "    grid_barrier(P->bar, ++nbar, nb);\n"
          "  }\n"
@@ -712,14 +779,17 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "    const double* sig_in = cur ? P->sigF1 : P->sigF0;\n"
          "    double* sig_out = cur ? P->sigF0 : P->sigF1;\n"
          "    const double w = linear ? (double)(t0 + it) : 1.0;\n"
+         "    const int par = (int)((P->xbase + it) & 1);        // portal-value buffer of this iteration\n"
+         "    const double* pvl = par ? P->pvl1 : P->pvl0;\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase A: micro units of player 1, then of player 2 (one list), one unit per team at a time\n"
          "    for (long long un = (long long)blockIdx.x * " << NT << " + team; un < nu0 + nu1; un += (long long)nb * " << NT << ") {\n"
-         "      if (un < nu0) micro_unit0(P, un, w, sig_in, sig_out, t_r, t_o, t_rn);\n"
-         "      else micro_unit1(P, un - nu0, w, sig_in, sig_out, t_r, t_o, t_rn);\n"
+         "      if (un < nu0) micro_unit0(P, un, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
+         "      else micro_unit1(P, un - nu0, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
          "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
-         "    grid_barrier(P->bar, ++nbar, nb);\n"
+         "    if (P->nranks > 1) grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1));\n"
+         "    else grid_barrier(P->bar, ++nbar, nb);\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)\n"
          "    if (lead >= 0) {\n"
@@ -730,8 +800,8 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "          cached_u = u;\n"
          "          __syncthreads();\n"
          "        }\n"
-         "        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, st);\n"
-         "        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, st);\n"
+         "        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, pvl, st);\n"
+         "        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, pvl, st);\n"
          "      }\n"
          "    }\n"
          "    tlc += 5;\n"
@@ -778,7 +848,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         if (last.portal_off + last.n_portal != P) return RLP_OK;
     }
     // CTA shape: RLP_FUSED_BLOCK threads (default 256), RLP_FUSED_MINB resident CTAs per SM (default 2)
-    int blk = 256, minb = 2;
+    int blk = 256, minb = 3;
     { const char *e = getenv("RLP_FUSED_BLOCK"); if (e && atoi(e) >= 32 && atoi(e) <= kMaxBlock && atoi(e) % 32 == 0) blk = atoi(e); }
     { const char *e = getenv("RLP_FUSED_MINB"); if (e && atoi(e) >= 1 && atoi(e) <= 8) minb = atoi(e); }
     const std::vector<int32_t> &srank = *cx.srank, &krank = *cx.krank;
@@ -969,10 +1039,11 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     // ---- shared-memory budget of the generated kernel (static shared memory only: 48 KB) -----------------------------
     Consts c;
     c.BLK = blk; c.MINB = minb;
-    // a warp per micro unit (no CTA-wide barrier in the micro phase) when a group fits a warp; RLP_FUSED_TEAM=cta
-    // forces the CTA-wide variant
-    c.TEAM = (mg[0].G <= 32 && mg[1].G <= 32) ? 32 : blk;
-    { const char *e = getenv("RLP_FUSED_TEAM"); if (e && e[0] == 'c') c.TEAM = blk; }
+    // The whole CTA works on one micro unit (BLK / G groups) by default.  RLP_FUSED_TEAM=warp gives every warp its own
+    // unit instead (no CTA-wide barrier in the micro phase; needs G <= 32); measured slower at Leduc-13 because the
+    // ordered sums then run on 11 lanes of every warp instead of on 4 full warps per CTA.
+    c.TEAM = blk;
+    { const char *e = getenv("RLP_FUSED_TEAM"); if (e && e[0] == 'w' && mg[0].G <= 32 && mg[1].G <= 32) c.TEAM = 32; }
     Terms mt[2] = {micro_terms(s, 0), micro_terms(s, 1)}, ut[2] = {upper_terms(s, 0), upper_terms(s, 1)};
     for (int pl = 0; pl < 2; ++pl) {
         c.G[pl] = mg[pl].G; c.GPC[pl] = std::max(1, c.TEAM / mg[pl].G); c.NG[pl] = (int)mg[pl].key.size();
@@ -1073,6 +1144,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         RLP_CUDA(fp->reach[pl].alloc((size_t)cx.kp * (size_t)c.NUG[pl]));
         RLP_CUDA(fp->mem_pc[pl].upload(h_pc, stream)); RLP_CUDA(fp->grp_fid[pl].upload(h_fid, stream));
         RLP_CUDA(fp->grp_col[pl].upload(h_col, stream)); RLP_CUDA(fp->grp_iset[pl].upload(h_iset, stream));
+        fp->h_grp_iset[pl] = h_iset; fp->mo[pl] = MO;
         fp->n_batches[pl] = (int)((NG + c.GPC[pl] - 1) / c.GPC[pl]);
         // upper groups
         const int GB = ug[pl].G, MB = (int)s.udec[pl].size();
@@ -1087,6 +1159,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         }
         RLP_CUDA(fp->tg_tile[pl].upload(h_tile, stream)); RLP_CUDA(fp->tg_fid[pl].upload(h_ufid, stream));
         RLP_CUDA(fp->tg_col[pl].upload(h_ucol, stream)); RLP_CUDA(fp->tg_iset[pl].upload(h_uiset, stream));
+        fp->h_tg_iset[pl] = h_uiset;
         fp->n_ugroups[pl] = (int)NU;
         RLP_CUDA(rlp::sync_stream(stream));
     }
@@ -1127,7 +1200,10 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.tg_col0 = fp->tg_col[0].p; h.tg_col1 = fp->tg_col[1].p; h.tg_iset0 = fp->tg_iset[0].p; h.tg_iset1 = fp->tg_iset[1].p;
     h.u_fid = fp->u_fid.p; h.u_pcs = uj.pcs.p; h.u_cprob = uj.cprob.p; h.u_pay1 = uj.pay1.p;
     h.fan_desc = reinterpret_cast<const int *>(uj.fan.p); h.fan_cp = uj.fan_cp.p;
-    h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p; h.portal_v = ts.portal_v1.p;
+    h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p;
+    h.pvl0 = h.pvl1 = h.pvA0 = h.pvB0 = ts.portal_v1.p;     // single GPU: one buffer, this rank only
+    h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr;
+    fp->pv_len = (size_t)T * (size_t)cx.kp;
     h.bar = fp->bar.p; h.tl = nullptr; h.tl_cap = 0;
     h.num_isets = I;
     h.first_group0 = 0; h.end_group0 = c.NG[0]; h.first_group1 = 0; h.end_group1 = c.NG[1];
@@ -1176,6 +1252,26 @@ int fused_stat(const rlp_tree *t, int which) {
 
 const std::string *fused_source(const rlp_tree *t) { return t->tiles.fused ? &t->tiles.fused->source : nullptr; }
 
+// Multi-GPU state of one solver (sharding by public state, see rlp_cfr_p2p_* below).
+struct P2P {
+    void *base = nullptr;               // this rank's exchange buffer: [portal values, even | odd | 8 flag words], IPC-exported
+    void *peer[8] = {};                 // the other ranks' buffers, opened through CUDA IPC
+    int rank = 0, nranks = 1;
+    bool active = false;
+    long long g_lo[2] = {0, 0}, g_hi[2] = {0, 0};   // this rank's micro groups per player (whole components)
+    int c_lo = 0, c_hi = 0;
+    unsigned long long xcount = 0;      // iterations exchanged so far = the last flag token
+};
+
+void p2p_release(rlp_cfr *c) {
+    P2P *x = static_cast<P2P *>(c->p2p);
+    if (!x) return;
+    for (int r = 0; r < 8; ++r) if (x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    if (x->base) cudaFree(x->base);
+    delete x;
+    c->p2p = nullptr;
+}
+
 // n iterations t0 .. t0+n-1 in ONE cooperative launch.  `tl` (device, nullable) receives globaltimer stamps of CTA 0:
 // per iteration {start, phase A done, barrier passed, phase B done}.
 int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaStream_t s, unsigned long long *tl, long long tl_cap) {
@@ -1185,9 +1281,7 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
     if (!c->sigF.p) {
         RLP_CUDA(c->sigF.alloc(2 * plane));
         RLP_CUDA(cudaMemsetAsync(c->sigF.p, 0, c->sigF.bytes(), s));
-        RLP_CUDA(c->fused_params.alloc(sizeof(FusedParams)));
         c->sigF_dirty = true;
-        c->fused_params_tl = (void *)-1;
     }
     if (c->sigF_dirty) {
         if (t->I > 0) {
@@ -1197,22 +1291,31 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
         c->sigF_cur = 0;
         c->sigF_dirty = false;
     }
-    if (c->fused_params_tl != (void *)tl) {
-        FusedParams h = f.host;
-        h.R = c->R.p; h.S = c->S.p; h.sigma_row = c->sigma.p; h.sigF0 = c->sigF.p; h.sigF1 = c->sigF.p + plane;
-        h.flags = c->flags.p; h.tl = tl; h.tl_cap = tl_cap;
-        RLP_CUDA(cudaMemcpyAsync(c->fused_params.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-        RLP_CUDA(cudaStreamSynchronize(s));              // `h` is a stack object
-        c->fused_params_tl = (void *)tl;
+    FusedParams hp = f.host;                              // passed BY VALUE (kernel parameter space)
+    hp.R = c->R.p; hp.S = c->S.p; hp.sigma_row = c->sigma.p; hp.sigF0 = c->sigF.p; hp.sigF1 = c->sigF.p + plane;
+    hp.flags = c->flags.p; hp.tl = tl; hp.tl_cap = tl_cap;
+    P2P *x = static_cast<P2P *>(c->p2p);
+    if (x && x->active) {                                 // sharded by public state: this rank's components only
+        double **pa = &hp.pvA0, **pb = &hp.pvB0;
+        unsigned long long **xf = &hp.xfp0;
+        for (int r = 0; r < x->nranks; ++r) {
+            char *base = static_cast<char *>(r == x->rank ? x->base : x->peer[r]);
+            pa[r] = reinterpret_cast<double *>(base);
+            pb[r] = reinterpret_cast<double *>(base) + f.pv_len;
+            xf[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(base) + 2 * f.pv_len);
+        }
+        hp.pvl0 = pa[x->rank]; hp.pvl1 = pb[x->rank]; hp.xfl = xf[x->rank];
+        hp.nranks = x->nranks; hp.rank = x->rank;
+        hp.first_group0 = x->g_lo[0]; hp.end_group0 = x->g_hi[0]; hp.first_group1 = x->g_lo[1]; hp.end_group1 = x->g_hi[1];
     }
     int64_t left = n_iters, tt = t0;
     while (left > 0) {
         const int chunk = (int)std::min<int64_t>(left, 1 << 20);
         RLP_CUDA(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int) * (32 + 32 * (size_t)f.grid + 1024), s));
-        const FusedParams *pp = reinterpret_cast<const FusedParams *>(c->fused_params.p);
         long long t_arg = tt;
+        if (x && x->active) hp.xbase = (long long)x->xcount;
         int iters = chunk, lin = linear_weight ? 1 : 0, cur0 = c->sigF_cur;
-        void *args[] = {&pp, &t_arg, &iters, &lin, &cur0};
+        void *args[] = {&hp, &t_arg, &iters, &lin, &cur0};
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)f.grid); cfg.blockDim = dim3((unsigned)f.block); cfg.stream = s;
         cudaLaunchAttribute attr[1];
@@ -1232,6 +1335,7 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
         if (e != cudaSuccess) return fail(RLP_ERR_CUDA, "launch of the fused iteration kernel: %s", cudaGetErrorString(e));
         rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
         c->sigF_cur = (c->sigF_cur + chunk) & 1;
+        if (x && x->active) x->xcount += (unsigned long long)chunk;
         left -= chunk; tt += chunk;
     }
     c->sigma_am_dirty = true;            // the five-kernel pipeline's action-major copy is stale now
@@ -1239,3 +1343,79 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
 }
 
 }  // namespace rlp
+
+// ---- multi-GPU: sharding by public state ------------------------------------------------------------------------
+// The micro subtrees fall into COMPONENTS (in Leduc: one per board card and round-1 betting line) that share no
+// information set; rank r sweeps the components [r * n / W, (r + 1) * n / W) and is the only one to hold current
+// regrets / action counts / strategy for their information sets.  What the ranks exchange is the VALUE of every micro
+// subtree (8 bytes each, 1.1 MB per iteration at Leduc-13 in total): the micro phase stores it straight into every
+// peer's buffer over NVLink, and the grid barrier that ends the phase doubles as the cross-GPU handshake (fused.cu,
+// grid_barrier_x).  The upper phase (round-1 information sets: 208 of 47 008 at Leduc-13) is replicated.  Every sum
+// keeps the single-GPU order, so the result is bit-identical to one GPU and to the reference -- unlike the all-reduce of
+// regret deltas (comm.cu), which changes the association.
+extern "C" int rlp_cfr_p2p_export(rlp_cfr *c, unsigned char *handle64) {
+    if (!c || !handle64) return fail(RLP_ERR_INVALID, "null argument");
+    if (!rlp::fused_available(c)) return fail(RLP_ERR_UNSUPPORTED, "sharding by public state needs the group-fused kernel");
+    rlp::p2p_release(c);
+    FusedPlan &f = *c->tree->tiles.fused;
+    std::unique_ptr<rlp::P2P> x(new rlp::P2P);
+    const size_t bytes = sizeof(double) * 2 * f.pv_len + sizeof(unsigned long long) * 8;
+    RLP_CUDA(cudaMalloc(&x->base, bytes));
+    RLP_CUDA(cudaMemset(x->base, 0, bytes));
+    cudaIpcMemHandle_t h;
+    RLP_CUDA(cudaIpcGetMemHandle(&h, x->base));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    c->p2p = x.release();
+    return RLP_OK;
+}
+
+extern "C" int rlp_cfr_p2p_connect(rlp_cfr *c, int rank, int nranks, const unsigned char *handles) {
+    if (!c || !handles || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fail(RLP_ERR_INVALID, "bad argument");
+    rlp::P2P *x = static_cast<rlp::P2P *>(c->p2p);
+    if (!x || !x->base) return fail(RLP_ERR_INVALID, "rlp_cfr_p2p_export has not been called");
+    FusedPlan &f = *c->tree->tiles.fused;
+    x->rank = rank; x->nranks = nranks;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        RLP_CUDA(cudaIpcOpenMemHandle(&x->peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    const int n = f.num_components;
+    x->c_lo = (int)((long long)rank * n / nranks); x->c_hi = (int)((long long)(rank + 1) * n / nranks);
+    for (int pl = 0; pl < 2; ++pl) {
+        const std::vector<int> &gc = f.group_comp[pl];
+        x->g_lo[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_lo) - gc.begin();
+        x->g_hi[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_hi) - gc.begin();
+    }
+    x->xcount = 0;
+    x->active = true;
+    return RLP_OK;
+}
+
+// owned[I] (canonical ids): 1 for the information sets whose regrets / action counts / strategy are current on this
+// rank and that this rank contributes when the ranks' arrays are merged (round-1 sets are replicated: rank 0 owns them).
+extern "C" int rlp_cfr_p2p_owned(rlp_cfr *c, unsigned char *owned) {
+    if (!c || !owned) return fail(RLP_ERR_INVALID, "null argument");
+    rlp::P2P *x = static_cast<rlp::P2P *>(c->p2p);
+    if (!x || !x->active) return fail(RLP_ERR_INVALID, "not connected");
+    rlp_tree *t = c->tree;
+    FusedPlan &f = *t->tiles.fused;
+    memset(owned, 0, (size_t)t->I);
+    for (int pl = 0; pl < 2; ++pl) {
+        for (long long g = x->g_lo[pl]; g < x->g_hi[pl]; ++g)
+            for (int j = 0; j < f.mo[pl]; ++j) owned[t->iset_of_srank[f.h_grp_iset[pl][(size_t)g * f.mo[pl] + j]]] = 1;
+        if (x->rank == 0)
+            for (int is : f.h_tg_iset[pl]) owned[t->iset_of_srank[is]] = 1;
+    }
+    return RLP_OK;
+}
+
+// 1 when the last sharded launch gave up waiting for a peer (the solver state is then undefined).
+extern "C" int rlp_cfr_p2p_failed(rlp_cfr *c) {
+    if (!c || !c->tree->tiles.fused) return 0;
+    unsigned int flag = 0;
+    cudaMemcpy(&flag, c->tree->tiles.fused->bar.p + 2, sizeof(flag), cudaMemcpyDeviceToHost);
+    return flag != 0;
+}

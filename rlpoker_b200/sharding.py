@@ -265,3 +265,99 @@ class ShardedCFR:
             self._one(linear_weight, keep_counter=False)
             self._last_linear = bool(linear_weight)
         self.nodes_touched += 2 * self.full.num_nodes * n
+
+
+# ---------------------------------------------------------------------------------------------------
+# sharding by public state (the group-fused kernel's multi-GPU mode)
+
+
+class PublicStateShardedCFR:
+    """Vanilla CFR over the ranks of a torch.distributed group, sharded by PUBLIC STATE instead of by deal.
+
+    Every rank holds the full tree; the micro subtrees fall into components that share no information set (Leduc: one
+    per board card and round-1 betting line) and rank r sweeps a contiguous range of them.  The only per-iteration
+    exchange is the value of every micro subtree, stored straight into the peers' buffers over NVLink by the micro
+    phase of the persistent kernel (csrc/fused.cu); there is no all-reduce and no host involvement inside a call.
+    Regrets / action counts / strategy of a component live on its rank only: ``merged()`` assembles the full arrays
+    (every information set is owned by exactly one rank, so the merge is a sum with zeros: exact).  All sums keep the
+    single-GPU order, hence results are bit-identical to one GPU and to the reference."""
+
+    def __init__(self, flat_tree, rank, world, group=None, stream=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from rlpoker_b200 import _lib
+        from rlpoker_b200.solver import DeviceCFR, DeviceTree
+        if world > 8:
+            raise ValueError("sharding by public state works inside one NVLink domain (<= 8 ranks)")
+        self.rank, self.world, self.group = rank, world, group
+        self.full = flat_tree
+        self.tree = DeviceTree(flat_tree, stream=stream)
+        self.solver = DeviceCFR(self.tree, stream=stream)
+        if self.tree.layout['fused'] != 1:
+            raise _lib.RlpError("this tree does not run the group-fused kernel: use ShardedCFR (deal sharding)")
+        lib = _lib.load()
+        mine = (C.c_uint8 * 64)()
+        _lib.check(lib.rlp_cfr_p2p_export(self.solver.handle, mine))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        handles = torch.zeros(world, 64, dtype=torch.uint8, device=dev)
+        me = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        if world > 1:
+            dist.all_gather_into_tensor(handles.view(-1), me, group=group)
+        else:
+            handles[0] = me
+        flat = handles.cpu().numpy().reshape(-1)
+        arr = (C.c_uint8 * (64 * world))(*flat.tolist())
+        rc = lib.rlp_cfr_p2p_connect(self.solver.handle, rank, world, arr)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)       # every rank takes the same path
+        if int(ok.item()) != 1:
+            raise _lib.RlpError("rlp_cfr_p2p_connect failed on at least one rank (this rank: status %d, %s)"
+                                % (rc, lib.rlp_last_error().decode()))
+        owned = np.zeros(flat_tree.num_infosets, np.uint8)
+        _lib.check(lib.rlp_cfr_p2p_owned(self.solver.handle, _lib.ptr(owned, _lib._u8p)))
+        self.owned_isets = owned.astype(bool)
+        self.owned_pairs = np.repeat(self.owned_isets, flat_tree.nact)
+        self.nodes_touched = 0
+
+    def iterate(self, n_iters, linear_weight=False):
+        """The same call on every rank; returns without synchronising (the ranks meet inside the kernel)."""
+        from rlpoker_b200 import _lib
+        self.solver.vanilla(int(n_iters), linear_weight=linear_weight)
+        self.nodes_touched += 2 * self.full.num_nodes * int(n_iters)
+
+    def check(self):
+        """Raises if a peer was lost during the last call (bounded wait inside the kernel)."""
+        import torch
+        from rlpoker_b200 import _lib
+        torch.cuda.synchronize()
+        if _lib.load().rlp_cfr_p2p_failed(self.solver.handle):
+            raise _lib.RlpError("a peer GPU did not reach the exchange barrier in time; the solver state is undefined")
+
+    def merged(self, which):
+        """The full [Q] array (canonical order) assembled from the owners, on every rank."""
+        import torch
+        import torch.distributed as dist
+        local = self.solver.read(which)
+        local[~self.owned_pairs] = 0.0
+        if self.world == 1:
+            return local
+        t = torch.from_numpy(local).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)      # x + 0 + ... + 0: exact
+        return t.cpu().numpy()
+
+    def gather_state(self):
+        """Make this rank's solver hold the complete regrets / action counts / strategy (e.g. before an evaluation or
+        a checkpoint); the solve can simply continue afterwards."""
+        from rlpoker_b200._lib import RLP_REGRET, RLP_SIGMA, RLP_STRAT_SUM
+        for which in (RLP_REGRET, RLP_STRAT_SUM, RLP_SIGMA):
+            self.solver.write(which, self.merged(which))
+
+    def close(self):
+        solver, self.solver = self.solver, None
+        if solver is not None:
+            solver.close()
+        tree, self.tree = self.tree, None
+        if tree is not None:
+            tree.close()

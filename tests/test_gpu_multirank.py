@@ -33,3 +33,17 @@ def test_two_rank_nccl_deal_sharded_vs_oracle(graph):
         pytest.skip('needs 2 GPUs')
     out = _torchrun(2, 'nccl_sharded_worker.py', [5, 23], env={'RLP_SHARD_CGRAPH': graph})
     assert 'nccl sharded ok' in out
+
+
+@pytest.mark.parametrize('n', [3, 6])
+def test_two_rank_public_state_sharding_bit_exact(n):
+    if _gpus() < 2:
+        pytest.skip('needs 2 GPUs')
+    out = _torchrun(2, 'p2p_sharded_worker.py', [n])
+    assert 'p2p sharded ok' in out
+
+
+def test_public_state_sharding_world_one():
+    """The same code path with a single rank (no peers): the group ranges, the owned mask and the merge."""
+    out = _torchrun(1, 'p2p_sharded_worker.py', [3])
+    assert 'p2p sharded ok' in out
