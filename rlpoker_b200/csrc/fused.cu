@@ -71,6 +71,7 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(unsigned long long *, xfp3) X(unsigned long long *, xfp4) X(unsigned long long *, xfp5)                        \
     X(unsigned long long *, xfp6) X(unsigned long long *, xfp7) /* flag arrays of every rank (peer mapped) */        \
     X(unsigned long long *, xfl)                              /* this rank's flag array: xfl[r] written by rank r */  \
+    X(const int *, own_idx) X(long long, n_own)               /* portal-value slots this rank computes (sorted) */   \
     X(long long, nranks) X(long long, rank) X(long long, xbase)                                                     \
     X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
     X(long long, num_isets) X(long long, first_group0) X(long long, end_group0) X(long long, first_group1)          \
@@ -105,6 +106,8 @@ struct FusedPlan {
     int num_components = 0;
     std::vector<int> group_comp[2];     // component of every group, fused order (multi-GPU sharding by public state)
     std::vector<int> h_grp_iset[2], h_tg_iset[2];   // host copies: internal information sets of the groups
+    std::vector<int> h_pidx0;           // host copy: portal-value slot of every (group member) of player 1's groups
+    int G0 = 0;
     int mo[2] = {0, 0};                 // own decisions per micro group
     size_t pv_len = 0;                  // doubles in one portal-value buffer
     std::string source;
@@ -245,9 +248,7 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         }
         o << "    sm_o[" << jj << " * SMS + tix] = w * own;\n  }\n";
     }
-    if (pl == 0)        // the subtree value goes to EVERY rank's buffer of this iteration's parity (peer stores over NVLink)
-        o << "  { double* const* pvp = par ? &P->pvB0 : &P->pvA0; const int nr = (int)P->nranks;\n"
-             "    for (int r = 0; r < nr; ++r) pvp[r][pi] = x0; }\n";
+    if (pl == 0) o << "  (par ? P->pvl1 : P->pvl0)[pi] = x0;\n";
     else o << "  (void)par;\n";
     o << "}\n";
 }
@@ -788,8 +789,21 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "      else micro_unit1(P, un - nu0, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
          "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
-         "    if (P->nranks > 1) grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1));\n"
-         "    else grid_barrier(P->bar, ++nbar, nb);\n"
+         "    if (P->nranks > 1) {\n"
+         "      // exchange step: once every local subtree value is in place, all CTAs copy this rank's values into every\n"
+         "      // peer's buffer with coalesced stores (NVLink), then the barrier that ends the phase shakes hands with the peers\n"
+         "      grid_barrier(P->bar, ++nbar, nb);\n"
+         "      double* const* pvp = par ? &P->pvB0 : &P->pvA0;\n"
+         "      const int nr = (int)P->nranks, me = (int)P->rank;\n"
+         "      for (long long x = (long long)blockIdx.x * BLOCK + threadIdx.x; x < P->n_own; x += (long long)nb * BLOCK) {\n"
+         "        const int idx = P->own_idx[x];\n"
+         "        const double v = __ldcg(pvl + idx);\n"
+         "        for (int r = 0; r < nr; ++r) if (r != me) pvp[r][idx] = v;\n"
+         "      }\n"
+         "      grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1));\n"
+         "    } else {\n"
+         "      grid_barrier(P->bar, ++nbar, nb);\n"
+         "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)\n"
          "    if (lead >= 0) {\n"
@@ -1145,6 +1159,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         RLP_CUDA(fp->mem_pc[pl].upload(h_pc, stream)); RLP_CUDA(fp->grp_fid[pl].upload(h_fid, stream));
         RLP_CUDA(fp->grp_col[pl].upload(h_col, stream)); RLP_CUDA(fp->grp_iset[pl].upload(h_iset, stream));
         fp->h_grp_iset[pl] = h_iset; fp->mo[pl] = MO;
+        if (pl == 0) { fp->h_pidx0 = h_pidx; fp->G0 = G; }
         fp->n_batches[pl] = (int)((NG + c.GPC[pl] - 1) / c.GPC[pl]);
         // upper groups
         const int GB = ug[pl].G, MB = (int)s.udec[pl].size();
@@ -1202,7 +1217,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.fan_desc = reinterpret_cast<const int *>(uj.fan.p); h.fan_cp = uj.fan_cp.p;
     h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p;
     h.pvl0 = h.pvl1 = h.pvA0 = h.pvB0 = ts.portal_v1.p;     // single GPU: one buffer, this rank only
-    h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr;
+    h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr; h.own_idx = nullptr; h.n_own = 0;
     fp->pv_len = (size_t)T * (size_t)cx.kp;
     h.bar = fp->bar.p; h.tl = nullptr; h.tl_cap = 0;
     h.num_isets = I;
@@ -1261,6 +1276,8 @@ struct P2P {
     long long g_lo[2] = {0, 0}, g_hi[2] = {0, 0};   // this rank's micro groups per player (whole components)
     int c_lo = 0, c_hi = 0;
     unsigned long long xcount = 0;      // iterations exchanged so far = the last flag token
+    rlp::DevBuf<int> own_idx;           // portal-value slots this rank computes, ascending
+    long long n_own = 0;
 };
 
 void p2p_release(rlp_cfr *c) {
@@ -1305,7 +1322,7 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
             xf[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(base) + 2 * f.pv_len);
         }
         hp.pvl0 = pa[x->rank]; hp.pvl1 = pb[x->rank]; hp.xfl = xf[x->rank];
-        hp.nranks = x->nranks; hp.rank = x->rank;
+        hp.nranks = x->nranks; hp.rank = x->rank; hp.own_idx = x->own_idx.p; hp.n_own = x->n_own;
         hp.first_group0 = x->g_lo[0]; hp.end_group0 = x->g_hi[0]; hp.first_group1 = x->g_lo[1]; hp.end_group1 = x->g_hi[1];
     }
     int64_t left = n_iters, tt = t0;
@@ -1388,6 +1405,13 @@ extern "C" int rlp_cfr_p2p_connect(rlp_cfr *c, int rank, int nranks, const unsig
         const std::vector<int> &gc = f.group_comp[pl];
         x->g_lo[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_lo) - gc.begin();
         x->g_hi[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_hi) - gc.begin();
+    }
+    {   // the portal-value slots this rank computes: the members of its player-1 groups
+        std::vector<int> idx(f.h_pidx0.begin() + x->g_lo[0] * f.G0, f.h_pidx0.begin() + x->g_hi[0] * f.G0);
+        std::sort(idx.begin(), idx.end());
+        x->n_own = (long long)idx.size();
+        RLP_CUDA(x->own_idx.upload(idx, nullptr));
+        RLP_CUDA(cudaDeviceSynchronize());
     }
     x->xcount = 0;
     x->active = true;
