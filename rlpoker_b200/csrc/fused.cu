@@ -72,7 +72,7 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(unsigned long long *, xfp6) X(unsigned long long *, xfp7) /* flag arrays of every rank (peer mapped) */        \
     X(unsigned long long *, xfl)                              /* this rank's flag array: xfl[r] written by rank r */  \
     X(const int *, own_idx) X(long long, n_own)               /* portal-value slots this rank computes (sorted) */   \
-    X(long long, nranks) X(long long, rank) X(long long, xbase)                                                     \
+    X(long long, nranks) X(long long, rank) X(long long, xbase) X(long long, xdebug)                                \
     X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
     X(long long, num_isets) X(long long, first_group0) X(long long, end_group0) X(long long, first_group1)          \
     X(long long, end_group1) X(long long, tl_cap)
@@ -134,6 +134,7 @@ struct Shape {
 struct Consts {
     int BLK, MINB;                      // CTA size, resident CTAs per SM asked of the compiler
     int TEAM;                           // threads that work on one micro unit together: 32 (a warp, __syncwarp) or BLK
+    int NPUSH;                          // CTAs that copy this rank's subtree values to the peers (multi-GPU)
     int G[2], GPC[2], NG[2], GB[2], NUG[2];
     long long NS[2];                    // slots = NG * G
     long long NF, T;
@@ -400,15 +401,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int k, 
 // `token` in every peer's flag array and waits until every peer has published it here, then releases the local CTAs.
 // System-scope fences order the peer stores of all local CTAs before the flag.  The wait is bounded: a lost peer
 // sets bar[2] (the host reports it) instead of hanging the GPU.
-__device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P, unsigned int k, unsigned int nb, unsigned long long token) {
+__device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P, unsigned int k, unsigned int nb, unsigned long long token,
+                                               bool pushed) {
   __shared__ int s_last;
   unsigned int* bar = P->bar;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    // only the CTAs that stored into peer memory pay for a system-scope fence (hundreds of them at once are slow)
+    if (pushed) __threadfence_system(); else __threadfence();
     const unsigned int prev = atomicAdd(bar, 1u);
     s_last = prev + 1u == k * nb;
-    __threadfence_system();
+    __threadfence();
   }
   __syncthreads();
   if (s_last) {
@@ -418,7 +421,7 @@ __device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P
       for (int r = 0; r < nr; ++r)
         if (r != me) asm volatile("st.release.sys.u64 [%0], %1;" :: "l"(peers[r] + me), "l"(token) : "memory");
       for (int r = 0; r < nr; ++r) {
-        if (r == me) continue;
+        if (r == me || (P->xdebug & 2)) continue;
         unsigned long long v = 0;
         long long spins = 0;
         for (;;) {
@@ -795,12 +798,14 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "      grid_barrier(P->bar, ++nbar, nb);\n"
          "      double* const* pvp = par ? &P->pvB0 : &P->pvA0;\n"
          "      const int nr = (int)P->nranks, me = (int)P->rank;\n"
-         "      for (long long x = (long long)blockIdx.x * BLOCK + threadIdx.x; x < P->n_own; x += (long long)nb * BLOCK) {\n"
-         "        const int idx = P->own_idx[x];\n"
-         "        const double v = __ldcg(pvl + idx);\n"
-         "        for (int r = 0; r < nr; ++r) if (r != me) pvp[r][idx] = v;\n"
-         "      }\n"
-         "      grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1));\n"
+         "      const unsigned int npush = nb < " << c.NPUSH << "u ? nb : " << c.NPUSH << "u;       // the CTAs that move the data (and pay a system-scope fence)\n"
+         "      if (blockIdx.x < npush && !(P->xdebug & 1))\n"
+         "        for (long long x = (long long)blockIdx.x * BLOCK + threadIdx.x; x < P->n_own; x += (long long)npush * BLOCK) {\n"
+         "          const int idx = P->own_idx[x];\n"
+         "          const double v = __ldcg(pvl + idx);\n"
+         "          for (int r = 0; r < nr; ++r) if (r != me) pvp[r][idx] = v;\n"
+         "        }\n"
+         "      grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), blockIdx.x < npush);\n"
          "    } else {\n"
          "      grid_barrier(P->bar, ++nbar, nb);\n"
          "    }\n"
@@ -1053,6 +1058,8 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     // ---- shared-memory budget of the generated kernel (static shared memory only: 48 KB) -----------------------------
     Consts c;
     c.BLK = blk; c.MINB = minb;
+    c.NPUSH = 64;
+    { const char *e = getenv("RLP_P2P_NPUSH"); if (e && atoi(e) >= 1) c.NPUSH = atoi(e); }
     // The whole CTA works on one micro unit (BLK / G groups) by default.  RLP_FUSED_TEAM=warp gives every warp its own
     // unit instead (no CTA-wide barrier in the micro phase; needs G <= 32); measured slower at Leduc-13 because the
     // ordered sums then run on 11 lanes of every warp instead of on 4 full warps per CTA.
@@ -1217,7 +1224,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.fan_desc = reinterpret_cast<const int *>(uj.fan.p); h.fan_cp = uj.fan_cp.p;
     h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p;
     h.pvl0 = h.pvl1 = h.pvA0 = h.pvB0 = ts.portal_v1.p;     // single GPU: one buffer, this rank only
-    h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr; h.own_idx = nullptr; h.n_own = 0;
+    h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr; h.own_idx = nullptr; h.n_own = 0; h.xdebug = 0;
     fp->pv_len = (size_t)T * (size_t)cx.kp;
     h.bar = fp->bar.p; h.tl = nullptr; h.tl_cap = 0;
     h.num_isets = I;
@@ -1323,6 +1330,7 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
         }
         hp.pvl0 = pa[x->rank]; hp.pvl1 = pb[x->rank]; hp.xfl = xf[x->rank];
         hp.nranks = x->nranks; hp.rank = x->rank; hp.own_idx = x->own_idx.p; hp.n_own = x->n_own;
+        { const char *e = getenv("RLP_P2P_DEBUG"); hp.xdebug = e ? atoi(e) : 0; }   // measurement only: 1 no push, 2 no wait
         hp.first_group0 = x->g_lo[0]; hp.end_group0 = x->g_hi[0]; hp.first_group1 = x->g_lo[1]; hp.end_group1 = x->g_hi[1];
     }
     int64_t left = n_iters, tt = t0;

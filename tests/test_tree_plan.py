@@ -27,7 +27,7 @@ def test_leduc_tiling_closed_forms(n):
     assert p['tile_nodes'] == 23 + 9 * boards and p['tile_nonterminals'] == 17
     assert p['infosets_upper'] == 8 * c and p['infosets_micro_only'] == ft.num_infosets - 8 * c
     assert p['largest_infoset'] == c - 1
-    assert p['kernels_failed'] == 0 and p['kernels_compiled'] == 2        # micro_k and upper_k0/1
+    assert p['kernels_failed'] == 0 and p['kernels_compiled'] == 3        # micro_k, upper_k0/1, cfr_fused_k
 
 
 def test_small_games_and_fallbacks():
@@ -59,3 +59,33 @@ def test_plan_rejects_malformed_trees():
     bad.infoset[dec[0]] = ft.infoset[dec[-1]]                          # information set spanning depths
     with pytest.raises(RlpError):
         _plan(bad)
+
+
+def test_fused_kernel_source_is_generated_and_compiles():
+    """The group-fused persistent kernel: generated for every Leduc-n (one micro shape, one upper shape, complete
+    groups) and compiled by NVRTC on the host; not generated for a deal shard (incomplete groups) nor for trees without
+    the structure."""
+    import ctypes as C
+    from conftest import make_game
+    from rlpoker_b200 import _lib
+    from rlpoker_b200.flatten import flatten
+    from rlpoker_b200.games.leduc_native import leduc_flat_tree
+    from rlpoker_b200.sharding import shard_flat_tree
+    from rlpoker_b200.solver import _tree_desc
+
+    def source_of(ft):
+        desc, keep = _tree_desc(ft)
+        stats, ln = np.zeros(16, np.int64), C.c_int64()
+        _lib.check(_lib.load().rlp_tree_plan_fused_source(C.byref(desc), _lib.ptr(stats, _lib._i64p), None, 0, C.byref(ln)))
+        buf = C.create_string_buffer(ln.value)
+        _lib.check(_lib.load().rlp_tree_plan_fused_source(C.byref(desc), _lib.ptr(stats, _lib._i64p), buf, ln.value, C.byref(ln)))
+        return buf.value.decode(), stats
+
+    for n in (2, 4, 18):                    # 18 ranks: groups of 34 subtrees (wider than a warp)
+        src, stats = source_of(leduc_flat_tree(n))
+        assert 'cfr_fused_k' in src and 'grid_barrier_x' in src and '__grid_constant__' in src
+        assert stats[12] == 3 and stats[13] == 0
+    src, stats = source_of(shard_flat_tree(leduc_flat_tree(4), 0, 2))
+    assert src == '' and stats[12] == 2
+    src, _ = source_of(flatten(make_game('ocp4')))
+    assert 'cfr_fused_k' not in src or src == ''

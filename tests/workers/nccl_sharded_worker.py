@@ -41,7 +41,11 @@ def main():
     np.testing.assert_allclose(s.strategy_sum, o.S, rtol=0, atol=1e-9)
     avg = o.average_strategy()[0]
     np.testing.assert_allclose(s.average, avg, rtol=0, atol=1e-9)
-    assert abs(s.exploitability()[0] - o.exploitability(avg)) <= 1e-7
+    # best response needs the WHOLE tree (a rank's solver only holds its deals): evaluate the replicated average there
+    from rlpoker_b200.solver import DeviceTree
+    full = DeviceTree(ft)
+    assert abs(full.exploitability(s.average) - o.exploitability(avg)) <= 1e-7
+    full.close()
     # replicas must be bitwise identical across ranks
     mine = torch.from_numpy(s.regrets).cuda()
     ref = mine.clone()
