@@ -10,6 +10,7 @@
 // The reference sums the same terms grouped by information-set node lists instead of by parent, so
 // values agree to a few ulp (tests hold 1e-12), not bit for bit.
 #include "cfr.cuh"
+#include "fused.cuh"
 
 using rlp::fail;
 
@@ -179,6 +180,12 @@ static int enqueue_best_response(rlp_cfr *c, const double *sigma_int, int player
 // value of the best response of `player` against sigma_int (internal pair order) -> *value_dev.
 // The ~4 L launches are captured once per (strategy buffer, responder) and replayed as a CUDA graph.
 int launch_best_response(rlp_cfr *c, const double *sigma_int, int player, double *value_dev, cudaStream_t s) {
+    if (rlp::fused_br_available(c)) {       // both responders in one cooperative launch on the micro / upper groups
+        int rc = rlp::fused_br(c, sigma_int, c->scalars.p + 8, s);
+        if (rc) return rc;
+        RLP_CUDA(cudaMemcpyAsync(value_dev, c->scalars.p + 8 + (player - 1), sizeof(double), cudaMemcpyDeviceToDevice, s));
+        return RLP_OK;
+    }
     rlp_cfr::BrGraph *hit = nullptr;
     for (auto &b : c->br_graphs) if (b.sigma == sigma_int && b.player == player) hit = &b;
     if (!hit) {
@@ -247,10 +254,16 @@ extern "C" int rlp_cfr_exploitability(rlp_cfr *c, int which, double *out3, void 
     } else {
         return fail(RLP_ERR_INVALID, "exploitability of array %d", which);
     }
-    int rc = rlp::launch_best_response(c, sg, 1, c->scalars.p + 0, s);
-    if (rc) return rc;
-    rc = rlp::launch_best_response(c, sg, 2, c->scalars.p + 1, s);
-    if (rc) return rc;
+    int rc;
+    if (rlp::fused_br_available(c)) {
+        rc = rlp::fused_br(c, sg, c->scalars.p + 0, s);          // {BR1, BR2} in one launch
+        if (rc) return rc;
+    } else {
+        rc = rlp::launch_best_response(c, sg, 1, c->scalars.p + 0, s);
+        if (rc) return rc;
+        rc = rlp::launch_best_response(c, sg, 2, c->scalars.p + 1, s);
+        if (rc) return rc;
+    }
     double h[2];
     RLP_CUDA(cudaMemcpyAsync(h, c->scalars.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     RLP_CUDA(cudaStreamSynchronize(s));
@@ -285,8 +298,8 @@ extern "C" int rlp_best_response(rlp_tree *t, const double *sigma, int player, d
         RLP_CUDA(cudaMemcpyAsync(tmp.data(), c->astar.p, sizeof(int32_t) * (size_t)t->I, cudaMemcpyDeviceToHost, s));
     }
     RLP_CUDA(cudaStreamSynchronize(s));
-    if (argmax_out)
-        for (int32_t k = 0; k < t->I; ++k) argmax_out[t->iset_of_srank[k]] = tmp[k];
+    if (argmax_out)        // -1 for the other player's information sets (the fused kernel answers for both responders)
+        for (int32_t k = 0; k < t->I; ++k) argmax_out[t->iset_of_srank[k]] = t->iset_player_h[k] == player ? tmp[k] : -1;
     return RLP_OK;
 }
 

@@ -39,6 +39,7 @@ struct rlp_cfr {
     rlp::DevBuf<double> sigma_am;
     bool sigma_am_dirty = true;
     // group-fused persistent kernel (fused.cu): strategy in the fused numbering, [2 buffers][action][fused id]
+    rlp::DevBuf<double> br_buf;              // scratch of the group-fused best-response kernel
     rlp::DevBuf<double> sigF;
     int sigF_cur = 0;                        // buffer holding the current strategy
     bool sigF_dirty = true;                  // c->sigma was changed by something other than the fused kernel

@@ -74,6 +74,12 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(const int *, own_idx) X(long long, n_own)               /* portal-value slots this rank computes (sorted) */   \
     X(long long, nranks) X(long long, rank) X(long long, xbase) X(long long, xdebug)                                \
     X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
+    X(const double *, br_sig)                                 /* best response: strategy, [action][fused id] */      \
+    X(double *, br_reach1) X(double *, br_reach2)             /* reach of player 1 / 2 to the portals under br_sig */  \
+    X(double *, br_pv1) X(double *, br_pv2)                   /* subtree values for responder 1 / 2 */                \
+    X(double *, br_top1) X(double *, br_top2)                 /* values of the trunk nodes and tile roots, by node id */ \
+    X(double *, br_out) X(int *, br_astar)                    /* {BR1, BR2}; chosen action per internal information set */ \
+    X(const int *, tile_root) X(const int *, g_first_child) X(const signed char *, g_player) X(long long, n_top)       \
     X(long long, num_isets) X(long long, first_group0) X(long long, end_group0) X(long long, first_group1)          \
     X(long long, end_group1) X(long long, tl_cap)
 
@@ -98,6 +104,10 @@ struct FusedPlan {
     rlp::DevBuf<signed char> paytab8;
     rlp::DevBuf<int> tg_tile[2], tg_fid[2], tg_col[2], tg_iset[2], u_fid;
     rlp::DevBuf<int> fid_of_iset;       // [I] internal -> fused
+    rlp::DevBuf<int> tile_root;         // [T] node id of every tile root
+    cudaKernel_t br_kernel = nullptr;   // best response on the groups (null when the tree does not qualify)
+    long long n_top = 0;                // nodes 0 .. n_top-1 are the all-chance trunk and the tile roots
+    int kp = 0, nug[2] = {0, 0};
     rlp::DevBuf<unsigned int> bar;
     long long NF = 0;
     int n_batches[2] = {0, 0}, n_ugroups[2] = {0, 0};
@@ -135,6 +145,7 @@ struct Consts {
     int BLK, MINB;                      // CTA size, resident CTAs per SM asked of the compiler
     int TEAM;                           // threads that work on one micro unit together: 32 (a warp, __syncwarp) or BLK
     int NPUSH;                          // CTAs that copy this rank's subtree values to the peers (multi-GPU)
+    int BR_OK, MAXA;                    // the best-response kernel is generated too; widest decision node
     int G[2], GPC[2], NG[2], GB[2], NUG[2];
     long long NS[2];                    // slots = NG * G
     long long NF, T;
@@ -338,8 +349,8 @@ void gen_upper_reach(std::ostringstream &o, const Shape &s, const Consts &c, int
     Terms t = upper_terms(s, pl);
     std::vector<int> own_jj(s.n_udec, -1);
     for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) own_jj[s.udec[pl][jj]] = (int)jj;
-    o << "__device__ __forceinline__ void upper_reach" << pl << "(const FusedParams* __restrict__ P, int u, const double* sm_s) {\n"
-         "  double* out = P->portal_p" << (pl + 1) << ";\n  const double q_0 = 1.0;\n";
+    o << "__device__ __forceinline__ void upper_reach" << pl << "(double* out, int u, const double* sm_s) {\n"
+         "  const double q_0 = 1.0;\n";
     for (int j = 0; j < n; ++j) {
         int kd = sh.kind[j];
         if (kd == -1 || kd == 3 || kd == 4) continue;
@@ -354,6 +365,246 @@ void gen_upper_reach(std::ostringstream &o, const Shape &s, const Consts &c, int
     }
     o << "}\n";
 }
+
+// ---- best response (rlpoker/best_response.py:9-141) on the same groups ---------------------------------------------------
+// Responder p's information sets are exactly the groups of p: the G threads of a group hold the G nodes of every
+// information set of the group, so Q[I, a] = sum over the nodes of I (ascending) of v(h.a) is an ordered sum over the
+// group's threads through shared memory, the arg-max is taken redundantly by every thread, and v(h) = v(h.a*).
+// v(z) = reach(z) * u_p(z) with reach = static chance reach x the opponent's strategy along the path (the responder's
+// own actions count 1), as in csrc/br.cu; the association of the reach products differs from the level sweep's, so
+// values agree with it (and with the reference) to a few ulp, not bit for bit -- the tests hold 1e-12.
+void emit_payoffs(std::ostringstream &o, const MicroTmpl &tm, const Consts &c) {
+    const int n = tm.n;
+    if (c.PAY8) {
+        o << "  const int4* pp = reinterpret_cast<const int4*>(P->paytab8 + (long long)pat * " << c.PAYROW << ");\n";
+        for (int q = 0; q < c.PAYROW / 16; ++q) o << "  const int4 pw" << q << " = __ldg(pp + " << q << ");\n";
+        for (int j = 0; j < n; ++j)
+            if (tm.rank[j] & 0x80) {
+                int tr = tm.rank[j] & 0x7F, q = tr / 16, wd = (tr % 16) / 4, by = tr % 4;
+                o << "  const double x" << j << " = (double)(int)(signed char)(pw" << q << "." << "xyzw"[wd] << " >> " << 8 * by << ");\n";
+            }
+    } else {
+        o << "  const double* pp = P->paytab + (long long)pat * " << c.NT << ";\n";
+        for (int j = 0; j < n; ++j)
+            if (tm.rank[j] & 0x80) o << "  const double x" << j << " = pp[" << (tm.rank[j] & 0x7F) << "];\n";
+    }
+}
+
+void gen_micro_br(std::ostringstream &o, const Shape &s, const Consts &c, int pl) {
+    const MicroTmpl &tm = *s.tm;
+    const int n = tm.n, n_nt = tm.n_nt, opp = 1 - pl;
+    std::vector<int> own_j(n_nt, -1), opp_j(n_nt, -1);
+    for (size_t j = 0; j < s.dec[pl].size(); ++j) own_j[s.dec[pl][j]] = (int)j;
+    for (size_t j = 0; j < s.dec[opp].size(); ++j) opp_j[s.dec[opp][j]] = (int)j;
+    const int G = c.G[pl], GPT = c.GPC[pl], MO = (int)s.dec[pl].size(), A = c.MAXA;
+    o << "__device__ __forceinline__ void micro_br" << pl << "(const FusedParams* __restrict__ P, long long unit, double* sm_q) {\n"
+         "  const int tix = threadIdx.x % TEAM;\n"
+         "  const int gl = tix / " << G << ", k = tix - gl * " << G << ";\n"
+         "  const long long g = unit * " << GPT << " + gl;\n"
+         "  const bool ok = gl < " << GPT << " && g < " << c.NG[pl] << "LL;\n"
+         "  const int glr = gl < " << GPT << " ? gl : 0;          // column block read by the reductions (idle lanes stay in bounds)\n"
+         "  const long long slot = ok ? g * " << G << " + k : 0;\n"
+         "  const int pat = P->mem_pat" << pl << "[slot], ri = P->mem_ridx" << pl << "[slot], pi = P->mem_pidx" << pl << "[slot];\n"
+         "  const double pcv = P->mem_pc" << pl << "[slot];\n";
+    for (int r = 0; r < n_nt; ++r)
+        if (opp_j[r] >= 0) o << "  const int f" << r << " = P->mem_opp" << pl << "[" << opp_j[r] << "LL * " << c.NS[pl] << "LL + slot];\n";
+    emit_payoffs(o, tm, c);
+    o << "  const double rho_0 = pcv * __ldcg(P->br_reach" << opp + 1 << " + ri);\n";
+    for (int j = 1; j < n; ++j)
+        if (opp_j[tm.par_rank[j]] >= 0)
+            o << "  const double s" << j << " = __ldcg(P->br_sig + " << (int)tm.par_slot[j] << "LL * " << c.NF << "LL + f" << (int)tm.par_rank[j] << ");\n";
+    for (int r = 0; r < n_nt; ++r) {                    // forward: reach (chance x opponent) of the non-terminal nodes
+        int j = tm.nt_node[r];
+        for (int kk = 0; kk < tm.nchild[j]; ++kk) {
+            int ch = tm.first_child[j] + kk;
+            if (tm.rank[ch] & 0x80) continue;
+            o << "  const double rho_" << (int)tm.rank[ch] << " = rho_" << r << (opp_j[r] >= 0 ? " * " + S_("s", ch) : std::string()) << ";\n";
+        }
+    }
+    for (int r = n_nt - 1; r >= 0; --r) {               // backward
+        int j = tm.nt_node[r], fc = tm.first_child[j], nc = tm.nchild[j];
+        for (int kk = 0; kk < nc; ++kk) {
+            int ch = fc + kk;
+            if (tm.rank[ch] & 0x80)
+                o << "  const double v" << ch << " = (rho_" << r << (opp_j[r] >= 0 ? " * " + S_("s", ch) : std::string()) << ") * "
+                  << (pl == 0 ? "" : "-") << "x" << ch << ";\n";
+            else
+                o << "  const double v" << ch << " = V" << (int)tm.rank[ch] << ";\n";
+        }
+        if (opp_j[r] >= 0) {
+            o << "  double V" << r << " = 0.0;\n";
+            for (int kk = 0; kk < nc; ++kk) o << "  V" << r << " = V" << r << " + v" << (fc + kk) << ";\n";
+        } else {
+            const int jj = own_j[r];
+            o << "  if (ok) {\n";
+            for (int kk = 0; kk < nc; ++kk) o << "    sm_q[" << (jj * A + kk) << " * SMS + tix] = v" << (fc + kk) << ";\n";
+            o << "  }\n  TEAM_SYNC();\n  double V" << r << ";\n  {\n    int best = 0; double bq = 0.0;\n";
+            for (int kk = 0; kk < nc; ++kk) {
+                o << "    { double q = 0.0; const double* col = sm_q + " << (jj * A + kk) << " * SMS + glr * " << G << ";\n"
+                     "      for (int m = 0; m < " << G << "; ++m) q = q + col[m];\n"
+                     "      if (" << (kk == 0 ? "true" : "q > bq") << ") { bq = q; best = " << kk << "; } }\n";
+            }
+            o << "    V" << r << " = v" << fc;
+            for (int kk = 1; kk < nc; ++kk) o << ";\n    if (best == " << kk << ") V" << r << " = v" << (fc + kk);
+            o << ";\n    if (ok && k == 0) P->br_astar[P->grp_iset" << pl << "[g * " << MO << " + " << jj << "]] = best;\n  }\n";
+        }
+    }
+    o << "  if (ok) P->br_pv" << pl + 1 << "[pi] = V0;\n  TEAM_SYNC();\n}\n";
+}
+
+// One upper group of the responder: fan-in (plain ordered sums of the subtree values), then every tile bottom-up with the
+// responder's round-1 information sets reduced across the tiles of the group.  Executed by the whole CTA (block barriers
+// inside); thread m < GB works on tile m.
+void gen_upper_br(std::ostringstream &o, const Shape &s, const Consts &c, int pl) {
+    const UpperShape &sh = *s.sh;
+    const int n = (int)sh.kind.size(), opp = 1 - pl, GB = c.GB[pl], A = c.MAXA, MB = (int)s.udec[pl].size();
+    std::vector<int> own_jj(s.n_udec, -1);
+    for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) own_jj[s.udec[pl][jj]] = (int)jj;
+    o << "__device__ __noinline__ void upper_br" << pl << "(const FusedParams* __restrict__ P, int u, double* sm_fan, double* sm_q, const int* sm_ut) {\n"
+         "  const int tid = threadIdx.x;\n"
+         "  const double* pvl = P->br_pv" << pl + 1 << ";\n"
+         "  const int* fd = P->fan_desc;\n"
+         "  for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
+         "    const int mm = x / " << std::max(1, c.F) << ", f = x - mm * " << std::max(1, c.F) << ";\n"
+         "    const int k0 = fd[4 * f], nch = fd[4 * f + 1];\n"
+         "    const double* pv = pvl + (long long)sm_ut[mm] * " << c.KP << "LL + k0;\n"
+         "    double acc = 0.0;\n"
+         "    for (int ch = 0; ch < nch; ++ch) acc = acc + __ldcg(pv + ch);\n"
+         "    sm_fan[x] = acc;\n"
+         "  }\n"
+         "  __syncthreads();\n"
+         "  const bool act = tid < " << GB << ";\n"
+         "  const int m = act ? tid : 0;\n"
+         "  const long long i = sm_ut[m];\n";
+    for (int j = 0; j < n; ++j)
+        if (s.dec_idx[j] >= 0) {
+            o << "  const double pc" << j << " = P->u_pcs[" << s.dec_idx[j] << "LL * " << c.T << "LL + i];\n";
+            if (sh.kind[j] == opp + 1) o << "  const int f" << j << " = sm_ut[" << c.GBS + s.dec_idx[j] * c.GBS << " + m];\n";
+        }
+    for (int j = 0; j < n; ++j)
+        if (s.term_idx[j] >= 0) o << "  const double x" << j << " = P->u_pay1[" << s.term_idx[j] << "LL * " << c.T << "LL + i];\n";
+    for (int j = 1; j < n; ++j)
+        if (s.parent[j] >= 0 && sh.kind[s.parent[j]] == opp + 1)
+            o << "  const double s" << j << " = __ldcg(P->br_sig + " << s.slot[j] << "LL * " << c.NF << "LL + f" << s.parent[j] << ");\n";
+    o << "  const double qo_0 = 1.0;\n";
+    for (int j = 0; j < n; ++j) {
+        int kd = sh.kind[j];
+        if (kd != 1 && kd != 2) continue;
+        for (int kk = 0; kk < sh.nchild[j]; ++kk) {
+            int ch = sh.first_child[j] + kk;
+            if (sh.kind[ch] != 1 && sh.kind[ch] != 2) continue;
+            o << "  const double qo_" << ch << " = qo_" << j << (kd == opp + 1 ? " * " + S_("s", ch) : std::string()) << ";\n";
+        }
+    }
+    for (int j = n - 1; j >= 0; --j) {
+        int kd = sh.kind[j];
+        if (kd != 1 && kd != 2) continue;
+        int fc = sh.first_child[j], nc = sh.nchild[j];
+        for (int kk = 0; kk < nc; ++kk) {
+            int ch = fc + kk, ck = sh.kind[ch];
+            if (ck == -1)
+                o << "  const double v" << ch << " = ((pc" << j << " * qo_" << j << ")" << (kd == opp + 1 ? " * " + S_("s", ch) : std::string()) << ") * "
+                  << (pl == 0 ? "" : "-") << "x" << ch << ";\n";
+            else if (ck == 4) o << "  const double v" << ch << " = sm_fan[m * " << std::max(1, c.F) << " + " << sh.fan_index[ch] << "];\n";
+            else if (ck == 3) o << "  const double v" << ch << " = __ldcg(pvl + i * " << c.KP << "LL + " << sh.portal_rank[ch] << ");\n";
+            else o << "  const double v" << ch << " = V" << ch << ";\n";
+        }
+        if (kd == opp + 1) {
+            o << "  double V" << j << " = 0.0;\n";
+            for (int kk = 0; kk < nc; ++kk) o << "  V" << j << " = V" << j << " + v" << (fc + kk) << ";\n";
+        } else {
+            const int jj = own_jj[s.dec_idx[j]];
+            o << "  if (act) {\n";
+            for (int kk = 0; kk < nc; ++kk) o << "    sm_q[" << (jj * A + kk) * GB << " + m] = v" << (fc + kk) << ";\n";
+            o << "  }\n  __syncthreads();\n  double V" << j << ";\n  {\n    int best = 0; double bq = 0.0;\n";
+            for (int kk = 0; kk < nc; ++kk)
+                o << "    { double q = 0.0; const double* col = sm_q + " << (jj * A + kk) * GB << ";\n"
+                     "      for (int mm = 0; mm < " << GB << "; ++mm) q = q + col[mm];\n"
+                     "      if (" << (kk == 0 ? "true" : "q > bq") << ") { bq = q; best = " << kk << "; } }\n";
+            o << "    V" << j << " = v" << fc;
+            for (int kk = 1; kk < nc; ++kk) o << ";\n    if (best == " << kk << ") V" << j << " = v" << (fc + kk);
+            o << ";\n    if (tid == 0) P->br_astar[sm_ut[" << c.UT_OWN + 2 * c.MBS << " + " << jj << "]] = best;\n  }\n";
+        }
+    }
+    o << "  if (act) P->br_top" << pl + 1 << "[P->tile_root[i]] = V0;\n"
+         "  __syncthreads();\n  (void)qo_0;\n}\n";
+    (void)MB;
+}
+
+void gen_br_kernel(std::ostringstream &o, const Shape &s, const Consts &c) {
+    Terms u0 = upper_terms(s, 0), u1 = upper_terms(s, 1);
+    const int NT = c.BLK / c.TEAM;
+    const int q_team = std::max((int)s.dec[0].size(), (int)s.dec[1].size()) * c.MAXA * (c.TEAM + 1);
+    const int q_up = std::max((int)s.udec[0].size() * c.GB[0], (int)s.udec[1].size() * c.GB[1]) * c.MAXA;
+    const int us_n = std::max(1, std::max(u0.kr, u1.kr));
+    const int fan_n = std::max(1, std::max(c.GB[0], c.GB[1]) * c.F);
+    o << "extern \"C\" __global__ void __launch_bounds__(BLOCK, " << c.MINB << ") br_fused_k(const __grid_constant__ FusedParams PV) {\n"
+         "  const FusedParams* __restrict__ P = &PV;\n"
+         "  __shared__ double sm_q[" << std::max(NT * q_team, q_up) << "];\n"
+         "  __shared__ double sm_fan[" << fan_n << "];\n"
+         "  __shared__ double sm_s[" << us_n << "];\n"
+         "  __shared__ int sm_ut[" << c.UT_N << "];\n"
+         "  __shared__ int s_lead;\n"
+         "  const unsigned int nb = gridDim.x;\n"
+         "  unsigned int nbar = 0;\n"
+         "  const int tid = threadIdx.x;\n"
+         "  const int NU0 = " << c.NUG[0] << ", NU1 = " << c.NUG[1] << ";\n"
+         "  if (tid == 0) {\n"
+         "    unsigned int smid; asm volatile(\"mov.u32 %0, %%smid;\" : \"=r\"(smid));\n"
+         "    const unsigned int rank = atomicAdd(P->bar + 32 + 32 * nb + (smid & 1023u), 1u);\n"
+         "    s_lead = rank == 0 ? (int)atomicAdd(P->bar + 1, 1u) : -1;\n"
+         "  }\n"
+         "  __syncthreads();\n"
+         "  const int lead = s_lead;\n"
+         "  // phase 0: both players' reach to the portals under the evaluated strategy\n"
+         "  for (int u = blockIdx.x; u < NU0 + NU1; u += nb) {\n"
+         "    if (u < NU0) {\n"
+         "      for (int x = tid; x < " << u0.kr << "; x += BLOCK) sm_s[x] = __ldcg(P->br_sig + (long long)UCA0[x] * " << c.NF << "LL + P->tg_fid0[u * " << s.udec[0].size() << " + UCJ0[x]]);\n"
+         "      __syncthreads();\n"
+         "      if (tid == 0) upper_reach0(P->br_reach1, u, sm_s);\n"
+         "    } else {\n"
+         "      const int uu = u - NU0;\n"
+         "      for (int x = tid; x < " << u1.kr << "; x += BLOCK) sm_s[x] = __ldcg(P->br_sig + (long long)UCA1[x] * " << c.NF << "LL + P->tg_fid1[uu * " << s.udec[1].size() << " + UCJ1[x]]);\n"
+         "      __syncthreads();\n"
+         "      if (tid == 0) upper_reach1(P->br_reach2, uu, sm_s);\n"
+         "    }\n"
+         "    __syncthreads();\n"
+         "  }\n"
+         "  grid_barrier(P->bar, ++nbar, nb);\n"
+         "  const int n_lead = (int)__ldcg(P->bar + 1);\n"
+         "  // phase 1: the micro groups of both responders\n"
+         "  {\n"
+         "    const int team = tid / TEAM;\n"
+         "    double* t_q = sm_q + team * " << q_team << ";\n"
+         "    const long long nu0 = " << (c.NG[0] + c.GPC[0] - 1) / c.GPC[0] << "LL, nu1 = " << (c.NG[1] + c.GPC[1] - 1) / c.GPC[1] << "LL;\n"
+         "    for (long long un = (long long)blockIdx.x * " << NT << " + team; un < nu0 + nu1; un += (long long)nb * " << NT << ") {\n"
+         "      if (un < nu0) micro_br0(P, un, t_q); else micro_br1(P, un - nu0, t_q);\n"
+         "    }\n"
+         "  }\n"
+         "  grid_barrier(P->bar, ++nbar, nb);\n"
+         "  // phase 2: the upper groups of both responders, one leader CTA per SM\n"
+         "  if (lead >= 0) {\n"
+         "    for (int u = lead; u < NU0 + NU1; u += n_lead) {\n"
+         "      if (u < NU0) upper_cache0(P, u, sm_ut); else upper_cache1(P, u - NU0, sm_ut);\n"
+         "      __syncthreads();\n"
+         "      if (u < NU0) upper_br0(P, u, sm_fan, sm_q, sm_ut); else upper_br1(P, u - NU0, sm_fan, sm_q, sm_ut);\n"
+         "    }\n"
+         "  }\n"
+         "  grid_barrier(P->bar, ++nbar, nb);\n"
+         "  // phase 3: the all-chance trunk above the tiles, children in order (one thread per responder)\n"
+         "  if (blockIdx.x < 2 && tid == 0) {\n"
+         "    double* val = blockIdx.x == 0 ? P->br_top1 : P->br_top2;\n"
+         "    for (long long node = P->n_top - 1; node >= 0; --node) {\n"
+         "      if (P->g_player[node] != 0) continue;\n"
+         "      double acc = 0.0;\n"
+         "      for (int ch = P->g_first_child[node]; ch < P->g_first_child[node + 1]; ++ch) acc = acc + __ldcg(val + ch);\n"
+         "      val[node] = acc;\n"
+         "    }\n"
+         "    P->br_out[blockIdx.x] = __ldcg(val);\n"
+         "  }\n"
+         "}\n";
+}
+
 
 std::string generate_source(const Shape &s, const Consts &c) {
     std::ostringstream o;
@@ -715,7 +966,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
         o << "  }\n"
              "  __syncthreads();\n"
              "  if (st && tid == 0) st[3] = now_ns();\n"
-             "  if (tid == 0) upper_reach" << pl << "(P, u, sm_s);\n"
+             "  if (tid == 0) upper_reach" << pl << "(P->portal_p" << pl + 1 << ", u, sm_s);\n"
              "  __syncthreads();\n"
              "  if (st && tid == 0) st[4] = now_ns();\n"
              "}\n";
@@ -828,6 +1079,10 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "    grid_barrier(P->bar, ++nbar, nb);\n"
          "  }\n"
          "}\n";
+    if (c.BR_OK) {
+        for (int pl = 0; pl < 2; ++pl) { gen_micro_br(o, s, c, pl); gen_upper_br(o, s, c, pl); }
+        gen_br_kernel(o, s, c);
+    }
     return o.str();
 }
 
@@ -1059,6 +1314,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     Consts c;
     c.BLK = blk; c.MINB = minb;
     c.NPUSH = 64;
+    c.BR_OK = 0; c.MAXA = std::max(1, (int)t->max_act);
     { const char *e = getenv("RLP_P2P_NPUSH"); if (e && atoi(e) >= 1) c.NPUSH = atoi(e); }
     // The whole CTA works on one micro unit (BLK / G groups) by default.  RLP_FUSED_TEAM=warp gives every warp its own
     // unit instead (no CTA-wide barrier in the micro phase; needs G <= 32); measured slower at Leduc-13 because the
@@ -1098,6 +1354,28 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         c.MBS = (int)std::max(s.udec[0].size(), s.udec[1].size());
         c.UT_OWN = c.GBS + s.n_udec * c.GBS;
         c.UT_N = c.UT_OWN + 3 * c.MBS;
+    }
+    // ---- best-response kernel: needs an all-chance trunk whose children are trunk nodes or tile roots, and no chance
+    // node inside a tile other than the fan-in nodes
+    long long n_top = 0;
+    {
+        bool ok = true;
+        for (size_t j = 0; j < sh.kind.size(); ++j) if (sh.kind[j] == 0) ok = false;
+        std::vector<uint8_t> is_root(d->num_nodes < (1 << 24) ? (size_t)d->num_nodes : 0, 0);
+        if (is_root.empty()) ok = false;
+        if (ok) {
+            for (int64_t k = 0; k < T; ++k) { n_top = std::max<long long>(n_top, (*cx.desc)[k].root_global + 1); is_root[(*cx.desc)[k].root_global] = 1; }
+            for (long long v = 0; v < n_top && ok; ++v) {
+                if (is_root[v]) continue;
+                if (d->player[v] != 0 || fc[v + 1] > n_top) ok = false;          // a trunk node: chance, children on top
+            }
+        }
+        const size_t q_team = std::max(s.dec[0].size(), s.dec[1].size()) * (size_t)c.MAXA * (c.TEAM + 1);
+        const size_t q_up = std::max(s.udec[0].size() * c.GB[0], s.udec[1].size() * c.GB[1]) * (size_t)c.MAXA;
+        const size_t br_smem = 8 * (std::max((size_t)(blk / c.TEAM) * q_team, q_up) + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 16) + 4 * (size_t)c.UT_N;
+        if (br_smem > 46 * 1024) ok = false;
+        { const char *e = getenv("RLP_NO_FUSED_BR"); if (e && e[0] == '1') ok = false; }
+        c.BR_OK = ok ? 1 : 0;
     }
     {
         size_t kr = std::max(mt[0].kr, mt[1].kr), mo = std::max(s.dec[0].size(), s.dec[1].size());
@@ -1192,6 +1470,12 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         RLP_CUDA(fp->u_fid.upload(h_ufid, stream));
         RLP_CUDA(fp->paytab.upload(paytab, stream));
         {
+            std::vector<int> roots_h(T);
+            for (int64_t k = 0; k < T; ++k) roots_h[k] = (*cx.desc)[k].root_global;
+            RLP_CUDA(fp->tile_root.upload(roots_h, stream));
+            fp->n_top = n_top; fp->kp = cx.kp; fp->nug[0] = c.NUG[0]; fp->nug[1] = c.NUG[1];
+        }
+        {
             std::vector<signed char> p8;
             if (c.PAY8) {
                 const size_t npat = paytab.size() / (size_t)NT;
@@ -1225,6 +1509,8 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p;
     h.pvl0 = h.pvl1 = h.pvA0 = h.pvB0 = ts.portal_v1.p;     // single GPU: one buffer, this rank only
     h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr; h.own_idx = nullptr; h.n_own = 0; h.xdebug = 0;
+    h.tile_root = fp->tile_root.p; h.g_first_child = t->first_child.p; h.g_player = reinterpret_cast<const signed char *>(t->player.p);
+    h.n_top = n_top;
     fp->pv_len = (size_t)T * (size_t)cx.kp;
     h.bar = fp->bar.p; h.tl = nullptr; h.tl_cap = 0;
     h.num_isets = I;
@@ -1234,6 +1520,10 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         if (cudaLibraryGetKernel(&fp->kernel, fp->lib, "cfr_fused_k") != cudaSuccess) {
             cudaGetLastError();
             return fail(RLP_ERR_CUDA, "generated library has no cfr_fused_k");
+        }
+        if (c.BR_OK && cudaLibraryGetKernel(&fp->br_kernel, fp->lib, "br_fused_k") != cudaSuccess) {
+            cudaGetLastError();
+            return fail(RLP_ERR_CUDA, "generated library has no br_fused_k");
         }
         int dev = 0, sms = 0, per_sm = 0;
         RLP_CUDA(cudaGetDevice(&dev));
@@ -1268,11 +1558,65 @@ int fused_stat(const rlp_tree *t, int which) {
         case 2: return f->n_ugroups[0] + f->n_ugroups[1];
         case 3: return f->grid;
         case 4: return f->num_components;
+        case 5: return f->br_kernel ? 1 : 0;
         default: return -1;
     }
 }
 
 const std::string *fused_source(const rlp_tree *t) { return t->tiles.fused ? &t->tiles.fused->source : nullptr; }
+
+bool fused_br_available(const rlp_cfr *c) {
+    const TileSet &ts = c->tree->tiles;
+    if (!ts.enabled || !ts.fused || !ts.fused->br_kernel) return false;
+    const char *off = getenv("RLP_NO_FUSED_BR");
+    return !(off && off[0] == '1');
+}
+
+// Best responses of BOTH players against sigma_int ([Q], device, internal pair order) in one cooperative launch:
+// values into out2_dev[0..1], chosen actions into c->astar (internal information-set ids).
+int fused_br(rlp_cfr *c, const double *sigma_int, double *out2_dev, cudaStream_t s) {
+    rlp_tree *t = c->tree;
+    FusedPlan &f = *t->tiles.fused;
+    const size_t plane = (size_t)f.NF * (size_t)std::max(1, f.max_act);
+    const size_t reach_n = (size_t)f.kp * (size_t)std::max(f.nug[0], f.nug[1]);
+    const size_t need = plane + 2 * reach_n + 2 * f.pv_len + 2 * (size_t)f.n_top + 8;
+    if (c->br_buf.n < need) RLP_CUDA(c->br_buf.alloc(need));
+    double *base = c->br_buf.p;
+    if (t->I > 0) {
+        k_sigma_fused<<<(unsigned)((t->I + 255) / 256), 256, 0, s>>>(t->I, f.NF, t->col_off.p, f.fid_of_iset.p, sigma_int, base);
+        RLP_LAUNCH_CHECK();
+    }
+    FusedParams hp = f.host;
+    hp.br_sig = base;
+    hp.br_reach1 = base + plane; hp.br_reach2 = hp.br_reach1 + reach_n;
+    hp.br_pv1 = hp.br_reach2 + reach_n; hp.br_pv2 = hp.br_pv1 + f.pv_len;
+    hp.br_top1 = hp.br_pv2 + f.pv_len; hp.br_top2 = hp.br_top1 + f.n_top;
+    hp.br_out = out2_dev; hp.br_astar = c->astar.p;
+    for (;;) {
+        RLP_CUDA(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int) * (32 + 32 * (size_t)f.grid + 1024), s));
+        void *args[] = {&hp};
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)f.grid); cfg.blockDim = dim3((unsigned)f.block); cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)f.br_kernel, args);
+        if (e == cudaErrorCooperativeLaunchTooLarge && f.grid > 1) {
+            cudaGetLastError();
+            int dev = 0, sms = 0;
+            RLP_CUDA(cudaGetDevice(&dev));
+            RLP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            if (f.grid <= sms) return fail(RLP_ERR_CUDA, "cooperative launch of %d CTAs refused", f.grid);
+            f.grid = sms;
+            continue;
+        }
+        if (e != cudaSuccess) return fail(RLP_ERR_CUDA, "launch of the fused best-response kernel: %s", cudaGetErrorString(e));
+        break;
+    }
+    rlp::g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RLP_OK;
+}
 
 // Multi-GPU state of one solver (sharding by public state, see rlp_cfr_p2p_* below).
 struct P2P {

@@ -31,6 +31,8 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream);
 bool fused_available(const rlp_cfr *c);
 int fused_stat(const rlp_tree *t, int which);
 const std::string *fused_source(const rlp_tree *t);
+bool fused_br_available(const rlp_cfr *c);
+int fused_br(rlp_cfr *c, const double *sigma_int, double *out2_dev, cudaStream_t s);
 int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaStream_t s, unsigned long long *tl,
               long long tl_cap);
 

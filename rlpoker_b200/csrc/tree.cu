@@ -86,6 +86,7 @@ extern "C" int64_t rlp_tree_stat(const rlp_tree *t, int which) {
         case 12: return rlp::fused_stat(t, 2);            // its upper groups per iteration
         case 13: return rlp::fused_stat(t, 3);            // its grid (CTAs, all co-resident)
         case 14: return rlp::fused_stat(t, 4);            // public-state components (sharding unit)
+        case 15: return rlp::fused_stat(t, 5);            // group-fused best-response kernel in use
         default: return -1;
     }
 }
@@ -225,6 +226,7 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
     RLP_CUDA(t->iset_size.upload(size_s, stream));
     RLP_CUDA(t->iset_level.upload(level_s, stream));
     RLP_CUDA(t->iset_player.upload(owner_s, stream));
+    t->iset_player_h = owner_s;
     RLP_CUDA(t->col_off.upload(t->col_off_h, stream));
     RLP_CUDA(t->iset_node_off.upload(node_off, stream));
     RLP_CUDA(t->iset_nodes.upload(nodes, stream));

@@ -36,6 +36,7 @@ struct rlp_tree {
     std::vector<int32_t> srank_of_iset;  // canonical -> internal
     std::vector<int64_t> canon_of_col;   // internal pair -> canonical pair
     std::vector<int64_t> col_off_h;      // internal [I+1]
+    std::vector<int8_t> iset_player_h;   // internal [I]: owner of every information set
 
     rlp::DevBuf<int32_t> first_child, colbase, srank, krank;
     rlp::DevBuf<int8_t> player;

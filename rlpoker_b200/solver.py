@@ -80,7 +80,7 @@ class DeviceTree:
     def layout(self):
         names = ['tiled', 'upper_tiles', 'micro_subtrees', 'micro_shapes', 'jit_shapes', 'zero_sum',
                  'largest_infoset', 'tile_block', 'tile_smem', 'upper_jit', 'fused', 'fused_batches',
-                 'fused_upper_groups', 'fused_grid', 'components']
+                 'fused_upper_groups', 'fused_grid', 'components', 'fused_br']
         return {n: int(_lib.load().rlp_tree_stat(self.handle, i)) for i, n in enumerate(names)}
 
     def best_response(self, sigma, player, want_argmax=False, stream=None):
