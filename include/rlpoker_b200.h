@@ -128,6 +128,20 @@ int rlp_cfr_vanilla_iters(rlp_cfr *cfr, int64_t t0, int64_t n_iters, int linear_
 int rlp_cfr_sampled_iters(rlp_cfr *cfr, int variant, int64_t lanes, uint64_t seed, int64_t t0,
                           int64_t n_iters, int linear_weight, void *stream);
 
+/*
+ * Sampled lanes sharded over ranks (every rank holds the whole tree and identical state).  Per iteration:
+ * rlp_cfr_sampled_local runs lanes [lane_base, lane_base + lanes) of the iteration -- the Philox counter carries the
+ * global lane id, so the draws do not depend on how the lanes are split -- into the zeroed delta buffer
+ * (rlp_cfr_delta_ptr: [2Q] doubles, regret deltas | sum deltas, internal pair order = the same on every rank) and sets
+ * the dict-membership flags (rlp_cfr_flags_ptr: [3 I] bytes); the caller sum-all-reduces the delta and max-all-reduces the
+ * flags (NCCL); rlp_cfr_sampled_finish adds the delta, runs regret matching and, for external sampling, the
+ * average-strategy walk.  rlp_nodes_touched counts this rank's lanes only.
+ */
+int rlp_cfr_sampled_local(rlp_cfr *cfr, int variant, int64_t lane_base, int64_t lanes, uint64_t seed, int64_t t,
+                          int linear_weight, void *stream);
+int rlp_cfr_sampled_finish(rlp_cfr *cfr, int variant, void *stream);
+void *rlp_cfr_flags_ptr(rlp_cfr *cfr);
+
 /* AverageStrategy update with the solver's current strategy (cfr_util.py:109-198): full-tree walk, pruned
  * below information sets that have no strategy entry; alpha lives in the RLP_STRAT_SUM array. */
 int rlp_cfr_update_average(rlp_cfr *cfr, double weight, void *stream);

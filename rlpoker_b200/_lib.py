@@ -53,6 +53,9 @@ SYMBOLS = {
     'rlp_cfr_reset': (C.c_int, [_vp, _vp]),
     'rlp_cfr_vanilla_iters': (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, _vp]),
     'rlp_cfr_sampled_iters': (C.c_int, [_vp, C.c_int, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int, _vp]),
+    'rlp_cfr_sampled_local': (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int, _vp]),
+    'rlp_cfr_sampled_finish': (C.c_int, [_vp, C.c_int, _vp]),
+    'rlp_cfr_flags_ptr': (_vp, [_vp]),
     'rlp_cfr_update_average': (C.c_int, [_vp, C.c_double, _vp]),
     'rlp_cfr_read': (C.c_int, [_vp, C.c_int, _dp, _vp]),
     'rlp_cfr_write': (C.c_int, [_vp, C.c_int, _dp, _vp]),

@@ -80,6 +80,8 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(double *, br_top1) X(double *, br_top2)                 /* values of the trunk nodes and tile roots, by node id */ \
     X(double *, br_out) X(int *, br_astar)                    /* {BR1, BR2}; chosen action per internal information set */ \
     X(const int *, tile_root) X(const int *, g_first_child) X(const signed char *, g_player) X(long long, n_top)       \
+    X(long long, n_tl) X(long long, tl0) X(long long, tl1) X(long long, tl2) X(long long, tl3) X(long long, tl4)       \
+    X(long long, tl5) X(long long, tl6) X(long long, tl7) X(long long, tl8) /* node ranges of the top levels */        \
     X(long long, num_isets) X(long long, first_group0) X(long long, end_group0) X(long long, first_group1)          \
     X(long long, end_group1) X(long long, tl_cap)
 
@@ -469,8 +471,12 @@ void gen_upper_br(std::ostringstream &o, const Shape &s, const Consts &c, int pl
          "    const int k0 = fd[4 * f], nch = fd[4 * f + 1];\n"
          "    const double* pv = pvl + (long long)sm_ut[mm] * " << c.KP << "LL + k0;\n"
          "    double acc = 0.0;\n"
-         "    for (int ch = 0; ch < nch; ++ch) acc = acc + __ldcg(pv + ch);\n"
-         "    sm_fan[x] = acc;\n"
+      << (c.NCH > 0 && c.NCH <= 32
+              ? "    double vv[" + std::to_string(c.NCH) + "];\n#pragma unroll\n    for (int ch = 0; ch < " + std::to_string(c.NCH) +
+                    "; ++ch) vv[ch] = __ldcg(pv + ch);\n#pragma unroll\n    for (int ch = 0; ch < " + std::to_string(c.NCH) +
+                    "; ++ch) acc = acc + vv[ch];\n    (void)nch;\n"
+              : std::string("    for (int ch = 0; ch < nch; ++ch) acc = acc + __ldcg(pv + ch);\n"))
+      << "    sm_fan[x] = acc;\n"
          "  }\n"
          "  __syncthreads();\n"
          "  const bool act = tid < " << GB << ";\n"
@@ -592,15 +598,29 @@ void gen_br_kernel(std::ostringstream &o, const Shape &s, const Consts &c) {
          "  }\n"
          "  grid_barrier(P->bar, ++nbar, nb);\n"
          "  // phase 3: the all-chance trunk above the tiles, children in order (one thread per responder)\n"
-         "  if (blockIdx.x < 2 && tid == 0) {\n"
+         "  if (blockIdx.x < 2) {\n"
          "    double* val = blockIdx.x == 0 ? P->br_top1 : P->br_top2;\n"
-         "    for (long long node = P->n_top - 1; node >= 0; --node) {\n"
-         "      if (P->g_player[node] != 0) continue;\n"
-         "      double acc = 0.0;\n"
-         "      for (int ch = P->g_first_child[node]; ch < P->g_first_child[node + 1]; ++ch) acc = acc + __ldcg(val + ch);\n"
-         "      val[node] = acc;\n"
+         "    const long long* lv = &P->tl0;\n"
+         "    for (int l = (int)P->n_tl - 1; l >= 0; --l) {          // one thread per trunk node of the level\n"
+         "      const long long hi = lv[l + 1] < P->n_top ? lv[l + 1] : P->n_top;\n"
+         "      for (long long node = lv[l] + tid; node < hi; node += BLOCK) {\n"
+         "        if (P->g_player[node] != 0) continue;\n"
+         "        double acc = 0.0;\n"
+         "        const int c0 = P->g_first_child[node], c1 = P->g_first_child[node + 1];\n"
+         "        int ch = c0;\n"
+         "        for (; ch + 8 <= c1; ch += 8) {\n"
+         "          double vv[8];\n"
+         "#pragma unroll\n"
+         "          for (int q = 0; q < 8; ++q) vv[q] = __ldcg(val + ch + q);\n"
+         "#pragma unroll\n"
+         "          for (int q = 0; q < 8; ++q) acc = acc + vv[q];\n"
+         "        }\n"
+         "        for (; ch < c1; ++ch) acc = acc + __ldcg(val + ch);\n"
+         "        val[node] = acc;\n"
+         "      }\n"
+         "      __syncthreads();\n"
          "    }\n"
-         "    P->br_out[blockIdx.x] = __ldcg(val);\n"
+         "    if (tid == 0) P->br_out[blockIdx.x] = __ldcg(val);\n"
          "  }\n"
          "}\n";
 }
@@ -1370,6 +1390,9 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
                 if (d->player[v] != 0 || fc[v + 1] > n_top) ok = false;          // a trunk node: chance, children on top
             }
         }
+        int n_tl = 0;
+        while (n_tl < t->L && t->level_off[n_tl] < n_top) ++n_tl;         // levels that hold top nodes
+        if (n_tl > 8) ok = false;
         const size_t q_team = std::max(s.dec[0].size(), s.dec[1].size()) * (size_t)c.MAXA * (c.TEAM + 1);
         const size_t q_up = std::max(s.udec[0].size() * c.GB[0], s.udec[1].size() * c.GB[1]) * (size_t)c.MAXA;
         const size_t br_smem = 8 * (std::max((size_t)(blk / c.TEAM) * q_team, q_up) + (size_t)std::max(c.GB[0], c.GB[1]) * std::max(1, c.F) + 16) + 4 * (size_t)c.UT_N;
@@ -1511,6 +1534,13 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr; h.own_idx = nullptr; h.n_own = 0; h.xdebug = 0;
     h.tile_root = fp->tile_root.p; h.g_first_child = t->first_child.p; h.g_player = reinterpret_cast<const signed char *>(t->player.p);
     h.n_top = n_top;
+    {
+        long long *lv = &h.tl0;
+        int n_tl = 0;
+        while (n_tl < t->L && n_tl < 8 && t->level_off[n_tl] < n_top) { lv[n_tl] = t->level_off[n_tl]; ++n_tl; }
+        lv[n_tl] = n_tl < t->L ? t->level_off[n_tl] : n_top;
+        h.n_tl = n_tl;
+    }
     fp->pv_len = (size_t)T * (size_t)cx.kp;
     h.bar = fp->bar.p; h.tl = nullptr; h.tl_cap = 0;
     h.num_isets = I;

@@ -64,12 +64,17 @@ __device__ inline int draw(const double *p, int n, double u) {
     return idx < n ? idx : n - 1;
 }
 
+// One stack frame of the depth-first walk.  External sampling needs no reach probabilities (its regret increment is
+// unweighted, external_cfr.py:143-152), and the action-value array is as wide as the game's widest information set: the
+// per-thread stack is what limits this kernel (it lives in local memory), so it is kept as small as the game allows
+// (Leduc external: 16 frames x 48 B instead of 32 x 104 B).
+template <int VARIANT, int MAXA>
 struct Frame {
     int node;
     int k;            // next child to visit
     double value;     // running expectation
-    double pc, p1, p2;
-    double va[kMaxAct];
+    double va[MAXA];
+    double reach[VARIANT == 0 ? 3 : 1];     // chance-sampled: pc, p1, p2
 };
 
 __device__ inline void add(double *p, double x, int atomic) {
@@ -77,24 +82,26 @@ __device__ inline void add(double *p, double x, int atomic) {
 }
 
 // variant 0: chance-sampled CFR (cfr.py:158-255); variant 1: external sampling (external_cfr.py:82-173)
-template <int VARIANT>
-__global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes) {
+template <int VARIANT, int MAXA, int DEPTH>
+__global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int64_t lane_base) {
     int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (tid >= 2 * lanes) return;
-    const uint32_t lane = (uint32_t)(tid >> 1);
+    const uint32_t lane = (uint32_t)((tid >> 1) + lane_base);     // global lane id: results do not depend on the sharding
     const int me = (int)(tid & 1) + 1;                  // traversing player
     const uint64_t iteration = (uint64_t)v.iter->t;
     const double w = v.iter->linear ? (double)v.iter->t : 1.0;
     uint32_t ndraw = 0;
     unsigned long long touched = 0;
-    Frame st[kMaxDepth];
+    typedef Frame<VARIANT, MAXA> F;
+    F st[DEPTH];
     int sp = 0;
-    st[0].node = 0; st[0].k = 0; st[0].value = 0.0; st[0].pc = 1.0; st[0].p1 = 1.0; st[0].p2 = 1.0;
+    st[0].node = 0; st[0].k = 0; st[0].value = 0.0;
+    if (VARIANT == 0) { st[0].reach[0] = 1.0; st[0].reach[1] = 1.0; st[0].reach[2] = 1.0; }
     touched++;
     double ret = 0.0;      // value returned by the frame that just finished
     bool have_ret = false;
     while (sp >= 0) {
-        Frame &f = st[sp];
+        F &f = st[sp];
         const int node = f.node;
         const int pl = v.player[node];
         if (pl < 0) {                                   // terminal: utility of the traverser
@@ -110,8 +117,9 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes) {
             if (have_ret) { --sp; continue; }           // the sampled child returned: pass its value up unchanged
             const double *p = pl == 0 ? v.cprob + fc : v.sigma + v.colbase[node];
             int a = draw(p, n, rlp::philox_uniform(v.seed, iteration, lane, (uint32_t)(me - 1), ndraw++));
-            Frame &c = st[sp + 1];
-            c.node = fc + a; c.k = 0; c.value = 0.0; c.pc = f.pc; c.p1 = f.p1; c.p2 = f.p2;
+            F &c = st[sp + 1];
+            c.node = fc + a; c.k = 0; c.value = 0.0;
+            if (VARIANT == 0) { c.reach[0] = f.reach[0]; c.reach[1] = f.reach[1]; c.reach[2] = f.reach[2]; }
             ++sp; touched++;
             continue;
         }
@@ -125,11 +133,13 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes) {
         }
         if (f.k < n) {
             int a = f.k++;
-            Frame &c = st[sp + 1];
+            F &c = st[sp + 1];
             c.node = fc + a; c.k = 0; c.value = 0.0;
-            c.pc = f.pc;
-            c.p1 = (VARIANT == 0 && pl == 1) ? sg[a] * f.p1 : f.p1;
-            c.p2 = (VARIANT == 0 && pl == 2) ? sg[a] * f.p2 : f.p2;
+            if (VARIANT == 0) {
+                c.reach[0] = f.reach[0];
+                c.reach[1] = pl == 1 ? sg[a] * f.reach[1] : f.reach[1];
+                c.reach[2] = pl == 2 ? sg[a] * f.reach[2] : f.reach[2];
+            }
             ++sp; touched++;
             continue;
         }
@@ -138,8 +148,8 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes) {
         if (VARIANT == 0) {
             v.in_R[s] = 1;
             if (pl == me) {
-                double pi_minus = me == 2 ? f.pc * f.p1 : f.pc * f.p2;
-                double pi_own = me == 1 ? f.p1 : f.p2;
+                double pi_minus = me == 2 ? f.reach[0] * f.reach[1] : f.reach[0] * f.reach[2];
+                double pi_own = me == 1 ? f.reach[1] : f.reach[2];
                 double *R = v.R + v.colbase[node], *S = v.S + v.colbase[node];
                 for (int a = 0; a < n; ++a) {
                     add(R + a, w * (f.va[a] - f.value) * pi_minus, v.atomic);
@@ -260,31 +270,62 @@ extern "C" int rlp_cfr_update_average(rlp_cfr *c, double weight, void *stream_) 
     return rlp::launch_average_walk(c, weight, (cudaStream_t)stream_);
 }
 
-extern "C" int rlp_cfr_sampled_iters(rlp_cfr *c, int variant, int64_t lanes, uint64_t seed, int64_t t0, int64_t n_iters,
-                                     int linear_weight, void *stream_) {
-    if (!c || lanes < 1 || n_iters < 0) return fail(RLP_ERR_INVALID, "bad argument");
+namespace {
+// Pick the smallest frame layout the game fits (the stack is per thread, in local memory).
+template <int VARIANT>
+int launch_lanes(const LaneView &v, rlp_tree *t, int64_t lanes, int64_t lane_base, cudaStream_t s) {
+    const unsigned g = grid_for(2 * lanes);
+    if (t->max_act <= 4 && t->L <= 16) k_lanes<VARIANT, 4, 16><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
+    else if (t->max_act <= 4) k_lanes<VARIANT, 4, kMaxDepth><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
+    else k_lanes<VARIANT, kMaxAct, kMaxDepth><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
+    RLP_LAUNCH_CHECK();
+    return RLP_OK;
+}
+
+int check_lanes(rlp_cfr *c, int variant, int64_t lanes) {
     if (variant != RLP_CHANCE_SAMPLED && variant != RLP_EXTERNAL_SAMPLED) return fail(RLP_ERR_INVALID, "variant %d", variant);
     rlp_tree *t = c->tree;
     if (t->L > kMaxDepth) return fail(RLP_ERR_UNSUPPORTED, "tree deeper than %d levels", kMaxDepth);
     if (t->max_act > kMaxAct) return fail(RLP_ERR_UNSUPPORTED, "more than %d actions in an information set", kMaxAct);
     if (t->max_chance > kMaxChance) return fail(RLP_ERR_UNSUPPORTED, "chance node wider than %d", kMaxChance);
     if (lanes > (int64_t)1 << 31) return fail(RLP_ERR_INVALID, "too many lanes");
-    cudaStream_t s = (cudaStream_t)stream_;
+    return RLP_OK;
+}
+
+LaneView lane_view(rlp_cfr *c, uint64_t seed, double *R, double *S, int atomic) {
+    rlp_tree *t = c->tree;
     LaneView v;
     v.first_child = t->first_child.p; v.colbase = t->colbase.p; v.srank = t->srank.p; v.player = t->player.p;
-    v.cprob = t->cprob.p; v.pay1 = t->pay1.p; v.pay2 = t->pay2.p; v.sigma = c->sigma.p; v.R = c->R.p; v.S = c->S.p;
+    v.cprob = t->cprob.p; v.pay1 = t->pay1.p; v.pay2 = t->pay2.p; v.sigma = c->sigma.p; v.R = R; v.S = S;
     v.in_R = c->flags.p; v.in_S = c->flags.p + (size_t)t->I; v.in_next = c->flags.p + 2 * (size_t)t->I;
-    v.iter = c->iter.p; v.seed = seed; v.zero_sum = t->zero_sum ? 1 : 0; v.atomic = lanes > 1;
+    v.iter = c->iter.p; v.seed = seed; v.zero_sum = t->zero_sum ? 1 : 0; v.atomic = atomic;
+    return v;
+}
+
+__global__ void __launch_bounds__(kBlock) k_add_delta(int64_t Q, const double *__restrict__ delta, double *R, double *S) {
+    int64_t q = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (q >= Q) return;
+    R[q] = R[q] + delta[q];
+    S[q] = S[q] + delta[Q + q];
+}
+}  // namespace
+
+extern "C" int rlp_cfr_sampled_iters(rlp_cfr *c, int variant, int64_t lanes, uint64_t seed, int64_t t0, int64_t n_iters,
+                                     int linear_weight, void *stream_) {
+    if (!c || lanes < 1 || n_iters < 0) return fail(RLP_ERR_INVALID, "bad argument");
+    { int rc = check_lanes(c, variant, lanes); if (rc) return rc; }
+    rlp_tree *t = c->tree;
+    cudaStream_t s = (cudaStream_t)stream_;
+    LaneView v = lane_view(c, seed, c->R.p, c->S.p, lanes > 1);
     k_set_iter2<<<1, 1, 0, s>>>(c->iter.p, (long long)t0, linear_weight);     // keeps the running touched count
     RLP_LAUNCH_CHECK();
     if (variant == RLP_EXTERNAL_SAMPLED) c->external_state = true;
     for (int64_t it = 0; it < n_iters; ++it) {
-        if (variant == RLP_CHANCE_SAMPLED) k_lanes<0><<<grid_for(2 * lanes), kBlock, 0, s>>>(v, lanes);
-        else k_lanes<1><<<grid_for(2 * lanes), kBlock, 0, s>>>(v, lanes);
-        RLP_LAUNCH_CHECK();
+        int rc = variant == RLP_CHANCE_SAMPLED ? launch_lanes<0>(v, t, lanes, 0, s) : launch_lanes<1>(v, t, lanes, 0, s);
+        if (rc) return rc;
         if (t->I > 0) { k_rm_all<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->R.p, c->sigma.p, c->iter.p); RLP_LAUNCH_CHECK(); }
         if (variant == RLP_EXTERNAL_SAMPLED) {
-            int rc = rlp::launch_average_walk(c, 1.0, s);
+            rc = rlp::launch_average_walk(c, 1.0, s);
             if (rc) return rc;
         }
     }
@@ -294,3 +335,48 @@ extern "C" int rlp_cfr_sampled_iters(rlp_cfr *c, int variant, int64_t lanes, uin
     c->dev_t = -1;
     return RLP_OK;
 }
+
+// ---- sampled lanes sharded over ranks ("shard lanes"; one exchange per iteration) -----------------------------
+// Every rank holds the full tree and identical regrets / sums / strategy.  Per iteration: rlp_cfr_sampled_local runs
+// this rank's lanes [lane_base, lane_base + lanes) -- the Philox counter carries the GLOBAL lane id, so the draws do not
+// depend on the number of ranks -- into the zeroed [2Q] delta buffer (rlp_cfr_delta_ptr: regret deltas | sum deltas,
+// internal pair order, the same on every rank) and sets the dict-membership flags (rlp_cfr_flags_ptr, [3 I] bytes);
+// the caller sum-all-reduces the delta and max-all-reduces the flags; rlp_cfr_sampled_finish adds the delta, runs regret
+// matching and, for external sampling, the average-strategy walk (replicated).
+extern "C" int rlp_cfr_sampled_local(rlp_cfr *c, int variant, int64_t lane_base, int64_t lanes, uint64_t seed, int64_t t,
+                                     int linear_weight, void *stream_) {
+    if (!c || lanes < 0 || lane_base < 0) return fail(RLP_ERR_INVALID, "bad argument");
+    { int rc = check_lanes(c, variant, lane_base + lanes); if (rc) return rc; }
+    rlp_tree *tr = c->tree;
+    cudaStream_t s = (cudaStream_t)stream_;
+    RLP_CUDA(cudaMemsetAsync(c->delta.p, 0, c->delta.bytes(), s));
+    k_set_iter2<<<1, 1, 0, s>>>(c->iter.p, (long long)t, linear_weight);
+    RLP_LAUNCH_CHECK();
+    if (lanes > 0) {
+        LaneView v = lane_view(c, seed, c->delta.p, c->delta.p + tr->Q, 1);
+        int rc = variant == RLP_CHANCE_SAMPLED ? launch_lanes<0>(v, tr, lanes, lane_base, s) : launch_lanes<1>(v, tr, lanes, lane_base, s);
+        if (rc) return rc;
+    }
+    c->touched_dirty = true;
+    return RLP_OK;
+}
+
+extern "C" int rlp_cfr_sampled_finish(rlp_cfr *c, int variant, void *stream_) {
+    if (!c) return fail(RLP_ERR_INVALID, "null solver");
+    if (variant != RLP_CHANCE_SAMPLED && variant != RLP_EXTERNAL_SAMPLED) return fail(RLP_ERR_INVALID, "variant %d", variant);
+    rlp_tree *t = c->tree;
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (t->Q > 0) { k_add_delta<<<grid_for(t->Q), kBlock, 0, s>>>(t->Q, c->delta.p, c->R.p, c->S.p); RLP_LAUNCH_CHECK(); }
+    if (t->I > 0) { k_rm_all<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->R.p, c->sigma.p, c->iter.p); RLP_LAUNCH_CHECK(); }
+    if (variant == RLP_EXTERNAL_SAMPLED) {
+        c->external_state = true;
+        int rc = rlp::launch_average_walk(c, 1.0, s);
+        if (rc) return rc;
+    }
+    c->sigma_am_dirty = true;
+    c->sigF_dirty = true;
+    c->dev_t = -1;
+    return RLP_OK;
+}
+
+extern "C" void *rlp_cfr_flags_ptr(rlp_cfr *c) { return c ? (void *)c->flags.p : nullptr; }

@@ -361,3 +361,72 @@ class PublicStateShardedCFR:
         tree, self.tree = self.tree, None
         if tree is not None:
             tree.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# sampled variants: lanes sharded over ranks
+
+
+class _DeviceBytes:
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {'shape': (count,), 'typestr': '|u1', 'data': (int(ptr), False), 'version': 2}
+
+
+class ShardedSampledCFR:
+    """Chance-sampled / external-sampling CFR with the traversal LANES of every iteration split over the ranks
+    (SURVEY 8e).  Every rank holds the whole tree and identical regrets / sums / strategy; lane ``l`` draws from the
+    Philox stream keyed by its GLOBAL id, so the result does not depend on the number of ranks (up to the order in
+    which the floating-point atomics add).  One exchange per iteration: a sum-all-reduce of the [2Q] deltas and a
+    max-all-reduce of the dict-membership flags (NCCL)."""
+
+    def __init__(self, flat_tree, rank, world, group=None, stream=None):
+        import torch
+        from rlpoker_b200 import _lib
+        from rlpoker_b200.solver import DeviceCFR, DeviceTree
+        self.rank, self.world, self.group = rank, world, group
+        self.full = flat_tree
+        self.tree = DeviceTree(flat_tree, stream=stream)
+        self.solver = DeviceCFR(self.tree, stream=stream)
+        lib = _lib.load()
+        self.delta = torch.as_tensor(_DeviceArray(lib.rlp_cfr_delta_ptr(self.solver.handle), 2 * flat_tree.num_pairs),
+                                     device='cuda')
+        self.flags = torch.as_tensor(_DeviceBytes(lib.rlp_cfr_flags_ptr(self.solver.handle), 3 * flat_tree.num_infosets),
+                                     device='cuda')
+
+    @staticmethod
+    def lane_range(lanes, rank, world):
+        """[lo, hi) of the ``lanes`` global lane ids that belong to ``rank``: contiguous, sizes differ by at most one."""
+        return lanes * rank // world, lanes * (rank + 1) // world
+
+    def iterate(self, variant, n_iters, lanes, seed=0, linear_weight=False):
+        import torch.distributed as dist
+        from rlpoker_b200 import _lib
+        from rlpoker_b200.solver import _stream_ptr
+        lib = _lib.load()
+        lo, hi = self.lane_range(int(lanes), self.rank, self.world)
+        for _ in range(int(n_iters)):
+            _lib.check(lib.rlp_cfr_sampled_local(self.solver.handle, int(variant), lo, hi - lo, int(seed), self.solver.t,
+                                                 int(bool(linear_weight)), _stream_ptr(None)))
+            if self.world > 1:
+                dist.all_reduce(self.delta, op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(self.flags, op=dist.ReduceOp.MAX, group=self.group)
+            _lib.check(lib.rlp_cfr_sampled_finish(self.solver.handle, int(variant), _stream_ptr(None)))
+            self.solver.t += 1
+
+    def nodes_touched(self):
+        """Sum over the ranks of the nodes their lanes visited."""
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([self.solver.nodes_touched], dtype=torch.int64, device='cuda')
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def close(self):
+        self.delta = self.flags = None
+        solver, self.solver = self.solver, None
+        if solver is not None:
+            solver.close()
+        tree, self.tree = self.tree, None
+        if tree is not None:
+            tree.close()

@@ -47,3 +47,12 @@ def test_public_state_sharding_world_one():
     """The same code path with a single rank (no peers): the group ranges, the owned mask and the merge."""
     out = _torchrun(1, 'p2p_sharded_worker.py', [3])
     assert 'p2p sharded ok' in out
+
+
+def test_sampled_lanes_world_one_and_two():
+    """Lane sharding of both sampled variants: one rank always, two ranks when the box has them."""
+    out = _torchrun(1, 'sampled_sharded_worker.py', [])
+    assert 'sampled sharded ok: world=1' in out
+    if _gpus() >= 2:
+        out = _torchrun(2, 'sampled_sharded_worker.py', [])
+        assert 'sampled sharded ok: world=2' in out

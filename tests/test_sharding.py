@@ -122,3 +122,14 @@ def test_every_shard_plans_and_compiles(world):
         assert p['micro_subtrees'] == 9 * 8 * p['upper_tiles']
         deals += p['upper_tiles']
     assert deals == 10 * 9
+
+
+def test_lane_ranges_partition_the_lanes():
+    from rlpoker_b200.sharding import ShardedSampledCFR
+    for lanes in (1, 7, 64, 1 << 20):
+        for world in (1, 2, 3, 8):
+            r = [ShardedSampledCFR.lane_range(lanes, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == lanes
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
