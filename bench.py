@@ -414,8 +414,16 @@ def main():
 
     # ---- the public Python API, wall clock (cfr() as a user calls it, FlatGame = no node objects) -----------
     e2e_api = None
-    if world == 1 and not args.no_extras:
-        e2e_api = time_python_api(ft, N)
+    extra = None
+    if not args.no_extras:
+        # free the Leduc-13 solver first: the extras build their own trees (Leduc-25 needs ~3 GB)
+        if world == 1:
+            e2e_api = time_python_api(ft, N)
+        extra = {}
+        if world == 1:
+            extra['br_sweep'] = br_sweep()
+            extra['config3'] = sampled_config3()
+        extra['leduc25'] = leduc25(rank, world, public)
 
     # ---- report -------------------------------------------------------------------------------------------
     if rank == 0:
@@ -444,6 +452,7 @@ def main():
                                 'max': max(e2e_rep)} if e2e_rep else None),
                     'path': 'C ABI with pinned host buffers: rlp_cfr_write x2 -> rlp_cfr_vanilla_iters -> rlp_cfr_read'},
             'e2e_api': e2e_api,
+            'extra': extra,
             'gpu_launches': int(launches),
             'clocks': clocks,
             'parity': parity,
@@ -458,6 +467,10 @@ def main():
                                               'reference algorithm, oracle/cfr_oracle.c)' % (nN, dN, threads),
                                     'single_thread_value': v1}
         print(json.dumps(line))
+        l25 = (extra or {}).get('leduc25') or {}
+        if l25.get('parity') is not None and not l25['parity']['bit_exact']:
+            parity['ok'] = False
+            parity['leduc25_failed'] = True
         if not parity['ok']:
             sys.stderr.write('bench.py: PARITY FAILED: %s\n' % json.dumps(parity))
             sys.stderr.flush()
@@ -496,6 +509,125 @@ def roofline_block(ft, layout, stages, fused, world, bytes_iter, iter_ms, achiev
                   'note': 'algorithmic bytes = SURVEY 8d formula (level sweep with reach/value arrays in HBM); the tiled '
                           'sweep keeps those on chip, so DRAM traffic (ncu) is ~4x lower than the formula'})
     return r
+
+
+def br_sweep(ranks=(3, 5, 7, 9, 11, 13, 17, 21, 25)):
+    """BASELINE config 5: exploitability (both best responses) of a 10-iteration CFR average on Leduc-n, the device call
+    (rlp_cfr_exploitability: one cooperative launch on the micro / upper groups + the host read-back) timed with CUDA
+    events, the oracle's best response (oracle/cfr_oracle.c, one host thread, recursion over information-set node
+    lists like best_response.py:9-100) timed beside it.  Best response runs as replicas on N > 1."""
+    import torch
+    from oracle import oracle as orc
+    from rlpoker_b200.games.leduc_native import leduc_flat_tree
+    from rlpoker_b200.solver import DeviceCFR, DeviceTree
+    rows = []
+    for n in ranks:
+        ft = leduc_flat_tree(n)
+        dt = DeviceTree(ft)
+        s = DeviceCFR(dt)
+        s.vanilla(10)
+        s.exploitability()
+        torch.cuda.synchronize()
+        reps = 20 if n <= 13 else 5
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            v = s.exploitability()
+        b.record()
+        torch.cuda.synchronize()
+        avg = s.average
+        o = orc.Oracle(orc.leduc_tree(n))
+        t0 = time.perf_counter()
+        want = o.exploitability(avg)
+        cpu_s = time.perf_counter() - t0
+        rows.append({'n': n, 'nodes': ft.num_nodes, 'gpu_us': a.elapsed_time(b) * 1e3 / reps, 'cpu_s': cpu_s, 'cpu_threads': 1,
+                     'exploitability': v[0], 'abs_diff_vs_cpu': abs(v[0] - want), 'fused_br': dt.layout.get('fused_br')})
+        del s, o
+        dt.close()
+    return rows
+
+
+def sampled_config3(lanes=1 << 20):
+    """BASELINE config 3: 2^20 traversal lanes per iteration on Leduc-3 (external sampling; chance sampling beside it)."""
+    import torch
+    from rlpoker_b200.games.leduc_native import leduc_flat_tree
+    from rlpoker_b200.solver import DeviceCFR, DeviceTree
+    dt = DeviceTree(leduc_flat_tree(3))
+    out = {'lanes': lanes, 'game': 'Leduc(get_deck(3, 2))'}
+    for variant, name in ((1, 'external'), (0, 'chance')):
+        s = DeviceCFR(dt)
+        s.sampled(variant, 2, lanes=lanes, seed=1)
+        torch.cuda.synchronize()
+        n0 = s.nodes_touched
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        s.sampled(variant, 4, lanes=lanes, seed=1)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 4
+        out[name] = {'ms_per_iteration': ms, 'node_updates_per_s': (s.nodes_touched - n0) / 4 / (ms * 1e-3)}
+        del s
+    dt.close()
+    return out
+
+
+def leduc25(rank, world, public):
+    """Leduc-25 (24 399 601 nodes): generation, upload, time per iteration on this many GPUs, and bit-exact parity of two
+    more iterations against the oracle (rank 0)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from rlpoker_b200._lib import RLP_REGRET, RLP_STRAT_SUM
+    from rlpoker_b200.games.leduc_native import leduc_flat_tree
+    from rlpoker_b200.solver import DeviceCFR, DeviceTree
+    t0 = time.perf_counter()
+    ft = leduc_flat_tree(25)
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    if world == 1:
+        dt = DeviceTree(ft)
+        core = DeviceCFR(dt)
+        run = core.vanilla
+        sh = None
+    else:
+        if not public:
+            return {'skipped': 'deal sharding is benchmarked on Leduc-13 only'}
+        from rlpoker_b200.sharding import PublicStateShardedCFR
+        sh = PublicStateShardedCFR(ft, rank, world)
+        core, dt, run = sh.solver, sh.tree, sh.iterate
+    torch.cuda.synchronize()
+    upload_s = time.perf_counter() - t0
+    run(10)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        run(10)
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    us_iter = float(ms.item()) * 1e3 / 50
+    core.reset()
+    run(2)
+    torch.cuda.synchronize()
+    if sh is not None:
+        sh.check()
+        got_R, got_S = sh.merged(RLP_REGRET), sh.merged(RLP_STRAT_SUM)
+    else:
+        got_R, got_S = core.read(RLP_REGRET), core.read(RLP_STRAT_SUM)
+    out = {'game': 'Leduc(get_deck(25, 2))', 'nodes': ft.num_nodes, 'infosets': ft.num_infosets, 'generate_s': gen_s,
+           'upload_tile_compile_s': upload_s, 'tree_device_bytes': dt.device_bytes, 'n_gpus': world,
+           'us_per_iteration': us_iter, 'node_updates_per_s': 2.0 * ft.num_nodes / (us_iter * 1e-6), 'layout': dt.layout}
+    if rank == 0:
+        o = oracle_for(ft)
+        o.vanilla_levels(2, threads=os.cpu_count() or 1)
+        out['parity'] = {'iterations': 2, 'bit_exact': bool(np.array_equal(got_R, o.R) and np.array_equal(got_S, o.S)),
+                         'max_abs_regret': float(np.abs(got_R - o.R).max())}
+    return out
 
 
 def time_python_api(ft, N):
