@@ -1381,8 +1381,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     {
         bool ok = true;
         for (size_t j = 0; j < sh.kind.size(); ++j) if (sh.kind[j] == 0) ok = false;
-        std::vector<uint8_t> is_root(d->num_nodes < (1 << 24) ? (size_t)d->num_nodes : 0, 0);
-        if (is_root.empty()) ok = false;
+        std::vector<uint8_t> is_root((size_t)d->num_nodes, 0);
         if (ok) {
             for (int64_t k = 0; k < T; ++k) { n_top = std::max<long long>(n_top, (*cx.desc)[k].root_global + 1); is_root[(*cx.desc)[k].root_global] = 1; }
             for (long long v = 0; v < n_top && ok; ++v) {
