@@ -206,18 +206,32 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
     for (size_t j = 0; j < s.dec[pl].size(); ++j) own_j[s.dec[pl][j]] = (int)j;
     for (size_t j = 0; j < s.dec[opp].size(); ++j) opp_j[s.dec[opp][j]] = (int)j;
     Terms t = micro_terms(s, pl);
-    o << "__device__ __forceinline__ void micro_eval" << pl << "(const FusedParams* __restrict__ P, long long g, int k, int tix, double w,\n"
-         "    const double* sig_in, double* sm_r, double* sm_o, int par) {\n"
-         "  const long long slot = g * " << c.G[pl] << " + k;\n"
-         "  const int pat = P->mem_pat" << pl << "[slot], ri = P->mem_ridx" << pl << "[slot], ro = P->grp_ridx" << pl << "[g];\n"
-         "  const double pcv = P->mem_pc" << pl << "[slot];\n";
-    if (pl == 0) o << "  const int pi = P->mem_pidx0[slot];\n";
+    // Static per-subtree / per-group indices: fetched one unit AHEAD by the caller (MIds), so the strategy and reach loads
+    // below can issue as soon as the unit starts.
+    o << "__device__ __forceinline__ MIds micro_ids" << pl << "(const FusedParams* __restrict__ P, long long g, int k, bool ok,\n"
+         "    long long ag, int aj, bool acc) {\n"
+         "  MIds id;\n"
+         "  const long long slot = ok ? g * " << c.G[pl] << " + k : 0;\n"
+         "  const long long gg = ok ? g : 0;\n"
+         "  id.pat = P->mem_pat" << pl << "[slot]; id.ri = P->mem_ridx" << pl << "[slot]; id.ro = P->grp_ridx" << pl << "[gg];\n"
+         "  id.pcv = P->mem_pc" << pl << "[slot];\n"
+         "  id.pi = " << (pl == 0 ? "P->mem_pidx0[slot]" : "0") << ";\n";
     for (int r = 0; r < n_nt; ++r) {
         if (own_j[r] >= 0)
-            o << "  const int f" << r << " = P->grp_fid" << pl << "[g * " << s.dec[pl].size() << " + " << own_j[r] << "];\n";
+            o << "  id.f[" << r << "] = P->grp_fid" << pl << "[gg * " << s.dec[pl].size() << " + " << own_j[r] << "];\n";
         else
-            o << "  const int f" << r << " = P->mem_opp" << pl << "[" << opp_j[r] << "LL * " << c.NS[pl] << "LL + slot];\n";
+            o << "  id.f[" << r << "] = P->mem_opp" << pl << "[" << opp_j[r] << "LL * " << c.NS[pl] << "LL + slot];\n";
     }
+    o << "  const long long agg = acc ? ag : 0;\n"
+         "  id.acol = P->grp_col" << pl << "[agg * " << s.dec[pl].size() << " + aj];\n"
+         "  id.afid = P->grp_fid" << pl << "[agg * " << s.dec[pl].size() << " + aj];\n"
+         "  return id;\n}\n";
+    o << "__device__ __forceinline__ void micro_eval" << pl << "(const FusedParams* __restrict__ P, const MIds& id, int tix, double w,\n"
+         "    const double* sig_in, double* sm_r, double* sm_o, int par) {\n"
+         "  const int pat = id.pat, ri = id.ri, ro = id.ro;\n"
+         "  const double pcv = id.pcv;\n";
+    if (pl == 0) o << "  const int pi = id.pi;\n";
+    for (int r = 0; r < n_nt; ++r) o << "  const int f" << r << " = id.f[" << r << "];\n";
     if (c.PAY8) {           // one or two 16-byte loads fetch all leaf payoffs of the subtree's pattern (exact: small integers)
         o << "  const int4* pp = reinterpret_cast<const int4*>(P->paytab8 + (long long)pat * " << c.PAYROW << ");\n";
         for (int q = 0; q < c.PAYROW / 16; ++q) o << "  const int4 pw" << q << " = __ldg(pp + " << q << ");\n";
@@ -741,6 +755,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
         for (size_t f = 0; f < c.fan_cps.size(); ++f) o << (f ? "," : "") << c.fan_cps[f];
         o << "};\n";
     }
+    o << "struct MIds { int pat, ri, ro, pi, acol, afid; double pcv; int f[" << (int)s.tm->n_nt << "]; };\n";
     for (int pl = 0; pl < 2; ++pl) {
         Terms mt = micro_terms(s, pl), ut = upper_terms(s, pl);
         emit_table(o, "MCJ", pl, mt.cj); emit_table(o, "MCA", pl, mt.ca); emit_table(o, "MCOFF", pl, mt.coff); emit_table(o, "MNA", pl, mt.na);
@@ -755,13 +770,25 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
         const int G = c.G[pl], GPC = c.GPC[pl], KR = mt.kr, MO = (int)s.dec[pl].size();
         const int GPT = GPC;                            // groups per team
         const std::string gfirst = "P->first_group" + std::to_string(pl), gend = "P->end_group" + std::to_string(pl);
-        o << "__device__ __forceinline__ void micro_unit" << pl << "(const FusedParams* __restrict__ P, long long unit, double w, const double* sig_in,\n"
-             "    double* sig_out, double* sm_r, double* sm_o, double* sm_rn, int par) {\n"
+        const bool one_pass = GPT * KR <= c.TEAM;      // every (set, action) of the unit has its own thread
+        // the static indices of a unit (fetched one unit ahead by the phase loop)
+        o << "__device__ __forceinline__ MIds micro_unit_ids" << pl << "(const FusedParams* __restrict__ P, long long unit) {\n"
              "  const int tix = threadIdx.x % TEAM;\n"
              "  const int gl = tix / " << G << ", k = tix - gl * " << G << ";\n"
              "  const long long g0 = " << gfirst << " + unit * " << GPT << ", gend = " << gend << ";\n"
              "  const long long g = g0 + gl;\n";
-        const bool one_pass = GPT * KR <= c.TEAM;      // every (set, action) of the unit has its own thread
+        if (one_pass)
+            o << "  const int agl = tix / " << KR << ", ci = tix - agl * " << KR << ";\n"
+                 "  const bool acc = tix < " << GPT * KR << " && g0 + agl < gend;\n"
+                 "  return micro_ids" << pl << "(P, g, k, gl < " << GPT << " && g < gend, g0 + agl, acc ? MCJ" << pl << "[ci] : 0, acc);\n}\n";
+        else
+            o << "  return micro_ids" << pl << "(P, g, k, gl < " << GPT << " && g < gend, 0, 0, false);\n}\n";
+        o << "__device__ __forceinline__ void micro_unit" << pl << "(const FusedParams* __restrict__ P, long long unit, const MIds& id, double w, const double* sig_in,\n"
+             "    double* sig_out, double* sm_r, double* sm_o, double* sm_rn, int par) {\n"
+             "  const int tix = threadIdx.x % TEAM;\n"
+             "  const int gl = tix / " << G << ";\n"
+             "  const long long g0 = " << gfirst << " + unit * " << GPT << ", gend = " << gend << ";\n"
+             "  const long long g = g0 + gl;\n";
         if (one_pass) {
             // the accumulating threads fetch regret, action count and strategy BEFORE the evaluation, so those loads
             // overlap it instead of sitting behind the team barrier
@@ -772,12 +799,12 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "  double r = 0.0, sa = 0.0, sg = 0.0;\n"
                  "  if (acc) {\n"
                  "    j = MCJ" << pl << "[ci]; a = MCA" << pl << "[ci];\n"
-                 "    col = P->grp_col" << pl << "[ag * " << MO << " + j] + a;\n"
-                 "    fid = P->grp_fid" << pl << "[ag * " << MO << " + j];\n"
+                 "    col = id.acol + a;\n"
+                 "    fid = id.afid;\n"
                  "    r = __ldcg(P->R + col); sa = __ldcg(P->S + col);\n"
                  "    sg = __ldcg(sig_in + (long long)a * " << c.NF << "LL + fid);\n"
                  "  }\n"
-                 "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, g, k, tix, w, sig_in, sm_r, sm_o, par);\n"
+                 "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, id, tix, w, sig_in, sm_r, sm_o, par);\n"
                  "  TEAM_SYNC();\n"
                  "  if (acc) {\n"
                  "    const double* cr = sm_r + ci * SMS + agl * " << G << ";\n"
@@ -798,7 +825,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "  TEAM_SYNC();\n"
                  "}\n";
         } else {
-            o << "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, g, k, tix, w, sig_in, sm_r, sm_o, par);\n"
+            o << "  if (gl < " << GPT << " && g < gend) micro_eval" << pl << "(P, id, tix, w, sig_in, sm_r, sm_o, par);\n"
                  "  TEAM_SYNC();\n"
                  "  for (int x = tix; x < " << GPT * KR << "; x += TEAM) {\n"
                  "    const int agl = x / " << KR << ", ci = x - agl * " << KR << ";\n"
@@ -886,6 +913,19 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
             // threads of a warp (stride = one fan-in node) hit different banks.
             const int nchunk = (GB + chunk - 1) / chunk;
             const std::string padq = c.NCH > 0 ? " + q / " + std::to_string(c.NCH) : std::string();
+            if (c.KP <= c.BLK && GB <= 32) {
+                // thread = one portal column of the unit: GB coalesced loads per thread, all in flight, no index arithmetic
+                o << "    double fv[" << GB << "];\n"
+                     "    const bool cok = tid < " << c.KP << ";\n"
+                     "    const int dst = tid" << (c.NCH > 0 ? " + tid / " + std::to_string(c.NCH) : std::string()) << ";\n"
+                     "#pragma unroll\n"
+                     "    for (int mm = 0; mm < " << GB << "; ++mm) if (cok) fv[mm] = __ldcg(pvl + (long long)tiles[mm] * " << c.KP << "LL + tid);\n"
+                     "#pragma unroll\n"
+                     "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
+                     "#pragma unroll\n"
+                     "      for (int mm = 0; mm < " << GB << "; ++mm)\n"
+                     "        if (cok && mm / " << chunk << " == c0) sm_r[(mm - c0 * " << chunk << ") * " << pv_pad << " + dst] = fv[mm];\n";
+            } else {
             o << "    double fv[" << NV << "];\n"
                  "#pragma unroll\n"
                  "    for (int i = 0; i < " << NV << "; ++i) {\n"
@@ -899,7 +939,9 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "        const int L = tid + i * BLOCK;\n"
                  "        const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << ";\n"
                  "        if (L < " << total_pv << " && mm / " << chunk << " == c0) sm_r[(mm - c0 * " << chunk << ") * " << pv_pad << " + q" << padq << "] = fv[i];\n"
-                 "      }\n"
+                 "      }\n";
+            }
+            o <<
                  "      __syncthreads();\n"
                  "      const int mc = " << GB << " - c0 * " << chunk << " < " << chunk << " ? " << GB << " - c0 * " << chunk << " : " << chunk << ";\n"
                  "      for (int x = tid; x < mc * " << c.F << "; x += BLOCK) {\n"
@@ -1058,9 +1100,20 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "    const double* pvl = par ? P->pvl1 : P->pvl0;\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase A: micro units of player 1, then of player 2 (one list), one unit per team at a time\n"
-         "    for (long long un = (long long)blockIdx.x * " << NT << " + team; un < nu0 + nu1; un += (long long)nb * " << NT << ") {\n"
-         "      if (un < nu0) micro_unit0(P, un, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
-         "      else micro_unit1(P, un - nu0, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
+         "    {\n"
+         "      const long long stride = (long long)nb * " << NT << ";\n"
+         "      long long un = (long long)blockIdx.x * " << NT << " + team;\n"
+         "      MIds cur;\n"
+         "      if (un < nu0 + nu1) cur = un < nu0 ? micro_unit_ids0(P, un) : micro_unit_ids1(P, un - nu0);\n"
+         "      while (un < nu0 + nu1) {\n"
+         "        const long long nx = un + stride;\n"
+         "        MIds nxt;                    // the next unit's static indices: in flight while this unit runs\n"
+         "        if (nx < nu0 + nu1) nxt = nx < nu0 ? micro_unit_ids0(P, nx) : micro_unit_ids1(P, nx - nu0);\n"
+         "        if (un < nu0) micro_unit0(P, un, cur, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
+         "        else micro_unit1(P, un - nu0, cur, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
+         "        cur = nxt;\n"
+         "        un = nx;\n"
+         "      }\n"
          "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    if (P->nranks > 1) {\n"
