@@ -148,6 +148,7 @@ struct Consts {
     int TEAM;                           // threads that work on one micro unit together: 32 (a warp, __syncwarp) or BLK
     int NPUSH;                          // CTAs that copy this rank's subtree values to the peers (multi-GPU)
     int BR_OK, MAXA;                    // the best-response kernel is generated too; widest decision node
+    int PREFETCH;                       // micro phase: fetch the next unit's static indices while the current one runs
     int G[2], GPC[2], NG[2], GB[2], NUG[2];
     long long NS[2];                    // slots = NG * G
     long long NF, T;
@@ -1102,19 +1103,25 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "    // phase A: micro units of player 1, then of player 2 (one list), one unit per team at a time\n"
          "    {\n"
          "      const long long stride = (long long)nb * " << NT << ";\n"
-         "      long long un = (long long)blockIdx.x * " << NT << " + team;\n"
-         "      MIds cur;\n"
-         "      if (un < nu0 + nu1) cur = un < nu0 ? micro_unit_ids0(P, un) : micro_unit_ids1(P, un - nu0);\n"
-         "      while (un < nu0 + nu1) {\n"
-         "        const long long nx = un + stride;\n"
-         "        MIds nxt;                    // the next unit's static indices: in flight while this unit runs\n"
-         "        if (nx < nu0 + nu1) nxt = nx < nu0 ? micro_unit_ids0(P, nx) : micro_unit_ids1(P, nx - nu0);\n"
-         "        if (un < nu0) micro_unit0(P, un, cur, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
-         "        else micro_unit1(P, un - nu0, cur, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
-         "        cur = nxt;\n"
-         "        un = nx;\n"
-         "      }\n"
-         "    }\n"
+         "      long long un = (long long)blockIdx.x * " << NT << " + team;\n";
+    if (c.PREFETCH)
+        o << "      MIds cur;\n"
+             "      if (un < nu0 + nu1) cur = un < nu0 ? micro_unit_ids0(P, un) : micro_unit_ids1(P, un - nu0);\n"
+             "      while (un < nu0 + nu1) {\n"
+             "        const long long nx = un + stride;\n"
+             "        MIds nxt;                    // the next unit's static indices: in flight while this unit runs\n"
+             "        if (nx < nu0 + nu1) nxt = nx < nu0 ? micro_unit_ids0(P, nx) : micro_unit_ids1(P, nx - nu0);\n"
+             "        if (un < nu0) micro_unit0(P, un, cur, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
+             "        else micro_unit1(P, un - nu0, cur, w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
+             "        cur = nxt;\n"
+             "        un = nx;\n"
+             "      }\n";
+    else
+        o << "      for (; un < nu0 + nu1; un += stride) {\n"
+             "        if (un < nu0) micro_unit0(P, un, micro_unit_ids0(P, un), w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
+             "        else micro_unit1(P, un - nu0, micro_unit_ids1(P, un - nu0), w, sig_in, sig_out, t_r, t_o, t_rn, par);\n"
+             "      }\n";
+    o << "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    if (P->nranks > 1) {\n"
          "      // exchange step: once every local subtree value is in place, all CTAs copy this rank's values into every\n"
@@ -1387,6 +1394,8 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     Consts c;
     c.BLK = blk; c.MINB = minb;
     c.NPUSH = 64;
+    c.PREFETCH = 0;
+    { const char *e = getenv("RLP_FUSED_PREFETCH"); if (e && e[0] == '1') c.PREFETCH = 1; }
     c.BR_OK = 0; c.MAXA = std::max(1, (int)t->max_act);
     { const char *e = getenv("RLP_P2P_NPUSH"); if (e && atoi(e) >= 1) c.NPUSH = atoi(e); }
     // The whole CTA works on one micro unit (BLK / G groups) by default.  RLP_FUSED_TEAM=warp gives every warp its own
