@@ -72,6 +72,7 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(unsigned long long *, xfp6) X(unsigned long long *, xfp7) /* flag arrays of every rank (peer mapped) */        \
     X(unsigned long long *, xfl)                              /* this rank's flag array: xfl[r] written by rank r */  \
     X(const int *, own_idx) X(long long, n_own)               /* portal-value slots this rank computes (sorted) */   \
+    X(const int *, col_owner)                                 /* [KP] rank that computes the subtrees of a portal column */ \
     X(long long, nranks) X(long long, rank) X(long long, xbase) X(long long, xdebug)                                \
     X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
     X(const double *, br_sig)                                 /* best response: strategy, [action][fused id] */      \
@@ -120,6 +121,8 @@ struct FusedPlan {
     std::vector<int> h_grp_iset[2], h_tg_iset[2];   // host copies: internal information sets of the groups
     std::vector<int> h_pidx0;           // host copy: portal-value slot of every (group member) of player 1's groups
     int G0 = 0;
+    std::vector<int> col_comp;          // [KP] component of the subtrees in portal column q (-1: differs between tiles)
+    rlp::DevBuf<int> col_owner_single;  // [KP] zeros: single-GPU owner table
     int mo[2] = {0, 0};                 // own decisions per micro group
     size_t pv_len = 0;                  // doubles in one portal-value buffer
     std::string source;
@@ -301,7 +304,7 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         if (sh.kind[j] == 3) o << "  double x" << j << ";\n";
     }
     o << "  double pad_;\n};\n"
-         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, const double* pvl, UIn" << pl << "& in) {\n";
+         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, int par, UIn" << pl << "& in) {\n";
     for (int j = 0; j < n; ++j)
         if (s.dec_idx[j] >= 0) {
             o << "  const int f" << j << " = sm_ut[" << c.GBS + s.dec_idx[j] * c.GBS << " + m];\n";
@@ -315,7 +318,7 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         if (s.parent[j] >= 0 && s.dec_idx[s.parent[j]] >= 0)
             o << "  in.s" << j << " = __ldcg(sig_in + " << s.slot[j] << "LL * " << c.NF << "LL + f" << s.parent[j] << ");\n";
     for (int j = 0; j < n; ++j)
-        if (sh.kind[j] == 3) o << "  in.x" << j << " = __ldcg(pvl + i * " << c.KP << "LL + " << sh.portal_rank[j] << ");\n";
+        if (sh.kind[j] == 3) o << "  in.x" << j << " = ld_pv(pv_source(P, par, " << sh.portal_rank[j] << ") + i * " << c.KP << "LL + " << sh.portal_rank[j] << ");\n";
     o << "  in.pad_ = 0.0;\n}\n";
     o << "__device__ __forceinline__ void upper_eval" << pl << "(int m, double w, const UIn" << pl << "& in, const double* sm_fan, double* sm_r, double* sm_o) {\n";
     for (int j = 0; j < n; ++j) {
@@ -682,6 +685,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int k, 
   }
   __syncthreads();
 }
+// Multi-GPU: the subtree values of portal column q live in the buffer of the rank that owns q's component; the upper phase
+// PULLS them over NVLink (peer-mapped memory, system-scope loads: never served from a stale L1 line).
+__device__ __forceinline__ const double* pv_source(const FusedParams* __restrict__ P, int par, int q) {
+  double* const* pvp = par ? &P->pvB0 : &P->pvA0;
+  return pvp[P->nranks > 1 ? P->col_owner[q] : 0];
+}
+__device__ __forceinline__ double ld_pv(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 // The same barrier with the exchange step of the multi-GPU solve folded in: the subtree values were stored straight
 // into every peer's buffer (NVLink peer stores) during the micro phase; the last CTA of this GPU to arrive publishes
 // `token` in every peer's flag array and waits until every peer has published it here, then releases the local CTAs.
@@ -704,17 +718,20 @@ __device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P
     if (threadIdx.x == 0) {
       const int nr = (int)P->nranks, me = (int)P->rank;
       unsigned long long* const* peers = &P->xfp0;
+      // ONE system-scope fence (it is what costs: it waits for this GPU's outstanding peer writes), then relaxed flag stores;
+      // a st.release per peer would repeat that fence for every peer
+      __threadfence_system();
       for (int r = 0; r < nr; ++r)
-        if (r != me) asm volatile("st.release.sys.u64 [%0], %1;" :: "l"(peers[r] + me), "l"(token) : "memory");
+        if (r != me) asm volatile("st.relaxed.sys.u64 [%0], %1;" :: "l"(peers[r] + me), "l"(token) : "memory");
       for (int r = 0; r < nr; ++r) {
         if (r == me || (P->xdebug & 2)) continue;
         unsigned long long v = 0;
         long long spins = 0;
         for (;;) {
-          asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(P->xfl + r) : "memory");
+          asm volatile("ld.relaxed.sys.u64 %0, [%1];" : "=l"(v) : "l"(P->xfl + r) : "memory");
           if (v >= token) break;
-          if (++spins > (1ll << 24)) { bar[2] = 1u; break; }      // ~seconds: give up, flag the error
-          __nanosleep(100);
+          if (++spins > (1ll << 25)) { bar[2] = 1u; break; }      // ~seconds: give up, flag the error
+          __nanosleep(40);
         }
       }
       __threadfence_system();
@@ -881,7 +898,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
              "}\n";
         o << "__device__ __noinline__ void upper_unit" << pl << "(const FusedParams* __restrict__ P, int u, double w, const double* sig_in,\n"
              "    double* sig_out, int reach_only, double* sm_fan, double* sm_r, double* sm_o, double* sm_rn, double* sm_s, const int* sm_ut,\n"
-             "    const double* pvl, unsigned long long* st) {\n"
+             "    int par, unsigned long long* st) {\n"
              "  const int tid = threadIdx.x;\n"
              "  const int* tiles = sm_ut;\n"
              "  if (reach_only) {\n"
@@ -902,7 +919,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "    }\n";
         o << "    const int* fd = P->fan_desc;\n"
              "    UIn" << pl << " uin;\n"
-             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], tid, sm_ut, sig_in, pvl, uin);\n"
+             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], tid, sm_ut, sig_in, par, uin);\n"
              "    if (st && tid == 0) st[0] = now_ns();\n";
         const int pv_pad = c.NCH > 0 ? c.KP + c.KP / c.NCH + 1 : c.KP;   // padded row of one tile's portal values in shared memory
         const int chunk = (c.sm_r_n + c.sm_o_n) / std::max(1, pv_pad);     // tiles per pass through the staging area (sm_r + sm_o)
@@ -920,7 +937,9 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                      "    const bool cok = tid < " << c.KP << ";\n"
                      "    const int dst = tid" << (c.NCH > 0 ? " + tid / " + std::to_string(c.NCH) : std::string()) << ";\n"
                      "#pragma unroll\n"
-                     "    for (int mm = 0; mm < " << GB << "; ++mm) if (cok) fv[mm] = __ldcg(pvl + (long long)tiles[mm] * " << c.KP << "LL + tid);\n"
+                     "    const double* src = pv_source(P, par, cok ? tid : 0) + tid;\n"
+                     "#pragma unroll\n"
+                     "    for (int mm = 0; mm < " << GB << "; ++mm) if (cok) fv[mm] = ld_pv(src + (long long)tiles[mm] * " << c.KP << "LL);\n"
                      "#pragma unroll\n"
                      "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
                      "#pragma unroll\n"
@@ -931,7 +950,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "#pragma unroll\n"
                  "    for (int i = 0; i < " << NV << "; ++i) {\n"
                  "      const int L = tid + i * BLOCK;\n"
-                 "      if (L < " << total_pv << ") { const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << "; fv[i] = __ldcg(pvl + (long long)tiles[mm] * " << c.KP << "LL + q); }\n"
+                 "      if (L < " << total_pv << ") { const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << "; fv[i] = ld_pv(pv_source(P, par, q) + (long long)tiles[mm] * " << c.KP << "LL + q); }\n"
                  "    }\n"
                  "#pragma unroll\n"
                  "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
@@ -961,7 +980,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      const int m = x / " << std::max(1, c.F) << ", f = x - m * " << std::max(1, c.F) << ";\n"
                  "      const long long i = tiles[m];\n"
                  "      const int k0 = fd[4 * f], e0 = fd[4 * f + 2];\n"
-                 "      const double* pv = pvl + i * " << c.KP << "LL + k0;\n"
+                 "      const double* pv = pv_source(P, par, k0) + i * " << c.KP << "LL + k0;     // (a fan-in node's children share an owner)\n"
                  "      const double* cp = P->fan_cp + (long long)e0 * " << c.T << "LL + i;\n"
                  "      double acc = 0.0;\n"
                  "      const int nch = fd[4 * f + 1];\n"
@@ -969,7 +988,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      for (; ch + 8 <= nch; ch += 8) {\n"
                  "        double e[8], v[8];\n"
                  "#pragma unroll\n"
-                 "        for (int q = 0; q < 8; ++q) { e[q] = cp[(long long)(ch + q) * " << c.T << "LL]; v[q] = __ldcg(pv + ch + q); }\n"
+                 "        for (int q = 0; q < 8; ++q) { e[q] = cp[(long long)(ch + q) * " << c.T << "LL]; v[q] = ld_pv(pv + ch + q); }\n"
                  "#pragma unroll\n"
                  "        for (int q = 0; q < 8; ++q) acc = acc + e[q] * v[q];\n"
                  "      }\n"
@@ -1098,7 +1117,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "    double* sig_out = cur ? P->sigF0 : P->sigF1;\n"
          "    const double w = linear ? (double)(t0 + it) : 1.0;\n"
          "    const int par = (int)((P->xbase + it) & 1);        // portal-value buffer of this iteration\n"
-         "    const double* pvl = par ? P->pvl1 : P->pvl0;\n"
+
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase A: micro units of player 1, then of player 2 (one list), one unit per team at a time\n"
          "    {\n"
@@ -1123,23 +1142,10 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
              "      }\n";
     o << "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
-         "    if (P->nranks > 1) {\n"
-         "      // exchange step: once every local subtree value is in place, all CTAs copy this rank's values into every\n"
-         "      // peer's buffer with coalesced stores (NVLink), then the barrier that ends the phase shakes hands with the peers\n"
-         "      grid_barrier(P->bar, ++nbar, nb);\n"
-         "      double* const* pvp = par ? &P->pvB0 : &P->pvA0;\n"
-         "      const int nr = (int)P->nranks, me = (int)P->rank;\n"
-         "      const unsigned int npush = nb < " << c.NPUSH << "u ? nb : " << c.NPUSH << "u;       // the CTAs that move the data (and pay a system-scope fence)\n"
-         "      if (blockIdx.x < npush && !(P->xdebug & 1))\n"
-         "        for (long long x = (long long)blockIdx.x * BLOCK + threadIdx.x; x < P->n_own; x += (long long)npush * BLOCK) {\n"
-         "          const int idx = P->own_idx[x];\n"
-         "          const double v = __ldcg(pvl + idx);\n"
-         "          for (int r = 0; r < nr; ++r) if (r != me) pvp[r][idx] = v;\n"
-         "        }\n"
-         "      grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), blockIdx.x < npush);\n"
-         "    } else {\n"
-         "      grid_barrier(P->bar, ++nbar, nb);\n"
-         "    }\n"
+         "    // Multi-GPU: every rank leaves the values of ITS subtrees in its own buffer; the barrier that ends the phase also\n"
+         "    // shakes hands with the peers, after which the upper phase pulls what it needs from the owners' buffers.\n"
+         "    if (P->nranks > 1) grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), false);\n"
+         "    else grid_barrier(P->bar, ++nbar, nb);\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)\n"
          "    if (lead >= 0) {\n"
@@ -1150,8 +1156,8 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "          cached_u = u;\n"
          "          __syncthreads();\n"
          "        }\n"
-         "        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, pvl, st);\n"
-         "        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, pvl, st);\n"
+         "        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, par, st);\n"
+         "        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, par, st);\n"
          "      }\n"
          "    }\n"
          "    tlc += 5;\n"
@@ -1593,6 +1599,17 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p;
     h.pvl0 = h.pvl1 = h.pvA0 = h.pvB0 = ts.portal_v1.p;     // single GPU: one buffer, this rank only
     h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr; h.own_idx = nullptr; h.n_own = 0; h.xdebug = 0;
+    {   // component of every portal column (Leduc: component = (board card, round-1 line) = the column itself)
+        fp->col_comp.assign(cx.kp, -2);
+        for (int64_t p = 0; p < P; ++p) {
+            int &cc = fp->col_comp[rank_of_portal[p]];
+            if (cc == -2) cc = comp_of[p]; else if (cc != comp_of[p]) cc = -1;
+        }
+        std::vector<int> zeros(cx.kp, 0);
+        RLP_CUDA(fp->col_owner_single.upload(zeros, stream));
+        RLP_CUDA(rlp::sync_stream(stream));
+        h.col_owner = fp->col_owner_single.p;
+    }
     h.tile_root = fp->tile_root.p; h.g_first_child = t->first_child.p; h.g_player = reinterpret_cast<const signed char *>(t->player.p);
     h.n_top = n_top;
     {
@@ -1720,6 +1737,7 @@ struct P2P {
     unsigned long long xcount = 0;      // iterations exchanged so far = the last flag token
     rlp::DevBuf<int> own_idx;           // portal-value slots this rank computes, ascending
     long long n_own = 0;
+    rlp::DevBuf<int> col_owner;         // [KP] owner rank of every portal column
 };
 
 void p2p_release(rlp_cfr *c) {
@@ -1765,6 +1783,7 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
         }
         hp.pvl0 = pa[x->rank]; hp.pvl1 = pb[x->rank]; hp.xfl = xf[x->rank];
         hp.nranks = x->nranks; hp.rank = x->rank; hp.own_idx = x->own_idx.p; hp.n_own = x->n_own;
+        hp.col_owner = x->col_owner.p;
         { const char *e = getenv("RLP_P2P_DEBUG"); hp.xdebug = e ? atoi(e) : 0; }   // measurement only: 1 no push, 2 no wait
         hp.first_group0 = x->g_lo[0]; hp.end_group0 = x->g_hi[0]; hp.first_group1 = x->g_lo[1]; hp.end_group1 = x->g_hi[1];
     }
@@ -1848,6 +1867,17 @@ extern "C" int rlp_cfr_p2p_connect(rlp_cfr *c, int rank, int nranks, const unsig
         const std::vector<int> &gc = f.group_comp[pl];
         x->g_lo[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_lo) - gc.begin();
         x->g_hi[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_hi) - gc.begin();
+    }
+    {   // which rank computes the subtrees of every portal column (the upper phase pulls their values from that rank)
+        std::vector<int> owner(f.col_comp.size(), 0);
+        for (size_t q = 0; q < owner.size(); ++q) {
+            const int cc = f.col_comp[q];
+            if (cc < 0) return fail(RLP_ERR_UNSUPPORTED, "the components of this tree do not follow the portal columns");
+            int r = 0;
+            while (r + 1 < nranks && (long long)(r + 1) * n / nranks <= cc) ++r;
+            owner[q] = r;
+        }
+        RLP_CUDA(x->col_owner.upload(owner, nullptr));
     }
     {   // the portal-value slots this rank computes: the members of its player-1 groups
         std::vector<int> idx(f.h_pidx0.begin() + x->g_lo[0] * f.G0, f.h_pidx0.begin() + x->g_hi[0] * f.G0);
