@@ -72,7 +72,7 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(unsigned long long *, xfp6) X(unsigned long long *, xfp7) /* flag arrays of every rank (peer mapped) */        \
     X(unsigned long long *, xfl)                              /* this rank's flag array: xfl[r] written by rank r */  \
     X(const int *, own_idx) X(long long, n_own)               /* portal-value slots this rank computes (sorted) */   \
-    X(const int *, col_owner)                                 /* [KP] rank that computes the subtrees of a portal column */ \
+    X(const unsigned char *, slot_owner)                      /* [T * KP] rank that computes the subtree behind a portal slot */ \
     X(long long, nranks) X(long long, rank) X(long long, xbase) X(long long, xdebug)                                \
     X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
     X(const double *, br_sig)                                 /* best response: strategy, [action][fused id] */      \
@@ -121,8 +121,7 @@ struct FusedPlan {
     std::vector<int> h_grp_iset[2], h_tg_iset[2];   // host copies: internal information sets of the groups
     std::vector<int> h_pidx0;           // host copy: portal-value slot of every (group member) of player 1's groups
     int G0 = 0;
-    std::vector<int> col_comp;          // [KP] component of the subtrees in portal column q (-1: differs between tiles)
-    rlp::DevBuf<int> col_owner_single;  // [KP] zeros: single-GPU owner table
+    std::vector<int> slot_comp;         // [T * KP] component of the subtree behind every portal slot (-1: no subtree)
     int mo[2] = {0, 0};                 // own decisions per micro group
     size_t pv_len = 0;                  // doubles in one portal-value buffer
     std::string source;
@@ -318,7 +317,7 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         if (s.parent[j] >= 0 && s.dec_idx[s.parent[j]] >= 0)
             o << "  in.s" << j << " = __ldcg(sig_in + " << s.slot[j] << "LL * " << c.NF << "LL + f" << s.parent[j] << ");\n";
     for (int j = 0; j < n; ++j)
-        if (sh.kind[j] == 3) o << "  in.x" << j << " = ld_pv(pv_source(P, par, " << sh.portal_rank[j] << ") + i * " << c.KP << "LL + " << sh.portal_rank[j] << ");\n";
+        if (sh.kind[j] == 3) o << "  in.x" << j << " = ld_pv(pv_source(P, par, i * " << c.KP << "LL + " << sh.portal_rank[j] << "));\n";
     o << "  in.pad_ = 0.0;\n}\n";
     o << "__device__ __forceinline__ void upper_eval" << pl << "(int m, double w, const UIn" << pl << "& in, const double* sm_fan, double* sm_r, double* sm_o) {\n";
     for (int j = 0; j < n; ++j) {
@@ -687,9 +686,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int k, 
 }
 // Multi-GPU: the subtree values of portal column q live in the buffer of the rank that owns q's component; the upper phase
 // PULLS them over NVLink (peer-mapped memory, system-scope loads: never served from a stale L1 line).
-__device__ __forceinline__ const double* pv_source(const FusedParams* __restrict__ P, int par, int q) {
+__device__ __forceinline__ const double* pv_source(const FusedParams* __restrict__ P, int par, long long slot) {
   double* const* pvp = par ? &P->pvB0 : &P->pvA0;
-  return pvp[P->nranks > 1 ? P->col_owner[q] : 0];
+  return pvp[P->nranks > 1 ? (int)__ldg(P->slot_owner + slot) : 0] + slot;
 }
 __device__ __forceinline__ double ld_pv(const double* p) {
   double v;
@@ -937,9 +936,8 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                      "    const bool cok = tid < " << c.KP << ";\n"
                      "    const int dst = tid" << (c.NCH > 0 ? " + tid / " + std::to_string(c.NCH) : std::string()) << ";\n"
                      "#pragma unroll\n"
-                     "    const double* src = pv_source(P, par, cok ? tid : 0) + tid;\n"
                      "#pragma unroll\n"
-                     "    for (int mm = 0; mm < " << GB << "; ++mm) if (cok) fv[mm] = ld_pv(src + (long long)tiles[mm] * " << c.KP << "LL);\n"
+                     "    for (int mm = 0; mm < " << GB << "; ++mm) if (cok) fv[mm] = ld_pv(pv_source(P, par, (long long)tiles[mm] * " << c.KP << "LL + tid));\n"
                      "#pragma unroll\n"
                      "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
                      "#pragma unroll\n"
@@ -950,7 +948,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "#pragma unroll\n"
                  "    for (int i = 0; i < " << NV << "; ++i) {\n"
                  "      const int L = tid + i * BLOCK;\n"
-                 "      if (L < " << total_pv << ") { const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << "; fv[i] = ld_pv(pv_source(P, par, q) + (long long)tiles[mm] * " << c.KP << "LL + q); }\n"
+                 "      if (L < " << total_pv << ") { const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << "; fv[i] = ld_pv(pv_source(P, par, (long long)tiles[mm] * " << c.KP << "LL + q)); }\n"
                  "    }\n"
                  "#pragma unroll\n"
                  "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
@@ -980,7 +978,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      const int m = x / " << std::max(1, c.F) << ", f = x - m * " << std::max(1, c.F) << ";\n"
                  "      const long long i = tiles[m];\n"
                  "      const int k0 = fd[4 * f], e0 = fd[4 * f + 2];\n"
-                 "      const double* pv = pv_source(P, par, k0) + i * " << c.KP << "LL + k0;     // (a fan-in node's children share an owner)\n"
+                 "      const long long pv = i * " << c.KP << "LL + k0;          // slot of the first child\n"
                  "      const double* cp = P->fan_cp + (long long)e0 * " << c.T << "LL + i;\n"
                  "      double acc = 0.0;\n"
                  "      const int nch = fd[4 * f + 1];\n"
@@ -988,7 +986,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      for (; ch + 8 <= nch; ch += 8) {\n"
                  "        double e[8], v[8];\n"
                  "#pragma unroll\n"
-                 "        for (int q = 0; q < 8; ++q) { e[q] = cp[(long long)(ch + q) * " << c.T << "LL]; v[q] = ld_pv(pv + ch + q); }\n"
+                 "        for (int q = 0; q < 8; ++q) { e[q] = cp[(long long)(ch + q) * " << c.T << "LL]; v[q] = ld_pv(pv_source(P, par, pv + ch + q)); }\n"
                  "#pragma unroll\n"
                  "        for (int q = 0; q < 8; ++q) acc = acc + e[q] * v[q];\n"
                  "      }\n"
@@ -1599,16 +1597,10 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p;
     h.pvl0 = h.pvl1 = h.pvA0 = h.pvB0 = ts.portal_v1.p;     // single GPU: one buffer, this rank only
     h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr; h.own_idx = nullptr; h.n_own = 0; h.xdebug = 0;
-    {   // component of every portal column (Leduc: component = (board card, round-1 line) = the column itself)
-        fp->col_comp.assign(cx.kp, -2);
-        for (int64_t p = 0; p < P; ++p) {
-            int &cc = fp->col_comp[rank_of_portal[p]];
-            if (cc == -2) cc = comp_of[p]; else if (cc != comp_of[p]) cc = -1;
-        }
-        std::vector<int> zeros(cx.kp, 0);
-        RLP_CUDA(fp->col_owner_single.upload(zeros, stream));
-        RLP_CUDA(rlp::sync_stream(stream));
-        h.col_owner = fp->col_owner_single.p;
+    {   // component of the subtree behind every portal slot
+        fp->slot_comp.assign((size_t)T * cx.kp, -1);
+        for (int64_t p = 0; p < P; ++p) fp->slot_comp[(size_t)tile_of_portal[p] * cx.kp + rank_of_portal[p]] = comp_of[p];
+        h.slot_owner = nullptr;          // single GPU: not read
     }
     h.tile_root = fp->tile_root.p; h.g_first_child = t->first_child.p; h.g_player = reinterpret_cast<const signed char *>(t->player.p);
     h.n_top = n_top;
@@ -1737,7 +1729,7 @@ struct P2P {
     unsigned long long xcount = 0;      // iterations exchanged so far = the last flag token
     rlp::DevBuf<int> own_idx;           // portal-value slots this rank computes, ascending
     long long n_own = 0;
-    rlp::DevBuf<int> col_owner;         // [KP] owner rank of every portal column
+    rlp::DevBuf<unsigned char> slot_owner;   // [T * KP] owner rank of every portal slot
 };
 
 void p2p_release(rlp_cfr *c) {
@@ -1783,7 +1775,7 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
         }
         hp.pvl0 = pa[x->rank]; hp.pvl1 = pb[x->rank]; hp.xfl = xf[x->rank];
         hp.nranks = x->nranks; hp.rank = x->rank; hp.own_idx = x->own_idx.p; hp.n_own = x->n_own;
-        hp.col_owner = x->col_owner.p;
+        hp.slot_owner = x->slot_owner.p;
         { const char *e = getenv("RLP_P2P_DEBUG"); hp.xdebug = e ? atoi(e) : 0; }   // measurement only: 1 no push, 2 no wait
         hp.first_group0 = x->g_lo[0]; hp.end_group0 = x->g_hi[0]; hp.first_group1 = x->g_lo[1]; hp.end_group1 = x->g_hi[1];
     }
@@ -1868,16 +1860,16 @@ extern "C" int rlp_cfr_p2p_connect(rlp_cfr *c, int rank, int nranks, const unsig
         x->g_lo[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_lo) - gc.begin();
         x->g_hi[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_hi) - gc.begin();
     }
-    {   // which rank computes the subtrees of every portal column (the upper phase pulls their values from that rank)
-        std::vector<int> owner(f.col_comp.size(), 0);
+    {   // which rank computes the subtree behind every portal slot (the upper phase pulls its value from that rank)
+        std::vector<unsigned char> owner(f.slot_comp.size(), 0);
         for (size_t q = 0; q < owner.size(); ++q) {
-            const int cc = f.col_comp[q];
-            if (cc < 0) return fail(RLP_ERR_UNSUPPORTED, "the components of this tree do not follow the portal columns");
+            const int cc = f.slot_comp[q];
+            if (cc < 0) continue;
             int r = 0;
             while (r + 1 < nranks && (long long)(r + 1) * n / nranks <= cc) ++r;
-            owner[q] = r;
+            owner[q] = (unsigned char)r;
         }
-        RLP_CUDA(x->col_owner.upload(owner, nullptr));
+        RLP_CUDA(x->slot_owner.upload(owner, nullptr));
     }
     {   // the portal-value slots this rank computes: the members of its player-1 groups
         std::vector<int> idx(f.h_pidx0.begin() + x->g_lo[0] * f.G0, f.h_pidx0.begin() + x->g_hi[0] * f.G0);
