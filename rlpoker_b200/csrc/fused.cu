@@ -62,7 +62,7 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(double *, R) X(double *, S) X(double *, sigma_row)      /* solver state, internal pair order */               \
     X(double *, sigF0) X(double *, sigF1)                     /* strategy, [action][fused id], two buffers */        \
     X(double *, portal_p1) X(double *, portal_p2)                                                                   \
-    X(double *, pvl0) X(double *, pvl1)                       /* portal values, this GPU, by iteration parity */     \
+    X(double *, pvl0) X(double *, pvl1)                       /* subtree values, this GPU, by iteration parity: [pass][upper group][portal][member] */ \
     X(double *, pvA0) X(double *, pvA1) X(double *, pvA2) X(double *, pvA3) X(double *, pvA4) X(double *, pvA5)     \
     X(double *, pvA6) X(double *, pvA7)                       /* even-iteration buffer of every rank (peer mapped) */ \
     X(double *, pvB0) X(double *, pvB1) X(double *, pvB2) X(double *, pvB3) X(double *, pvB4) X(double *, pvB5)     \
@@ -71,9 +71,7 @@ int compile_and_load_source(const std::string &src, cudaLibrary_t *lib_out, std:
     X(unsigned long long *, xfp3) X(unsigned long long *, xfp4) X(unsigned long long *, xfp5)                        \
     X(unsigned long long *, xfp6) X(unsigned long long *, xfp7) /* flag arrays of every rank (peer mapped) */        \
     X(unsigned long long *, xfl)                              /* this rank's flag array: xfl[r] written by rank r */  \
-    X(const int *, own_idx) X(long long, n_own)               /* portal-value slots this rank computes (sorted) */   \
-    X(const unsigned char *, slot_owner)                      /* [T * KP] rank that computes the subtree behind a portal slot */ \
-    X(long long, nranks) X(long long, rank) X(long long, xbase) X(long long, xdebug)                                \
+    X(long long, nranks) X(long long, rank) X(long long, xbase)                                                     \
     X(unsigned char *, flags) X(unsigned int *, bar) X(unsigned long long *, tl)                                    \
     X(const double *, br_sig)                                 /* best response: strategy, [action][fused id] */      \
     X(double *, br_reach1) X(double *, br_reach2)             /* reach of player 1 / 2 to the portals under br_sig */  \
@@ -119,11 +117,9 @@ struct FusedPlan {
     int num_components = 0;
     std::vector<int> group_comp[2];     // component of every group, fused order (multi-GPU sharding by public state)
     std::vector<int> h_grp_iset[2], h_tg_iset[2];   // host copies: internal information sets of the groups
-    std::vector<int> h_pidx0;           // host copy: portal-value slot of every (group member) of player 1's groups
-    int G0 = 0;
-    std::vector<int> slot_comp;         // [T * KP] component of the subtree behind every portal slot (-1: no subtree)
     int mo[2] = {0, 0};                 // own decisions per micro group
-    size_t pv_len = 0;                  // doubles in one portal-value buffer
+    size_t pv_len = 0;                  // doubles in one pass's subtree-value array (T * KP)
+    rlp::DevBuf<double> pvbuf;          // single GPU: [2 passes][T * KP]
     std::string source;
     ~FusedPlan() { if (lib) cudaLibraryUnload(lib); }
 };
@@ -160,6 +156,8 @@ struct Consts {
     int PAYROW;
     std::vector<double> fan_cps;        // one chance probability per fan-in node when it is the same for all edges / tiles
     int sm_r_n, sm_o_n;                 // doubles in the kernel's sm_r / sm_o arrays (contiguous: the fan-in stages through both)
+    long long PVLEN;                    // doubles in one pass's subtree-value array (T * KP)
+    std::vector<FanDesc> fans;
     int GBS, MBS, UT_OWN, UT_N;         // layout of the cached per-unit tables (ints): strides and the offset of the own-decision part
 };
 
@@ -218,7 +216,7 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
          "  const long long gg = ok ? g : 0;\n"
          "  id.pat = P->mem_pat" << pl << "[slot]; id.ri = P->mem_ridx" << pl << "[slot]; id.ro = P->grp_ridx" << pl << "[gg];\n"
          "  id.pcv = P->mem_pc" << pl << "[slot];\n"
-         "  id.pi = " << (pl == 0 ? "P->mem_pidx0[slot]" : "0") << ";\n";
+         "  id.pi = P->mem_pidx" << pl << "[slot];\n";
     for (int r = 0; r < n_nt; ++r) {
         if (own_j[r] >= 0)
             o << "  id.f[" << r << "] = P->grp_fid" << pl << "[gg * " << s.dec[pl].size() << " + " << own_j[r] << "];\n";
@@ -233,7 +231,7 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
          "    const double* sig_in, double* sm_r, double* sm_o, int par) {\n"
          "  const int pat = id.pat, ri = id.ri, ro = id.ro;\n"
          "  const double pcv = id.pcv;\n";
-    if (pl == 0) o << "  const int pi = id.pi;\n";
+    o << "  const int pi = id.pi;\n";
     for (int r = 0; r < n_nt; ++r) o << "  const int f" << r << " = id.f[" << r << "];\n";
     if (c.PAY8) {           // one or two 16-byte loads fetch all leaf payoffs of the subtree's pattern (exact: small integers)
         o << "  const int4* pp = reinterpret_cast<const int4*>(P->paytab8 + (long long)pat * " << c.PAYROW << ");\n";
@@ -279,8 +277,11 @@ void gen_micro_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         }
         o << "    sm_o[" << jj << " * SMS + tix] = w * own;\n  }\n";
     }
-    if (pl == 0) o << "  (par ? P->pvl1 : P->pvl0)[pi] = x0;\n";
-    else o << "  (void)par;\n";
+    // The subtree value goes to this pass's array (laid out for this player's upper groups: [group][portal][member], so
+    // the G threads of a group store consecutive words) in the buffer of this iteration's parity -- of EVERY rank: the
+    // peers' buffers are mapped (CUDA IPC), the stores travel over NVLink while the phase is still running.
+    o << "  { double* const* pvp = par ? &P->pvB0 : &P->pvA0; const int nr = (int)P->nranks;\n"
+         "    for (int r = 0; r < nr; ++r) pvp[r][pi] = x0; }\n";
     o << "}\n";
 }
 
@@ -303,7 +304,7 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         if (sh.kind[j] == 3) o << "  double x" << j << ";\n";
     }
     o << "  double pad_;\n};\n"
-         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, int par, UIn" << pl << "& in) {\n";
+         "__device__ __forceinline__ void upper_load" << pl << "(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, const double* blk, UIn" << pl << "& in) {\n";
     for (int j = 0; j < n; ++j)
         if (s.dec_idx[j] >= 0) {
             o << "  const int f" << j << " = sm_ut[" << c.GBS + s.dec_idx[j] * c.GBS << " + m];\n";
@@ -317,7 +318,7 @@ void gen_upper_eval(std::ostringstream &o, const Shape &s, const Consts &c, int 
         if (s.parent[j] >= 0 && s.dec_idx[s.parent[j]] >= 0)
             o << "  in.s" << j << " = __ldcg(sig_in + " << s.slot[j] << "LL * " << c.NF << "LL + f" << s.parent[j] << ");\n";
     for (int j = 0; j < n; ++j)
-        if (sh.kind[j] == 3) o << "  in.x" << j << " = ld_pv(pv_source(P, par, i * " << c.KP << "LL + " << sh.portal_rank[j] << "));\n";
+        if (sh.kind[j] == 3) o << "  in.x" << j << " = __ldcg(blk + " << sh.portal_rank[j] * c.GB[pl] << " + m);\n";
     o << "  in.pad_ = 0.0;\n}\n";
     o << "__device__ __forceinline__ void upper_eval" << pl << "(int m, double w, const UIn" << pl << "& in, const double* sm_fan, double* sm_r, double* sm_o) {\n";
     for (int j = 0; j < n; ++j) {
@@ -468,7 +469,7 @@ void gen_micro_br(std::ostringstream &o, const Shape &s, const Consts &c, int pl
             o << ";\n    if (ok && k == 0) P->br_astar[P->grp_iset" << pl << "[g * " << MO << " + " << jj << "]] = best;\n  }\n";
         }
     }
-    o << "  if (ok) P->br_pv" << pl + 1 << "[pi] = V0;\n  TEAM_SYNC();\n}\n";
+    o << "  if (ok) P->br_pv1[pi] = V0;\n  TEAM_SYNC();\n}\n";
 }
 
 // One upper group of the responder: fan-in (plain ordered sums of the subtree values), then every tile bottom-up with the
@@ -481,18 +482,18 @@ void gen_upper_br(std::ostringstream &o, const Shape &s, const Consts &c, int pl
     for (size_t jj = 0; jj < s.udec[pl].size(); ++jj) own_jj[s.udec[pl][jj]] = (int)jj;
     o << "__device__ __noinline__ void upper_br" << pl << "(const FusedParams* __restrict__ P, int u, double* sm_fan, double* sm_q, const int* sm_ut) {\n"
          "  const int tid = threadIdx.x;\n"
-         "  const double* pvl = P->br_pv" << pl + 1 << ";\n"
+         "  const double* pvl = P->br_pv1 + " << (long long)pl * c.PVLEN << "LL + (long long)u * " << (long long)c.KP * GB << "LL;\n"
          "  const int* fd = P->fan_desc;\n"
          "  for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
          "    const int mm = x / " << std::max(1, c.F) << ", f = x - mm * " << std::max(1, c.F) << ";\n"
          "    const int k0 = fd[4 * f], nch = fd[4 * f + 1];\n"
-         "    const double* pv = pvl + (long long)sm_ut[mm] * " << c.KP << "LL + k0;\n"
+         "    const double* pv = pvl + (long long)k0 * " << GB << " + mm;\n"
          "    double acc = 0.0;\n"
       << (c.NCH > 0 && c.NCH <= 32
               ? "    double vv[" + std::to_string(c.NCH) + "];\n#pragma unroll\n    for (int ch = 0; ch < " + std::to_string(c.NCH) +
-                    "; ++ch) vv[ch] = __ldcg(pv + ch);\n#pragma unroll\n    for (int ch = 0; ch < " + std::to_string(c.NCH) +
+                    "; ++ch) vv[ch] = __ldcg(pv + ch * " + std::to_string(GB) + ");\n#pragma unroll\n    for (int ch = 0; ch < " + std::to_string(c.NCH) +
                     "; ++ch) acc = acc + vv[ch];\n    (void)nch;\n"
-              : std::string("    for (int ch = 0; ch < nch; ++ch) acc = acc + __ldcg(pv + ch);\n"))
+              : std::string("    for (int ch = 0; ch < nch; ++ch) acc = acc + __ldcg(pv + ch * ") + std::to_string(GB) + ");\n")
       << "    sm_fan[x] = acc;\n"
          "  }\n"
          "  __syncthreads();\n"
@@ -529,7 +530,7 @@ void gen_upper_br(std::ostringstream &o, const Shape &s, const Consts &c, int pl
                 o << "  const double v" << ch << " = ((pc" << j << " * qo_" << j << ")" << (kd == opp + 1 ? " * " + S_("s", ch) : std::string()) << ") * "
                   << (pl == 0 ? "" : "-") << "x" << ch << ";\n";
             else if (ck == 4) o << "  const double v" << ch << " = sm_fan[m * " << std::max(1, c.F) << " + " << sh.fan_index[ch] << "];\n";
-            else if (ck == 3) o << "  const double v" << ch << " = __ldcg(pvl + i * " << c.KP << "LL + " << sh.portal_rank[ch] << ");\n";
+            else if (ck == 3) o << "  const double v" << ch << " = __ldcg(pvl + " << sh.portal_rank[ch] * GB << " + m);\n";
             else o << "  const double v" << ch << " = V" << ch << ";\n";
         }
         if (kd == opp + 1) {
@@ -684,17 +685,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int k, 
   }
   __syncthreads();
 }
-// Multi-GPU: the subtree values of portal column q live in the buffer of the rank that owns q's component; the upper phase
-// PULLS them over NVLink (peer-mapped memory, system-scope loads: never served from a stale L1 line).
-__device__ __forceinline__ const double* pv_source(const FusedParams* __restrict__ P, int par, long long slot) {
-  double* const* pvp = par ? &P->pvB0 : &P->pvA0;
-  return pvp[P->nranks > 1 ? (int)__ldg(P->slot_owner + slot) : 0] + slot;
-}
-__device__ __forceinline__ double ld_pv(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
 // The same barrier with the exchange step of the multi-GPU solve folded in: the subtree values were stored straight
 // into every peer's buffer (NVLink peer stores) during the micro phase; the last CTA of this GPU to arrive publishes
 // `token` in every peer's flag array and waits until every peer has published it here, then releases the local CTAs.
@@ -723,7 +713,7 @@ __device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P
       for (int r = 0; r < nr; ++r)
         if (r != me) asm volatile("st.relaxed.sys.u64 [%0], %1;" :: "l"(peers[r] + me), "l"(token) : "memory");
       for (int r = 0; r < nr; ++r) {
-        if (r == me || (P->xdebug & 2)) continue;
+        if (r == me) continue;
         unsigned long long v = 0;
         long long spins = 0;
         for (;;) {
@@ -916,84 +906,83 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                  "      ar = __ldcg(P->R + acol); asa = __ldcg(P->S + acol);\n"
                  "      asg = __ldcg(sig_in + (long long)aa * " << c.NF << "LL + afid);\n"
                  "    }\n";
+        // this unit's subtree values: one contiguous block [portal][member] of this player's array
         o << "    const int* fd = P->fan_desc;\n"
+             "    const double* blk = (par ? P->pvl1 : P->pvl0) + " << (long long)pl * c.PVLEN << "LL + (long long)u * " << (long long)c.KP * GB << "LL;\n"
              "    UIn" << pl << " uin;\n"
-             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], tid, sm_ut, sig_in, par, uin);\n"
+             "    if (tid < " << GB << ") upper_load" << pl << "(P, tiles[tid], tid, sm_ut, sig_in, blk, uin);\n"
              "    if (st && tid == 0) st[0] = now_ns();\n";
-        const int pv_pad = c.NCH > 0 ? c.KP + c.KP / c.NCH + 1 : c.KP;   // padded row of one tile's portal values in shared memory
-        const int chunk = (c.sm_r_n + c.sm_o_n) / std::max(1, pv_pad);     // tiles per pass through the staging area (sm_r + sm_o)
-        const int total_pv = GB * c.KP, NV = (total_pv + c.BLK - 1) / c.BLK;
-        if (!c.fan_cps.empty() && chunk >= 1 && NV <= 40) {
-            // The unit's portal values: every thread fetches its share with coalesced loads, ALL in flight at once (they stay
-            // in registers), then they pass through shared memory a few tiles at a time and one thread per (tile, fan-in
-            // node) adds chance probability x value in child order.  Rows are padded by one word per fan-in node so that the
-            // threads of a warp (stride = one fan-in node) hit different banks.
-            const int nchunk = (GB + chunk - 1) / chunk;
-            const std::string padq = c.NCH > 0 ? " + q / " + std::to_string(c.NCH) : std::string();
-            if (c.KP <= c.BLK && GB <= 32) {
-                // thread = one portal column of the unit: GB coalesced loads per thread, all in flight, no index arithmetic
-                o << "    double fv[" << GB << "];\n"
-                     "    const bool cok = tid < " << c.KP << ";\n"
-                     "    const int dst = tid" << (c.NCH > 0 ? " + tid / " + std::to_string(c.NCH) : std::string()) << ";\n"
-                     "#pragma unroll\n"
-                     "#pragma unroll\n"
-                     "    for (int mm = 0; mm < " << GB << "; ++mm) if (cok) fv[mm] = ld_pv(pv_source(P, par, (long long)tiles[mm] * " << c.KP << "LL + tid));\n"
-                     "#pragma unroll\n"
-                     "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
-                     "#pragma unroll\n"
-                     "      for (int mm = 0; mm < " << GB << "; ++mm)\n"
-                     "        if (cok && mm / " << chunk << " == c0) sm_r[(mm - c0 * " << chunk << ") * " << pv_pad << " + dst] = fv[mm];\n";
-            } else {
-            o << "    double fv[" << NV << "];\n"
-                 "#pragma unroll\n"
-                 "    for (int i = 0; i < " << NV << "; ++i) {\n"
-                 "      const int L = tid + i * BLOCK;\n"
-                 "      if (L < " << total_pv << ") { const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << "; fv[i] = ld_pv(pv_source(P, par, (long long)tiles[mm] * " << c.KP << "LL + q)); }\n"
-                 "    }\n"
-                 "#pragma unroll\n"
-                 "    for (int c0 = 0; c0 < " << nchunk << "; ++c0) {\n"
-                 "#pragma unroll\n"
-                 "      for (int i = 0; i < " << NV << "; ++i) {\n"
-                 "        const int L = tid + i * BLOCK;\n"
-                 "        const int mm = L / " << c.KP << ", q = L - mm * " << c.KP << ";\n"
-                 "        if (L < " << total_pv << " && mm / " << chunk << " == c0) sm_r[(mm - c0 * " << chunk << ") * " << pv_pad << " + q" << padq << "] = fv[i];\n"
-                 "      }\n";
+        {
+            // Fan-in.  The block is copied through shared memory in its own layout (rows = portals, GB values each: the
+            // threads of the sums below -- one per (tile, fan-in node) -- then read consecutive words), a few fan-in
+            // nodes at a time when it does not fit at once.  When the whole block fits the registers of the CTA, every
+            // load is issued before the first store (one memory round trip).
+            const int stage = c.sm_r_n + c.sm_o_n;
+            std::vector<int> k0s, nchs;
+            for (const FanDesc &fd : c.fans) { k0s.push_back(fd.k0); nchs.push_back(fd.nchild); }
+            std::vector<std::pair<int, int>> chunks;        // [first fan, end fan)
+            for (int f0 = 0; f0 < c.F;) {
+                int f1 = f0, rows = 0;
+                while (f1 < c.F && (rows + nchs[f1]) * GB <= stage) { rows += nchs[f1]; ++f1; }
+                if (f1 == f0) { chunks.clear(); break; }     // a single fan-in node does not fit
+                chunks.push_back({f0, f1});
+                f0 = f1;
             }
-            o <<
-                 "      __syncthreads();\n"
-                 "      const int mc = " << GB << " - c0 * " << chunk << " < " << chunk << " ? " << GB << " - c0 * " << chunk << " : " << chunk << ";\n"
-                 "      for (int x = tid; x < mc * " << c.F << "; x += BLOCK) {\n"
-                 "        const int mm = x / " << std::max(1, c.F) << ", f = x - mm * " << std::max(1, c.F) << ";\n"
-                 "        const int k0 = fd[4 * f], nch = fd[4 * f + 1];\n"
-                 "        const double e = FCP[f];\n"
-                 "        const double* pv = sm_r + mm * " << pv_pad << " + k0" << (c.NCH > 0 ? " + k0 / " + std::to_string(c.NCH) : std::string()) << ";\n"
-                 "        double acc = 0.0;\n"
-                 "        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch];\n"
-                 "        sm_fan[(c0 * " << chunk << " + mm) * " << std::max(1, c.F) << " + f] = acc;\n"
-                 "      }\n"
-                 "      __syncthreads();\n"
-                 "    }\n";
-        } else {
-            o << "    for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
-                 "      const int m = x / " << std::max(1, c.F) << ", f = x - m * " << std::max(1, c.F) << ";\n"
-                 "      const long long i = tiles[m];\n"
-                 "      const int k0 = fd[4 * f], e0 = fd[4 * f + 2];\n"
-                 "      const long long pv = i * " << c.KP << "LL + k0;          // slot of the first child\n"
-                 "      const double* cp = P->fan_cp + (long long)e0 * " << c.T << "LL + i;\n"
-                 "      double acc = 0.0;\n"
-                 "      const int nch = fd[4 * f + 1];\n"
-                 "      int ch = 0;\n"
-                 "      for (; ch + 8 <= nch; ch += 8) {\n"
-                 "        double e[8], v[8];\n"
-                 "#pragma unroll\n"
-                 "        for (int q = 0; q < 8; ++q) { e[q] = cp[(long long)(ch + q) * " << c.T << "LL]; v[q] = ld_pv(pv_source(P, par, pv + ch + q)); }\n"
-                 "#pragma unroll\n"
-                 "        for (int q = 0; q < 8; ++q) acc = acc + e[q] * v[q];\n"
-                 "      }\n"
-                 "      for (; ch < nch; ++ch) acc = acc + cp[(long long)ch * " << c.T << "LL] * __ldcg(pv + ch);\n"
-                 "      sm_fan[x] = acc;\n"
-                 "    }\n"
-                 "    __syncthreads();\n";
+            // consecutive fan-in nodes must cover consecutive portal rows for the linear copy
+            bool linear = !chunks.empty();
+            for (int f = 0; f + 1 < c.F; ++f) if (k0s[f] + nchs[f] != k0s[f + 1]) linear = false;
+            const long long total = (long long)c.KP * GB;
+            const int NV = (int)((total + c.BLK - 1) / c.BLK);
+            const bool in_regs = linear && NV <= 32 && c.F > 0 && k0s[0] == 0 && k0s.back() + nchs.back() == c.KP;
+            const std::string ecp = c.fan_cps.empty() ? "" : "FCP[f]";
+            auto emit_sums = [&](int f0, int f1, int row0) {
+                o << "      for (int x = tid; x < " << (f1 - f0) * GB << "; x += BLOCK) {\n"
+                     "        const int fl = x / " << GB << ", m = x - fl * " << GB << ", f = " << f0 << " + fl;\n"
+                     "        const int k0 = fd[4 * f], nch = fd[4 * f + 1];\n";
+                if (c.fan_cps.empty())
+                    o << "        const double* cp = P->fan_cp + (long long)fd[4 * f + 2] * " << c.T << "LL + tiles[m];\n";
+                else
+                    o << "        const double e = FCP[f];\n";
+                o << "        const double* pv = sm_r + (k0 - " << row0 << ") * " << GB << " + m;\n"
+                     "        double acc = 0.0;\n"
+                     "        for (int ch = 0; ch < nch; ++ch) acc = acc + " << (c.fan_cps.empty() ? "cp[(long long)ch * " + std::to_string(c.T) + "LL]" : std::string("e")) << " * pv[ch * " << GB << "];\n"
+                     "        sm_fan[m * " << std::max(1, c.F) << " + f] = acc;\n"
+                     "      }\n";
+            };
+            if (in_regs) {
+                o << "    double fv[" << NV << "];\n"
+                     "#pragma unroll\n"
+                     "    for (int i = 0; i < " << NV << "; ++i) { const int L = tid + i * BLOCK; if (L < " << total << ") fv[i] = __ldcg(blk + L); }\n";
+                for (auto &ch : chunks) {
+                    const int lo = k0s[ch.first] * GB, hi = (k0s[ch.second - 1] + nchs[ch.second - 1]) * GB;
+                    o << "    {\n#pragma unroll\n"
+                         "      for (int i = 0; i < " << NV << "; ++i) { const int L = tid + i * BLOCK; if (L >= " << lo << " && L < " << hi << ") sm_r[L - " << lo << "] = fv[i]; }\n"
+                         "      __syncthreads();\n";
+                    emit_sums(ch.first, ch.second, k0s[ch.first]);
+                    o << "      __syncthreads();\n    }\n";
+                }
+            } else if (linear) {
+                for (auto &ch : chunks) {
+                    const int lo = k0s[ch.first] * GB, hi = (k0s[ch.second - 1] + nchs[ch.second - 1]) * GB;
+                    o << "    {\n"
+                         "      for (int L = " << lo << " + tid; L < " << hi << "; L += BLOCK) sm_r[L - " << lo << "] = __ldcg(blk + L);\n"
+                         "      __syncthreads();\n";
+                    emit_sums(ch.first, ch.second, k0s[ch.first]);
+                    o << "      __syncthreads();\n    }\n";
+                }
+            } else {        // no staging: every (tile, fan-in node) thread reads its values from the block directly
+                o << "    for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
+                     "      const int f = x / " << GB << ", m = x - f * " << GB << ";\n"
+                     "      const int k0 = fd[4 * f], nch = fd[4 * f + 1];\n"
+                     "      const double* cp = P->fan_cp + (long long)fd[4 * f + 2] * " << c.T << "LL + tiles[m];\n"
+                     "      const double* pv = blk + (long long)k0 * " << GB << " + m;\n"
+                     "      double acc = 0.0;\n"
+                     "      for (int ch = 0; ch < nch; ++ch) acc = acc + cp[(long long)ch * " << c.T << "LL] * __ldcg(pv + (long long)ch * " << GB << ");\n"
+                     "      sm_fan[m * " << std::max(1, c.F) << " + f] = acc;\n"
+                     "    }\n"
+                     "    __syncthreads();\n";
+            }
+            (void)ecp;
         }
         o <<
              "    if (st && tid == 0) st[1] = now_ns();\n"
@@ -1140,9 +1129,9 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
              "      }\n";
     o << "    }\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
-         "    // Multi-GPU: every rank leaves the values of ITS subtrees in its own buffer; the barrier that ends the phase also\n"
-         "    // shakes hands with the peers, after which the upper phase pulls what it needs from the owners' buffers.\n"
-         "    if (P->nranks > 1) grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), false);\n"
+         "    // Multi-GPU: the micro phase has stored the values of this rank's subtrees into every rank's buffer; the barrier\n"
+         "    // that ends the phase also shakes hands with the peers (each CTA fences its peer stores at system scope first).\n"
+         "    if (P->nranks > 1) grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), true);\n"
          "    else grid_barrier(P->bar, ++nbar, nb);\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)\n"
@@ -1414,6 +1403,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         c.GB[pl] = ug[pl].G; c.NUG[pl] = (int)ug[pl].key.size();
     }
     c.NF = NF; c.T = T; c.NT = NT; c.KP = cx.kp; c.F = (int)cx.fans->size();
+    c.PVLEN = (long long)T * cx.kp; c.fans = *cx.fans;
     c.NCH = cx.fans->empty() ? 0 : (*cx.fans)[0].nchild;
     for (const FanDesc &fd : *cx.fans) if (fd.nchild != c.NCH) c.NCH = 0;
     // one chance probability per fan-in node when all its edges in all tiles agree (Leduc: 1 / #remaining cards)
@@ -1480,12 +1470,16 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     fp->NF = NF; fp->max_act = t->max_act; fp->num_components = ncomp; fp->block = blk;
     const std::vector<int> &ridx = *cx.ridx;
     // upper group of every tile, per player (a player's reach of a portal depends only on that player's upper group)
-    std::vector<int> tile_ug[2];
+    std::vector<int> tile_ug[2], tile_mi[2];
     for (int pl = 0; pl < 2; ++pl) {
-        tile_ug[pl].assign(T, -1);
+        tile_ug[pl].assign(T, -1); tile_mi[pl].assign(T, -1);
         for (size_t g = 0; g < ug[pl].key.size(); ++g)
-            for (int k = 0; k < ug[pl].G; ++k) tile_ug[pl][ug[pl].members[g * ug[pl].G + k]] = (int)g;
+            for (int k = 0; k < ug[pl].G; ++k) {
+                tile_ug[pl][ug[pl].members[g * ug[pl].G + k]] = (int)g;
+                tile_mi[pl][ug[pl].members[g * ug[pl].G + k]] = k;
+            }
     }
+    if (2 * (long long)T * cx.kp >= (long long)INT32_MAX) return RLP_OK;
     std::vector<int> tile_of_portal(P), rank_of_portal(P);
     for (int64_t k = 0; k < T; ++k)
         for (int q = 0; q < (*cx.desc)[k].n_portal; ++q) {
@@ -1513,7 +1507,11 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
                     if (k == 0) h_gridx[gi] = own;
                     else if (h_gridx[gi] != own) return RLP_OK;      // members of a group must share their own reach
                 }
-                h_pidx[slot] = tile_of_portal[p] * cx.kp + rank_of_portal[p];
+                {   // value slot: [pass][upper group of this player][portal][member of the upper group]
+                    const int tile = tile_of_portal[p];
+                    h_pidx[slot] = (int)((long long)pl * T * cx.kp +
+                                         ((long long)tile_ug[pl][tile] * cx.kp + rank_of_portal[p]) * ug[pl].G + tile_mi[pl][tile]);
+                }
                 h_pc[slot] = (*cx.pcs)[(*cx.portal_node)[p]];
             }
             const int64_t p0 = mg[pl].members[(size_t)g * G];
@@ -1532,7 +1530,7 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
         RLP_CUDA(fp->mem_pc[pl].upload(h_pc, stream)); RLP_CUDA(fp->grp_fid[pl].upload(h_fid, stream));
         RLP_CUDA(fp->grp_col[pl].upload(h_col, stream)); RLP_CUDA(fp->grp_iset[pl].upload(h_iset, stream));
         fp->h_grp_iset[pl] = h_iset; fp->mo[pl] = MO;
-        if (pl == 0) { fp->h_pidx0 = h_pidx; fp->G0 = G; }
+
         fp->n_batches[pl] = (int)((NG + c.GPC[pl] - 1) / c.GPC[pl]);
         // upper groups
         const int GB = ug[pl].G, MB = (int)s.udec[pl].size();
@@ -1595,13 +1593,9 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     h.u_fid = fp->u_fid.p; h.u_pcs = uj.pcs.p; h.u_cprob = uj.cprob.p; h.u_pay1 = uj.pay1.p;
     h.fan_desc = reinterpret_cast<const int *>(uj.fan.p); h.fan_cp = uj.fan_cp.p;
     h.portal_p1 = fp->reach[0].p; h.portal_p2 = fp->reach[1].p;
-    h.pvl0 = h.pvl1 = h.pvA0 = h.pvB0 = ts.portal_v1.p;     // single GPU: one buffer, this rank only
-    h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr; h.own_idx = nullptr; h.n_own = 0; h.xdebug = 0;
-    {   // component of the subtree behind every portal slot
-        fp->slot_comp.assign((size_t)T * cx.kp, -1);
-        for (int64_t p = 0; p < P; ++p) fp->slot_comp[(size_t)tile_of_portal[p] * cx.kp + rank_of_portal[p]] = comp_of[p];
-        h.slot_owner = nullptr;          // single GPU: not read
-    }
+    RLP_CUDA(fp->pvbuf.alloc(2 * (size_t)T * (size_t)cx.kp));
+    h.pvl0 = h.pvl1 = h.pvA0 = h.pvB0 = fp->pvbuf.p;        // single GPU: one buffer, this rank only
+    h.nranks = 1; h.rank = 0; h.xbase = 0; h.xfl = nullptr;
     h.tile_root = fp->tile_root.p; h.g_first_child = t->first_child.p; h.g_player = reinterpret_cast<const signed char *>(t->player.p);
     h.n_top = n_top;
     {
@@ -1689,7 +1683,7 @@ int fused_br(rlp_cfr *c, const double *sigma_int, double *out2_dev, cudaStream_t
     FusedParams hp = f.host;
     hp.br_sig = base;
     hp.br_reach1 = base + plane; hp.br_reach2 = hp.br_reach1 + reach_n;
-    hp.br_pv1 = hp.br_reach2 + reach_n; hp.br_pv2 = hp.br_pv1 + f.pv_len;
+    hp.br_pv1 = hp.br_reach2 + reach_n; hp.br_pv2 = hp.br_pv1 + f.pv_len;     // one array: [pass][group][portal][member]
     hp.br_top1 = hp.br_pv2 + f.pv_len; hp.br_top2 = hp.br_top1 + f.n_top;
     hp.br_out = out2_dev; hp.br_astar = c->astar.p;
     for (;;) {
@@ -1727,9 +1721,6 @@ struct P2P {
     long long g_lo[2] = {0, 0}, g_hi[2] = {0, 0};   // this rank's micro groups per player (whole components)
     int c_lo = 0, c_hi = 0;
     unsigned long long xcount = 0;      // iterations exchanged so far = the last flag token
-    rlp::DevBuf<int> own_idx;           // portal-value slots this rank computes, ascending
-    long long n_own = 0;
-    rlp::DevBuf<unsigned char> slot_owner;   // [T * KP] owner rank of every portal slot
 };
 
 void p2p_release(rlp_cfr *c) {
@@ -1770,13 +1761,11 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
         for (int r = 0; r < x->nranks; ++r) {
             char *base = static_cast<char *>(r == x->rank ? x->base : x->peer[r]);
             pa[r] = reinterpret_cast<double *>(base);
-            pb[r] = reinterpret_cast<double *>(base) + f.pv_len;
-            xf[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(base) + 2 * f.pv_len);
+            pb[r] = reinterpret_cast<double *>(base) + 2 * f.pv_len;
+            xf[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(base) + 4 * f.pv_len);
         }
         hp.pvl0 = pa[x->rank]; hp.pvl1 = pb[x->rank]; hp.xfl = xf[x->rank];
-        hp.nranks = x->nranks; hp.rank = x->rank; hp.own_idx = x->own_idx.p; hp.n_own = x->n_own;
-        hp.slot_owner = x->slot_owner.p;
-        { const char *e = getenv("RLP_P2P_DEBUG"); hp.xdebug = e ? atoi(e) : 0; }   // measurement only: 1 no push, 2 no wait
+        hp.nranks = x->nranks; hp.rank = x->rank;
         hp.first_group0 = x->g_lo[0]; hp.end_group0 = x->g_hi[0]; hp.first_group1 = x->g_lo[1]; hp.end_group1 = x->g_hi[1];
     }
     int64_t left = n_iters, tt = t0;
@@ -1830,7 +1819,7 @@ extern "C" int rlp_cfr_p2p_export(rlp_cfr *c, unsigned char *handle64) {
     rlp::p2p_release(c);
     FusedPlan &f = *c->tree->tiles.fused;
     std::unique_ptr<rlp::P2P> x(new rlp::P2P);
-    const size_t bytes = sizeof(double) * 2 * f.pv_len + sizeof(unsigned long long) * 8;
+    const size_t bytes = sizeof(double) * 4 * f.pv_len + sizeof(unsigned long long) * 8;     // [parity][pass][T * KP] | flags
     RLP_CUDA(cudaMalloc(&x->base, bytes));
     RLP_CUDA(cudaMemset(x->base, 0, bytes));
     cudaIpcMemHandle_t h;
@@ -1859,24 +1848,6 @@ extern "C" int rlp_cfr_p2p_connect(rlp_cfr *c, int rank, int nranks, const unsig
         const std::vector<int> &gc = f.group_comp[pl];
         x->g_lo[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_lo) - gc.begin();
         x->g_hi[pl] = std::lower_bound(gc.begin(), gc.end(), x->c_hi) - gc.begin();
-    }
-    {   // which rank computes the subtree behind every portal slot (the upper phase pulls its value from that rank)
-        std::vector<unsigned char> owner(f.slot_comp.size(), 0);
-        for (size_t q = 0; q < owner.size(); ++q) {
-            const int cc = f.slot_comp[q];
-            if (cc < 0) continue;
-            int r = 0;
-            while (r + 1 < nranks && (long long)(r + 1) * n / nranks <= cc) ++r;
-            owner[q] = (unsigned char)r;
-        }
-        RLP_CUDA(x->slot_owner.upload(owner, nullptr));
-    }
-    {   // the portal-value slots this rank computes: the members of its player-1 groups
-        std::vector<int> idx(f.h_pidx0.begin() + x->g_lo[0] * f.G0, f.h_pidx0.begin() + x->g_hi[0] * f.G0);
-        std::sort(idx.begin(), idx.end());
-        x->n_own = (long long)idx.size();
-        RLP_CUDA(x->own_idx.upload(idx, nullptr));
-        RLP_CUDA(cudaDeviceSynchronize());
     }
     x->xcount = 0;
     x->active = true;
