@@ -147,6 +147,7 @@ struct Consts {
     int NPUSH;                          // CTAs that copy this rank's subtree values to the peers (multi-GPU)
     int BR_OK, MAXA;                    // the best-response kernel is generated too; widest decision node
     int PREFETCH;                       // micro phase: fetch the next unit's static indices while the current one runs
+    int XFENCE_ALL;                     // multi-GPU: every CTA fences its peer stores at system scope (else only the last arriver)
     int G[2], GPC[2], NG[2], GB[2], NUG[2];
     long long NS[2];                    // slots = NG * G
     long long NF, T;
@@ -962,13 +963,41 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
                     o << "      __syncthreads();\n    }\n";
                 }
             } else if (linear) {
+                // several passes through the staging area: the NEXT pass's values are fetched into registers while the sums
+                // of the current one run, so a pass costs max(load latency, sums) instead of their sum
+                int nvc = 0;
                 for (auto &ch : chunks) {
                     const int lo = k0s[ch.first] * GB, hi = (k0s[ch.second - 1] + nchs[ch.second - 1]) * GB;
-                    o << "    {\n"
-                         "      for (int L = " << lo << " + tid; L < " << hi << "; L += BLOCK) sm_r[L - " << lo << "] = __ldcg(blk + L);\n"
-                         "      __syncthreads();\n";
-                    emit_sums(ch.first, ch.second, k0s[ch.first]);
-                    o << "      __syncthreads();\n    }\n";
+                    nvc = std::max(nvc, (hi - lo + c.BLK - 1) / c.BLK);
+                }
+                if (nvc <= 32) {
+                    o << "    double fv[" << nvc << "];\n";
+                    auto emit_load = [&](size_t ci) {
+                        const int lo = k0s[chunks[ci].first] * GB, hi = (k0s[chunks[ci].second - 1] + nchs[chunks[ci].second - 1]) * GB;
+                        o << "#pragma unroll\n"
+                             "      for (int i = 0; i < " << nvc << "; ++i) { const int L = " << lo << " + tid + i * BLOCK; if (L < " << hi << ") fv[i] = __ldcg(blk + L); }\n";
+                    };
+                    o << "    {\n";
+                    emit_load(0);
+                    o << "    }\n";
+                    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+                        const int lo = k0s[chunks[ci].first] * GB, hi = (k0s[chunks[ci].second - 1] + nchs[chunks[ci].second - 1]) * GB;
+                        o << "    {\n#pragma unroll\n"
+                             "      for (int i = 0; i < " << nvc << "; ++i) { const int L = tid + i * BLOCK; if (L < " << hi - lo << ") sm_r[L] = fv[i]; }\n"
+                             "      __syncthreads();\n";
+                        if (ci + 1 < chunks.size()) emit_load(ci + 1);
+                        emit_sums(chunks[ci].first, chunks[ci].second, k0s[chunks[ci].first]);
+                        o << "      __syncthreads();\n    }\n";
+                    }
+                } else {
+                    for (auto &ch : chunks) {
+                        const int lo = k0s[ch.first] * GB, hi = (k0s[ch.second - 1] + nchs[ch.second - 1]) * GB;
+                        o << "    {\n"
+                             "      for (int L = " << lo << " + tid; L < " << hi << "; L += BLOCK) sm_r[L - " << lo << "] = __ldcg(blk + L);\n"
+                             "      __syncthreads();\n";
+                        emit_sums(ch.first, ch.second, k0s[ch.first]);
+                        o << "      __syncthreads();\n    }\n";
+                    }
                 }
             } else {        // no staging: every (tile, fan-in node) thread reads its values from the block directly
                 o << "    for (int x = tid; x < " << GB * c.F << "; x += BLOCK) {\n"
@@ -1131,7 +1160,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // Multi-GPU: the micro phase has stored the values of this rank's subtrees into every rank's buffer; the barrier\n"
          "    // that ends the phase also shakes hands with the peers (each CTA fences its peer stores at system scope first).\n"
-         "    if (P->nranks > 1) grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), true);\n"
+         "    if (P->nranks > 1) grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), " << (c.XFENCE_ALL ? "true" : "false") << ");\n"
          "    else grid_barrier(P->bar, ++nbar, nb);\n"
          "    if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();\n"
          "    // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)\n"
@@ -1388,6 +1417,12 @@ int plan_fused(const FusedCtx &cx, cudaStream_t stream) {
     c.BLK = blk; c.MINB = minb;
     c.NPUSH = 64;
     c.PREFETCH = 0;
+    // Multi-GPU: by default only the LAST CTA to arrive at the exchange barrier issues a system-scope fence before it
+    // publishes the flag.  The other CTAs' peer stores are ordered before it by causality (store -> bar.sync -> gpu-scope
+    // fence + arrive -> the last arriver's gpu-scope acquire -> its system-scope fence; PTX fences are cumulative), and a
+    // system fence in each of ~440 CTAs costs 3-4 us per iteration.  RLP_P2P_FENCE_ALL=1 fences in every CTA.
+    c.XFENCE_ALL = 0;
+    { const char *e = getenv("RLP_P2P_FENCE_ALL"); if (e && e[0] == '1') c.XFENCE_ALL = 1; }
     { const char *e = getenv("RLP_FUSED_PREFETCH"); if (e && e[0] == '1') c.PREFETCH = 1; }
     c.BR_OK = 0; c.MAXA = std::max(1, (int)t->max_act);
     { const char *e = getenv("RLP_P2P_NPUSH"); if (e && atoi(e) >= 1) c.NPUSH = atoi(e); }
