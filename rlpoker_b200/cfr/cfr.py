@@ -253,3 +253,80 @@ def cfr(*args, **kwargs):
 
 def evaluate_strategies(game, strategy, num_iters=500):
     return game.expected_value(strategy, strategy, num_iters)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference's recursion entry points under their own names (cfr.py:158, external_cfr.py:82).  The device has no
+# node-by-node recursion to offer: these run ONE traversal of the whole tree for one player on the device and write
+# the result into the caller's dictionaries exactly as the reference's recursion leaves them, so code that drives
+# the reference's inner loop by hand (`for i in [1, 2]: cfr_recursive(game, game.root, i, t, 1.0, 1.0, 1.0, ...)`)
+# keeps working.  Only the root call is supported (a call on an inner node raises).
+
+
+def _shim_solver(game):
+    solver = getattr(game, '_shim_solver', None)
+    if solver is None:
+        solver = DeviceCFR(device_tree(game))
+        try:
+            game._shim_solver = solver
+        except AttributeError:
+            pass
+    return solver
+
+
+def _dict_to_array(ft, d, default):
+    out = np.empty(ft.num_pairs, np.float64)
+    keys = ft.info_set_keys
+    for i in range(ft.num_infosets):
+        lo, k = int(ft.act_off[i]), int(ft.nact[i])
+        entry = d[keys[i]] if keys[i] in d else None
+        if entry is None:
+            out[lo:lo + k] = default(k)
+        else:
+            out[lo:lo + k] = [entry[a] for a in ft.actions_of(i)]
+    return out
+
+
+def cfr_recursive(game, node, i, t, pi_c, pi_1, pi_2, regrets, action_counts, strategy_t, strategy_t_1, cfr_state,
+                  use_chance_sampling=False, weight=1.0):
+    """One traversal for player ``i`` against the frozen ``strategy_t`` (cfr.py:158-255): updates ``regrets``,
+    ``action_counts`` and ``strategy_t_1`` for player i's information sets, fills ``strategy_t`` lazily with uniform
+    entries, counts the nodes and returns player i's value of the root."""
+    from rlpoker_b200._lib import RLP_REGRET
+    from rlpoker_b200.cfr.cfr_metrics import node_values
+    if node is not game.root or (pi_c, pi_1, pi_2) != (1.0, 1.0, 1.0):
+        raise ValueError("cfr_recursive is only available as a whole-tree traversal: call it on game.root with unit reaches")
+    if use_chance_sampling:
+        raise NotImplementedError("chance-sampled traversals run as device lanes: use cfr(..., use_chance_sampling=True)")
+    if weight not in (1.0, float(t)):
+        raise ValueError("weight must be 1.0 or t (cfr.py:106)")
+    ft = flatten(game)
+    keys = ft.info_set_keys
+    for idx in range(ft.num_infosets):                      # lazily-uniform strategy_t (cfr.py:198-199)
+        if keys[idx] not in strategy_t:
+            strategy_t[keys[idx]] = ActionFloat.initialise_uniform(ft.actions_of(idx))
+    sigma = _dict_to_array(ft, strategy_t, lambda k: 1.0 / float(k))
+    R0 = _dict_to_array(ft, regrets, lambda k: 0.0)
+    S0 = _dict_to_array(ft, action_counts, lambda k: 0.0)
+    solver = _shim_solver(game)
+    solver.reset()
+    solver.write(RLP_REGRET, R0)
+    solver.write(RLP_STRAT_SUM, S0)
+    solver.write(RLP_SIGMA, sigma)
+    solver.t = int(t)
+    solver.vanilla(1, linear_weight=(weight != 1.0))
+    R1, S1, sig1 = solver.read(RLP_REGRET), solver.read(RLP_STRAT_SUM), solver.read(RLP_SIGMA)
+    for idx in range(ft.num_infosets):
+        lo, k = int(ft.act_off[idx]), int(ft.nact[idx])
+        acts = ft.actions_of(idx)
+        key = keys[idx]
+        if key not in regrets:                              # every visited information set gets a regret entry (cfr.py:229-230)
+            regrets[key] = ActionFloat.initialise_zero(acts)
+        if int(ft.iset_player[idx]) != i:
+            continue
+        regrets[key] = ActionFloat({a: float(R1[lo + j]) for j, a in enumerate(acts)})
+        action_counts[key] = ActionFloat({a: float(S1[lo + j]) for j, a in enumerate(acts)})
+        strategy_t_1[key] = ActionFloat({a: float(sig1[lo + j]) for j, a in enumerate(acts)})
+    cfr_state.nodes_touched += ft.num_nodes
+    v1, v2 = node_values(game, DeviceStrategy(ft, sigma), DeviceStrategy(ft, sigma))
+    return float(v1[0] if i == 1 else v2[0])

@@ -73,3 +73,10 @@ def update_average_strategy(game, average_strategy, strategy, weight=1.0):
     solver.write_flags(present, bit=4)
     _lib.check(_lib.load().rlp_cfr_update_average(solver.handle, C.c_double(weight), _stream_ptr(None)))
     return average_strategy
+
+
+def update_average_strategy_recursive(game, node, average_strategy, strategy, pi1=1.0, pi2=1.0, pic=1.0, weight=1.0):
+    """The reference's recursion entry (cfr_util.py:129-198); available as the whole-tree walk only."""
+    if node is not game.root or (pi1, pi2) != (1.0, 1.0):
+        raise ValueError("update_average_strategy_recursive is only available on game.root with unit reaches")
+    update_average_strategy(game, average_strategy, strategy, weight=weight)

@@ -59,3 +59,10 @@ def external_sampling_cfr(experiment, game, num_iters=1000, experiment_writer=No
                 saver.save_best_strategy(average(), t_last, exploitability)
         t += n
     return average(), exploitabilities, history
+
+
+def external_sampling_cfr_recursive(game, node, player, regrets, strategy_t, strategy_t_1, cfr_state):
+    """The reference's recursion entry (external_cfr.py:82-173).  A sampled traversal draws from numpy's global RNG in
+    the reference and from a counter-based Philox stream here, so a single call cannot reproduce the reference's walk;
+    the traversals run as device lanes through ``external_sampling_cfr``."""
+    raise NotImplementedError("external-sampling traversals run as device lanes: use external_sampling_cfr(...)")

@@ -21,6 +21,7 @@ constexpr int kMaxChance = 128;   // widest chance node (numpy's pairwise sum is
 inline unsigned grid_for(int64_t n, int b = kBlock) { return (unsigned)((n + b - 1) / b); }
 
 struct LaneView {
+    const int4 *rec;                       // packed node records (tree.cuh)
     const int32_t *first_child, *colbase, *srank;
     const int8_t *player;
     const double *cprob, *pay1, *pay2, *sigma;
@@ -108,27 +109,28 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int
     for (;;) {
         // ---- phase 1: walk until a draw is needed ----------------------------------------------------------
         bool need = false;
-        int d_fc = 0, d_n = 0, d_pl = 0, d_node = 0;
+        int d_fc = 0, d_n = 0, d_pl = 0, d_col = 0;
         while (sp >= 0) {
             F &f = st[sp];
             const int node = f.node;
-            const int pl = v.player[node];
-            if (pl < 0) {                                   // terminal: utility of the traverser
+            const int4 rec = __ldg(v.rec + node);           // {first child, #children | (player + 1) << 8, colbase, srank}
+            const int pl = (rec.y >> 8) - 1;
+            if (pl < 0) {                                   // terminal (only the root can get here: leaves are handled inline)
                 ret = me == 1 ? v.pay1[node] : (v.zero_sum ? -v.pay1[node] : v.pay2[node]);
                 have_ret = true;
                 --sp;
                 continue;
             }
-            const int fc = v.first_child[node];
-            const int n = v.first_child[node + 1] - fc;
+            const int fc = rec.x;
+            const int n = rec.y & 0xff;
             const bool sampled_here = pl == 0 || (VARIANT == 1 && pl != me);
             if (sampled_here) {
                 if (have_ret) { --sp; continue; }           // the sampled child returned: pass its value up unchanged
-                need = true; d_fc = fc; d_n = n; d_pl = pl; d_node = node;
+                need = true; d_fc = fc; d_n = n; d_pl = pl; d_col = rec.z;
                 break;
             }
             // decision node whose actions are all explored (chance-sampled: every player node; external: own nodes)
-            const double *sg = v.sigma + v.colbase[node];
+            const double *sg = v.sigma + rec.z;
             if (have_ret) {                                  // child f.k-1 just returned
                 have_ret = false;
                 int a = f.k - 1;
@@ -137,24 +139,32 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int
             }
             if (f.k < n) {
                 int a = f.k++;
+                const int child = fc + a;
+                touched++;
+                if (v.player[child] < 0) {                  // a leaf: its value is known without a frame of its own
+                    const double u = me == 1 ? v.pay1[child] : (v.zero_sum ? -v.pay1[child] : v.pay2[child]);
+                    f.va[a] = u;
+                    f.value += sg[a] * u;
+                    continue;
+                }
                 F &c = st[sp + 1];
-                c.node = fc + a; c.k = 0; c.value = 0.0;
+                c.node = child; c.k = 0; c.value = 0.0;
                 if (VARIANT == 0) {
                     c.reach[0] = f.reach[0];
                     c.reach[1] = pl == 1 ? sg[a] * f.reach[1] : f.reach[1];
                     c.reach[2] = pl == 2 ? sg[a] * f.reach[2] : f.reach[2];
                 }
-                ++sp; touched++;
+                ++sp;
                 continue;
             }
             // all children done: update (cfr.py:229-252 / external_cfr.py:143-157)
-            const int s = v.srank[node];
+            const int s = rec.w;
             if (VARIANT == 0) {
                 v.in_R[s] = 1;
                 if (pl == me) {
                     double pi_minus = me == 2 ? f.reach[0] * f.reach[1] : f.reach[0] * f.reach[2];
                     double pi_own = me == 1 ? f.reach[1] : f.reach[2];
-                    double *R = v.R + v.colbase[node], *S = v.S + v.colbase[node];
+                    double *R = v.R + rec.z, *S = v.S + rec.z;
                     for (int a = 0; a < n; ++a) {
                         add(R + a, w * (f.va[a] - f.value) * pi_minus, v.atomic);
                         add(S + a, w * pi_own * sg[a], v.atomic);
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int
                     v.in_next[s] = 1;
                 }
             } else {
-                double *R = v.R + v.colbase[node];
+                double *R = v.R + rec.z;
                 for (int a = 0; a < n; ++a) add(R + a, f.va[a] - f.value, v.atomic);
                 v.in_R[s] = 1;
                 v.in_next[s] = 1;
@@ -175,13 +185,20 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int
         if (!__any_sync(0xffffffffu, need)) break;          // every lane of the warp has finished its traversal
         // ---- phase 2: the draws of the warp, together ---------------------------------------------------------
         if (need) {
-            const double *p = d_pl == 0 ? v.cprob + d_fc : v.sigma + v.colbase[d_node];
+            const double *p = d_pl == 0 ? v.cprob + d_fc : v.sigma + d_col;
             const int a = draw(p, d_n, rlp::philox_uniform(v.seed, iteration, lane, (uint32_t)(me - 1), ndraw++));
-            F &f = st[sp];
-            F &c = st[sp + 1];
-            c.node = d_fc + a; c.k = 0; c.value = 0.0;
-            if (VARIANT == 0) { c.reach[0] = f.reach[0]; c.reach[1] = f.reach[1]; c.reach[2] = f.reach[2]; }
-            ++sp; touched++;
+            const int child = d_fc + a;
+            touched++;
+            if (v.player[child] < 0) {                      // the drawn child is a leaf: its value returns at once
+                ret = me == 1 ? v.pay1[child] : (v.zero_sum ? -v.pay1[child] : v.pay2[child]);
+                have_ret = true;
+            } else {
+                F &f = st[sp];
+                F &c = st[sp + 1];
+                c.node = child; c.k = 0; c.value = 0.0;
+                if (VARIANT == 0) { c.reach[0] = f.reach[0]; c.reach[1] = f.reach[1]; c.reach[2] = f.reach[2]; }
+                ++sp;
+            }
         }
     }
     if (touched) atomicAdd(&v.iter->touched, touched);
@@ -311,6 +328,7 @@ int check_lanes(rlp_cfr *c, int variant, int64_t lanes) {
 LaneView lane_view(rlp_cfr *c, uint64_t seed, double *R, double *S, int atomic) {
     rlp_tree *t = c->tree;
     LaneView v;
+    v.rec = t->node_rec.p;
     v.first_child = t->first_child.p; v.colbase = t->colbase.p; v.srank = t->srank.p; v.player = t->player.p;
     v.cprob = t->cprob.p; v.pay1 = t->pay1.p; v.pay2 = t->pay2.p; v.sigma = c->sigma.p; v.R = R; v.S = S;
     v.in_R = c->flags.p; v.in_S = c->flags.p + (size_t)t->I; v.in_next = c->flags.p + 2 * (size_t)t->I;

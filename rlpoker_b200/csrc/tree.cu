@@ -44,7 +44,7 @@ int build_tiles(const rlp_tree_desc *d, rlp_tree *t, const std::vector<int32_t> 
 
 int64_t rlp_tree::bytes() const {
     return (int64_t)(first_child.bytes() + colbase.bytes() + srank.bytes() + krank.bytes() + player.bytes() +
-                     cprob.bytes() + pay1.bytes() + pay2.bytes() + koff_col.bytes() + koff_iset.bytes() +
+                     cprob.bytes() + pay1.bytes() + pay2.bytes() + node_rec.bytes() + koff_col.bytes() + koff_iset.bytes() +
                      iset_size.bytes() + iset_level.bytes() + iset_player.bytes() + col_off.bytes() +
                      iset_node_off.bytes() + iset_nodes.bytes() + d_canon_of_col.bytes()) + tiles.bytes();
 }
@@ -214,6 +214,13 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
     RLP_CUDA(t->colbase.upload(colbase, stream));
     RLP_CUDA(t->srank.upload(srank, stream));
     RLP_CUDA(t->krank.upload(krank, stream));
+    {
+        std::vector<int4> rec((size_t)N);
+        for (int64_t i = 0; i < N; ++i)
+            rec[i] = make_int4(fc[i], (fc[i + 1] - fc[i]) | ((int)(pl[i] + 1) << 8), colbase[i], srank[i]);
+        RLP_CUDA(t->node_rec.upload(rec, stream));
+        RLP_CUDA(rlp::sync_stream(stream));
+    }
     RLP_CUDA(t->cprob.upload(cp, stream));
     RLP_CUDA(t->pay1.upload(p1, stream));
     if (!zs) {

@@ -41,6 +41,7 @@ struct rlp_tree {
     rlp::DevBuf<int32_t> first_child, colbase, srank, krank;
     rlp::DevBuf<int8_t> player;
     rlp::DevBuf<double> cprob, pay1, pay2;
+    rlp::DevBuf<int4> node_rec;                   // [N] {first_child, #children | (player + 1) << 8, colbase, srank}: one 16-byte load per visit
     rlp::DevBuf<int64_t> koff_col, koff_iset;     // [Kmax+1]
     rlp::DevBuf<int32_t> iset_size, iset_level;   // [I] internal order
     rlp::DevBuf<int8_t> iset_player;              // [I]

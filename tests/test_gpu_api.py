@@ -221,3 +221,30 @@ def test_command_line_front_end(tmp_path):
         [sys.executable, os.path.join(ROOT, 'examples', 'cfr.py'), '--exp_name', 'cli2', '--cfr_algorithm', 'external',
          '--num_iters', '201', '--lanes', '64', '--seed', '1', '--no_immediate_regret'], cwd=str(tmp_path), text=True)
     assert 't: 200, nodes touched:' in out
+
+
+def test_cfr_recursive_entry_point_drives_the_reference_loop(golden_arrays):
+    """The reference's inner loop driven by hand through `cfr_recursive` (cfr.py:105-122) gives the reference's numbers."""
+    from oracle import oracle as orc
+    from rlpoker_b200.cfr import cfr_util
+    from rlpoker_b200.cfr.cfr import cfr_recursive, compute_average_strategy
+    from rlpoker_b200.extensive_game import Strategy
+    from rlpoker_b200.flatten import flatten, strategy_to_array
+    game = make_game('leduc2')
+    regrets, action_counts = {}, {}
+    state = cfr_util.CFRState()
+    strategy_t, strategy_t_1 = Strategy.initialise(), Strategy.initialise()
+    for t in range(6):
+        values = [cfr_recursive(game, game.root, i, t, 1.0, 1.0, 1.0, regrets, action_counts, strategy_t, strategy_t_1,
+                                state, use_chance_sampling=False, weight=float(t)) for i in (1, 2)]
+        assert values[0] == -values[1]
+        strategy_t = strategy_t_1.copy()
+    ft = flatten(game)
+    got_R = np.array([regrets[k][a] for i, k in enumerate(ft.info_set_keys) for a in ft.actions_of(i)])
+    assert np.array_equal(got_R, golden_arrays['vanilla_linear_leduc2_T6_R'])
+    avg = strategy_to_array(ft, compute_average_strategy(action_counts))[0]
+    assert np.array_equal(avg, golden_arrays['vanilla_linear_leduc2_T6_avg'])
+    assert state.nodes_touched == 2 * 6 * ft.num_nodes
+    with pytest.raises(ValueError):
+        cfr_recursive(game, game.root.children[next(iter(game.root.children))], 1, 0, 1.0, 1.0, 1.0, regrets, action_counts,
+                      strategy_t, strategy_t_1, state)
