@@ -83,15 +83,16 @@ __device__ inline void add(double *p, double x, int atomic) {
 }
 
 // variant 0: chance-sampled CFR (cfr.py:158-255); variant 1: external sampling (external_cfr.py:82-173)
-// The walk alternates two phases per warp.  Phase 1: every thread advances its own depth-first walk until it stands on a
-// node where an action has to be DRAWN (or the traversal is over) -- cheap bookkeeping, divergent.  Phase 2: the threads
-// that need a draw perform it TOGETHER (Philox + numpy's sampler with its divisions is by far the longest straight piece of
-// the walk; running it converged instead of inside a five-way branch took the average active lanes per instruction from
-// 6.4 to the low twenties).
+// The walk keeps a stack frame only for the decision nodes whose actions are ALL explored (external sampling: the
+// traverser's own nodes; chance sampling: every player node).  Sampled nodes (chance, and the opponent under external
+// sampling) pass their child's value up unchanged, so they need no frame: the walk simply moves on to the drawn child.
+// Leaves are valued where they are met.  The walk alternates two phases per warp.  Phase 1: every thread advances its
+// own walk until it stands on a node where an action has to be DRAWN (or the traversal is over) -- cheap bookkeeping,
+// divergent.  Phase 2: the threads that need a draw perform it TOGETHER (Philox + numpy's sampler with its divisions
+// is the longest straight piece of the walk).
 template <int VARIANT, int MAXA, int DEPTH>
 __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int64_t lane_base) {
     int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const bool idle = tid >= 2 * lanes;                 // keeps running: the warp votes below need every lane
     const uint32_t lane = (uint32_t)((tid >> 1) + lane_base);     // global lane id: results do not depend on the sharding
     const int me = (int)(tid & 1) + 1;                  // traversing player
     const uint64_t iteration = (uint64_t)v.iter->t;
@@ -100,61 +101,64 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int
     unsigned long long touched = 0;
     typedef Frame<VARIANT, MAXA> F;
     F st[DEPTH];
-    int sp = idle ? -1 : 0;
-    st[0].node = 0; st[0].k = 0; st[0].value = 0.0;
-    if (VARIANT == 0) { st[0].reach[0] = 1.0; st[0].reach[1] = 1.0; st[0].reach[2] = 1.0; }
-    if (!idle) touched++;
-    double ret = 0.0;      // value returned by the frame that just finished
-    bool have_ret = false;
+    enum { ENTER = 0, RET = 1, NEXT = 2 };
+    int sp = -1, cur = 0, mode = ENTER;
+    bool done = tid >= 2 * lanes;                       // idle threads keep running: the warp votes below need every lane
+    double pr0 = 1.0, pr1 = 1.0, pr2 = 1.0;             // reach of `cur` (chance-sampled variant)
+    if (!done) touched++;
+    double ret = 0.0;                                   // value delivered to the top frame in mode RET
+    auto payoff = [&](int node) { return me == 1 ? v.pay1[node] : (v.zero_sum ? -v.pay1[node] : v.pay2[node]); };
     for (;;) {
         // ---- phase 1: walk until a draw is needed ----------------------------------------------------------
         bool need = false;
         int d_fc = 0, d_n = 0, d_pl = 0, d_col = 0;
-        while (sp >= 0) {
-            F &f = st[sp];
-            const int node = f.node;
-            const int4 rec = __ldg(v.rec + node);           // {first child, #children | (player + 1) << 8, colbase, srank}
-            const int pl = (rec.y >> 8) - 1;
-            if (pl < 0) {                                   // terminal (only the root can get here: leaves are handled inline)
-                ret = me == 1 ? v.pay1[node] : (v.zero_sum ? -v.pay1[node] : v.pay2[node]);
-                have_ret = true;
-                --sp;
+        while (!done) {
+            if (mode == ENTER) {
+                const int4 rec = __ldg(v.rec + cur);        // {first child, #children | (player + 1) << 8, colbase, srank}
+                const int pl = (rec.y >> 8) - 1;
+                if (pl < 0) { ret = payoff(cur); mode = RET; continue; }
+                if (pl == 0 || (VARIANT == 1 && pl != me)) {
+                    need = true; d_fc = rec.x; d_n = rec.y & 0xff; d_pl = pl; d_col = rec.z;
+                    break;
+                }
+                F &f = st[++sp];                            // a node whose actions are all explored
+                f.node = cur; f.k = 0; f.value = 0.0;
+                if (VARIANT == 0) { f.reach[0] = pr0; f.reach[1] = pr1; f.reach[2] = pr2; }
+                mode = NEXT;
                 continue;
             }
-            const int fc = rec.x;
-            const int n = rec.y & 0xff;
-            const bool sampled_here = pl == 0 || (VARIANT == 1 && pl != me);
-            if (sampled_here) {
-                if (have_ret) { --sp; continue; }           // the sampled child returned: pass its value up unchanged
-                need = true; d_fc = fc; d_n = n; d_pl = pl; d_col = rec.z;
-                break;
-            }
-            // decision node whose actions are all explored (chance-sampled: every player node; external: own nodes)
-            const double *sg = v.sigma + rec.z;
-            if (have_ret) {                                  // child f.k-1 just returned
-                have_ret = false;
-                int a = f.k - 1;
+            if (mode == RET) {                              // `ret` is the value of the child the top frame visited last
+                if (sp < 0) { done = true; break; }
+                F &f = st[sp];
+                const int a = f.k - 1;
+                const double sga = v.sigma[__ldg(v.rec + f.node).z + a];
                 f.va[a] = ret;
-                f.value += sg[a] * ret;
+                f.value += sga * ret;
+                mode = NEXT;
+                continue;
             }
+            // NEXT: the top frame visits its next child, or finishes
+            F &f = st[sp];
+            const int4 rec = __ldg(v.rec + f.node);
+            const int pl = (rec.y >> 8) - 1, fc = rec.x, n = rec.y & 0xff;
+            const double *sg = v.sigma + rec.z;
             if (f.k < n) {
-                int a = f.k++;
+                const int a = f.k++;
                 const int child = fc + a;
                 touched++;
-                if (v.player[child] < 0) {                  // a leaf: its value is known without a frame of its own
-                    const double u = me == 1 ? v.pay1[child] : (v.zero_sum ? -v.pay1[child] : v.pay2[child]);
+                if (v.player[child] < 0) {                  // a leaf: valued in place
+                    const double u = payoff(child);
                     f.va[a] = u;
                     f.value += sg[a] * u;
                     continue;
                 }
-                F &c = st[sp + 1];
-                c.node = child; c.k = 0; c.value = 0.0;
+                cur = child;
                 if (VARIANT == 0) {
-                    c.reach[0] = f.reach[0];
-                    c.reach[1] = pl == 1 ? sg[a] * f.reach[1] : f.reach[1];
-                    c.reach[2] = pl == 2 ? sg[a] * f.reach[2] : f.reach[2];
+                    pr0 = f.reach[0];
+                    pr1 = pl == 1 ? sg[a] * f.reach[1] : f.reach[1];
+                    pr2 = pl == 2 ? sg[a] * f.reach[2] : f.reach[2];
                 }
-                ++sp;
+                mode = ENTER;
                 continue;
             }
             // all children done: update (cfr.py:229-252 / external_cfr.py:143-157)
@@ -179,8 +183,8 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int
                 v.in_next[s] = 1;
             }
             ret = f.value;
-            have_ret = true;
             --sp;
+            mode = RET;
         }
         if (!__any_sync(0xffffffffu, need)) break;          // every lane of the warp has finished its traversal
         // ---- phase 2: the draws of the warp, together ---------------------------------------------------------
@@ -189,16 +193,8 @@ __global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int
             const int a = draw(p, d_n, rlp::philox_uniform(v.seed, iteration, lane, (uint32_t)(me - 1), ndraw++));
             const int child = d_fc + a;
             touched++;
-            if (v.player[child] < 0) {                      // the drawn child is a leaf: its value returns at once
-                ret = me == 1 ? v.pay1[child] : (v.zero_sum ? -v.pay1[child] : v.pay2[child]);
-                have_ret = true;
-            } else {
-                F &f = st[sp];
-                F &c = st[sp + 1];
-                c.node = child; c.k = 0; c.value = 0.0;
-                if (VARIANT == 0) { c.reach[0] = f.reach[0]; c.reach[1] = f.reach[1]; c.reach[2] = f.reach[2]; }
-                ++sp;
-            }
+            if (v.player[child] < 0) { ret = payoff(child); mode = RET; }     // the drawn child is a leaf
+            else { cur = child; mode = ENTER; }                             // (its reach is that of the sampled node)
         }
     }
     if (touched) atomicAdd(&v.iter->touched, touched);
