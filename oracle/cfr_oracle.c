@@ -157,7 +157,7 @@ static inline void philox_round(uint32_t c[4], const uint32_t k[2]) {
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
 
-/* Philox-4x32-10; counter = (draw, traversing player, lane, iteration), key = seed. */
+/* Philox-4x32-10; counter = (node of the draw, traversing player, lane, iteration), key = seed. */
 double orc_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t lane, uint32_t trav, uint32_t draw) {
     uint32_t c[4] = {draw, trav, lane, (uint32_t)iteration};
     uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32)};
@@ -171,12 +171,17 @@ double orc_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t lane, uint
     return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
 }
 
-static double next_uniform(orc_rng *g) {
+/* The uniform for the draw at `node`.  kind 0 consumes the recorded stream in visit order (the reference's numpy
+ * generator); kind 1 is counter based and keyed by the NODE the draw happens at -- a traversal visits a node at most
+ * once, so the key is unique, and it does not depend on the order the traversal's nodes are processed in (the device
+ * processes a traversal level by level, not depth first). */
+static double next_uniform(orc_rng *g, int32_t node) {
     if (g->kind == 0) {
         if (g->stream_pos >= g->stream_len) { g->exhausted = 1; return 0.0; }
         return g->stream[g->stream_pos++];
     }
-    return orc_philox_uniform(g->seed, g->iteration, g->lane, g->trav, g->draw++);
+    g->draw++;
+    return orc_philox_uniform(g->seed, g->iteration, g->lane, g->trav, (uint32_t)node);
 }
 
 /* util.py:17-27 -> RandomState.choice(p=...): normalise, cumsum, renormalise, searchsorted right. */
@@ -214,7 +219,7 @@ static double cfr_rec(cfr_ctx *c, int32_t node, int i, double pi_c, double pi_1,
     int n = t->first_child[node + 1] - fc;
     if (pl == 0) {
         if (c->sampling) {
-            int a = orc_draw(t->cprob + fc, n, next_uniform(c->rng));
+            int a = orc_draw(t->cprob + fc, n, next_uniform(c->rng, node));
             return cfr_rec(c, fc + a, i, pi_c, pi_1, pi_2);
         }
         double value = 0.0;
@@ -419,7 +424,7 @@ static double ext_rec(cfr_ctx *c, int32_t node, int player) {
     int32_t fc = t->first_child[node];
     int n = t->first_child[node + 1] - fc;
     if (pl == 0) {
-        int a = orc_draw(t->cprob + fc, n, next_uniform(c->rng));
+        int a = orc_draw(t->cprob + fc, n, next_uniform(c->rng, node));
         return ext_rec(c, fc + a, player);
     }
     int32_t I = t->infoset[node];
@@ -437,7 +442,7 @@ static double ext_rec(cfr_ctx *c, int32_t node, int player) {
         c->in_next[I] = 1;
         return eu;
     }
-    int a = orc_draw(sg, n, next_uniform(c->rng));
+    int a = orc_draw(sg, n, next_uniform(c->rng, node));
     return ext_rec(c, fc + a, player);
 }
 

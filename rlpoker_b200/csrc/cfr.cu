@@ -652,6 +652,11 @@ extern "C" uint64_t rlp_nodes_touched(rlp_cfr *c) {
     if (c->touched_dirty) {      // sampled lanes count on the device
         cudaDeviceSynchronize();
         cudaMemcpy(&dev, &c->iter.p->touched, sizeof(dev), cudaMemcpyDeviceToHost);
+        if (c->fr_count.p) {    // the frontier form of the lanes flags a record overflow instead of writing out of bounds
+            unsigned int over = 0;
+            cudaMemcpy(&over, c->fr_count.p + c->fr_levels, sizeof(over), cudaMemcpyDeviceToHost);
+            if (over) { fail(RLP_ERR_CUDA, "sampled lanes: frontier records overflowed their bound"); return 0; }
+        }
     }
     return c->nodes_touched + dev;
 }

@@ -50,6 +50,14 @@ struct rlp_cfr {
     rlp::DevBuf<double> contrib_r, contrib_o;
     rlp::DevBuf<int32_t> astar;              // [I] best-response action per information set
     rlp::DevBuf<IterState> iter;
+    // frontier records of the level-synchronous sampled lanes (sampled.cu), sized for `fr_lanes` lanes of `fr_variant`
+    rlp::DevBuf<int32_t> fr_node, fr_trav, fr_child;
+    rlp::DevBuf<double> fr_val, fr_reach;
+    rlp::DevBuf<unsigned int> fr_count;
+    rlp::DevBuf<double> lane_acc;            // zeroed accumulator copies of the batched lanes
+    int64_t fr_lanes = 0;
+    int fr_variant = -1;
+    int fr_levels = 0;
     rlp::DevBuf<unsigned long long> timeline;
     rlp::DevBuf<double> scalars;             // small device scratch for reductions
     uint64_t nodes_touched = 0;              // host-side count (vanilla); sampled lanes count in iter->touched

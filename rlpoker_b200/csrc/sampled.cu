@@ -6,7 +6,7 @@
 // breadth-first arrays against the strategy frozen for the iteration; chance (and, for external
 // sampling, opponent) actions are drawn with the reference's sampler (rlpoker/util.py:17-27 ->
 // numpy RandomState.choice: normalise, cumsum, renormalise, searchsorted-right) from a counter-based
-// Philox-4x32-10 stream keyed (seed; iteration, lane, player, draw index), so a CPU run fed the same
+// Philox-4x32-10 stream keyed (seed; iteration, lane, player, node of the draw), so a CPU run fed the same
 // stream reproduces every lane exactly.  lanes == 1 is the reference algorithm bit for bit (plain adds in
 // visit order); lanes > 1 is mini-batch MCCFR with fp64 atomics (order of adds not deterministic).
 #include "cfr.cuh"
@@ -25,7 +25,9 @@ struct LaneView {
     const int32_t *first_child, *colbase, *srank;
     const int8_t *player;
     const double *cprob, *pay1, *pay2, *sigma;
-    double *R, *S;
+    double *R, *S;                         // lanes == 1: the solver's arrays; else copy 0 of the accumulators below
+    int64_t copy_stride;                   // batched lanes add into one of (copy_mask + 1) zeroed copies, picked by the
+    unsigned copy_mask;                    //   block index: the 10^6 adds of a level to the few root sets do not serialise
     uint8_t *in_R, *in_S, *in_next;       // [I] each
     IterState *iter;
     uint64_t seed;
@@ -78,6 +80,12 @@ struct Frame {
     double reach[VARIANT == 0 ? 3 : 1];     // chance-sampled: pc, p1, p2
 };
 
+// Dictionary-membership flags only ever go 0 -> 1: test before storing, or every traversal of every iteration rewrites
+// the same few cache lines (the stores of 10^6 lanes to one line serialise in its L2 slice).
+__device__ inline void mark(uint8_t *flag) {
+    if (*flag == 0) *flag = 1;
+}
+
 __device__ inline void add(double *p, double x, int atomic) {
     if (atomic) atomicAdd(p, x); else *p = *p + x;
 }
@@ -90,114 +98,321 @@ __device__ inline void add(double *p, double x, int atomic) {
 // own walk until it stands on a node where an action has to be DRAWN (or the traversal is over) -- cheap bookkeeping,
 // divergent.  Phase 2: the threads that need a draw perform it TOGETHER (Philox + numpy's sampler with its divisions
 // is the longest straight piece of the walk).
-template <int VARIANT, int MAXA, int DEPTH>
-__global__ void __launch_bounds__(kBlock) k_lanes(LaneView v, int64_t lanes, int64_t lane_base) {
+// The frame being worked on lives in REGISTERS (its action values are written with unrolled selects, never indexed);
+// local memory only holds the frames below it, written when a deeper explored node is entered and read back when that
+// node is finished -- a few times per traversal instead of at every child.
+template <int VARIANT, int MAXA, int DEPTH, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_lanes(LaneView v, int64_t lanes, int64_t lane_base) {
     int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const uint32_t lane = (uint32_t)((tid >> 1) + lane_base);     // global lane id: results do not depend on the sharding
     const int me = (int)(tid & 1) + 1;                  // traversing player
     const uint64_t iteration = (uint64_t)v.iter->t;
     const double w = v.iter->linear ? (double)v.iter->t : 1.0;
-    uint32_t ndraw = 0;
+    const int64_t copy = (int64_t)(blockIdx.x & v.copy_mask) * v.copy_stride;
     unsigned long long touched = 0;
     typedef Frame<VARIANT, MAXA> F;
-    F st[DEPTH];
+    F st[DEPTH];                                        // the frames BELOW the one in registers
     enum { ENTER = 0, RET = 1, NEXT = 2 };
-    int sp = -1, cur = 0, mode = ENTER;
+    int sp = 0, cur = 0, mode = ENTER;                  // sp: live frames (the top one in t_*)
+    int t_node = 0, t_fc = 0, t_n = 0, t_pl = 0, t_col = 0, t_s = 0, t_k = 0;
+    uint32_t t_leaf = 0;                                // leaf mask of the top frame's children (explored nodes: <= kMaxAct)
+    double t_val = 0.0, t_va[MAXA], t_r0 = 1.0, t_r1 = 1.0, t_r2 = 1.0;
+#pragma unroll
+    for (int i = 0; i < MAXA; ++i) t_va[i] = 0.0;
     bool done = tid >= 2 * lanes;                       // idle threads keep running: the warp votes below need every lane
     double pr0 = 1.0, pr1 = 1.0, pr2 = 1.0;             // reach of `cur` (chance-sampled variant)
     if (!done) touched++;
     double ret = 0.0;                                   // value delivered to the top frame in mode RET
     auto payoff = [&](int node) { return me == 1 ? v.pay1[node] : (v.zero_sum ? -v.pay1[node] : v.pay2[node]); };
+    auto set_va = [&](int a, double x) {
+#pragma unroll
+        for (int i = 0; i < MAXA; ++i) if (i == a) t_va[i] = x;
+    };
     for (;;) {
         // ---- phase 1: walk until a draw is needed ----------------------------------------------------------
         bool need = false;
         int d_fc = 0, d_n = 0, d_pl = 0, d_col = 0;
+        uint32_t d_leaf = 0;
         while (!done) {
             if (mode == ENTER) {
                 const int4 rec = __ldg(v.rec + cur);        // {first child, #children | (player + 1) << 8, colbase, srank}
-                const int pl = (rec.y >> 8) - 1;
+                const int pl = ((rec.y >> 8) & 0xff) - 1;
                 if (pl < 0) { ret = payoff(cur); mode = RET; continue; }
                 if (pl == 0 || (VARIANT == 1 && pl != me)) {
-                    need = true; d_fc = rec.x; d_n = rec.y & 0xff; d_pl = pl; d_col = rec.z;
+                    need = true; d_fc = rec.x; d_n = rec.y & 0xff; d_pl = pl; d_col = rec.z; d_leaf = (uint32_t)rec.y >> 16;
                     break;
                 }
-                F &f = st[++sp];                            // a node whose actions are all explored
-                f.node = cur; f.k = 0; f.value = 0.0;
-                if (VARIANT == 0) { f.reach[0] = pr0; f.reach[1] = pr1; f.reach[2] = pr2; }
+                if (sp > 0) {                               // a node whose actions are all explored: new top frame
+                    F &f = st[sp - 1];
+                    f.node = t_node; f.k = t_k; f.value = t_val;
+#pragma unroll
+                    for (int i = 0; i < MAXA; ++i) f.va[i] = t_va[i];
+                    if (VARIANT == 0) { f.reach[0] = t_r0; f.reach[1] = t_r1; f.reach[2] = t_r2; }
+                }
+                ++sp;
+                t_node = cur; t_fc = rec.x; t_n = rec.y & 0xff; t_pl = pl; t_col = rec.z; t_s = rec.w;
+                t_leaf = (uint32_t)rec.y >> 16;
+                t_k = 0; t_val = 0.0;
+                if (VARIANT == 0) { t_r0 = pr0; t_r1 = pr1; t_r2 = pr2; }
                 mode = NEXT;
                 continue;
             }
             if (mode == RET) {                              // `ret` is the value of the child the top frame visited last
-                if (sp < 0) { done = true; break; }
-                F &f = st[sp];
-                const int a = f.k - 1;
-                const double sga = v.sigma[__ldg(v.rec + f.node).z + a];
-                f.va[a] = ret;
-                f.value += sga * ret;
+                if (sp == 0) { done = true; break; }
+                const int a = t_k - 1;
+                const double sga = v.sigma[t_col + a];
+                set_va(a, ret);
+                t_val += sga * ret;
                 mode = NEXT;
                 continue;
             }
             // NEXT: the top frame visits its next child, or finishes
-            F &f = st[sp];
-            const int4 rec = __ldg(v.rec + f.node);
-            const int pl = (rec.y >> 8) - 1, fc = rec.x, n = rec.y & 0xff;
-            const double *sg = v.sigma + rec.z;
-            if (f.k < n) {
-                const int a = f.k++;
-                const int child = fc + a;
+            if (t_k < t_n) {
+                const int a = t_k++;
+                const int child = t_fc + a;
                 touched++;
-                if (v.player[child] < 0) {                  // a leaf: valued in place
+                if ((t_leaf >> a) & 1) {                    // a leaf: valued in place
                     const double u = payoff(child);
-                    f.va[a] = u;
-                    f.value += sg[a] * u;
+                    set_va(a, u);
+                    t_val += v.sigma[t_col + a] * u;
                     continue;
                 }
                 cur = child;
                 if (VARIANT == 0) {
-                    pr0 = f.reach[0];
-                    pr1 = pl == 1 ? sg[a] * f.reach[1] : f.reach[1];
-                    pr2 = pl == 2 ? sg[a] * f.reach[2] : f.reach[2];
+                    const double sga = v.sigma[t_col + a];
+                    pr0 = t_r0;
+                    pr1 = t_pl == 1 ? sga * t_r1 : t_r1;
+                    pr2 = t_pl == 2 ? sga * t_r2 : t_r2;
                 }
                 mode = ENTER;
                 continue;
             }
             // all children done: update (cfr.py:229-252 / external_cfr.py:143-157)
-            const int s = rec.w;
             if (VARIANT == 0) {
-                v.in_R[s] = 1;
-                if (pl == me) {
-                    double pi_minus = me == 2 ? f.reach[0] * f.reach[1] : f.reach[0] * f.reach[2];
-                    double pi_own = me == 1 ? f.reach[1] : f.reach[2];
-                    double *R = v.R + rec.z, *S = v.S + rec.z;
-                    for (int a = 0; a < n; ++a) {
-                        add(R + a, w * (f.va[a] - f.value) * pi_minus, v.atomic);
-                        add(S + a, w * pi_own * sg[a], v.atomic);
-                    }
-                    v.in_S[s] = 1;
-                    v.in_next[s] = 1;
+                mark(v.in_R + t_s);
+                if (t_pl == me) {
+                    double pi_minus = me == 2 ? t_r0 * t_r1 : t_r0 * t_r2;
+                    double pi_own = me == 1 ? t_r1 : t_r2;
+                    double *R = v.R + copy + t_col, *S = v.S + copy + t_col;
+#pragma unroll
+                    for (int a = 0; a < MAXA; ++a)
+                        if (a < t_n) {
+                            add(R + a, w * (t_va[a] - t_val) * pi_minus, v.atomic);
+                            add(S + a, w * pi_own * v.sigma[t_col + a], v.atomic);
+                        }
+                    mark(v.in_S + t_s);
+                    mark(v.in_next + t_s);
                 }
             } else {
-                double *R = v.R + rec.z;
-                for (int a = 0; a < n; ++a) add(R + a, f.va[a] - f.value, v.atomic);
-                v.in_R[s] = 1;
-                v.in_next[s] = 1;
+                double *R = v.R + copy + t_col;
+#pragma unroll
+                for (int a = 0; a < MAXA; ++a)
+                    if (a < t_n) add(R + a, t_va[a] - t_val, v.atomic);
+                mark(v.in_R + t_s);
+                mark(v.in_next + t_s);
             }
-            ret = f.value;
+            ret = t_val;
             --sp;
+            if (sp > 0) {                                   // the frame below becomes the top frame again
+                const F &f = st[sp - 1];
+                t_node = f.node; t_k = f.k; t_val = f.value;
+#pragma unroll
+                for (int i = 0; i < MAXA; ++i) t_va[i] = f.va[i];
+                if (VARIANT == 0) { t_r0 = f.reach[0]; t_r1 = f.reach[1]; t_r2 = f.reach[2]; }
+                const int4 rec = __ldg(v.rec + t_node);
+                t_fc = rec.x; t_n = rec.y & 0xff; t_pl = ((rec.y >> 8) & 0xff) - 1; t_col = rec.z; t_s = rec.w;
+                t_leaf = (uint32_t)rec.y >> 16;
+            }
             mode = RET;
         }
         if (!__any_sync(0xffffffffu, need)) break;          // every lane of the warp has finished its traversal
         // ---- phase 2: the draws of the warp, together ---------------------------------------------------------
         if (need) {
             const double *p = d_pl == 0 ? v.cprob + d_fc : v.sigma + d_col;
-            const int a = draw(p, d_n, rlp::philox_uniform(v.seed, iteration, lane, (uint32_t)(me - 1), ndraw++));
+            const int a = draw(p, d_n, rlp::philox_uniform(v.seed, iteration, lane, (uint32_t)(me - 1), (uint32_t)cur));
             const int child = d_fc + a;
             touched++;
-            if (v.player[child] < 0) { ret = payoff(child); mode = RET; }     // the drawn child is a leaf
+            const bool leaf = a < 16 ? (d_leaf >> a) & 1 : v.player[child] < 0;
+            if (leaf) { ret = payoff(child); mode = RET; }                  // the drawn child is a leaf
             else { cur = child; mode = ENTER; }                             // (its reach is that of the sampled node)
         }
     }
     if (touched) atomicAdd(&v.iter->touched, touched);
+}
+
+// ---- the same traversals, level by level ---------------------------------------------------------------------------
+// With many lanes the depth-first kernel above is bound by divergence: the threads of a warp stand at different places of
+// their walks.  The frontier form keeps one RECORD per visited non-terminal node of every traversal, grouped by depth:
+// a forward pass per level draws the sampled actions / expands the explored nodes into the next level's records (a warp
+// reserves its children with one atomic on the level counter), a backward pass per level turns children values into
+// node values and regret / strategy-sum increments.  Every thread of a launch does the same step of the walk, the values
+// are the depth-first kernel's bit for bit (same operands, same order within a node), terminal children never become
+// records, and the Philox key (node of the draw) does not depend on the processing order.
+constexpr int kFBlock = 256;
+constexpr int kTouchedParts = 64;
+struct Frontier {
+    int32_t *node, *trav, *child;      // child: first record of the children at the next level, or ~node of a drawn terminal
+    double *val, *reach;               // reach: [3][capacity] (chance-sampled variant)
+    unsigned int *count;               // [levels + 1] records per level; the last word flags a capacity overflow
+    unsigned long long *touched;       // [kTouchedParts] visit counts, folded into IterState::touched at the end
+    int64_t off[kMaxDepth + 1];        // first record of each level
+    int64_t total;
+    int levels;
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kFBlock) k_front_root(LaneView v, Frontier f, int64_t lanes) {
+    int64_t tid = (int64_t)blockIdx.x * kFBlock + threadIdx.x;
+    if (tid == 0) {
+        f.count[0] = (unsigned int)(2 * lanes);
+        f.touched[0] = (unsigned long long)(2 * lanes);
+    }
+    if (tid >= 2 * lanes) return;
+    f.node[tid] = 0;
+    f.trav[tid] = (int32_t)tid;
+    if (VARIANT == 0) { f.reach[tid] = 1.0; f.reach[f.total + tid] = 1.0; f.reach[2 * f.total + tid] = 1.0; }
+}
+
+__global__ void k_front_touched(Frontier f, IterState *iter) {
+    unsigned long long x = f.touched[threadIdx.x] + f.touched[threadIdx.x + 32];
+    for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (threadIdx.x == 0) iter->touched += x;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kFBlock) k_front_expand(LaneView v, Frontier f, int level, int64_t lane_base) {
+    __shared__ int s_new[kFBlock / 32];
+    __shared__ unsigned int s_touched[kFBlock / 32], s_base;
+    const unsigned int count = f.count[level];
+    if ((int64_t)blockIdx.x * kFBlock >= count) return;          // the whole block is past the end
+    const int64_t i = (int64_t)blockIdx.x * kFBlock + threadIdx.x;
+    const bool live = i < count;
+    const int64_t at = f.off[level] + i, next = f.off[level + 1];
+    const int64_t cap = f.off[level + 2] - next;
+    int node = 0, tr = 0, fc = 0, n = 0, pl = 0, col = 0, n_new = 0, a_drawn = 0;
+    uint32_t mask = 0, touched = 0;
+    bool sampled = false;
+    if (live) {
+        node = f.node[at]; tr = f.trav[at];
+        const int4 rec = __ldg(v.rec + node);
+        fc = rec.x; n = rec.y & 0xff; pl = ((rec.y >> 8) & 0xff) - 1; col = rec.z;
+        const uint32_t leaf = (uint32_t)rec.y >> 16;
+        const int me = (tr & 1) + 1;
+        sampled = pl == 0 || (VARIANT == 1 && pl != me);
+        if (sampled) {
+            const uint32_t lane = (uint32_t)((tr >> 1) + lane_base);
+            const double *p = pl == 0 ? v.cprob + fc : v.sigma + col;
+            a_drawn = draw(p, n, rlp::philox_uniform(v.seed, (uint64_t)v.iter->t, lane, (uint32_t)(me - 1), (uint32_t)node));
+            const bool is_leaf = a_drawn < 16 ? (leaf >> a_drawn) & 1 : v.player[fc + a_drawn] < 0;
+            n_new = is_leaf ? 0 : 1;
+            touched = 1;
+        } else {
+            mask = ~leaf & ((1u << n) - 1u);                    // explored nodes have at most kMaxAct children
+            n_new = __popc(mask);
+            touched = (uint32_t)n;
+        }
+    }
+    // the block reserves its children records with ONE atomic on the level counter (a counter shared by 10^5 warps
+    // would take an atomic per warp at about one per clock)
+    int incl = n_new;
+    uint32_t tsum = touched;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)(threadIdx.x & 31) >= d) incl += o;
+        tsum += __shfl_xor_sync(0xffffffffu, tsum, d);
+    }
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 31) { s_new[wid] = incl; s_touched[wid] = tsum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        unsigned int tt = 0;
+        for (int k = 0; k < kFBlock / 32; ++k) { int x = s_new[k]; s_new[k] = tot; tot += x; tt += s_touched[k]; }
+        s_base = tot ? atomicAdd(f.count + level + 1, (unsigned int)tot) : 0u;
+        if (tt) atomicAdd(f.touched + (blockIdx.x & (kTouchedParts - 1)), (unsigned long long)tt);
+    }
+    __syncthreads();
+    if (!live) return;
+    const int64_t c0 = (int64_t)s_base + s_new[wid] + incl - n_new;
+    if (c0 + n_new > cap) { f.count[f.levels] = 1; f.child[at] = 0; return; }       // cannot happen: the bounds are exact
+    if (sampled) {
+        const int child = fc + a_drawn;
+        if (n_new == 0) { f.child[at] = ~child; return; }
+        f.child[at] = (int32_t)c0;
+        f.node[next + c0] = child;
+        f.trav[next + c0] = tr;
+        if (VARIANT == 0)
+            for (int k = 0; k < 3; ++k) f.reach[k * f.total + next + c0] = f.reach[k * f.total + at];
+        return;
+    }
+    f.child[at] = (int32_t)c0;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    if (VARIANT == 0) { r0 = f.reach[at]; r1 = f.reach[f.total + at]; r2 = f.reach[2 * f.total + at]; }
+    int j = 0;
+    for (int a = 0; a < n; ++a) {
+        if (!((mask >> a) & 1)) continue;
+        const int64_t to = next + c0 + j++;
+        f.node[to] = fc + a;
+        f.trav[to] = tr;
+        if (VARIANT == 0) {
+            const double sga = v.sigma[col + a];
+            f.reach[to] = r0;
+            f.reach[f.total + to] = pl == 1 ? sga * r1 : r1;
+            f.reach[2 * f.total + to] = pl == 2 ? sga * r2 : r2;
+        }
+    }
+}
+
+template <int VARIANT, int MAXA>
+__global__ void __launch_bounds__(kFBlock) k_front_collect(LaneView v, Frontier f, int level) {
+    const int64_t i = (int64_t)blockIdx.x * kFBlock + threadIdx.x;
+    if (i >= f.count[level]) return;
+    const int64_t at = f.off[level] + i, next = f.off[level + 1];
+    const int node = f.node[at], tr = f.trav[at], c0 = f.child[at];
+    const int4 rec = __ldg(v.rec + node);
+    const int fc = rec.x, n = rec.y & 0xff, pl = ((rec.y >> 8) & 0xff) - 1, col = rec.z, s = rec.w;
+    const uint32_t leaf = (uint32_t)rec.y >> 16;
+    const int me = (tr & 1) + 1;
+    auto payoff = [&](int x) { return me == 1 ? v.pay1[x] : (v.zero_sum ? -v.pay1[x] : v.pay2[x]); };
+    if (pl == 0 || (VARIANT == 1 && pl != me)) {                // a sampled node hands its child's value up
+        f.val[at] = c0 < 0 ? payoff(~c0) : f.val[next + c0];
+        return;
+    }
+    double va[MAXA], value = 0.0;
+    int j = 0;
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) {
+        va[a] = 0.0;
+        if (a < n) {
+            va[a] = (leaf >> a) & 1 ? payoff(fc + a) : f.val[next + c0 + j++];
+            value += v.sigma[col + a] * va[a];
+        }
+    }
+    f.val[at] = value;
+    const double w = v.iter->linear ? (double)v.iter->t : 1.0;
+    const int64_t copy = (int64_t)(blockIdx.x & v.copy_mask) * v.copy_stride;
+    if (VARIANT == 0) {                                         // cfr.py:229-252
+        mark(v.in_R + s);
+        if (pl == me) {
+            const double r0 = f.reach[at], r1 = f.reach[f.total + at], r2 = f.reach[2 * f.total + at];
+            const double pi_minus = me == 2 ? r0 * r1 : r0 * r2, pi_own = me == 1 ? r1 : r2;
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a)
+                if (a < n) {
+                    atomicAdd(v.R + copy + col + a, w * (va[a] - value) * pi_minus);
+                    atomicAdd(v.S + copy + col + a, w * pi_own * v.sigma[col + a]);
+                }
+            mark(v.in_S + s);
+            mark(v.in_next + s);
+        }
+    } else {                                                    // external_cfr.py:143-157
+#pragma unroll
+        for (int a = 0; a < MAXA; ++a)
+            if (a < n) atomicAdd(v.R + copy + col + a, va[a] - value);
+        mark(v.in_R + s);
+        mark(v.in_next + s);
+    }
 }
 
 __global__ void k_set_iter2(IterState *it, long long t, int linear) {
@@ -300,13 +515,106 @@ extern "C" int rlp_cfr_update_average(rlp_cfr *c, double weight, void *stream_) 
 }
 
 namespace {
-// Pick the smallest frame layout the game fits (the stack is per thread, in local memory).
+// Most frontier records per depth that the two traversals of ONE lane can hold: explored nodes add their children's
+// bounds, sampled nodes take the largest (exact per depth; terminal nodes hold no record).
+const std::vector<int64_t> &lane_widths(rlp_tree *t, int variant) {
+    std::vector<int64_t> &w = t->lane_width[variant];
+    if (!w.empty()) return w;
+    const int L = t->L;
+    w.assign((size_t)L, 0);
+    const std::vector<int32_t> &fc = t->first_child_h;
+    const std::vector<int8_t> &pl = t->player_h;
+    for (int me = 1; me <= 2; ++me) {
+        std::vector<int64_t> below, cur;        // [node of the level][depth]
+        for (int l = L - 1; l >= 0; --l) {
+            const int64_t lo = t->level_off[l], hi = t->level_off[l + 1];
+            cur.assign((size_t)(hi - lo) * L, 0);
+            for (int64_t x = lo; x < hi; ++x) {
+                if (pl[x] < 0) continue;
+                int64_t *row = &cur[(size_t)(x - lo) * L];
+                row[l] = 1;
+                const bool explored = variant == 0 ? pl[x] > 0 : pl[x] == me;
+                for (int32_t ch = fc[x]; ch < fc[x + 1]; ++ch) {
+                    if (pl[ch] < 0) continue;
+                    const int64_t *crow = &below[(size_t)(ch - hi) * L];
+                    for (int d = l + 1; d < L; ++d) row[d] = explored ? row[d] + crow[d] : std::max(row[d], crow[d]);
+                }
+            }
+            below.swap(cur);
+        }
+        for (int d = 0; d < L; ++d) w[d] += below[d];
+    }
+    return w;
+}
+
+constexpr int64_t kFrontierMinLanes = 4096;     // below this the depth-first kernel is launch-count cheaper
+constexpr size_t kFrontierMaxBytes = (size_t)32 << 30;
+
+// Sizes (and on first use allocates) the frontier records for `lanes` lanes; false: use the depth-first kernel.
+bool frontier_for(rlp_cfr *c, int variant, int64_t lanes, Frontier *f) {
+    static const bool off = getenv("RLP_LANES_DFS") != nullptr;
+    if (off || lanes < kFrontierMinLanes || rlp::g_dry_run) return false;
+    rlp_tree *t = c->tree;
+    const std::vector<int64_t> &w = lane_widths(t, variant);
+    int levels = 0;
+    int64_t per_lane = 0;
+    for (int d = 0; d < t->L; ++d) if (w[d] > 0) { levels = d + 1; per_lane += w[d]; }
+    for (int d = 0; d < levels; ++d) if (w[d] * lanes >= ((int64_t)1 << 31)) return false;
+    const size_t total = (size_t)per_lane * (size_t)lanes;
+    const size_t bytes = total * (12 + 8 + (variant == 0 ? 24 : 0));
+    if (bytes > kFrontierMaxBytes) return false;
+    if (c->fr_lanes < lanes || c->fr_variant != variant) {
+        c->fr_lanes = 0;
+        c->fr_reach.release();
+        if (c->fr_node.alloc(total) != cudaSuccess || c->fr_trav.alloc(total) != cudaSuccess ||
+            c->fr_child.alloc(total) != cudaSuccess || c->fr_val.alloc(total) != cudaSuccess ||
+            (variant == 0 && c->fr_reach.alloc(3 * total) != cudaSuccess) ||
+            c->fr_count.alloc(64 + 2 * kTouchedParts) != cudaSuccess) {
+            cudaGetLastError();
+            c->fr_node.release(); c->fr_trav.release(); c->fr_child.release(); c->fr_val.release(); c->fr_reach.release();
+            return false;                       // not enough memory for the records: the depth-first kernel needs none
+        }
+        c->fr_lanes = lanes; c->fr_variant = variant;
+    }
+    // the buffers may be larger than this call needs (fewer lanes than at allocation): lay the levels out for `lanes`
+    f->node = c->fr_node.p; f->trav = c->fr_trav.p; f->child = c->fr_child.p; f->val = c->fr_val.p; f->reach = c->fr_reach.p;
+    f->count = c->fr_count.p; f->levels = levels;
+    f->touched = (unsigned long long *)(c->fr_count.p + 64);     // count words first (kMaxDepth + 2 <= 64), then the visit counts
+    int64_t at = 0;
+    for (int d = 0; d <= kMaxDepth; ++d) { f->off[d] = at; if (d < levels) at += w[d] * lanes; }
+    f->total = (int64_t)(c->fr_node.n);         // stride of the three reach planes
+    c->fr_levels = levels;
+    return true;
+}
+
 template <int VARIANT>
-int launch_lanes(const LaneView &v, rlp_tree *t, int64_t lanes, int64_t lane_base, cudaStream_t s) {
+int launch_frontier(const LaneView &v, const Frontier &f, rlp_tree *t, int64_t lanes, int64_t lane_base, cudaStream_t s) {
+    RLP_CUDA(cudaMemsetAsync(f.count, 0, sizeof(unsigned int) * (size_t)(64 + 2 * kTouchedParts), s));
+    k_front_root<VARIANT><<<grid_for(2 * lanes, kFBlock), kFBlock, 0, s>>>(v, f, lanes); RLP_LAUNCH_CHECK();
+    for (int l = 0; l < f.levels; ++l) {
+        const int64_t cap = f.off[l + 1] - f.off[l];
+        k_front_expand<VARIANT><<<grid_for(cap, kFBlock), kFBlock, 0, s>>>(v, f, l, lane_base); RLP_LAUNCH_CHECK();
+    }
+    for (int l = f.levels - 1; l >= 0; --l) {
+        const int64_t cap = f.off[l + 1] - f.off[l];
+        if (t->max_act <= 4) k_front_collect<VARIANT, 4><<<grid_for(cap, kFBlock), kFBlock, 0, s>>>(v, f, l);
+        else k_front_collect<VARIANT, kMaxAct><<<grid_for(cap, kFBlock), kFBlock, 0, s>>>(v, f, l);
+        RLP_LAUNCH_CHECK();
+    }
+    k_front_touched<<<1, 32, 0, s>>>(f, v.iter); RLP_LAUNCH_CHECK();
+    return RLP_OK;
+}
+
+// Many lanes: level by level (frontier records).  Few lanes, or no room for the records: depth first, with the smallest
+// frame layout the game fits (that stack is per thread, in local memory).
+template <int VARIANT>
+int launch_lanes(rlp_cfr *c, const LaneView &v, rlp_tree *t, int64_t lanes, int64_t lane_base, cudaStream_t s) {
+    Frontier f;
+    if (v.atomic && frontier_for(c, VARIANT, lanes, &f)) return launch_frontier<VARIANT>(v, f, t, lanes, lane_base, s);
     const unsigned g = grid_for(2 * lanes);
-    if (t->max_act <= 4 && t->L <= 16) k_lanes<VARIANT, 4, 16><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
-    else if (t->max_act <= 4) k_lanes<VARIANT, 4, kMaxDepth><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
-    else k_lanes<VARIANT, kMaxAct, kMaxDepth><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
+    if (t->max_act <= 4 && t->L <= 16) k_lanes<VARIANT, 4, 16, 10><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
+    else if (t->max_act <= 4) k_lanes<VARIANT, 4, kMaxDepth, 1><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
+    else k_lanes<VARIANT, kMaxAct, kMaxDepth, 1><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
     RLP_LAUNCH_CHECK();
     return RLP_OK;
 }
@@ -327,9 +635,44 @@ LaneView lane_view(rlp_cfr *c, uint64_t seed, double *R, double *S, int atomic) 
     v.rec = t->node_rec.p;
     v.first_child = t->first_child.p; v.colbase = t->colbase.p; v.srank = t->srank.p; v.player = t->player.p;
     v.cprob = t->cprob.p; v.pay1 = t->pay1.p; v.pay2 = t->pay2.p; v.sigma = c->sigma.p; v.R = R; v.S = S;
+    v.copy_stride = 0; v.copy_mask = 0;
     v.in_R = c->flags.p; v.in_S = c->flags.p + (size_t)t->I; v.in_next = c->flags.p + 2 * (size_t)t->I;
     v.iter = c->iter.p; v.seed = seed; v.zero_sum = t->zero_sum ? 1 : 0; v.atomic = atomic;
     return v;
+}
+
+// Batched lanes: the adds go to `copies` zeroed accumulator copies ([copy][regret increments | sum increments]), folded
+// into the target afterwards.  Without the copies the adds of one level to the handful of information sets near the root
+// (10^6 lanes -> 3 x 10^6 adds on one cache line) serialise in one L2 slice and dominate the iteration.
+int lane_accumulators(rlp_cfr *c, LaneView *v, cudaStream_t s) {
+    rlp_tree *t = c->tree;
+    const int64_t stride = (2 * t->Q + 15) / 16 * 16;
+    int copies = 64;
+    while (copies > 1 && (size_t)copies * (size_t)stride * sizeof(double) > ((size_t)64 << 20)) copies >>= 1;
+    if (c->lane_acc.n != (size_t)copies * (size_t)stride) RLP_CUDA(c->lane_acc.alloc((size_t)copies * (size_t)stride));
+    RLP_CUDA(cudaMemsetAsync(c->lane_acc.p, 0, c->lane_acc.bytes(), s));
+    v->R = c->lane_acc.p; v->S = c->lane_acc.p + t->Q;
+    v->copy_stride = stride; v->copy_mask = (unsigned)(copies - 1);
+    return RLP_OK;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_fold_copies(int64_t Q, int copies, int64_t stride, const double *__restrict__ acc, double *R, double *S) {
+    int64_t q = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (q >= 2 * Q) return;
+    double sum = 0.0;
+    for (int k = 0; k < copies; ++k) sum += acc[(int64_t)k * stride + q];
+    double *to = q < Q ? R + q : S + (q - Q);
+    *to = *to + sum;
+}
+
+int fold_accumulators(rlp_cfr *c, const LaneView &v, double *R, double *S, cudaStream_t s) {
+    const int64_t Q = c->tree->Q;
+    if (Q > 0) {
+        k_fold_copies<<<grid_for(2 * Q), kBlock, 0, s>>>(Q, (int)v.copy_mask + 1, v.copy_stride, c->lane_acc.p, R, S);
+        RLP_LAUNCH_CHECK();
+    }
+    return RLP_OK;
 }
 
 __global__ void __launch_bounds__(kBlock) k_add_delta(int64_t Q, const double *__restrict__ delta, double *R, double *S) {
@@ -351,8 +694,10 @@ extern "C" int rlp_cfr_sampled_iters(rlp_cfr *c, int variant, int64_t lanes, uin
     RLP_LAUNCH_CHECK();
     if (variant == RLP_EXTERNAL_SAMPLED) c->external_state = true;
     for (int64_t it = 0; it < n_iters; ++it) {
-        int rc = variant == RLP_CHANCE_SAMPLED ? launch_lanes<0>(v, t, lanes, 0, s) : launch_lanes<1>(v, t, lanes, 0, s);
+        if (lanes > 1) { int rc = lane_accumulators(c, &v, s); if (rc) return rc; }
+        int rc = variant == RLP_CHANCE_SAMPLED ? launch_lanes<0>(c, v, t, lanes, 0, s) : launch_lanes<1>(c, v, t, lanes, 0, s);
         if (rc) return rc;
+        if (lanes > 1) { rc = fold_accumulators(c, v, c->R.p, c->S.p, s); if (rc) return rc; }
         if (t->I > 0) { k_rm_all<<<grid_for(t->I), kBlock, 0, s>>>(t->I, t->col_off.p, c->R.p, c->sigma.p, c->iter.p); RLP_LAUNCH_CHECK(); }
         if (variant == RLP_EXTERNAL_SAMPLED) {
             rc = rlp::launch_average_walk(c, 1.0, s);
@@ -384,7 +729,11 @@ extern "C" int rlp_cfr_sampled_local(rlp_cfr *c, int variant, int64_t lane_base,
     RLP_LAUNCH_CHECK();
     if (lanes > 0) {
         LaneView v = lane_view(c, seed, c->delta.p, c->delta.p + tr->Q, 1);
-        int rc = variant == RLP_CHANCE_SAMPLED ? launch_lanes<0>(v, tr, lanes, lane_base, s) : launch_lanes<1>(v, tr, lanes, lane_base, s);
+        int rc = lane_accumulators(c, &v, s);
+        if (rc) return rc;
+        rc = variant == RLP_CHANCE_SAMPLED ? launch_lanes<0>(c, v, tr, lanes, lane_base, s) : launch_lanes<1>(c, v, tr, lanes, lane_base, s);
+        if (rc) return rc;
+        rc = fold_accumulators(c, v, c->delta.p, c->delta.p + tr->Q, s);
         if (rc) return rc;
     }
     c->touched_dirty = true;

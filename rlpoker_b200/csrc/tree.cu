@@ -216,11 +216,18 @@ extern "C" int rlp_tree_upload(const rlp_tree_desc *d, void *stream_, rlp_tree *
     RLP_CUDA(t->krank.upload(krank, stream));
     {
         std::vector<int4> rec((size_t)N);
-        for (int64_t i = 0; i < N; ++i)
-            rec[i] = make_int4(fc[i], (fc[i + 1] - fc[i]) | ((int)(pl[i] + 1) << 8), colbase[i], srank[i]);
+        for (int64_t i = 0; i < N; ++i) {
+            uint32_t leaf = 0;          // bit a: child a is a leaf (first 16 children; wider nodes look the child up)
+            for (int a = 0; a < fc[i + 1] - fc[i] && a < 16; ++a)
+                if (pl[fc[i] + a] < 0) leaf |= 1u << a;
+            rec[i] = make_int4(fc[i], (int)((uint32_t)(fc[i + 1] - fc[i]) | ((uint32_t)(pl[i] + 1) << 8) | (leaf << 16)),
+                               colbase[i], srank[i]);
+        }
         RLP_CUDA(t->node_rec.upload(rec, stream));
         RLP_CUDA(rlp::sync_stream(stream));
     }
+    t->first_child_h = fc;
+    t->player_h = pl;
     RLP_CUDA(t->cprob.upload(cp, stream));
     RLP_CUDA(t->pay1.upload(p1, stream));
     if (!zs) {

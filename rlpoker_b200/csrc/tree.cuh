@@ -37,11 +37,14 @@ struct rlp_tree {
     std::vector<int64_t> canon_of_col;   // internal pair -> canonical pair
     std::vector<int64_t> col_off_h;      // internal [I+1]
     std::vector<int8_t> iset_player_h;   // internal [I]: owner of every information set
+    std::vector<int32_t> first_child_h;  // host copies of the structure (frontier bounds of the sampled lanes)
+    std::vector<int8_t> player_h;
+    std::vector<int64_t> lane_width[2];  // [variant][level]: most frontier records one lane (both traversals) can hold; lazily filled
 
     rlp::DevBuf<int32_t> first_child, colbase, srank, krank;
     rlp::DevBuf<int8_t> player;
     rlp::DevBuf<double> cprob, pay1, pay2;
-    rlp::DevBuf<int4> node_rec;                   // [N] {first_child, #children | (player + 1) << 8, colbase, srank}: one 16-byte load per visit
+    rlp::DevBuf<int4> node_rec;                   // [N] {first_child, #children | (player + 1) << 8 | leaf mask of the first 16 children << 16, colbase, srank}
     rlp::DevBuf<int64_t> koff_col, koff_iset;     // [Kmax+1]
     rlp::DevBuf<int32_t> iset_size, iset_level;   // [I] internal order
     rlp::DevBuf<int8_t> iset_player;              // [I]

@@ -63,14 +63,17 @@ def test_external_single_lane_bit_exact(name, T):
     assert abs(s.exploitability()[0] - o.exploitability(o.alpha_strategy())) < 1e-12
 
 
+@pytest.mark.parametrize('name,lanes,T', [('leduc3', 96, 6), ('leduc3', 5000, 3), ('ocp4', 4096, 3), ('leduc5', 4100, 2)])
 @pytest.mark.parametrize('variant', ['chance', 'external'])
-def test_batched_lanes_match_oracle_to_rounding(variant):
-    """lanes > 1: same traversals as the oracle's lane loop, summed with atomics (order differs)."""
+def test_batched_lanes_match_oracle_to_rounding(variant, name, lanes, T):
+    """lanes > 1: same traversals as the oracle's lane loop, summed with atomics (order differs).  From 4096 lanes on the
+    device runs the traversals level by level (frontier records, sampled.cu) instead of depth first: same draws (the
+    Philox key is the node of the draw), same values, same node counts."""
     from oracle import oracle as orc
     from rlpoker_b200._lib import RLP_CHANCE_SAMPLED, RLP_EXTERNAL_SAMPLED
-    s = _solver('leduc3')
-    o = orc.Oracle(oracle_tree('leduc3'))
-    lanes, T, seed = 96, 6, 99
+    s = _solver(name)
+    o = orc.Oracle(oracle_tree(name))
+    seed = 99
     if variant == 'chance':
         s.sampled(RLP_CHANCE_SAMPLED, T, lanes=lanes, seed=seed)
         o.cfr_recursive(T, sampling=True, lanes=lanes, rng=orc.rng_philox(seed))
