@@ -145,7 +145,7 @@ __host__ __device__ inline double philox_uniform(uint64_t seed, uint64_t iterati
         k1 += 0xBB67AE85u;
     }
     uint32_t a = c0 >> 5, b = c1 >> 6;
-    return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);     // 2^-53: the same bits as the division
 }
 
 }  // namespace rlp

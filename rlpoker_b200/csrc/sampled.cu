@@ -10,6 +10,7 @@
 // stream reproduces every lane exactly.  lanes == 1 is the reference algorithm bit for bit (plain adds in
 // visit order); lanes > 1 is mini-batch MCCFR with fp64 atomics (order of adds not deterministic).
 #include "cfr.cuh"
+#include <cstring>
 
 using rlp::fail;
 
@@ -54,7 +55,7 @@ __device__ inline double numpy_sum(const double *p, int n) {
 }
 
 // RandomState.choice(len(p), p=p/np.sum(p)) given the uniform u.
-__device__ inline int draw(const double *p, int n, double u) {
+__device__ inline int draw_wide(const double *p, int n, double u) {
     double tot = numpy_sum(p, n);
     double last = 0.0;
     for (int a = 0; a < n; ++a) last += p[a] / tot;
@@ -65,6 +66,36 @@ __device__ inline int draw(const double *p, int n, double u) {
         if (run / last <= u) idx = a + 1; else break;
     }
     return idx < n ? idx : n - 1;
+}
+
+// The same for up to four outcomes, from registers.  IEEE division by exactly 1.0 returns its operand, so the two
+// normalisations are skipped when the sums are exactly 1.0 (uniform thirds, most regret-matched strategies): the same
+// bits as draw_wide with a fraction of its divisions.
+__device__ inline int draw(const double *p, int n, double u) {
+    if (n > 4) return draw_wide(p, n, u);
+    double q0 = p[0], q1 = n > 1 ? p[1] : 0.0, q2 = n > 2 ? p[2] : 0.0, q3 = n > 3 ? p[3] : 0.0;
+    double tot = 0.0 + q0;
+    if (n > 1) tot += q1;
+    if (n > 2) tot += q2;
+    if (n > 3) tot += q3;
+    if (tot != 1.0) { q0 = q0 / tot; q1 = q1 / tot; q2 = q2 / tot; q3 = q3 / tot; }
+    double last = 0.0 + q0;
+    if (n > 1) last += q1;
+    if (n > 2) last += q2;
+    if (n > 3) last += q3;
+    const bool unit = last == 1.0;
+    double run = 0.0 + q0;
+    if (!((unit ? run : run / last) <= u)) return 0;
+    if (n == 1) return 0;
+    run += q1;
+    if (!((unit ? run : run / last) <= u)) return 1;
+    if (n == 2) return 1;
+    run += q2;
+    if (!((unit ? run : run / last) <= u)) return 2;
+    if (n == 3) return 2;
+    run += q3;
+    if (!((unit ? run : run / last) <= u)) return 3;
+    return 3;
 }
 
 // One stack frame of the depth-first walk.  External sampling needs no reach probabilities (its regret increment is
@@ -252,7 +283,8 @@ constexpr int kFBlock = 256;
 constexpr int kTouchedParts = 64;
 struct Frontier {
     int32_t *node, *trav, *child;      // child: first record of the children at the next level, or ~node of a drawn terminal
-    double *val, *reach;               // reach: [3][capacity] (chance-sampled variant)
+    double *val, *reach;               // reach: [2][capacity], the players' own reach (chance-sampled variant; the
+                                       //   chance factor of a chance-SAMPLED walk stays 1.0 and 1.0 * x == x)
     unsigned int *count;               // [levels + 1] records per level; the last word flags a capacity overflow
     unsigned long long *touched;       // [kTouchedParts] visit counts, folded into IterState::touched at the end
     int64_t off[kMaxDepth + 1];        // first record of each level
@@ -268,9 +300,11 @@ __global__ void __launch_bounds__(kFBlock) k_front_root(LaneView v, Frontier f, 
         f.touched[0] = (unsigned long long)(2 * lanes);
     }
     if (tid >= 2 * lanes) return;
+    // traversal id = 2 * lane + (traversing player - 1).  Player 1's traversals first, then player 2's: whether a node
+    // is explored or sampled depends on the traverser, and a block's children stay together, so warps stay of one kind.
     f.node[tid] = 0;
-    f.trav[tid] = (int32_t)tid;
-    if (VARIANT == 0) { f.reach[tid] = 1.0; f.reach[f.total + tid] = 1.0; f.reach[2 * f.total + tid] = 1.0; }
+    f.trav[tid] = (int32_t)(tid < lanes ? 2 * tid : 2 * (tid - lanes) + 1);
+    if (VARIANT == 0) { f.reach[tid] = 1.0; f.reach[f.total + tid] = 1.0; }
 }
 
 __global__ void k_front_touched(Frontier f, IterState *iter) {
@@ -343,12 +377,12 @@ __global__ void __launch_bounds__(kFBlock) k_front_expand(LaneView v, Frontier f
         f.node[next + c0] = child;
         f.trav[next + c0] = tr;
         if (VARIANT == 0)
-            for (int k = 0; k < 3; ++k) f.reach[k * f.total + next + c0] = f.reach[k * f.total + at];
+            for (int k = 0; k < 2; ++k) f.reach[k * f.total + next + c0] = f.reach[k * f.total + at];
         return;
     }
     f.child[at] = (int32_t)c0;
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-    if (VARIANT == 0) { r0 = f.reach[at]; r1 = f.reach[f.total + at]; r2 = f.reach[2 * f.total + at]; }
+    double r1 = 0.0, r2 = 0.0;
+    if (VARIANT == 0) { r1 = f.reach[at]; r2 = f.reach[f.total + at]; }
     int j = 0;
     for (int a = 0; a < n; ++a) {
         if (!((mask >> a) & 1)) continue;
@@ -357,9 +391,8 @@ __global__ void __launch_bounds__(kFBlock) k_front_expand(LaneView v, Frontier f
         f.trav[to] = tr;
         if (VARIANT == 0) {
             const double sga = v.sigma[col + a];
-            f.reach[to] = r0;
-            f.reach[f.total + to] = pl == 1 ? sga * r1 : r1;
-            f.reach[2 * f.total + to] = pl == 2 ? sga * r2 : r2;
+            f.reach[to] = pl == 1 ? sga * r1 : r1;
+            f.reach[f.total + to] = pl == 2 ? sga * r2 : r2;
         }
     }
 }
@@ -395,8 +428,8 @@ __global__ void __launch_bounds__(kFBlock) k_front_collect(LaneView v, Frontier 
     if (VARIANT == 0) {                                         // cfr.py:229-252
         mark(v.in_R + s);
         if (pl == me) {
-            const double r0 = f.reach[at], r1 = f.reach[f.total + at], r2 = f.reach[2 * f.total + at];
-            const double pi_minus = me == 2 ? r0 * r1 : r0 * r2, pi_own = me == 1 ? r1 : r2;
+            const double r1 = f.reach[at], r2 = f.reach[f.total + at];
+            const double pi_minus = me == 2 ? r1 : r2, pi_own = me == 1 ? r1 : r2;
 #pragma unroll
             for (int a = 0; a < MAXA; ++a)
                 if (a < n) {
@@ -552,8 +585,15 @@ constexpr size_t kFrontierMaxBytes = (size_t)32 << 30;
 
 // Sizes (and on first use allocates) the frontier records for `lanes` lanes; false: use the depth-first kernel.
 bool frontier_for(rlp_cfr *c, int variant, int64_t lanes, Frontier *f) {
-    static const bool off = getenv("RLP_LANES_DFS") != nullptr;
-    if (off || lanes < kFrontierMinLanes || rlp::g_dry_run) return false;
+    // External sampling: 2.1 ms against 2.9 ms per 2^20 lanes on Leduc-3.  Chance sampling explores every player node:
+    // three times the records, whose traffic costs more than the divergence it removes (8.0 against 7.4 ms), so it
+    // stays depth first unless RLP_LANES_FRONTIER=all asks otherwise (tests/test_gpu_sampled.py runs it that way).
+    static const int mode = [] {
+        if (getenv("RLP_LANES_DFS")) return 0;
+        const char *e = getenv("RLP_LANES_FRONTIER");
+        return e && !strcmp(e, "all") ? 2 : 1;
+    }();
+    if (mode == 0 || (mode == 1 && variant == 0) || lanes < kFrontierMinLanes || rlp::g_dry_run) return false;
     rlp_tree *t = c->tree;
     const std::vector<int64_t> &w = lane_widths(t, variant);
     int levels = 0;
@@ -561,14 +601,14 @@ bool frontier_for(rlp_cfr *c, int variant, int64_t lanes, Frontier *f) {
     for (int d = 0; d < t->L; ++d) if (w[d] > 0) { levels = d + 1; per_lane += w[d]; }
     for (int d = 0; d < levels; ++d) if (w[d] * lanes >= ((int64_t)1 << 31)) return false;
     const size_t total = (size_t)per_lane * (size_t)lanes;
-    const size_t bytes = total * (12 + 8 + (variant == 0 ? 24 : 0));
+    const size_t bytes = total * (12 + 8 + (variant == 0 ? 16 : 0));
     if (bytes > kFrontierMaxBytes) return false;
     if (c->fr_lanes < lanes || c->fr_variant != variant) {
         c->fr_lanes = 0;
         c->fr_reach.release();
         if (c->fr_node.alloc(total) != cudaSuccess || c->fr_trav.alloc(total) != cudaSuccess ||
             c->fr_child.alloc(total) != cudaSuccess || c->fr_val.alloc(total) != cudaSuccess ||
-            (variant == 0 && c->fr_reach.alloc(3 * total) != cudaSuccess) ||
+            (variant == 0 && c->fr_reach.alloc(2 * total) != cudaSuccess) ||
             c->fr_count.alloc(64 + 2 * kTouchedParts) != cudaSuccess) {
             cudaGetLastError();
             c->fr_node.release(); c->fr_trav.release(); c->fr_child.release(); c->fr_val.release(); c->fr_reach.release();
@@ -582,7 +622,7 @@ bool frontier_for(rlp_cfr *c, int variant, int64_t lanes, Frontier *f) {
     f->touched = (unsigned long long *)(c->fr_count.p + 64);     // count words first (kMaxDepth + 2 <= 64), then the visit counts
     int64_t at = 0;
     for (int d = 0; d <= kMaxDepth; ++d) { f->off[d] = at; if (d < levels) at += w[d] * lanes; }
-    f->total = (int64_t)(c->fr_node.n);         // stride of the three reach planes
+    f->total = (int64_t)(c->fr_node.n);         // stride of the two reach planes
     c->fr_levels = levels;
     return true;
 }

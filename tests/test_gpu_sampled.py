@@ -86,6 +86,32 @@ def test_batched_lanes_match_oracle_to_rounding(variant, name, lanes, T):
     assert np.array_equal(s.flags(), _flags(o))
 
 
+def test_chance_sampled_frontier_form_in_a_subprocess():
+    """Chance sampling runs depth first by default (fewer bytes than its frontier records); RLP_LANES_FRONTIER=all
+    selects the level-by-level form, which must give the same traversals.  The switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, sys\n"
+        "sys.path.insert(0, 'tests')\n"
+        "from conftest import make_game, oracle_tree\n"
+        "from oracle import oracle as orc\n"
+        "from rlpoker_b200.solver import DeviceCFR, device_tree\n"
+        "from rlpoker_b200._lib import RLP_CHANCE_SAMPLED\n"
+        "s = DeviceCFR(device_tree(make_game('leduc3'))); o = orc.Oracle(oracle_tree('leduc3'))\n"
+        "s.sampled(RLP_CHANCE_SAMPLED, 3, lanes=4500, seed=7, linear_weight=True)\n"
+        "o.cfr_recursive(3, sampling=True, lanes=4500, rng=orc.rng_philox(7), linear_weight=True)\n"
+        "assert s.nodes_touched == o.nodes_touched\n"
+        "np.testing.assert_allclose(s.regrets, o.R, rtol=1e-9, atol=1e-9)\n"
+        "np.testing.assert_allclose(s.strategy_sum, o.S, rtol=1e-9, atol=1e-9)\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RLP_LANES_FRONTIER='all')
+    out = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
+
+
 def test_sampled_convergence_statistics(golden):
     """Exploitability after 2000 chance-sampled iterations: the reference (numpy RNG, seed 0) got 1.1967;
     different random streams scatter around that.  16 Philox seeds must bracket it."""
