@@ -423,6 +423,8 @@ def main():
         if world == 1:
             extra['br_sweep'] = br_sweep()
             extra['config3'] = sampled_config3()
+        else:
+            extra['config3'] = sampled_config3_sharded(rank, world)
         extra['leduc25'] = leduc25(rank, world, public)
 
     # ---- report -------------------------------------------------------------------------------------------
@@ -568,6 +570,34 @@ def sampled_config3(lanes=1 << 20):
         out[name] = {'ms_per_iteration': ms, 'node_updates_per_s': (s.nodes_touched - n0) / 4 / (ms * 1e-3)}
         del s
     dt.close()
+    return out
+
+
+def sampled_config3_sharded(rank, world, lanes=1 << 20):
+    """BASELINE config 3 at N > 1: the 2^20 lanes of every iteration split over the ranks (ShardedSampledCFR: one NCCL
+    sum of the [2Q] increments and one max of the membership flags per iteration); device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from rlpoker_b200.games.leduc_native import leduc_flat_tree
+    from rlpoker_b200.sharding import ShardedSampledCFR
+    out = {'lanes': lanes, 'game': 'Leduc(get_deck(3, 2))', 'sharding': 'lanes x%d + NCCL all-reduce per iteration' % world}
+    for variant, name in ((1, 'external'), (0, 'chance')):
+        sh = ShardedSampledCFR(leduc_flat_tree(3), rank, world)
+        sh.iterate(variant, 3, lanes, seed=1)
+        torch.cuda.synchronize()
+        n0 = sh.nodes_touched()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sh.iterate(variant, 8, lanes, seed=1)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / 8], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[name] = {'ms_per_iteration': ms, 'node_updates_per_s': (sh.nodes_touched() - n0) / 8 / (ms * 1e-3)}
+        sh.close()
     return out
 
 

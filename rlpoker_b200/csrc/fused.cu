@@ -650,6 +650,7 @@ std::string generate_source(const Shape &s, const Consts &c) {
     o.precision(17);
     o << "struct FusedParams {\n" << kFusedFieldsText << "};\n"
       << "#define BLOCK " << c.BLK << "\n"
+      << (getenv("RLP_P2P_DEBUG") ? "#define XDEBUG 1\n" : "")
       // row stride of the per-thread shared arrays: odd, so the (set, action) threads of the ordered sums -- which read
       // different ROWS at the same column -- fall into different banks (a stride of BLOCK doubles is 11-way conflicted)
       << "#define TEAM " << c.TEAM << "\n"
@@ -657,6 +658,16 @@ std::string generate_source(const Shape &s, const Consts &c) {
       << (c.TEAM == 32 ? "#define TEAM_SYNC() __syncwarp()\n" : "#define TEAM_SYNC() __syncthreads()\n")
       << R"(
 __device__ __forceinline__ unsigned long long now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#ifdef XDEBUG   // RLP_P2P_DEBUG: the last arriver of the cross-GPU barrier adds up where its time goes (bar[8..17], ns)
+__device__ __forceinline__ void xdbg(unsigned int* bar, int i, unsigned long long& t0) {
+  unsigned long long t = now_ns();
+  atomicAdd((unsigned long long*)(bar + 8) + i, i ? t - t0 : 1ull);
+  t0 = t;
+}
+#define XDBG(i) xdbg(bar, i, xdbg_t);
+#else
+#define XDBG(i)
+#endif
 // Grid barrier for co-resident CTAs (cooperative launch).  bar[0] counts arrivals (monotone over the launch); the LAST
 // arriver of barrier number `k` writes k into a private flag word of every CTA (bar[32 + 32 * cta], 128 bytes apart,
 // so spread over the L2 slices) and each waiting CTA polls only its own word: no address is polled by more than one
@@ -710,9 +721,13 @@ __device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P
       unsigned long long* const* peers = &P->xfp0;
       // ONE system-scope fence (it is what costs: it waits for this GPU's outstanding peer writes), then relaxed flag stores;
       // a st.release per peer would repeat that fence for every peer
+      unsigned long long xdbg_t = 0; (void)xdbg_t;
+      XDBG(0)
       __threadfence_system();
+      XDBG(1)
       for (int r = 0; r < nr; ++r)
         if (r != me) asm volatile("st.relaxed.sys.u64 [%0], %1;" :: "l"(peers[r] + me), "l"(token) : "memory");
+      XDBG(2)
       for (int r = 0; r < nr; ++r) {
         if (r == me) continue;
         unsigned long long v = 0;
@@ -724,7 +739,9 @@ __device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P
           __nanosleep(40);
         }
       }
+      XDBG(3)
       __threadfence_system();
+      XDBG(4)
     }
     __syncthreads();
     for (unsigned int c = threadIdx.x; c < nb; c += BLOCK)
@@ -1834,6 +1851,14 @@ int fused_run(rlp_cfr *c, int64_t t0, int64_t n_iters, int linear_weight, cudaSt
         left -= chunk; tt += chunk;
     }
     c->sigma_am_dirty = true;            // the five-kernel pipeline's action-major copy is stale now
+    if (x && x->active && getenv("RLP_P2P_DEBUG")) {      // where the last arriver of the cross-GPU barrier spent its time
+        unsigned long long h[5] = {0, 0, 0, 0, 0};
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, f.bar.p + 8, sizeof(h), cudaMemcpyDeviceToHost);
+        if (h[0])
+            fprintf(stderr, "[rlp p2p rank %d] %llu exchanges: fence %.2f us, flag stores %.2f us, wait for peers %.2f us, fence %.2f us\n",
+                    x->rank, h[0], 1e-3 * h[1] / h[0], 1e-3 * h[2] / h[0], 1e-3 * h[3] / h[0], 1e-3 * h[4] / h[0]);
+    }
     return RLP_OK;
 }
 
