@@ -135,7 +135,9 @@ int rlp_cfr_sampled_iters(rlp_cfr *cfr, int variant, int64_t lanes, uint64_t see
  * (rlp_cfr_delta_ptr: [2Q] doubles, regret deltas | sum deltas, internal pair order = the same on every rank) and sets
  * the dict-membership flags (rlp_cfr_flags_ptr: [3 I] bytes); the caller sum-all-reduces the delta and max-all-reduces the
  * flags (NCCL); rlp_cfr_sampled_finish adds the delta, runs regret matching and, for external sampling, the
- * average-strategy walk.  rlp_nodes_touched counts this rank's lanes only.
+ * average-strategy walk.  rlp_nodes_touched counts this rank's lanes only.  t < 0 keeps the iteration counter and
+ * weighting flag on the device (rlp_cfr_sampled_finish advances the counter), so that a local / all-reduce / finish
+ * sequence captured in a CUDA graph can be replayed for the following iterations.
  */
 int rlp_cfr_sampled_local(rlp_cfr *cfr, int variant, int64_t lane_base, int64_t lanes, uint64_t seed, int64_t t,
                           int linear_weight, void *stream);

@@ -765,8 +765,10 @@ extern "C" int rlp_cfr_sampled_local(rlp_cfr *c, int variant, int64_t lane_base,
     rlp_tree *tr = c->tree;
     cudaStream_t s = (cudaStream_t)stream_;
     RLP_CUDA(cudaMemsetAsync(c->delta.p, 0, c->delta.bytes(), s));
-    k_set_iter2<<<1, 1, 0, s>>>(c->iter.p, (long long)t, linear_weight);
-    RLP_LAUNCH_CHECK();
+    if (t >= 0) {           // t < 0: the device-side counter goes on (graph replay)
+        k_set_iter2<<<1, 1, 0, s>>>(c->iter.p, (long long)t, linear_weight);
+        RLP_LAUNCH_CHECK();
+    }
     if (lanes > 0) {
         LaneView v = lane_view(c, seed, c->delta.p, c->delta.p + tr->Q, 1);
         int rc = lane_accumulators(c, &v, s);

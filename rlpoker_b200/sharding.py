@@ -392,25 +392,55 @@ class ShardedSampledCFR:
                                      device='cuda')
         self.flags = torch.as_tensor(_DeviceBytes(lib.rlp_cfr_flags_ptr(self.solver.handle), 3 * flat_tree.num_infosets),
                                      device='cuda')
+        self._graph = None
+        self._graph_key = None
 
     @staticmethod
     def lane_range(lanes, rank, world):
         """[lo, hi) of the ``lanes`` global lane ids that belong to ``rank``: contiguous, sizes differ by at most one."""
         return lanes * rank // world, lanes * (rank + 1) // world
 
-    def iterate(self, variant, n_iters, lanes, seed=0, linear_weight=False):
+    def _one(self, variant, lo, hi, seed, t, linear_weight):
+        """One iteration on torch's current stream: local lanes, the two all-reduces, finish."""
         import torch.distributed as dist
         from rlpoker_b200 import _lib
         from rlpoker_b200.solver import _stream_ptr
         lib = _lib.load()
+        _lib.check(lib.rlp_cfr_sampled_local(self.solver.handle, int(variant), lo, hi - lo, int(seed), int(t),
+                                             int(bool(linear_weight)), _stream_ptr(None)))
+        if self.world > 1:
+            dist.all_reduce(self.delta, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.flags, op=dist.ReduceOp.MAX, group=self.group)
+        _lib.check(lib.rlp_cfr_sampled_finish(self.solver.handle, int(variant), _stream_ptr(None)))
+
+    def iterate(self, variant, n_iters, lanes, seed=0, linear_weight=False, graph=None):
+        """``n_iters`` iterations of ``lanes`` global lanes.  An iteration is ~70 launches (level-by-level lanes, the
+        average-strategy walk, two all-reduces); split over 8 ranks the kernels are short and the launches dominate, so
+        from the third iteration of a call on the iteration is replayed as ONE CUDA graph (``graph=False``: eager).
+        The graph has no per-iteration argument: the device-side iteration counter keys the Philox stream."""
+        import torch
+        n_iters = int(n_iters)
         lo, hi = self.lane_range(int(lanes), self.rank, self.world)
-        for _ in range(int(n_iters)):
-            _lib.check(lib.rlp_cfr_sampled_local(self.solver.handle, int(variant), lo, hi - lo, int(seed), self.solver.t,
-                                                 int(bool(linear_weight)), _stream_ptr(None)))
-            if self.world > 1:
-                dist.all_reduce(self.delta, op=dist.ReduceOp.SUM, group=self.group)
-                dist.all_reduce(self.flags, op=dist.ReduceOp.MAX, group=self.group)
-            _lib.check(lib.rlp_cfr_sampled_finish(self.solver.handle, int(variant), _stream_ptr(None)))
+        key = (int(variant), lo, hi, int(seed), bool(linear_weight))
+        if graph is None:
+            graph = self.world > 1
+        done = 0
+        # the first iterations run eagerly: they set the device-side counter and allocate whatever the lanes need
+        while done < n_iters and (not graph or self._graph_key != key and done < 2 or done < 1):
+            self._one(variant, lo, hi, seed, self.solver.t, linear_weight)
+            self.solver.t += 1
+            done += 1
+        if done == n_iters:
+            return
+        if self._graph_key != key:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._one(variant, lo, hi, seed, -1, linear_weight)
+            # the capture recorded the iteration without running it
+            self._graph, self._graph_key = g, key
+        for _ in range(n_iters - done):
+            self._graph.replay()
             self.solver.t += 1
 
     def nodes_touched(self):
@@ -423,6 +453,7 @@ class ShardedSampledCFR:
         return int(t.item())
 
     def close(self):
+        self._graph = self._graph_key = None
         self.delta = self.flags = None
         solver, self.solver = self.solver, None
         if solver is not None:

@@ -22,9 +22,12 @@ def main():
     from rlpoker_b200.flatten import flatten
     from rlpoker_b200.sharding import ShardedSampledCFR
     ft = flatten(make_game('leduc3'))
-    for variant, lanes, iters in ((0, 37, 6), (1, 101, 8)):
+    # 9000 lanes: the level-by-level lane kernels; two calls: the second one replays the CUDA graph the first captured
+    for variant, lanes, iters in ((0, 37, 6), (1, 101, 8), (1, 9000, 7)):
         sh = ShardedSampledCFR(ft, rank, world)
-        sh.iterate(variant, iters, lanes, seed=11)
+        sh.iterate(variant, iters - 3, lanes, seed=11)
+        sh.iterate(variant, 3, lanes, seed=11)
+        assert world == 1 or sh._graph is not None
         torch.cuda.synchronize()
         o = orc.Oracle(oracle_tree('leduc3'))
         if variant == 0:
