@@ -14,3 +14,12 @@ RLP_FUSED_DUMP=/root/repo/gpurun_out/cfr_fused_k.cu timeout 300 ncu --set full -
     -k regex:br_fused_k -s 2 -c 1 -o gpurun_out/r2_br_full python tools/br_probe.py 13 > gpurun_out/ncu_br_r2.log 2>&1
 tail -2 gpurun_out/ncu_full_r2.log gpurun_out/ncu_br_r2.log
 ls -la gpurun_out | tail -8
+# sampled lanes (config 3): launch list of the level-by-level kernels and one full capture each of a mid-level expand / collect
+timeout 120 python tools/lanes_launches.py 1 > gpurun_out/lanes_plain_r2.log 2>&1 || exit 1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_front --csv \
+    --log-file gpurun_out/lanes_launches_r2.csv python tools/lanes_launches.py 1 > gpurun_out/ncu_lanes_launches_r2.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_front_expand -s 20 -c 1 \
+    -o gpurun_out/r2_lanes_expand python tools/lanes_launches.py 1 > gpurun_out/ncu_lanes_expand_r2.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_front_collect -s 17 -c 1 \
+    -o gpurun_out/r2_lanes_collect python tools/lanes_launches.py 1 > gpurun_out/ncu_lanes_collect_r2.log 2>&1
+ls -la gpurun_out | tail -8
