@@ -107,13 +107,13 @@ def dominant_kernel_roofline(layout, stages, peak, strategy_bytes):
 # subtree, 8 decision nodes and 9 board-deal chance nodes per upper tile.
 #   micro subtree, per pass (it is evaluated once per player): 4 opponent information-set ids (i32), payoff pattern id,
 #     opponent-reach index (i32), static chance reach (f64), the opponent's reach at its root (f64) [the own reach, the
-#     own ids and the 16-byte payoff pattern are per GROUP of 2n-2 subtrees]; the first pass also reads the value index
-#     (i32) and writes the subtree value (f64) -- once per rank when sharded
+#     own ids and the 16-byte payoff pattern are per GROUP of 2n-2 subtrees]; every pass writes the subtree value for
+#     its player (f64, block layout [pass][upper group][portal][member]) -- to every rank's buffer when sharded
 #   upper tile, per pass: the values of its 9 x (2n-2) micro subtrees (f64) and 22 strategy probabilities
 #   (information set, action) pair: regret and action count read + written, strategy read, written twice
 #     (row-major for the API, fused numbering for the next iteration)
 FUSED_MICRO_BYTES_PER_PASS = 4 * 4 + 4 + 4 + 8 + 8
-FUSED_MICRO_BYTES = 2 * FUSED_MICRO_BYTES_PER_PASS + (4 + 8)
+FUSED_MICRO_BYTES = 2 * (FUSED_MICRO_BYTES_PER_PASS + 8)
 FUSED_PAIR_BYTES = 4 * 8 + 8 + 2 * 8
 
 
@@ -121,7 +121,7 @@ def fused_bytes_per_iteration(ft, layout, world=1):
     """Per GPU: the micro subtrees and their information sets are divided over the ranks, the upper tiles replicated."""
     boards = RANKS * 2 - 2
     tile = 2 * (9 * boards * 8 + 22 * 8)
-    micro = layout['micro_subtrees'] * (FUSED_MICRO_BYTES + 8 * (world - 1))
+    micro = layout['micro_subtrees'] * (FUSED_MICRO_BYTES + 2 * 8 * (world - 1))
     return micro / world + layout['upper_tiles'] * tile + ft.num_pairs * FUSED_PAIR_BYTES / world
 
 

@@ -67,12 +67,9 @@ unsigned long long * xfp5;
 unsigned long long * xfp6;
 unsigned long long * xfp7;
 unsigned long long * xfl;
-const int * own_idx;
-long long n_own;
 long long nranks;
 long long rank;
 long long xbase;
-long long xdebug;
 unsigned char * flags;
 unsigned int * bar;
 unsigned long long * tl;
@@ -112,6 +109,16 @@ long long tl_cap;
 #define TEAM_SYNC() __syncthreads()
 
 __device__ __forceinline__ unsigned long long now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#ifdef XDEBUG   // RLP_P2P_DEBUG: the last arriver of the cross-GPU barrier adds up where its time goes (bar[8..17], ns)
+__device__ __forceinline__ void xdbg(unsigned int* bar, int i, unsigned long long& t0) {
+  unsigned long long t = now_ns();
+  atomicAdd((unsigned long long*)(bar + 8) + i, i ? t - t0 : 1ull);
+  t0 = t;
+}
+#define XDBG(i) xdbg(bar, i, xdbg_t);
+#else
+#define XDBG(i)
+#endif
 // Grid barrier for co-resident CTAs (cooperative launch).  bar[0] counts arrivals (monotone over the launch); the LAST
 // arriver of barrier number `k` writes k into a private flag word of every CTA (bar[32 + 32 * cta], 128 bytes apart,
 // so spread over the L2 slices) and each waiting CTA polls only its own word: no address is polled by more than one
@@ -163,20 +170,29 @@ __device__ __forceinline__ void grid_barrier_x(const FusedParams* __restrict__ P
     if (threadIdx.x == 0) {
       const int nr = (int)P->nranks, me = (int)P->rank;
       unsigned long long* const* peers = &P->xfp0;
+      // ONE system-scope fence (it is what costs: it waits for this GPU's outstanding peer writes), then relaxed flag stores;
+      // a st.release per peer would repeat that fence for every peer
+      unsigned long long xdbg_t = 0; (void)xdbg_t;
+      XDBG(0)
+      __threadfence_system();
+      XDBG(1)
       for (int r = 0; r < nr; ++r)
-        if (r != me) asm volatile("st.release.sys.u64 [%0], %1;" :: "l"(peers[r] + me), "l"(token) : "memory");
+        if (r != me) asm volatile("st.relaxed.sys.u64 [%0], %1;" :: "l"(peers[r] + me), "l"(token) : "memory");
+      XDBG(2)
       for (int r = 0; r < nr; ++r) {
-        if (r == me || (P->xdebug & 2)) continue;
+        if (r == me) continue;
         unsigned long long v = 0;
         long long spins = 0;
         for (;;) {
-          asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(P->xfl + r) : "memory");
+          asm volatile("ld.relaxed.sys.u64 %0, [%1];" : "=l"(v) : "l"(P->xfl + r) : "memory");
           if (v >= token) break;
-          if (++spins > (1ll << 24)) { bar[2] = 1u; break; }      // ~seconds: give up, flag the error
-          __nanosleep(100);
+          if (++spins > (1ll << 25)) { bar[2] = 1u; break; }      // ~seconds: give up, flag the error
+          __nanosleep(40);
         }
       }
+      XDBG(3)
       __threadfence_system();
+      XDBG(4)
     }
     __syncthreads();
     for (unsigned int c = threadIdx.x; c < nb; c += BLOCK)
@@ -210,6 +226,7 @@ __device__ __forceinline__ double rm_one(const double* r, int na, int a) {
   return mine / (s + c);
 }
 __constant__ double FCP[9] = {0.041666666666666664,0.041666666666666664,0.041666666666666664,0.041666666666666664,0.041666666666666664,0.041666666666666664,0.041666666666666664,0.041666666666666664,0.041666666666666664};
+struct MIds { int pat, ri, ro, pi, acol, afid; double pcv; int f[8]; };
 __constant__ int MCJ0[11] = {0,0,1,1,1,2,2,2,3,3,3};
 __constant__ int MCA0[11] = {0,1,0,1,2,0,1,2,0,1,2};
 __constant__ int MCOFF0[4] = {0,2,5,8};
@@ -218,20 +235,40 @@ __constant__ int UCJ0[11] = {0,0,1,1,1,2,2,2,3,3,3};
 __constant__ int UCA0[11] = {0,1,0,1,2,0,1,2,0,1,2};
 __constant__ int UCOFF0[4] = {0,2,5,8};
 __constant__ int UNA0[4] = {2,3,3,3};
-__device__ __forceinline__ void micro_eval0(const FusedParams* __restrict__ P, long long g, int k, int tix, double w,
+__device__ __forceinline__ MIds micro_ids0(const FusedParams* __restrict__ P, long long g, int k, bool ok,
+    long long ag, int aj, bool acc) {
+  MIds id;
+  const long long slot = ok ? g * 24 + k : 0;
+  const long long gg = ok ? g : 0;
+  id.pat = P->mem_pat0[slot]; id.ri = P->mem_ridx0[slot]; id.ro = P->grp_ridx0[gg];
+  id.pcv = P->mem_pc0[slot];
+  id.pi = P->mem_pidx0[slot];
+  id.f[0] = P->mem_opp0[0LL * 140400LL + slot];
+  id.f[1] = P->grp_fid0[gg * 4 + 0];
+  id.f[2] = P->grp_fid0[gg * 4 + 1];
+  id.f[3] = P->mem_opp0[1LL * 140400LL + slot];
+  id.f[4] = P->mem_opp0[2LL * 140400LL + slot];
+  id.f[5] = P->grp_fid0[gg * 4 + 2];
+  id.f[6] = P->grp_fid0[gg * 4 + 3];
+  id.f[7] = P->mem_opp0[3LL * 140400LL + slot];
+  const long long agg = acc ? ag : 0;
+  id.acol = P->grp_col0[agg * 4 + aj];
+  id.afid = P->grp_fid0[agg * 4 + aj];
+  return id;
+}
+__device__ __forceinline__ void micro_eval0(const FusedParams* __restrict__ P, const MIds& id, int tix, double w,
     const double* sig_in, double* sm_r, double* sm_o, int par) {
-  const long long slot = g * 24 + k;
-  const int pat = P->mem_pat0[slot], ri = P->mem_ridx0[slot], ro = P->grp_ridx0[g];
-  const double pcv = P->mem_pc0[slot];
-  const int pi = P->mem_pidx0[slot];
-  const int f0 = P->mem_opp0[0LL * 140400LL + slot];
-  const int f1 = P->grp_fid0[g * 4 + 0];
-  const int f2 = P->grp_fid0[g * 4 + 1];
-  const int f3 = P->mem_opp0[1LL * 140400LL + slot];
-  const int f4 = P->mem_opp0[2LL * 140400LL + slot];
-  const int f5 = P->grp_fid0[g * 4 + 2];
-  const int f6 = P->grp_fid0[g * 4 + 3];
-  const int f7 = P->mem_opp0[3LL * 140400LL + slot];
+  const int pat = id.pat, ri = id.ri, ro = id.ro;
+  const double pcv = id.pcv;
+  const int pi = id.pi;
+  const int f0 = id.f[0];
+  const int f1 = id.f[1];
+  const int f2 = id.f[2];
+  const int f3 = id.f[3];
+  const int f4 = id.f[4];
+  const int f5 = id.f[5];
+  const int f6 = id.f[6];
+  const int f7 = id.f[7];
   const int4* pp = reinterpret_cast<const int4*>(P->paytab8 + (long long)pat * 16);
   const int4 pw0 = __ldg(pp + 0);
   const double x3 = (double)(int)(signed char)(pw0.x >> 0);
@@ -359,7 +396,8 @@ __device__ __forceinline__ void micro_eval0(const FusedParams* __restrict__ P, l
   a0 = a0 + s1 * x1;
   a0 = a0 + s2 * x2;
   const double x0 = a0;
-  (par ? P->pvl1 : P->pvl0)[pi] = x0;
+  { double* const* pvp = par ? &P->pvB0 : &P->pvA0; const int nr = (int)P->nranks;
+    for (int r = 0; r < nr; ++r) pvp[r][pi] = x0; }
 }
 struct UIn0 {
   double pc0;
@@ -396,7 +434,7 @@ struct UIn0 {
   double s22;
   double pad_;
 };
-__device__ __forceinline__ void upper_load0(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, const double* pvl, UIn0& in) {
+__device__ __forceinline__ void upper_load0(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, const double* blk, UIn0& in) {
   const int f0 = sm_ut[25 + m];
   in.pc0 = P->u_pcs[0LL * 650LL + i];
   const int f1 = sm_ut[50 + m];
@@ -598,19 +636,40 @@ __constant__ int UCJ1[11] = {0,0,1,1,1,2,2,2,3,3,3};
 __constant__ int UCA1[11] = {0,1,0,1,2,0,1,2,0,1,2};
 __constant__ int UCOFF1[4] = {0,2,5,8};
 __constant__ int UNA1[4] = {2,3,3,3};
-__device__ __forceinline__ void micro_eval1(const FusedParams* __restrict__ P, long long g, int k, int tix, double w,
+__device__ __forceinline__ MIds micro_ids1(const FusedParams* __restrict__ P, long long g, int k, bool ok,
+    long long ag, int aj, bool acc) {
+  MIds id;
+  const long long slot = ok ? g * 24 + k : 0;
+  const long long gg = ok ? g : 0;
+  id.pat = P->mem_pat1[slot]; id.ri = P->mem_ridx1[slot]; id.ro = P->grp_ridx1[gg];
+  id.pcv = P->mem_pc1[slot];
+  id.pi = P->mem_pidx1[slot];
+  id.f[0] = P->grp_fid1[gg * 4 + 0];
+  id.f[1] = P->mem_opp1[0LL * 140400LL + slot];
+  id.f[2] = P->mem_opp1[1LL * 140400LL + slot];
+  id.f[3] = P->grp_fid1[gg * 4 + 1];
+  id.f[4] = P->grp_fid1[gg * 4 + 2];
+  id.f[5] = P->mem_opp1[2LL * 140400LL + slot];
+  id.f[6] = P->mem_opp1[3LL * 140400LL + slot];
+  id.f[7] = P->grp_fid1[gg * 4 + 3];
+  const long long agg = acc ? ag : 0;
+  id.acol = P->grp_col1[agg * 4 + aj];
+  id.afid = P->grp_fid1[agg * 4 + aj];
+  return id;
+}
+__device__ __forceinline__ void micro_eval1(const FusedParams* __restrict__ P, const MIds& id, int tix, double w,
     const double* sig_in, double* sm_r, double* sm_o, int par) {
-  const long long slot = g * 24 + k;
-  const int pat = P->mem_pat1[slot], ri = P->mem_ridx1[slot], ro = P->grp_ridx1[g];
-  const double pcv = P->mem_pc1[slot];
-  const int f0 = P->grp_fid1[g * 4 + 0];
-  const int f1 = P->mem_opp1[0LL * 140400LL + slot];
-  const int f2 = P->mem_opp1[1LL * 140400LL + slot];
-  const int f3 = P->grp_fid1[g * 4 + 1];
-  const int f4 = P->grp_fid1[g * 4 + 2];
-  const int f5 = P->mem_opp1[2LL * 140400LL + slot];
-  const int f6 = P->mem_opp1[3LL * 140400LL + slot];
-  const int f7 = P->grp_fid1[g * 4 + 3];
+  const int pat = id.pat, ri = id.ri, ro = id.ro;
+  const double pcv = id.pcv;
+  const int pi = id.pi;
+  const int f0 = id.f[0];
+  const int f1 = id.f[1];
+  const int f2 = id.f[2];
+  const int f3 = id.f[3];
+  const int f4 = id.f[4];
+  const int f5 = id.f[5];
+  const int f6 = id.f[6];
+  const int f7 = id.f[7];
   const int4* pp = reinterpret_cast<const int4*>(P->paytab8 + (long long)pat * 16);
   const int4 pw0 = __ldg(pp + 0);
   const double x3 = (double)(int)(signed char)(pw0.x >> 0);
@@ -738,7 +797,8 @@ __device__ __forceinline__ void micro_eval1(const FusedParams* __restrict__ P, l
     sm_r[1 * SMS + tix] = w * (-x2 - vp) * opp;
     sm_o[0 * SMS + tix] = w * own;
   }
-  (void)par;
+  { double* const* pvp = par ? &P->pvB0 : &P->pvA0; const int nr = (int)P->nranks;
+    for (int r = 0; r < nr; ++r) pvp[r][pi] = x0; }
 }
 struct UIn1 {
   double pc1;
@@ -775,7 +835,7 @@ struct UIn1 {
   double s22;
   double pad_;
 };
-__device__ __forceinline__ void upper_load1(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, const double* pvl, UIn1& in) {
+__device__ __forceinline__ void upper_load1(const FusedParams* __restrict__ P, long long i, int m, const int* sm_ut, const double* sig_in, const double* blk, UIn1& in) {
   const int f0 = sm_ut[25 + m];
   const int f1 = sm_ut[50 + m];
   in.pc1 = P->u_pcs[1LL * 650LL + i];
@@ -969,10 +1029,19 @@ __device__ __forceinline__ void upper_reach1(double* out, int u, const double* s
   out[4368 + u] = q_16;
   out[4992 + u] = q_16;
 }
-__device__ __forceinline__ void micro_unit0(const FusedParams* __restrict__ P, long long unit, double w, const double* sig_in,
-    double* sig_out, double* sm_r, double* sm_o, double* sm_rn, int par) {
+__device__ __forceinline__ MIds micro_unit_ids0(const FusedParams* __restrict__ P, long long unit) {
   const int tix = threadIdx.x % TEAM;
   const int gl = tix / 24, k = tix - gl * 24;
+  const long long g0 = P->first_group0 + unit * 10, gend = P->end_group0;
+  const long long g = g0 + gl;
+  const int agl = tix / 11, ci = tix - agl * 11;
+  const bool acc = tix < 110 && g0 + agl < gend;
+  return micro_ids0(P, g, k, gl < 10 && g < gend, g0 + agl, acc ? MCJ0[ci] : 0, acc);
+}
+__device__ __forceinline__ void micro_unit0(const FusedParams* __restrict__ P, long long unit, const MIds& id, double w, const double* sig_in,
+    double* sig_out, double* sm_r, double* sm_o, double* sm_rn, int par) {
+  const int tix = threadIdx.x % TEAM;
+  const int gl = tix / 24;
   const long long g0 = P->first_group0 + unit * 10, gend = P->end_group0;
   const long long g = g0 + gl;
   const int agl = tix / 11, ci = tix - agl * 11;
@@ -982,12 +1051,12 @@ __device__ __forceinline__ void micro_unit0(const FusedParams* __restrict__ P, l
   double r = 0.0, sa = 0.0, sg = 0.0;
   if (acc) {
     j = MCJ0[ci]; a = MCA0[ci];
-    col = P->grp_col0[ag * 4 + j] + a;
-    fid = P->grp_fid0[ag * 4 + j];
+    col = id.acol + a;
+    fid = id.afid;
     r = __ldcg(P->R + col); sa = __ldcg(P->S + col);
     sg = __ldcg(sig_in + (long long)a * 47008LL + fid);
   }
-  if (gl < 10 && g < gend) micro_eval0(P, g, k, tix, w, sig_in, sm_r, sm_o, par);
+  if (gl < 10 && g < gend) micro_eval0(P, id, tix, w, sig_in, sm_r, sm_o, par);
   TEAM_SYNC();
   if (acc) {
     const double* cr = sm_r + ci * SMS + agl * 24;
@@ -1022,7 +1091,7 @@ __device__ __noinline__ void upper_cache0(const FusedParams* __restrict__ P, int
 }
 __device__ __noinline__ void upper_unit0(const FusedParams* __restrict__ P, int u, double w, const double* sig_in,
     double* sig_out, int reach_only, double* sm_fan, double* sm_r, double* sm_o, double* sm_rn, double* sm_s, const int* sm_ut,
-    const double* pvl, unsigned long long* st) {
+    int par, unsigned long long* st) {
   const int tid = threadIdx.x;
   const int* tiles = sm_ut;
   if (reach_only) {
@@ -1041,33 +1110,40 @@ __device__ __noinline__ void upper_unit0(const FusedParams* __restrict__ P, int 
       asg = __ldcg(sig_in + (long long)aa * 47008LL + afid);
     }
     const int* fd = P->fan_desc;
+    const double* blk = (par ? P->pvl1 : P->pvl0) + 0LL + (long long)u * 5400LL;
     UIn0 uin;
-    if (tid < 25) upper_load0(P, tiles[tid], tid, sm_ut, sig_in, pvl, uin);
+    if (tid < 25) upper_load0(P, tiles[tid], tid, sm_ut, sig_in, blk, uin);
     if (st && tid == 0) st[0] = now_ns();
     double fv[22];
 #pragma unroll
-    for (int i = 0; i < 22; ++i) {
-      const int L = tid + i * BLOCK;
-      if (L < 5400) { const int mm = L / 216, q = L - mm * 216; fv[i] = __ldcg(pvl + (long long)tiles[mm] * 216LL + q); }
-    }
+    for (int i = 0; i < 22; ++i) { const int L = tid + i * BLOCK; if (L < 5400) fv[i] = __ldcg(blk + L); }
+    {
 #pragma unroll
-    for (int c0 = 0; c0 < 2; ++c0) {
-#pragma unroll
-      for (int i = 0; i < 22; ++i) {
-        const int L = tid + i * BLOCK;
-        const int mm = L / 216, q = L - mm * 216;
-        if (L < 5400 && mm / 17 == c0) sm_r[(mm - c0 * 17) * 226 + q + q / 24] = fv[i];
-      }
+      for (int i = 0; i < 22; ++i) { const int L = tid + i * BLOCK; if (L >= 0 && L < 3600) sm_r[L - 0] = fv[i]; }
       __syncthreads();
-      const int mc = 25 - c0 * 17 < 17 ? 25 - c0 * 17 : 17;
-      for (int x = tid; x < mc * 9; x += BLOCK) {
-        const int mm = x / 9, f = x - mm * 9;
+      for (int x = tid; x < 150; x += BLOCK) {
+        const int fl = x / 25, m = x - fl * 25, f = 0 + fl;
         const int k0 = fd[4 * f], nch = fd[4 * f + 1];
         const double e = FCP[f];
-        const double* pv = sm_r + mm * 226 + k0 + k0 / 24;
+        const double* pv = sm_r + (k0 - 0) * 25 + m;
         double acc = 0.0;
-        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch];
-        sm_fan[(c0 * 17 + mm) * 9 + f] = acc;
+        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch * 25];
+        sm_fan[m * 9 + f] = acc;
+      }
+      __syncthreads();
+    }
+    {
+#pragma unroll
+      for (int i = 0; i < 22; ++i) { const int L = tid + i * BLOCK; if (L >= 3600 && L < 5400) sm_r[L - 3600] = fv[i]; }
+      __syncthreads();
+      for (int x = tid; x < 75; x += BLOCK) {
+        const int fl = x / 25, m = x - fl * 25, f = 6 + fl;
+        const int k0 = fd[4 * f], nch = fd[4 * f + 1];
+        const double e = FCP[f];
+        const double* pv = sm_r + (k0 - 144) * 25 + m;
+        double acc = 0.0;
+        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch * 25];
+        sm_fan[m * 9 + f] = acc;
       }
       __syncthreads();
     }
@@ -1098,10 +1174,19 @@ __device__ __noinline__ void upper_unit0(const FusedParams* __restrict__ P, int 
   __syncthreads();
   if (st && tid == 0) st[4] = now_ns();
 }
-__device__ __forceinline__ void micro_unit1(const FusedParams* __restrict__ P, long long unit, double w, const double* sig_in,
-    double* sig_out, double* sm_r, double* sm_o, double* sm_rn, int par) {
+__device__ __forceinline__ MIds micro_unit_ids1(const FusedParams* __restrict__ P, long long unit) {
   const int tix = threadIdx.x % TEAM;
   const int gl = tix / 24, k = tix - gl * 24;
+  const long long g0 = P->first_group1 + unit * 10, gend = P->end_group1;
+  const long long g = g0 + gl;
+  const int agl = tix / 11, ci = tix - agl * 11;
+  const bool acc = tix < 110 && g0 + agl < gend;
+  return micro_ids1(P, g, k, gl < 10 && g < gend, g0 + agl, acc ? MCJ1[ci] : 0, acc);
+}
+__device__ __forceinline__ void micro_unit1(const FusedParams* __restrict__ P, long long unit, const MIds& id, double w, const double* sig_in,
+    double* sig_out, double* sm_r, double* sm_o, double* sm_rn, int par) {
+  const int tix = threadIdx.x % TEAM;
+  const int gl = tix / 24;
   const long long g0 = P->first_group1 + unit * 10, gend = P->end_group1;
   const long long g = g0 + gl;
   const int agl = tix / 11, ci = tix - agl * 11;
@@ -1111,12 +1196,12 @@ __device__ __forceinline__ void micro_unit1(const FusedParams* __restrict__ P, l
   double r = 0.0, sa = 0.0, sg = 0.0;
   if (acc) {
     j = MCJ1[ci]; a = MCA1[ci];
-    col = P->grp_col1[ag * 4 + j] + a;
-    fid = P->grp_fid1[ag * 4 + j];
+    col = id.acol + a;
+    fid = id.afid;
     r = __ldcg(P->R + col); sa = __ldcg(P->S + col);
     sg = __ldcg(sig_in + (long long)a * 47008LL + fid);
   }
-  if (gl < 10 && g < gend) micro_eval1(P, g, k, tix, w, sig_in, sm_r, sm_o, par);
+  if (gl < 10 && g < gend) micro_eval1(P, id, tix, w, sig_in, sm_r, sm_o, par);
   TEAM_SYNC();
   if (acc) {
     const double* cr = sm_r + ci * SMS + agl * 24;
@@ -1151,7 +1236,7 @@ __device__ __noinline__ void upper_cache1(const FusedParams* __restrict__ P, int
 }
 __device__ __noinline__ void upper_unit1(const FusedParams* __restrict__ P, int u, double w, const double* sig_in,
     double* sig_out, int reach_only, double* sm_fan, double* sm_r, double* sm_o, double* sm_rn, double* sm_s, const int* sm_ut,
-    const double* pvl, unsigned long long* st) {
+    int par, unsigned long long* st) {
   const int tid = threadIdx.x;
   const int* tiles = sm_ut;
   if (reach_only) {
@@ -1170,33 +1255,40 @@ __device__ __noinline__ void upper_unit1(const FusedParams* __restrict__ P, int 
       asg = __ldcg(sig_in + (long long)aa * 47008LL + afid);
     }
     const int* fd = P->fan_desc;
+    const double* blk = (par ? P->pvl1 : P->pvl0) + 140400LL + (long long)u * 5400LL;
     UIn1 uin;
-    if (tid < 25) upper_load1(P, tiles[tid], tid, sm_ut, sig_in, pvl, uin);
+    if (tid < 25) upper_load1(P, tiles[tid], tid, sm_ut, sig_in, blk, uin);
     if (st && tid == 0) st[0] = now_ns();
     double fv[22];
 #pragma unroll
-    for (int i = 0; i < 22; ++i) {
-      const int L = tid + i * BLOCK;
-      if (L < 5400) { const int mm = L / 216, q = L - mm * 216; fv[i] = __ldcg(pvl + (long long)tiles[mm] * 216LL + q); }
-    }
+    for (int i = 0; i < 22; ++i) { const int L = tid + i * BLOCK; if (L < 5400) fv[i] = __ldcg(blk + L); }
+    {
 #pragma unroll
-    for (int c0 = 0; c0 < 2; ++c0) {
-#pragma unroll
-      for (int i = 0; i < 22; ++i) {
-        const int L = tid + i * BLOCK;
-        const int mm = L / 216, q = L - mm * 216;
-        if (L < 5400 && mm / 17 == c0) sm_r[(mm - c0 * 17) * 226 + q + q / 24] = fv[i];
-      }
+      for (int i = 0; i < 22; ++i) { const int L = tid + i * BLOCK; if (L >= 0 && L < 3600) sm_r[L - 0] = fv[i]; }
       __syncthreads();
-      const int mc = 25 - c0 * 17 < 17 ? 25 - c0 * 17 : 17;
-      for (int x = tid; x < mc * 9; x += BLOCK) {
-        const int mm = x / 9, f = x - mm * 9;
+      for (int x = tid; x < 150; x += BLOCK) {
+        const int fl = x / 25, m = x - fl * 25, f = 0 + fl;
         const int k0 = fd[4 * f], nch = fd[4 * f + 1];
         const double e = FCP[f];
-        const double* pv = sm_r + mm * 226 + k0 + k0 / 24;
+        const double* pv = sm_r + (k0 - 0) * 25 + m;
         double acc = 0.0;
-        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch];
-        sm_fan[(c0 * 17 + mm) * 9 + f] = acc;
+        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch * 25];
+        sm_fan[m * 9 + f] = acc;
+      }
+      __syncthreads();
+    }
+    {
+#pragma unroll
+      for (int i = 0; i < 22; ++i) { const int L = tid + i * BLOCK; if (L >= 3600 && L < 5400) sm_r[L - 3600] = fv[i]; }
+      __syncthreads();
+      for (int x = tid; x < 75; x += BLOCK) {
+        const int fl = x / 25, m = x - fl * 25, f = 6 + fl;
+        const int k0 = fd[4 * f], nch = fd[4 * f + 1];
+        const double e = FCP[f];
+        const double* pv = sm_r + (k0 - 144) * 25 + m;
+        double acc = 0.0;
+        for (int ch = 0; ch < nch; ++ch) acc = acc + e * pv[ch * 25];
+        sm_fan[m * 9 + f] = acc;
       }
       __syncthreads();
     }
@@ -1278,31 +1370,21 @@ extern "C" __global__ void __launch_bounds__(BLOCK, 3) cfr_fused_k(const __grid_
     double* sig_out = cur ? P->sigF0 : P->sigF1;
     const double w = linear ? (double)(t0 + it) : 1.0;
     const int par = (int)((P->xbase + it) & 1);        // portal-value buffer of this iteration
-    const double* pvl = par ? P->pvl1 : P->pvl0;
     if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();
     // phase A: micro units of player 1, then of player 2 (one list), one unit per team at a time
-    for (long long un = (long long)blockIdx.x * 1 + team; un < nu0 + nu1; un += (long long)nb * 1) {
-      if (un < nu0) micro_unit0(P, un, w, sig_in, sig_out, t_r, t_o, t_rn, par);
-      else micro_unit1(P, un - nu0, w, sig_in, sig_out, t_r, t_o, t_rn, par);
+    {
+      const long long stride = (long long)nb * 1;
+      long long un = (long long)blockIdx.x * 1 + team;
+      for (; un < nu0 + nu1; un += stride) {
+        if (un < nu0) micro_unit0(P, un, micro_unit_ids0(P, un), w, sig_in, sig_out, t_r, t_o, t_rn, par);
+        else micro_unit1(P, un - nu0, micro_unit_ids1(P, un - nu0), w, sig_in, sig_out, t_r, t_o, t_rn, par);
+      }
     }
     if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();
-    if (P->nranks > 1) {
-      // exchange step: once every local subtree value is in place, all CTAs copy this rank's values into every
-      // peer's buffer with coalesced stores (NVLink), then the barrier that ends the phase shakes hands with the peers
-      grid_barrier(P->bar, ++nbar, nb);
-      double* const* pvp = par ? &P->pvB0 : &P->pvA0;
-      const int nr = (int)P->nranks, me = (int)P->rank;
-      const unsigned int npush = nb < 64u ? nb : 64u;       // the CTAs that move the data (and pay a system-scope fence)
-      if (blockIdx.x < npush && !(P->xdebug & 1))
-        for (long long x = (long long)blockIdx.x * BLOCK + threadIdx.x; x < P->n_own; x += (long long)npush * BLOCK) {
-          const int idx = P->own_idx[x];
-          const double v = __ldcg(pvl + idx);
-          for (int r = 0; r < nr; ++r) if (r != me) pvp[r][idx] = v;
-        }
-      grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), blockIdx.x < npush);
-    } else {
-      grid_barrier(P->bar, ++nbar, nb);
-    }
+    // Multi-GPU: the micro phase has stored the values of this rank's subtrees into every rank's buffer; the barrier
+    // that ends the phase also shakes hands with the peers (each CTA fences its peer stores at system scope first).
+    if (P->nranks > 1) grid_barrier_x(P, ++nbar, nb, (unsigned long long)(P->xbase + it + 1), false);
+    else grid_barrier(P->bar, ++nbar, nb);
     if (log && tlc < P->tl_cap) P->tl[tlc++] = now_ns();
     // phase B: upper groups (fan-in, tile, round-1 information sets, reach for the next iteration)
     if (lead >= 0) {
@@ -1313,8 +1395,8 @@ extern "C" __global__ void __launch_bounds__(BLOCK, 3) cfr_fused_k(const __grid_
           cached_u = u;
           __syncthreads();
         }
-        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, pvl, st);
-        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, pvl, st);
+        if (u < NU0) upper_unit0(P, u, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, par, st);
+        else upper_unit1(P, u - NU0, w, sig_in, sig_out, 0, sm_fan, sm_r, sm_o, sm_rn, sm_s, sm_ut, par, st);
       }
     }
     tlc += 5;
@@ -1500,16 +1582,16 @@ __device__ __forceinline__ void micro_br0(const FusedParams* __restrict__ P, lon
 }
 __device__ __noinline__ void upper_br0(const FusedParams* __restrict__ P, int u, double* sm_fan, double* sm_q, const int* sm_ut) {
   const int tid = threadIdx.x;
-  const double* pvl = P->br_pv1;
+  const double* pvl = P->br_pv1 + 0LL + (long long)u * 5400LL;
   const int* fd = P->fan_desc;
   for (int x = tid; x < 225; x += BLOCK) {
     const int mm = x / 9, f = x - mm * 9;
     const int k0 = fd[4 * f], nch = fd[4 * f + 1];
-    const double* pv = pvl + (long long)sm_ut[mm] * 216LL + k0;
+    const double* pv = pvl + (long long)k0 * 25 + mm;
     double acc = 0.0;
     double vv[24];
 #pragma unroll
-    for (int ch = 0; ch < 24; ++ch) vv[ch] = __ldcg(pv + ch);
+    for (int ch = 0; ch < 24; ++ch) vv[ch] = __ldcg(pv + ch * 25);
 #pragma unroll
     for (int ch = 0; ch < 24; ++ch) acc = acc + vv[ch];
     (void)nch;
@@ -1857,21 +1939,21 @@ __device__ __forceinline__ void micro_br1(const FusedParams* __restrict__ P, lon
     if (best == 1) V0 = v2;
     if (ok && k == 0) P->br_astar[P->grp_iset1[g * 4 + 0]] = best;
   }
-  if (ok) P->br_pv2[pi] = V0;
+  if (ok) P->br_pv1[pi] = V0;
   TEAM_SYNC();
 }
 __device__ __noinline__ void upper_br1(const FusedParams* __restrict__ P, int u, double* sm_fan, double* sm_q, const int* sm_ut) {
   const int tid = threadIdx.x;
-  const double* pvl = P->br_pv2;
+  const double* pvl = P->br_pv1 + 140400LL + (long long)u * 5400LL;
   const int* fd = P->fan_desc;
   for (int x = tid; x < 225; x += BLOCK) {
     const int mm = x / 9, f = x - mm * 9;
     const int k0 = fd[4 * f], nch = fd[4 * f + 1];
-    const double* pv = pvl + (long long)sm_ut[mm] * 216LL + k0;
+    const double* pv = pvl + (long long)k0 * 25 + mm;
     double acc = 0.0;
     double vv[24];
 #pragma unroll
-    for (int ch = 0; ch < 24; ++ch) vv[ch] = __ldcg(pv + ch);
+    for (int ch = 0; ch < 24; ++ch) vv[ch] = __ldcg(pv + ch * 25);
 #pragma unroll
     for (int ch = 0; ch < 24; ++ch) acc = acc + vv[ch];
     (void)nch;

@@ -599,6 +599,7 @@ bool frontier_for(rlp_cfr *c, int variant, int64_t lanes, Frontier *f) {
     int levels = 0;
     int64_t per_lane = 0;
     for (int d = 0; d < t->L; ++d) if (w[d] > 0) { levels = d + 1; per_lane += w[d]; }
+    if (levels == 0) return false;              // the root is terminal: nothing to record
     for (int d = 0; d < levels; ++d) if (w[d] * lanes >= ((int64_t)1 << 31)) return false;
     const size_t total = (size_t)per_lane * (size_t)lanes;
     const size_t bytes = total * (12 + 8 + (variant == 0 ? 16 : 0));

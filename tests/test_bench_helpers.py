@@ -34,3 +34,21 @@ def test_traffic_json_is_reproducible_from_the_committed_capture():
         want = json.load(f)
     assert got['dram_bytes_per_iteration'] == want['dram_bytes_per_iteration'] == bench.traffic_per_iteration()
     assert got['kernels'] == want['kernels']
+
+
+def test_round2_summaries_are_reproducible_from_the_committed_captures(tmp_path):
+    """profiles/r2_ncu_summary.json and r2_fused_traffic.json (what bench.py reports as roofline.traffic for the fused
+    kernel) are derived from the committed raw pages by tools/ncu_summary_r2.py."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import ncu_summary_r2
+    with open(os.path.join(ROOT, 'profiles', 'r2_ncu_summary.json')) as f:
+        want_summary = json.load(f)
+    with open(os.path.join(ROOT, 'profiles', 'r2_fused_traffic.json')) as f:
+        want_traffic = json.load(f)
+    got = {name: ncu_summary_r2.first_launch(os.path.join(ROOT, 'profiles', fn)) for name, fn in ncu_summary_r2.FILES.items()}
+    assert json.loads(json.dumps(got)) == want_summary
+    k = got['cfr_fused_k']
+    per_iter = (ncu_summary_r2.to_bytes(k['dram__bytes_read.sum']) + ncu_summary_r2.to_bytes(k['dram__bytes_write.sum'])) / 10
+    assert per_iter == want_traffic['dram_bytes_per_iteration'] == bench.traffic_per_iteration(fused=True)
+    assert per_iter < 0.2 * bench.FUSED_MICRO_BYTES * 140400          # 1.5 MB against 13.5 MB: the working set is L2-resident
