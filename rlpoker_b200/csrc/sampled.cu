@@ -558,18 +558,18 @@ const std::vector<int64_t> &lane_widths(rlp_tree *t, int variant) {
     const std::vector<int32_t> &fc = t->first_child_h;
     const std::vector<int8_t> &pl = t->player_h;
     for (int me = 1; me <= 2; ++me) {
-        std::vector<int64_t> below, cur;        // [node of the level][depth]
+        std::vector<int32_t> below, cur;        // [node of the level][depth]; a count never exceeds the level's size
         for (int l = L - 1; l >= 0; --l) {
             const int64_t lo = t->level_off[l], hi = t->level_off[l + 1];
             cur.assign((size_t)(hi - lo) * L, 0);
             for (int64_t x = lo; x < hi; ++x) {
                 if (pl[x] < 0) continue;
-                int64_t *row = &cur[(size_t)(x - lo) * L];
+                int32_t *row = &cur[(size_t)(x - lo) * L];
                 row[l] = 1;
                 const bool explored = variant == 0 ? pl[x] > 0 : pl[x] == me;
                 for (int32_t ch = fc[x]; ch < fc[x + 1]; ++ch) {
                     if (pl[ch] < 0) continue;
-                    const int64_t *crow = &below[(size_t)(ch - hi) * L];
+                    const int32_t *crow = &below[(size_t)(ch - hi) * L];
                     for (int d = l + 1; d < L; ++d) row[d] = explored ? row[d] + crow[d] : std::max(row[d], crow[d]);
                 }
             }
@@ -653,7 +653,7 @@ int launch_lanes(rlp_cfr *c, const LaneView &v, rlp_tree *t, int64_t lanes, int6
     Frontier f;
     if (v.atomic && frontier_for(c, VARIANT, lanes, &f)) return launch_frontier<VARIANT>(v, f, t, lanes, lane_base, s);
     const unsigned g = grid_for(2 * lanes);
-    if (t->max_act <= 4 && t->L <= 16) k_lanes<VARIANT, 4, 16, 10><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
+    if (t->max_act <= 4 && t->L <= 16) k_lanes<VARIANT, 4, 16, 10><<<g, kBlock, 0, s>>>(v, lanes, lane_base);   // 10 CTAs / SM: measured best of 1 / 8 / 10
     else if (t->max_act <= 4) k_lanes<VARIANT, 4, kMaxDepth, 1><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
     else k_lanes<VARIANT, kMaxAct, kMaxDepth, 1><<<g, kBlock, 0, s>>>(v, lanes, lane_base);
     RLP_LAUNCH_CHECK();
