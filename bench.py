@@ -423,6 +423,7 @@ def main():
         if world == 1:
             extra['br_sweep'] = br_sweep()
             extra['config3'] = sampled_config3()
+            extra['exploitability_vs_time'] = exploitability_vs_time()
         else:
             extra['config3'] = sampled_config3_sharded(rank, world)
         extra['leduc25'] = leduc25(rank, world, public)
@@ -547,6 +548,47 @@ def br_sweep(ranks=(3, 5, 7, 9, 11, 13, 17, 21, 25)):
         del s, o
         dt.close()
     return rows
+
+
+def exploitability_vs_time(checkpoints=(10, 30, 100, 300, 1000, 3000)):
+    """The second half of BASELINE's metric: exploitability of the average strategy against wall-clock solve time, vanilla
+    CFR on Leduc-13 from scratch, one GPU.  `seconds` is host wall clock from the first iteration to the moment the
+    exploitability of that checkpoint is on the host (every evaluation so far included).  Beside it the CPU port on all
+    host threads up to the checkpoint it reaches within ~6 s; equal iteration counts must give equal exploitability."""
+    import torch
+    from oracle import oracle as orc
+    from rlpoker_b200.games.leduc_native import leduc_flat_tree
+    from rlpoker_b200.solver import DeviceCFR, DeviceTree
+    dt = DeviceTree(leduc_flat_tree(RANKS))
+    s = DeviceCFR(dt)
+    s.vanilla(10)
+    s.exploitability()
+    s.reset()
+    torch.cuda.synchronize()
+    points, done = [], 0
+    t0 = time.perf_counter()
+    for T in checkpoints:
+        s.vanilla(T - done)
+        done = T
+        e = s.exploitability()[0]           # synchronises: the value is on the host
+        points.append({'iterations': T, 'seconds': time.perf_counter() - t0, 'exploitability': e})
+    del s
+    dt.close()
+    threads = os.cpu_count() or 1
+    o = orc.Oracle(orc.leduc_tree(RANKS))
+    cpu, done = [], 0
+    t0 = time.perf_counter()
+    for T in checkpoints:
+        if cpu and (time.perf_counter() - t0) / done * T > 6.0:
+            break
+        o.vanilla_levels(T - done, threads=threads)
+        done = T
+        e = o.exploitability(o.average_strategy()[0])
+        cpu.append({'iterations': T, 'seconds': time.perf_counter() - t0, 'exploitability': e})
+    for c, g in zip(cpu, points):
+        c['abs_diff_vs_gpu'] = abs(c['exploitability'] - g['exploitability'])
+    return {'game': 'Leduc(get_deck(13, 2))', 'algorithm': 'vanilla CFR, average strategy', 'gpu': points,
+            'cpu_port': {'threads': threads, 'points': cpu}}
 
 
 def sampled_config3(lanes=1 << 20):
