@@ -424,6 +424,7 @@ def main():
             extra['br_sweep'] = br_sweep()
             extra['config3'] = sampled_config3()
             extra['exploitability_vs_time'] = exploitability_vs_time()
+            extra['config1'] = readme_config1()
         else:
             extra['config3'] = sampled_config3_sharded(rank, world)
         extra['leduc25'] = leduc25(rank, world, public)
@@ -718,6 +719,29 @@ def time_python_api(ft, N):
         dt = time.perf_counter() - t0
         out[name] = {'seconds': dt, 'value': 2.0 * N * 100 / dt, 'evaluations': len(expl),
                      'final_exploitability': expl[-1][1], 'kwargs': kw}
+    return out
+
+
+def readme_config1(iters=2000):
+    """BASELINE config 1: the README's call -- chance-sampling ``cfr()`` on ``Leduc.create_game(3)`` plus the
+    best-response exploitability -- through the Python API, one traversal lane per iteration like the reference
+    (wall clock; game construction and upload not timed).  BASELINE.md section 2 measured the reference at 29.7 ms per
+    chance-sampled iteration and 0.10 s per compute_exploitability call (container CPU, one thread)."""
+    from rlpoker_b200.best_response import compute_exploitability
+    from rlpoker_b200.cfr.cfr import cfr
+    from rlpoker_b200.games.leduc import Leduc
+    game = Leduc.create_game(3)
+    cfr(game, num_iters=10, use_chance_sampling=True, verbose=False)
+    out = {'call': 'cfr(Leduc.create_game(3), num_iters=%d, use_chance_sampling=True) + compute_exploitability' % iters}
+    for name, kw in (('default', {}), ('lean', {'immediate_regret': False, 'keep_strategies': 0})):
+        t0 = time.perf_counter()
+        avg, expl, hist = cfr(game, num_iters=iters, use_chance_sampling=True, verbose=False, **kw)
+        t1 = time.perf_counter()
+        e = compute_exploitability(game, avg)
+        t2 = time.perf_counter()
+        out[name] = {'cfr_seconds': t1 - t0, 'ms_per_iteration': 1e3 * (t1 - t0) / iters, 'exploitability_seconds': t2 - t1,
+                     'exploitability': e, 'kwargs': kw}
+    out['reference'] = {'ms_per_iteration': 29.7, 'exploitability_seconds': 0.10, 'source': 'BASELINE.md section 2'}
     return out
 
 

@@ -2,13 +2,14 @@
 // use_chance_sampling=True and rlpoker/cfr/external_cfr.py:82-173) plus the full-tree average-strategy
 // walk of rlpoker/cfr/cfr_util.py:109-198 as a forward level sweep.
 //
-// One thread = one traversal (lane, traversing player): an explicit-stack depth-first walk over the
-// breadth-first arrays against the strategy frozen for the iteration; chance (and, for external
-// sampling, opponent) actions are drawn with the reference's sampler (rlpoker/util.py:17-27 ->
+// One traversal per (lane, traversing player) against the strategy frozen for the iteration; chance (and, for
+// external sampling, opponent) actions are drawn with the reference's sampler (rlpoker/util.py:17-27 ->
 // numpy RandomState.choice: normalise, cumsum, renormalise, searchsorted-right) from a counter-based
 // Philox-4x32-10 stream keyed (seed; iteration, lane, player, node of the draw), so a CPU run fed the same
 // stream reproduces every lane exactly.  lanes == 1 is the reference algorithm bit for bit (plain adds in
 // visit order); lanes > 1 is mini-batch MCCFR with fp64 atomics (order of adds not deterministic).
+// Two forms of the same traversals: depth first, one thread per traversal with an explicit stack (k_lanes), and --
+// for many lanes -- level by level over frontier records (k_front_*); DESIGN.md section 6 has the measurements.
 #include "cfr.cuh"
 #include <cstring>
 
@@ -23,7 +24,6 @@ inline unsigned grid_for(int64_t n, int b = kBlock) { return (unsigned)((n + b -
 
 struct LaneView {
     const int4 *rec;                       // packed node records (tree.cuh)
-    const int32_t *first_child, *colbase, *srank;
     const int8_t *player;
     const double *cprob, *pay1, *pay2, *sigma;
     double *R, *S;                         // lanes == 1: the solver's arrays; else copy 0 of the accumulators below
@@ -98,10 +98,9 @@ __device__ inline int draw(const double *p, int n, double u) {
     return 3;
 }
 
-// One stack frame of the depth-first walk.  External sampling needs no reach probabilities (its regret increment is
-// unweighted, external_cfr.py:143-152), and the action-value array is as wide as the game's widest information set: the
-// per-thread stack is what limits this kernel (it lives in local memory), so it is kept as small as the game allows
-// (Leduc external: 16 frames x 48 B instead of 32 x 104 B).
+// One saved frame of the depth-first walk (the frame being worked on is in registers, see k_lanes).  External sampling
+// needs no reach probabilities (its regret increment is unweighted, external_cfr.py:143-152), and the action-value array is
+// as wide as the game's widest information set, so the local-memory stack stays as small as the game allows.
 template <int VARIANT, int MAXA>
 struct Frame {
     int node;
@@ -674,7 +673,7 @@ LaneView lane_view(rlp_cfr *c, uint64_t seed, double *R, double *S, int atomic) 
     rlp_tree *t = c->tree;
     LaneView v;
     v.rec = t->node_rec.p;
-    v.first_child = t->first_child.p; v.colbase = t->colbase.p; v.srank = t->srank.p; v.player = t->player.p;
+    v.player = t->player.p;
     v.cprob = t->cprob.p; v.pay1 = t->pay1.p; v.pay2 = t->pay2.p; v.sigma = c->sigma.p; v.R = R; v.S = S;
     v.copy_stride = 0; v.copy_mask = 0;
     v.in_R = c->flags.p; v.in_S = c->flags.p + (size_t)t->I; v.in_next = c->flags.p + 2 * (size_t)t->I;
