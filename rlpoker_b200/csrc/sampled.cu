@@ -272,38 +272,73 @@ __global__ void __launch_bounds__(kBlock, MINB) k_lanes(LaneView v, int64_t lane
 
 // ---- the same traversals, level by level ---------------------------------------------------------------------------
 // With many lanes the depth-first kernel above is bound by divergence: the threads of a warp stand at different places of
-// their walks.  The frontier form keeps one RECORD per visited non-terminal node of every traversal, grouped by depth:
-// a forward pass per level draws the sampled actions / expands the explored nodes into the next level's records (a warp
-// reserves its children with one atomic on the level counter), a backward pass per level turns children values into
-// node values and regret / strategy-sum increments.  Every thread of a launch does the same step of the walk, the values
-// are the depth-first kernel's bit for bit (same operands, same order within a node), terminal children never become
+// their walks.  The frontier form keeps one RECORD per EXPLORED node of every traversal (a node whose actions are all
+// followed: the traverser's own nodes under external sampling, every player node under chance sampling), grouped by
+// the number of explored ancestors.  Sampled nodes never become records: whoever steps onto one keeps drawing until
+// the walk stands on an explored node (-> a record at the next level) or on a terminal node (-> a record that only
+// carries the payoff).  A forward pass per level expands the explored nodes (a block reserves its children with one
+// atomic on the level counter), a backward pass per level turns children values into node values and regret /
+// strategy-sum increments.  Every thread of a launch does the same step of the walk, the values are the depth-first
+// kernel's bit for bit (same operands, same order within a node), terminal children of explored nodes never become
 // records, and the Philox key (node of the draw) does not depend on the processing order.
 constexpr int kFBlock = 256;
 constexpr int kTouchedParts = 64;
 struct Frontier {
-    int32_t *node, *trav, *child;      // child: first record of the children at the next level, or ~node of a drawn terminal
+    int32_t *node, *trav, *child;      // node: the explored node, or ~terminal where a sampled chain ended;
+                                       // child: first record of the node's non-terminal children at the next level
     double *val, *reach;               // reach: [2][capacity], the players' own reach (chance-sampled variant; the
                                        //   chance factor of a chance-SAMPLED walk stays 1.0 and 1.0 * x == x)
     unsigned int *count;               // [levels + 1] records per level; the last word flags a capacity overflow
     unsigned long long *touched;       // [kTouchedParts] visit counts, folded into IterState::touched at the end
-    int64_t off[kMaxDepth + 1];        // first record of each level
+    int64_t off[kMaxDepth + 2];        // first record of each level
     int64_t total;
     int levels;
 };
 
+// From `cur`, draw through sampled nodes until the walk stands on an explored or a terminal node; returns that node
+// (~node for a terminal one) and counts the nodes stepped onto.
 template <int VARIANT>
-__global__ void __launch_bounds__(kFBlock) k_front_root(LaneView v, Frontier f, int64_t lanes) {
-    int64_t tid = (int64_t)blockIdx.x * kFBlock + threadIdx.x;
-    if (tid == 0) {
-        f.count[0] = (unsigned int)(2 * lanes);
-        f.touched[0] = (unsigned long long)(2 * lanes);
+__device__ __forceinline__ int follow_chain(const LaneView &v, int cur, int me, uint32_t lane, uint64_t iteration, uint32_t &touched) {
+    for (;;) {
+        const int4 rec = __ldg(v.rec + cur);
+        const int pl = ((rec.y >> 8) & 0xff) - 1;
+        if (pl < 0) return ~cur;
+        if (!(pl == 0 || (VARIANT == 1 && pl != me))) return cur;
+        const int fc = rec.x, n = rec.y & 0xff;
+        const double *p = pl == 0 ? v.cprob + fc : v.sigma + rec.z;
+        cur = fc + draw(p, n, rlp::philox_uniform(v.seed, iteration, lane, (uint32_t)(me - 1), (uint32_t)cur));
+        touched++;
     }
-    if (tid >= 2 * lanes) return;
-    // traversal id = 2 * lane + (traversing player - 1).  Player 1's traversals first, then player 2's: whether a node
-    // is explored or sampled depends on the traverser, and a block's children stay together, so warps stay of one kind.
-    f.node[tid] = 0;
-    f.trav[tid] = (int32_t)(tid < lanes ? 2 * tid : 2 * (tid - lanes) + 1);
-    if (VARIANT == 0) { f.reach[tid] = 1.0; f.reach[f.total + tid] = 1.0; }
+}
+
+__device__ __forceinline__ void count_touched(const Frontier &f, uint32_t touched, unsigned int *s_touched) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, d);
+    if ((threadIdx.x & 31) == 0) s_touched[threadIdx.x >> 5] = touched;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tt = 0;
+        for (int k = 0; k < kFBlock / 32; ++k) tt += s_touched[k];
+        if (tt) atomicAdd(f.touched + (blockIdx.x & (kTouchedParts - 1)), (unsigned long long)tt);
+    }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kFBlock) k_front_root(LaneView v, Frontier f, int64_t lanes, int64_t lane_base) {
+    __shared__ unsigned int s_touched[kFBlock / 32];
+    const int64_t tid = (int64_t)blockIdx.x * kFBlock + threadIdx.x;
+    if (tid == 0) f.count[0] = (unsigned int)(2 * lanes);
+    uint32_t touched = 0;
+    if (tid < 2 * lanes) {
+        // traversal id = 2 * lane + (traversing player - 1).  Player 1's traversals first, then player 2's: which nodes
+        // are explored depends on the traverser, and a block's children stay together, so warps stay of one kind.
+        const int tr = (int)(tid < lanes ? 2 * tid : 2 * (tid - lanes) + 1);
+        touched = 1;
+        f.node[tid] = follow_chain<VARIANT>(v, 0, (tr & 1) + 1, (uint32_t)((tr >> 1) + lane_base), (uint64_t)v.iter->t, touched);
+        f.trav[tid] = tr;
+        if (VARIANT == 0) { f.reach[tid] = 1.0; f.reach[f.total + tid] = 1.0; }
+    }
+    count_touched(f, touched, s_touched);
 }
 
 __global__ void k_front_touched(Frontier f, IterState *iter) {
@@ -319,28 +354,16 @@ __global__ void __launch_bounds__(kFBlock) k_front_expand(LaneView v, Frontier f
     const unsigned int count = f.count[level];
     if ((int64_t)blockIdx.x * kFBlock >= count) return;          // the whole block is past the end
     const int64_t i = (int64_t)blockIdx.x * kFBlock + threadIdx.x;
-    const bool live = i < count;
     const int64_t at = f.off[level] + i, next = f.off[level + 1];
     const int64_t cap = f.off[level + 2] - next;
-    int node = 0, tr = 0, fc = 0, n = 0, pl = 0, col = 0, n_new = 0, a_drawn = 0;
+    int node = -1, tr = 0, fc = 0, n = 0, pl = 0, col = 0, n_new = 0;
     uint32_t mask = 0, touched = 0;
-    bool sampled = false;
-    if (live) {
+    if (i < count) {
         node = f.node[at]; tr = f.trav[at];
-        const int4 rec = __ldg(v.rec + node);
-        fc = rec.x; n = rec.y & 0xff; pl = ((rec.y >> 8) & 0xff) - 1; col = rec.z;
-        const uint32_t leaf = (uint32_t)rec.y >> 16;
-        const int me = (tr & 1) + 1;
-        sampled = pl == 0 || (VARIANT == 1 && pl != me);
-        if (sampled) {
-            const uint32_t lane = (uint32_t)((tr >> 1) + lane_base);
-            const double *p = pl == 0 ? v.cprob + fc : v.sigma + col;
-            a_drawn = draw(p, n, rlp::philox_uniform(v.seed, (uint64_t)v.iter->t, lane, (uint32_t)(me - 1), (uint32_t)node));
-            const bool is_leaf = a_drawn < 16 ? (leaf >> a_drawn) & 1 : v.player[fc + a_drawn] < 0;
-            n_new = is_leaf ? 0 : 1;
-            touched = 1;
-        } else {
-            mask = ~leaf & ((1u << n) - 1u);                    // explored nodes have at most kMaxAct children
+        if (node >= 0) {                                        // (a negative node is the terminal end of a sampled chain)
+            const int4 rec = __ldg(v.rec + node);
+            fc = rec.x; n = rec.y & 0xff; pl = ((rec.y >> 8) & 0xff) - 1; col = rec.z;
+            mask = ~((uint32_t)rec.y >> 16) & ((1u << n) - 1u);  // explored nodes have at most kMaxAct children
             n_new = __popc(mask);
             touched = (uint32_t)n;
         }
@@ -348,52 +371,45 @@ __global__ void __launch_bounds__(kFBlock) k_front_expand(LaneView v, Frontier f
     // the block reserves its children records with ONE atomic on the level counter (a counter shared by 10^5 warps
     // would take an atomic per warp at about one per clock)
     int incl = n_new;
-    uint32_t tsum = touched;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         int o = __shfl_up_sync(0xffffffffu, incl, d);
         if ((int)(threadIdx.x & 31) >= d) incl += o;
-        tsum += __shfl_xor_sync(0xffffffffu, tsum, d);
     }
     const int wid = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 31) { s_new[wid] = incl; s_touched[wid] = tsum; }
+    if ((threadIdx.x & 31) == 31) s_new[wid] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
         int tot = 0;
-        unsigned int tt = 0;
-        for (int k = 0; k < kFBlock / 32; ++k) { int x = s_new[k]; s_new[k] = tot; tot += x; tt += s_touched[k]; }
+        for (int k = 0; k < kFBlock / 32; ++k) { int x = s_new[k]; s_new[k] = tot; tot += x; }
         s_base = tot ? atomicAdd(f.count + level + 1, (unsigned int)tot) : 0u;
-        if (tt) atomicAdd(f.touched + (blockIdx.x & (kTouchedParts - 1)), (unsigned long long)tt);
     }
     __syncthreads();
-    if (!live) return;
-    const int64_t c0 = (int64_t)s_base + s_new[wid] + incl - n_new;
-    if (c0 + n_new > cap) { f.count[f.levels] = 1; f.child[at] = 0; return; }       // cannot happen: the bounds are exact
-    if (sampled) {
-        const int child = fc + a_drawn;
-        if (n_new == 0) { f.child[at] = ~child; return; }
-        f.child[at] = (int32_t)c0;
-        f.node[next + c0] = child;
-        f.trav[next + c0] = tr;
-        if (VARIANT == 0)
-            for (int k = 0; k < 2; ++k) f.reach[k * f.total + next + c0] = f.reach[k * f.total + at];
-        return;
-    }
-    f.child[at] = (int32_t)c0;
-    double r1 = 0.0, r2 = 0.0;
-    if (VARIANT == 0) { r1 = f.reach[at]; r2 = f.reach[f.total + at]; }
-    int j = 0;
-    for (int a = 0; a < n; ++a) {
-        if (!((mask >> a) & 1)) continue;
-        const int64_t to = next + c0 + j++;
-        f.node[to] = fc + a;
-        f.trav[to] = tr;
-        if (VARIANT == 0) {
-            const double sga = v.sigma[col + a];
-            f.reach[to] = pl == 1 ? sga * r1 : r1;
-            f.reach[f.total + to] = pl == 2 ? sga * r2 : r2;
+    if (n_new > 0) {
+        const int64_t c0 = (int64_t)s_base + s_new[wid] + incl - n_new;
+        if (c0 + n_new > cap) { f.count[f.levels] = 1; f.child[at] = 0; n_new = 0; }     // cannot happen: the bounds are exact
+        else {
+            f.child[at] = (int32_t)c0;
+            const int me = (tr & 1) + 1;
+            const uint32_t lane = (uint32_t)((tr >> 1) + lane_base);
+            const uint64_t iteration = (uint64_t)v.iter->t;
+            double r1 = 0.0, r2 = 0.0;
+            if (VARIANT == 0) { r1 = f.reach[at]; r2 = f.reach[f.total + at]; }
+            int j = 0;
+            for (int a = 0; a < n; ++a) {
+                if (!((mask >> a) & 1)) continue;
+                const int64_t to = next + c0 + j++;
+                f.node[to] = follow_chain<VARIANT>(v, fc + a, me, lane, iteration, touched);
+                f.trav[to] = tr;
+                if (VARIANT == 0) {
+                    const double sga = v.sigma[col + a];
+                    f.reach[to] = pl == 1 ? sga * r1 : r1;
+                    f.reach[f.total + to] = pl == 2 ? sga * r2 : r2;
+                }
+            }
         }
     }
+    count_touched(f, touched, s_touched);
 }
 
 template <int VARIANT, int MAXA>
@@ -401,16 +417,14 @@ __global__ void __launch_bounds__(kFBlock) k_front_collect(LaneView v, Frontier 
     const int64_t i = (int64_t)blockIdx.x * kFBlock + threadIdx.x;
     if (i >= f.count[level]) return;
     const int64_t at = f.off[level] + i, next = f.off[level + 1];
-    const int node = f.node[at], tr = f.trav[at], c0 = f.child[at];
+    const int node = f.node[at], tr = f.trav[at];
+    const int me = (tr & 1) + 1;
+    auto payoff = [&](int x) { return me == 1 ? v.pay1[x] : (v.zero_sum ? -v.pay1[x] : v.pay2[x]); };
+    if (node < 0) { f.val[at] = payoff(~node); return; }        // a sampled chain that ended on a terminal node
+    const int c0 = f.child[at];
     const int4 rec = __ldg(v.rec + node);
     const int fc = rec.x, n = rec.y & 0xff, pl = ((rec.y >> 8) & 0xff) - 1, col = rec.z, s = rec.w;
     const uint32_t leaf = (uint32_t)rec.y >> 16;
-    const int me = (tr & 1) + 1;
-    auto payoff = [&](int x) { return me == 1 ? v.pay1[x] : (v.zero_sum ? -v.pay1[x] : v.pay2[x]); };
-    if (pl == 0 || (VARIANT == 1 && pl != me)) {                // a sampled node hands its child's value up
-        f.val[at] = c0 < 0 ? payoff(~c0) : f.val[next + c0];
-        return;
-    }
     double va[MAXA], value = 0.0;
     int j = 0;
 #pragma unroll
@@ -547,34 +561,41 @@ extern "C" int rlp_cfr_update_average(rlp_cfr *c, double weight, void *stream_) 
 }
 
 namespace {
-// Most frontier records per depth that the two traversals of ONE lane can hold: explored nodes add their children's
-// bounds, sampled nodes take the largest (exact per depth; terminal nodes hold no record).
+// Most frontier records per level (= number of explored ancestors) that the two traversals of ONE lane can hold.
+// chain(x) = records of a walk that steps onto x: a terminal node leaves one payoff record at the current level; a
+// sampled node takes the largest of its children's (exact per level); an explored node leaves one record and its
+// non-terminal children start chains one level further down.
 const std::vector<int64_t> &lane_widths(rlp_tree *t, int variant) {
     std::vector<int64_t> &w = t->lane_width[variant];
     if (!w.empty()) return w;
     const int L = t->L;
-    w.assign((size_t)L, 0);
+    w.assign((size_t)L + 1, 0);
     const std::vector<int32_t> &fc = t->first_child_h;
     const std::vector<int8_t> &pl = t->player_h;
+    const int E = L + 1;                        // explored ancestors < L
     for (int me = 1; me <= 2; ++me) {
-        std::vector<int32_t> below, cur;        // [node of the level][depth]; a count never exceeds the level's size
+        std::vector<int32_t> below, cur;        // [node of the tree level][explored level, relative to the node's own]
         for (int l = L - 1; l >= 0; --l) {
             const int64_t lo = t->level_off[l], hi = t->level_off[l + 1];
-            cur.assign((size_t)(hi - lo) * L, 0);
+            cur.assign((size_t)(hi - lo) * E, 0);
             for (int64_t x = lo; x < hi; ++x) {
-                if (pl[x] < 0) continue;
-                int32_t *row = &cur[(size_t)(x - lo) * L];
-                row[l] = 1;
+                int32_t *row = &cur[(size_t)(x - lo) * E];
+                if (pl[x] < 0) { row[0] = 1; continue; }
                 const bool explored = variant == 0 ? pl[x] > 0 : pl[x] == me;
+                if (explored) row[0] = 1;
                 for (int32_t ch = fc[x]; ch < fc[x + 1]; ++ch) {
-                    if (pl[ch] < 0) continue;
-                    const int32_t *crow = &below[(size_t)(ch - hi) * L];
-                    for (int d = l + 1; d < L; ++d) row[d] = explored ? row[d] + crow[d] : std::max(row[d], crow[d]);
+                    const int32_t *crow = &below[(size_t)(ch - hi) * E];
+                    if (explored) {
+                        if (pl[ch] < 0) continue;                       // terminal children of explored nodes: no record
+                        for (int d = 0; d + 1 < E; ++d) row[d + 1] += crow[d];
+                    } else {
+                        for (int d = 0; d < E; ++d) row[d] = std::max(row[d], crow[d]);
+                    }
                 }
             }
             below.swap(cur);
         }
-        for (int d = 0; d < L; ++d) w[d] += below[d];
+        for (int d = 0; d < E; ++d) w[d] += below[d];
     }
     return w;
 }
@@ -597,7 +618,7 @@ bool frontier_for(rlp_cfr *c, int variant, int64_t lanes, Frontier *f) {
     const std::vector<int64_t> &w = lane_widths(t, variant);
     int levels = 0;
     int64_t per_lane = 0;
-    for (int d = 0; d < t->L; ++d) if (w[d] > 0) { levels = d + 1; per_lane += w[d]; }
+    for (int d = 0; d < (int)w.size() && d < kMaxDepth; ++d) if (w[d] > 0) { levels = d + 1; per_lane += w[d]; }
     if (levels == 0) return false;              // the root is terminal: nothing to record
     for (int d = 0; d < levels; ++d) if (w[d] * lanes >= ((int64_t)1 << 31)) return false;
     const size_t total = (size_t)per_lane * (size_t)lanes;
@@ -621,7 +642,7 @@ bool frontier_for(rlp_cfr *c, int variant, int64_t lanes, Frontier *f) {
     f->count = c->fr_count.p; f->levels = levels;
     f->touched = (unsigned long long *)(c->fr_count.p + 64);     // count words first (kMaxDepth + 2 <= 64), then the visit counts
     int64_t at = 0;
-    for (int d = 0; d <= kMaxDepth; ++d) { f->off[d] = at; if (d < levels) at += w[d] * lanes; }
+    for (int d = 0; d <= kMaxDepth + 1; ++d) { f->off[d] = at; if (d < levels) at += w[d] * lanes; }
     f->total = (int64_t)(c->fr_node.n);         // stride of the two reach planes
     c->fr_levels = levels;
     return true;
@@ -630,7 +651,7 @@ bool frontier_for(rlp_cfr *c, int variant, int64_t lanes, Frontier *f) {
 template <int VARIANT>
 int launch_frontier(const LaneView &v, const Frontier &f, rlp_tree *t, int64_t lanes, int64_t lane_base, cudaStream_t s) {
     RLP_CUDA(cudaMemsetAsync(f.count, 0, sizeof(unsigned int) * (size_t)(64 + 2 * kTouchedParts), s));
-    k_front_root<VARIANT><<<grid_for(2 * lanes, kFBlock), kFBlock, 0, s>>>(v, f, lanes); RLP_LAUNCH_CHECK();
+    k_front_root<VARIANT><<<grid_for(2 * lanes, kFBlock), kFBlock, 0, s>>>(v, f, lanes, lane_base); RLP_LAUNCH_CHECK();
     for (int l = 0; l < f.levels; ++l) {
         const int64_t cap = f.off[l + 1] - f.off[l];
         k_front_expand<VARIANT><<<grid_for(cap, kFBlock), kFBlock, 0, s>>>(v, f, l, lane_base); RLP_LAUNCH_CHECK();
