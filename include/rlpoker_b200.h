@@ -100,6 +100,13 @@ int rlp_tree_plan(const rlp_tree_desc *desc, int64_t *stats16);
  * (empty string when the tree does not qualify): *len = bytes needed incl. NUL; buf (nullable) gets up to cap bytes. */
 int rlp_tree_plan_fused_source(const rlp_tree_desc *desc, int64_t *stats16, char *buf, int64_t cap, int64_t *len);
 
+/*
+ * Host only.  Record capacities of the level-by-level sampled lanes (rlp_cfr_sampled_iters with many lanes) for ONE lane,
+ * both traversals: out33[e] = most records a lane can hold whose node has e explored ancestors (explored = every action
+ * followed: the traverser's own nodes for RLP_EXTERNAL_SAMPLED, every player node for RLP_CHANCE_SAMPLED), zero padded.
+ */
+int rlp_tree_plan_lane_records(const rlp_tree_desc *desc, int variant, int64_t *out33);
+
 /* ---- solver --------------------------------------------------------------------------- */
 typedef enum { RLP_REGRET = 0, RLP_STRAT_SUM = 1, RLP_SIGMA = 2, RLP_AVERAGE = 3, RLP_CUM_IMM_REGRET = 4 } rlp_which;
 typedef enum { RLP_CHANCE_SAMPLED = 0, RLP_EXTERNAL_SAMPLED = 1 } rlp_variant;

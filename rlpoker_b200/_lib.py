@@ -45,6 +45,7 @@ SYMBOLS = {
     'rlp_tree_stat': (C.c_int64, [_vp, C.c_int]),
     'rlp_tree_plan': (C.c_int, [C.POINTER(TreeDesc), _i64p]),
     'rlp_tree_plan_fused_source': (C.c_int, [C.POINTER(TreeDesc), _i64p, C.c_char_p, C.c_int64, _i64p]),
+    'rlp_tree_plan_lane_records': (C.c_int, [C.POINTER(TreeDesc), C.c_int, _i64p]),
     'rlp_cfr_fused_timeline': (C.c_int, [_vp, C.c_int64, C.c_int, C.POINTER(C.c_uint64), _vp]),
     'rlp_leduc_generate': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _i8p, _i32p,
                                      _dp, _dp, _dp, _i32p, _u8p]),

@@ -554,6 +554,11 @@ int launch_average_walk(rlp_cfr *c, double weight, cudaStream_t s) {
 }
 }  // namespace rlp
 
+namespace { const std::vector<int64_t> &lane_widths(rlp_tree *t, int variant); }
+namespace rlp {
+const std::vector<int64_t> &lane_record_bounds(rlp_tree *t, int variant) { return lane_widths(t, variant); }
+}  // namespace rlp
+
 extern "C" int rlp_cfr_update_average(rlp_cfr *c, double weight, void *stream_) {
     if (!c) return fail(RLP_ERR_INVALID, "null solver");
     c->external_state = true;

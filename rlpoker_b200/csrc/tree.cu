@@ -279,6 +279,23 @@ extern "C" int rlp_tree_plan_fused_source(const rlp_tree_desc *d, int64_t *stats
     return RLP_OK;
 }
 
+namespace rlp { const std::vector<int64_t> &lane_record_bounds(rlp_tree *t, int variant); }
+
+// Host-only: the per-level record capacities of the level-by-level sampled lanes for ONE lane (both traversals), i.e.
+// out[e] = most records with e explored ancestors; zero-padded to 33 entries.
+extern "C" int rlp_tree_plan_lane_records(const rlp_tree_desc *d, int variant, int64_t *out33) {
+    if (!d || !out33 || (variant != 0 && variant != 1)) return fail(RLP_ERR_INVALID, "bad argument");
+    rlp::g_dry_run = true;
+    rlp_tree *t = nullptr;
+    int rc = rlp_tree_upload(d, nullptr, &t);
+    rlp::g_dry_run = false;
+    if (rc) return rc;
+    const std::vector<int64_t> &w = rlp::lane_record_bounds(t, variant);
+    for (int k = 0; k < 33; ++k) out33[k] = k < (int)w.size() ? w[k] : 0;
+    delete t;
+    return RLP_OK;
+}
+
 extern "C" int rlp_tree_plan(const rlp_tree_desc *d, int64_t *stats16);
 extern "C" int rlp_tree_plan(const rlp_tree_desc *d, int64_t *stats16) {
     if (!d || !stats16) return fail(RLP_ERR_INVALID, "null argument");

@@ -53,6 +53,15 @@ def plan_tree(flat_tree):
     return dict(zip(names, (int(x) for x in out)))
 
 
+def plan_lane_records(flat_tree, variant):
+    """Host-only: per level (number of explored ancestors) the most records ONE lane of the level-by-level sampled
+    kernels can hold (rlp_tree_plan_lane_records); the device buffers are ``lanes`` times this."""
+    desc, keep = _tree_desc(flat_tree)
+    out = np.zeros(33, np.int64)
+    check(_lib.load().rlp_tree_plan_lane_records(C.byref(desc), int(variant), ptr(out, _lib._i64p)))
+    return out
+
+
 class DeviceTree:
     def __init__(self, flat_tree, stream=None):
         _lib.require_device()
